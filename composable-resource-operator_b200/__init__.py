@@ -1,0 +1,412 @@
+"""composable-resource-operator_b200 — B200-native post-attach probe + spec path.
+
+Thin ctypes binding of ``libcroprobe.so`` (the C ABI in ``include/croprobe.h``),
+the same entry points a Go host binds with cgo.  The package
+name is not a Python identifier; import it with::
+
+    import importlib
+    cro = importlib.import_module("composable-resource-operator_b200")
+
+There is no CPU fallback: if the shared library is missing the import raises,
+and ``ProbeContext`` raises ``ProbeError`` when no CUDA device is usable.  The
+host-side mirror of the reference interface (parse / decide / emit / attach
+step) lives in the library too (``csrc/identity.cpp``, ``csrc/reconcile.cpp``);
+this module only marshals arguments.
+
+Reference slots (paths relative to the reference tree):
+  enumerate / parse     internal/utils/gpus.go:878-919, 921-962, 1014-1089
+  visibility decision   internal/utils/gpus.go:54-86
+  attach step           internal/controller/composableresource_controller.go:200-287
+  wire structs          internal/cdi/fti/fm/api/*.go, fti/cm/client.go:62-79,
+                        sunfish/client.go:48-61, api/v1alpha1/*_types.go
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+from typing import Dict, List, Optional, Tuple
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcroprobe.so")
+
+ABI_VERSION = 1
+MAX_DEVICES = 16
+
+OK = 0
+ERR_INVALID_ARG, ERR_ABI_MISMATCH, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM = -1, -2, -3, -4, -5
+ERR_CHECKSUM, ERR_BUFFER_SMALL, ERR_NCCL, ERR_DEADLINE, ERR_UNSUPPORTED = -6, -7, -8, -9, -10
+ERR_PARSE, ERR_EXEC, ERR_P2P, ERR_INTERNAL = -11, -12, -13, -14
+
+F_SKIP_COPY, F_SKIP_P2P, F_SKIP_NCCL, F_NO_NVML, F_VERIFY_COPY, F_LAZY_ALLOC = 1, 2, 4, 8, 16, 32
+READ_AUTO, READ_LDG, READ_TMA, READ_LDG256 = 0, 1, 2, 3
+COPY_AUTO, COPY_LDG, COPY_TMA = 0, 1, 2
+
+
+class ProbeError(RuntimeError):
+    def __init__(self, code: int, msg: str = "") -> None:
+        self.code = code
+        super().__init__("croprobe error %d (%s)%s" % (code, strerror(code), (": " + msg) if msg else ""))
+
+
+class Opts(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", ctypes.c_uint32), ("flags", ctypes.c_uint32),
+        ("sweep_bytes", ctypes.c_uint64), ("p2p_bytes", ctypes.c_uint64), ("seed_base", ctypes.c_uint64),
+        ("read_sweeps", ctypes.c_uint32), ("copy_sweeps", ctypes.c_uint32), ("latency_hops", ctypes.c_uint32),
+        ("read_variant", ctypes.c_uint32), ("copy_variant", ctypes.c_uint32), ("deadline_ms", ctypes.c_int32),
+        ("n_devices", ctypes.c_int32), ("devices", ctypes.c_int32 * MAX_DEVICES), ("reserved", ctypes.c_uint32 * 8),
+    ]
+
+
+class DevInfo(ctypes.Structure):
+    _fields_ = [
+        ("cuda_ordinal", ctypes.c_int32), ("device_minor", ctypes.c_int32),
+        ("gpu_uuid", ctypes.c_char * 48), ("pci_bus_id", ctypes.c_char * 24), ("name", ctypes.c_char * 64),
+        ("hbm_bytes_total", ctypes.c_uint64), ("sm_count", ctypes.c_uint32),
+        ("cc_major", ctypes.c_uint32), ("cc_minor", ctypes.c_uint32), ("identity_source", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32 * 4),
+    ]
+
+
+class ProbeResult(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", ctypes.c_uint32), ("status", ctypes.c_int32),
+        ("cuda_ordinal", ctypes.c_int32), ("device_minor", ctypes.c_int32),
+        ("gpu_uuid", ctypes.c_char * 48), ("pci_bus_id", ctypes.c_char * 24),
+        ("hbm_bytes_total", ctypes.c_uint64), ("sweep_bytes", ctypes.c_uint64), ("seed", ctypes.c_uint64),
+        ("checksum_xor", ctypes.c_uint64), ("checksum_sum", ctypes.c_uint64),
+        ("fill_ns", ctypes.c_uint64), ("read_best_ns", ctypes.c_uint64), ("read_median_ns", ctypes.c_uint64),
+        ("copy_best_ns", ctypes.c_uint64), ("copy_median_ns", ctypes.c_uint64),
+        ("sm_count", ctypes.c_uint32), ("sm_clock_mhz", ctypes.c_uint32), ("mem_clock_mhz", ctypes.c_uint32),
+        ("ecc_errors", ctypes.c_uint32),
+        ("p2p_read_ns", ctypes.c_uint64 * 8), ("p2p_checksum_xor", ctypes.c_uint64 * 8),
+        ("p2p_latency_ns_x16", ctypes.c_uint32 * 8), ("p2p_access", ctypes.c_uint8 * 8),
+        ("p2p_bytes", ctypes.c_uint64), ("expect_xor", ctypes.c_uint64), ("expect_sum", ctypes.c_uint64),
+        ("read_variant", ctypes.c_uint32), ("copy_variant", ctypes.c_uint32),
+        ("read_sweeps", ctypes.c_uint32), ("copy_sweeps", ctypes.c_uint32),
+        ("copy_checksum_xor", ctypes.c_uint64), ("copy_checksum_sum", ctypes.c_uint64),
+        ("rank", ctypes.c_uint32), ("world", ctypes.c_uint32), ("reserved", ctypes.c_uint8 * 96),
+    ]
+
+
+class SweepResult(ctypes.Structure):
+    _fields_ = [("bytes", ctypes.c_uint64), ("ns", ctypes.c_uint64), ("checksum_xor", ctypes.c_uint64),
+                ("checksum_sum", ctypes.c_uint64), ("variant", ctypes.c_uint32), ("launches", ctypes.c_uint32)]
+
+
+assert ctypes.sizeof(ProbeResult) == 512, ctypes.sizeof(ProbeResult)
+
+# Every symbol include/croprobe.h declares; tests check the library exports all of them.
+EXPORTS = [
+    "cro_probe_init", "cro_probe_destroy", "cro_device_count", "cro_enumerate", "cro_emit_csv",
+    "cro_parse_gpu_csv", "cro_parse_proc_csv", "cro_proc_information_to_line", "cro_check_gpu_visible",
+    "cro_normalize", "cro_probe_device", "cro_probe_all", "cro_result_device_ptr", "cro_hbm_fill",
+    "cro_hbm_read_checksum", "cro_hbm_copy", "cro_hbm_read_checksum_dst", "cro_hbm_expected_checksum",
+    "cro_inject_fault", "cro_read_words", "cro_hbm_read_loop", "cro_hbm_copy_loop", "cro_hbm_fill_loop",
+    "cro_device_seed", "cro_launch_count", "cro_emit_status_json", "cro_emit_scalar_status_json",
+    "cro_emit_fm_scale_up", "cro_emit_fm_scale_down", "cro_emit_cm_scale_up", "cro_emit_cm_scale_down",
+    "cro_emit_sunfish_request", "cro_emit_probe_annotations_json", "cro_fm_parse_scale_up_response",
+    "cro_reconcile_attach", "cro_strerror", "cro_last_error", "cro_version",
+]
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libcroprobe.so is not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C composable-resource-operator_b200/csrc`.  There is no CPU fallback for the probe path."
+            % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    c, sz, psz = ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)
+    vp, i32, u32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64
+    out = [c, sz, psz]
+    sig = {
+        "cro_probe_init": (i32, [ctypes.POINTER(Opts), ctypes.POINTER(vp)]),
+        "cro_probe_destroy": (None, [vp]),
+        "cro_device_count": (i32, [vp, ctypes.POINTER(i32)]),
+        "cro_enumerate": (i32, [vp, ctypes.POINTER(DevInfo), i32, ctypes.POINTER(i32)]),
+        "cro_emit_csv": (i32, [ctypes.POINTER(DevInfo), i32, c] + out),
+        "cro_parse_gpu_csv": (i32, [c, c, c, c] + out),
+        "cro_parse_proc_csv": (i32, [c, c, c, c] + out),
+        "cro_proc_information_to_line": (i32, [c] + out),
+        "cro_check_gpu_visible": (i32, [ctypes.POINTER(DevInfo), i32, c, ctypes.POINTER(i32)]),
+        "cro_normalize": (i32, [i32, c] + out),
+        "cro_probe_device": (i32, [vp, i32, ctypes.POINTER(ProbeResult)]),
+        "cro_probe_all": (i32, [vp, ctypes.POINTER(ProbeResult), i32, ctypes.POINTER(i32)]),
+        "cro_result_device_ptr": (i32, [vp, i32, ctypes.POINTER(u64)]),
+        "cro_hbm_fill": (i32, [vp, i32, ctypes.POINTER(SweepResult)]),
+        "cro_hbm_fill_loop": (i32, [vp, i32, u32, ctypes.POINTER(SweepResult)]),
+        "cro_hbm_read_checksum": (i32, [vp, i32, u32, ctypes.POINTER(SweepResult)]),
+        "cro_hbm_read_checksum_dst": (i32, [vp, i32, u32, ctypes.POINTER(SweepResult)]),
+        "cro_hbm_read_loop": (i32, [vp, i32, u32, u32, ctypes.POINTER(SweepResult)]),
+        "cro_hbm_copy": (i32, [vp, i32, u32, ctypes.POINTER(SweepResult)]),
+        "cro_hbm_copy_loop": (i32, [vp, i32, u32, u32, ctypes.POINTER(SweepResult)]),
+        "cro_hbm_expected_checksum": (i32, [vp, i32, ctypes.POINTER(SweepResult)]),
+        "cro_inject_fault": (i32, [vp, i32, u64, u64]),
+        "cro_read_words": (i32, [vp, i32, u64, u64, ctypes.POINTER(u64)]),
+        "cro_device_seed": (i32, [vp, i32, ctypes.POINTER(u64)]),
+        "cro_launch_count": (u64, [vp]),
+        "cro_emit_status_json": (i32, [c, c, c, c] + out),
+        "cro_emit_scalar_status_json": (i32, [c, c, c, c, c] + out),
+        "cro_emit_fm_scale_up": (i32, [c, c, c, c] + out),
+        "cro_emit_fm_scale_down": (i32, [c, c, c, c] + out),
+        "cro_emit_cm_scale_up": (i32, [c, i32] + out),
+        "cro_emit_cm_scale_down": (i32, [c, i32, c] + out),
+        "cro_emit_sunfish_request": (i32, [c, ctypes.c_longlong, c, c] + out),
+        "cro_emit_probe_annotations_json": (i32, [ctypes.POINTER(ProbeResult)] + out),
+        "cro_fm_parse_scale_up_response": (i32, [c, c, c, c, c, sz, c, sz, c, sz]),
+        "cro_reconcile_attach": (i32, [vp, c] + out),
+        "cro_strerror": (c, [i32]),
+        "cro_last_error": (i32, [vp, c, sz]),
+        "cro_version": (c, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)   # AttributeError == a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def strerror(code: int) -> str:
+    return lib.cro_strerror(code).decode()
+
+
+def version() -> str:
+    return lib.cro_version().decode()
+
+
+def _b(s) -> Optional[bytes]:
+    if s is None:
+        return None
+    return s if isinstance(s, bytes) else s.encode("utf-8", "surrogateescape")
+
+
+def _text_call(fn, *args, cap: int = 1 << 16) -> Tuple[int, bytes]:
+    buf = ctypes.create_string_buffer(cap)
+    n = ctypes.c_size_t(0)
+    rc = fn(*args, buf, cap, ctypes.byref(n))
+    if rc == ERR_BUFFER_SMALL and n.value + 1 > cap:
+        return _text_call(fn, *args, cap=n.value + 1)
+    return rc, buf.raw[: n.value]
+
+
+def _text(fn, *args) -> str:
+    rc, raw = _text_call(fn, *args)
+    if rc != OK:
+        raise ProbeError(rc, raw.decode("utf-8", "replace"))
+    return raw.decode("utf-8", "surrogateescape")
+
+
+# ---- host-side mirror of the reference text path (no GPU needed) -------------------
+def getGPUInfoFromNvidiaSmiOutput(std_out: str, std_err: str, exec_err: Optional[str], queryArgs: str) -> Tuple[int, str]:
+    """Parse rule of getGPUInfoFromNvidiaPod (internal/utils/gpus.go:896-916).
+    Returns (code, text): Go JSON of the []map[string]string, or the error text."""
+    rc, raw = _text_call(lib.cro_parse_gpu_csv, _b(std_out), _b(std_err), _b(exec_err), _b(queryArgs))
+    return rc, raw.decode("utf-8", "surrogateescape")
+
+
+def getGPUInfoFromProcOutput(std_out: str, std_err: str, exec_err: Optional[str], queryArgs: str) -> Tuple[int, str]:
+    """Parse rule of getGPUInfoFromProcInCroNodeAgentPod (internal/utils/gpus.go:1045-1089)."""
+    rc, raw = _text_call(lib.cro_parse_proc_csv, _b(std_out), _b(std_err), _b(exec_err), _b(queryArgs))
+    return rc, raw.decode("utf-8", "surrogateescape")
+
+
+def proc_information_to_line(text: str) -> str:
+    return _text(lib.cro_proc_information_to_line, _b(text))
+
+
+def normalize(kind: int, s: str) -> str:
+    return _text(lib.cro_normalize, kind, _b(s))
+
+
+def emit_csv(devs: List[DevInfo], query: str) -> str:
+    arr = (DevInfo * max(1, len(devs)))(*devs)
+    return _text(lib.cro_emit_csv, arr, len(devs), _b(query))
+
+
+def CheckGPUVisible(devs: List[DevInfo], device_id: str) -> bool:
+    """internal/utils/gpus.go:73-84 over an enumerated device list."""
+    arr = (DevInfo * max(1, len(devs)))(*devs)
+    v = ctypes.c_int(0)
+    rc = lib.cro_check_gpu_visible(arr, len(devs), _b(device_id), ctypes.byref(v))
+    if rc != OK:
+        raise ProbeError(rc)
+    return bool(v.value)
+
+
+def emit_status_json(state: str, error: str = "", device_id: str = "", cdi_device_id: str = "") -> str:
+    return _text(lib.cro_emit_status_json, _b(state), _b(error), _b(device_id), _b(cdi_device_id))
+
+
+def emit_scalar_status_json(state: str, device_id: str = "", cdi_device_id: str = "", node_name: str = "",
+                            error: str = "") -> str:
+    return _text(lib.cro_emit_scalar_status_json, _b(state), _b(device_id), _b(cdi_device_id), _b(node_name), _b(error))
+
+
+def emit_fm_scale_up(tenant: str, mach: str, res_type: str, model: str) -> str:
+    return _text(lib.cro_emit_fm_scale_up, _b(tenant), _b(mach), _b(res_type), _b(model))
+
+
+def emit_fm_scale_down(tenant: str, mach: str, res_type: str, res_uuid: str) -> str:
+    return _text(lib.cro_emit_fm_scale_down, _b(tenant), _b(mach), _b(res_type), _b(res_uuid))
+
+
+def emit_cm_scale_up(spec_uuid: str, device_count: int) -> str:
+    return _text(lib.cro_emit_cm_scale_up, _b(spec_uuid), device_count)
+
+
+def emit_cm_scale_down(spec_uuid: str, device_count: int, device_id: str) -> str:
+    return _text(lib.cro_emit_cm_scale_down, _b(spec_uuid), device_count, _b(device_id))
+
+
+def emit_sunfish_request(name: str, count: int, proc_type: str, model: str) -> str:
+    return _text(lib.cro_emit_sunfish_request, _b(name), count, _b(proc_type), _b(model))
+
+
+def emit_probe_annotations_json(r: ProbeResult) -> str:
+    return _text(lib.cro_emit_probe_annotations_json, ctypes.byref(r))
+
+
+def fm_parse_scale_up_response(body: str, name: str, res_type: str, model: str) -> Tuple[str, str, str]:
+    """(deviceID, CDIDeviceID, err) per internal/cdi/fti/fm/client.go:184-213."""
+    dev, cdi, err = (ctypes.create_string_buffer(256) for _ in range(3))
+    err = ctypes.create_string_buffer(1024)
+    rc = lib.cro_fm_parse_scale_up_response(_b(body), _b(name), _b(res_type), _b(model), dev, 256, cdi, 256, err, 1024)
+    if rc != OK:
+        return "", "", err.value.decode()
+    return dev.value.decode(), cdi.value.decode(), ""
+
+
+def reconcile_attach(ctx: Optional["ProbeContext"], request: Dict) -> Dict:
+    """One pass of handleAttachingState (composableresource_controller.go:200-287).
+    ``ctx`` may be None when ``request['enumeration']`` supplies the exec output."""
+    handle = ctx.handle if ctx is not None else None
+    rc, raw = _text_call(lib.cro_reconcile_attach, handle, _b(json.dumps(request)))
+    if rc != OK:
+        raise ProbeError(rc, raw.decode("utf-8", "replace"))
+    out = json.loads(raw.decode("utf-8"))
+    out["_raw"] = raw.decode("utf-8")
+    return out
+
+
+# ---- the probe context (needs a B200) ------------------------------------------------
+class ProbeContext:
+    """Long-lived probe context: resident sweep buffers, streams, events.
+
+    Takes the slot of utils.RunNvidiaSmi + utils.CheckGPUVisible
+    (internal/utils/gpus.go:666-689, 54-86)."""
+
+    def __init__(self, sweep_bytes: int = 0, devices: Optional[List[int]] = None, flags: int = 0,
+                 read_sweeps: int = 0, copy_sweeps: int = 0, read_variant: int = READ_AUTO,
+                 copy_variant: int = COPY_AUTO, p2p_bytes: int = 0, latency_hops: int = 0,
+                 deadline_ms: int = 0, seed_base: int = 0) -> None:
+        o = Opts()
+        o.abi_version = ABI_VERSION
+        o.flags = flags
+        o.sweep_bytes = sweep_bytes
+        o.p2p_bytes = p2p_bytes
+        o.seed_base = seed_base
+        o.read_sweeps, o.copy_sweeps = read_sweeps, copy_sweeps
+        o.latency_hops = latency_hops
+        o.read_variant, o.copy_variant = read_variant, copy_variant
+        o.deadline_ms = deadline_ms
+        if devices:
+            o.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                o.devices[i] = d
+        h = ctypes.c_void_p()
+        rc = lib.cro_probe_init(ctypes.byref(o), ctypes.byref(h))
+        if rc != OK:
+            raise ProbeError(rc, "cro_probe_init")
+        self.handle = h
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            lib.cro_probe_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self) -> "ProbeContext":
+        return self
+
+    def __exit__(self, *a) -> None:
+        self.close()
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, allow=()) -> int:
+        if rc != OK and rc not in allow:
+            buf = ctypes.create_string_buffer(1024)
+            lib.cro_last_error(self.handle, buf, 1024)
+            raise ProbeError(rc, buf.value.decode("utf-8", "replace"))
+        return rc
+
+    def device_count(self) -> int:
+        n = ctypes.c_int()
+        self._check(lib.cro_device_count(self.handle, ctypes.byref(n)))
+        return n.value
+
+    def enumerate(self) -> List[DevInfo]:
+        n = ctypes.c_int()
+        arr = (DevInfo * MAX_DEVICES)()
+        self._check(lib.cro_enumerate(self.handle, arr, MAX_DEVICES, ctypes.byref(n)))
+        return [arr[i] for i in range(n.value)]
+
+    def seed(self, dev: int = 0) -> int:
+        s = ctypes.c_uint64()
+        self._check(lib.cro_device_seed(self.handle, dev, ctypes.byref(s)))
+        return s.value
+
+    def probe_device(self, dev: int = 0, allow_checksum_error: bool = False) -> ProbeResult:
+        r = ProbeResult()
+        self._check(lib.cro_probe_device(self.handle, dev, ctypes.byref(r)),
+                    allow=(ERR_CHECKSUM,) if allow_checksum_error else ())
+        return r
+
+    def probe_all(self) -> List[ProbeResult]:
+        arr = (ProbeResult * MAX_DEVICES)()
+        n = ctypes.c_int()
+        self._check(lib.cro_probe_all(self.handle, arr, MAX_DEVICES, ctypes.byref(n)))
+        return [arr[i] for i in range(n.value)]
+
+    def result_device_ptr(self, dev: int = 0) -> int:
+        p = ctypes.c_uint64()
+        self._check(lib.cro_result_device_ptr(self.handle, dev, ctypes.byref(p)))
+        return p.value
+
+    def _sweep(self, fn, *args) -> SweepResult:
+        r = SweepResult()
+        self._check(fn(self.handle, *args, ctypes.byref(r)))
+        return r
+
+    def hbm_fill(self, dev: int = 0, iters: int = 1) -> SweepResult:
+        return self._sweep(lib.cro_hbm_fill_loop, dev, iters)
+
+    def hbm_read_checksum(self, dev: int = 0, variant: int = READ_AUTO, iters: int = 1, dst: bool = False) -> SweepResult:
+        if dst:
+            return self._sweep(lib.cro_hbm_read_checksum_dst, dev, variant)
+        return self._sweep(lib.cro_hbm_read_loop, dev, variant, iters)
+
+    def hbm_copy(self, dev: int = 0, variant: int = COPY_AUTO, iters: int = 1) -> SweepResult:
+        return self._sweep(lib.cro_hbm_copy_loop, dev, variant, iters)
+
+    def hbm_expected_checksum(self, dev: int = 0) -> SweepResult:
+        return self._sweep(lib.cro_hbm_expected_checksum, dev)
+
+    def inject_fault(self, dev: int, word_index: int, mask: int) -> None:
+        self._check(lib.cro_inject_fault(self.handle, dev, word_index, mask))
+
+    def read_words(self, dev: int, first: int, n: int) -> List[int]:
+        arr = (ctypes.c_uint64 * n)()
+        self._check(lib.cro_read_words(self.handle, dev, first, n, arr))
+        return list(arr)
+
+    def launch_count(self) -> int:
+        return int(lib.cro_launch_count(self.handle))

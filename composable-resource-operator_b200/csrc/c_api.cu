@@ -1,0 +1,533 @@
+// c_api.cu — extern "C" surface of libcroprobe (include/croprobe.h).
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+
+#include "../../include/croprobe.h"
+#include "gojson.hpp"
+#include "identity.hpp"
+#include "probe.hpp"
+#include "reconcile.hpp"
+
+using namespace cro;
+
+static_assert(sizeof(cro_probe_result) == 512, "cro_probe_result is the 512-byte all-gather payload");
+static_assert(offsetof(cro_probe_result, gpu_uuid) == 16, "layout");
+static_assert(offsetof(cro_probe_result, pci_bus_id) == 64, "layout");
+static_assert(offsetof(cro_probe_result, checksum_xor) == 112, "layout");
+static_assert(offsetof(cro_probe_result, p2p_read_ns) == 184, "layout");
+static_assert(offsetof(cro_probe_result, p2p_access) == 344, "layout");
+static_assert(offsetof(cro_probe_result, rank) == 408, "layout");
+
+namespace {
+
+int copy_out(const std::string& s, char* buf, size_t cap, size_t* len) {
+    if (len) *len = s.size();
+    if (!buf || cap < s.size() + 1) return CRO_ERR_BUFFER_SMALL;
+    memcpy(buf, s.data(), s.size());
+    buf[s.size()] = '\0';
+    return CRO_OK;
+}
+
+std::string S(const char* p) { return p ? std::string(p) : std::string(); }
+
+std::string fixed_str(const char* p, size_t cap) { return std::string(p, strnlen(p, cap)); }
+
+// bytes per ns == GB/s; one decimal, integer arithmetic only.
+std::string gbs_x10(uint64_t bytes, uint64_t ns) {
+    if (ns == 0) return "0.0";
+    const unsigned __int128 v = (unsigned __int128)bytes * 10u / ns;
+    const uint64_t q = (uint64_t)v;
+    return std::to_string(q / 10) + "." + std::to_string(q % 10);
+}
+
+std::string hex16(uint64_t v) {
+    char b[24];
+    snprintf(b, sizeof b, "%016llx", (unsigned long long)v);
+    return b;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cro_version(void) { return "croprobe 0.1.0 (sm_100a)"; }
+
+const char* cro_strerror(int code) {
+    switch (code) {
+        case CRO_OK: return "ok";
+        case CRO_ERR_INVALID_ARG: return "invalid argument";
+        case CRO_ERR_ABI_MISMATCH: return "abi version mismatch";
+        case CRO_ERR_NO_DEVICE: return "no CUDA device";
+        case CRO_ERR_CUDA: return "cuda runtime error";
+        case CRO_ERR_OOM: return "sweep buffer allocation failed";
+        case CRO_ERR_CHECKSUM: return "hbm checksum mismatch";
+        case CRO_ERR_BUFFER_SMALL: return "output buffer too small";
+        case CRO_ERR_NCCL: return "nccl error";
+        case CRO_ERR_DEADLINE: return "deadline exceeded";
+        case CRO_ERR_UNSUPPORTED: return "unsupported field";
+        case CRO_ERR_PARSE: return "parse error";
+        case CRO_ERR_EXEC: return "enumerate command failed";
+        case CRO_ERR_P2P: return "peer access error";
+        case CRO_ERR_INTERNAL: return "internal error";
+        default: return "unknown error";
+    }
+}
+
+int cro_last_error(cro_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(ctx->err_mu);
+    return copy_out(ctx->last_error, buf, cap, nullptr);
+}
+
+int cro_probe_init(const cro_opts* opts, cro_ctx** out) { return ctx_create(opts, out); }
+void cro_probe_destroy(cro_ctx* ctx) { ctx_destroy(ctx); }
+
+int cro_device_count(cro_ctx* ctx, int* n) {
+    if (!ctx || !n) return CRO_ERR_INVALID_ARG;
+    *n = (int)ctx->devs.size();
+    return CRO_OK;
+}
+
+int cro_enumerate(cro_ctx* ctx, cro_dev_info* out, int cap, int* n) {
+    if (!ctx || !n) return CRO_ERR_INVALID_ARG;
+    *n = (int)ctx->devs.size();
+    if (*n == 0) return CRO_OK;
+    if (!out || cap < *n) return CRO_ERR_BUFFER_SMALL;
+    for (int i = 0; i < *n; ++i) out[i] = ctx->devs[(size_t)i]->info;
+    return CRO_OK;
+}
+
+int cro_emit_csv(const cro_dev_info* devs, int n, const char* query, char* buf, size_t cap, size_t* len) {
+    if (!query || (n > 0 && !devs)) return CRO_ERR_INVALID_ARG;
+    std::string out, err;
+    int rc = identity::EmitCsv(devs, n, query, &out, &err);
+    if (rc != CRO_OK) {
+        copy_out(err, buf, cap, len);
+        return rc;
+    }
+    return copy_out(out, buf, cap, len);
+}
+
+static int finish_parse(const identity::GpuInfoResult& r, char* buf, size_t cap, size_t* len) {
+    if (r.code != CRO_OK) {
+        int rc = copy_out(r.error, buf, cap, len);
+        return rc == CRO_OK ? r.code : rc;
+    }
+    return copy_out(identity::GpuInfosToJson(r), buf, cap, len);
+}
+
+int cro_parse_gpu_csv(const char* std_out, const char* std_err, const char* exec_err, const char* query,
+                      char* buf, size_t cap, size_t* len) {
+    if (!query) return CRO_ERR_INVALID_ARG;
+    return finish_parse(identity::getGPUInfoFromNvidiaSmiOutput(S(std_out), S(std_err), exec_err, query),
+                        buf, cap, len);
+}
+
+int cro_parse_proc_csv(const char* std_out, const char* std_err, const char* exec_err, const char* query,
+                       char* buf, size_t cap, size_t* len) {
+    if (!query) return CRO_ERR_INVALID_ARG;
+    return finish_parse(identity::getGPUInfoFromProcOutput(S(std_out), S(std_err), exec_err, query), buf,
+                        cap, len);
+}
+
+int cro_proc_information_to_line(const char* text, char* buf, size_t cap, size_t* len) {
+    if (!text) return CRO_ERR_INVALID_ARG;
+    return copy_out(identity::ProcInformationToLine(text), buf, cap, len);
+}
+
+int cro_check_gpu_visible(const cro_dev_info* devs, int n, const char* device_id, int* visible) {
+    if (!visible || !device_id || (n > 0 && !devs)) return CRO_ERR_INVALID_ARG;
+    *visible = identity::CheckGPUVisible(devs, n, device_id) ? 1 : 0;
+    return CRO_OK;
+}
+
+int cro_normalize(int kind, const char* in, char* buf, size_t cap, size_t* len) {
+    if (!in) return CRO_ERR_INVALID_ARG;
+    std::string out;
+    int rc = identity::Normalize(kind, in, &out);
+    if (rc) return rc;
+    return copy_out(out, buf, cap, len);
+}
+
+int cro_probe_device(cro_ctx* ctx, int dev_index, cro_probe_result* out) {
+    if (!ctx) return CRO_ERR_INVALID_ARG;
+    return ctx_probe_device(ctx, dev_index, out);
+}
+
+int cro_probe_all(cro_ctx* ctx, cro_probe_result* out, int cap, int* n) {
+    return ctx_probe_all(ctx, out, cap, n);
+}
+
+int cro_result_device_ptr(cro_ctx* ctx, int dev_index, uint64_t* dptr) {
+    if (!ctx || !dptr || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return CRO_ERR_INVALID_ARG;
+    *dptr = (uint64_t)(uintptr_t)ctx->devs[(size_t)dev_index]->d_result;
+    return CRO_OK;
+}
+
+int cro_hbm_fill(cro_ctx* ctx, int i, cro_sweep_result* out) { return ctx ? ctx_fill(ctx, i, 1, out) : CRO_ERR_INVALID_ARG; }
+int cro_hbm_fill_loop(cro_ctx* ctx, int i, uint32_t iters, cro_sweep_result* out) {
+    return ctx ? ctx_fill(ctx, i, iters, out) : CRO_ERR_INVALID_ARG;
+}
+int cro_hbm_read_checksum(cro_ctx* ctx, int i, uint32_t variant, cro_sweep_result* out) {
+    return ctx ? ctx_read(ctx, i, variant, 1, false, out) : CRO_ERR_INVALID_ARG;
+}
+int cro_hbm_read_checksum_dst(cro_ctx* ctx, int i, uint32_t variant, cro_sweep_result* out) {
+    return ctx ? ctx_read(ctx, i, variant, 1, true, out) : CRO_ERR_INVALID_ARG;
+}
+int cro_hbm_read_loop(cro_ctx* ctx, int i, uint32_t variant, uint32_t iters, cro_sweep_result* out) {
+    return ctx ? ctx_read(ctx, i, variant, iters, false, out) : CRO_ERR_INVALID_ARG;
+}
+int cro_hbm_copy(cro_ctx* ctx, int i, uint32_t variant, cro_sweep_result* out) {
+    return ctx ? ctx_copy(ctx, i, variant, 1, out) : CRO_ERR_INVALID_ARG;
+}
+int cro_hbm_copy_loop(cro_ctx* ctx, int i, uint32_t variant, uint32_t iters, cro_sweep_result* out) {
+    return ctx ? ctx_copy(ctx, i, variant, iters, out) : CRO_ERR_INVALID_ARG;
+}
+int cro_hbm_expected_checksum(cro_ctx* ctx, int i, cro_sweep_result* out) {
+    return ctx ? ctx_expected(ctx, i, out) : CRO_ERR_INVALID_ARG;
+}
+int cro_inject_fault(cro_ctx* ctx, int i, uint64_t word, uint64_t mask) {
+    return ctx ? ctx_inject(ctx, i, word, mask) : CRO_ERR_INVALID_ARG;
+}
+int cro_read_words(cro_ctx* ctx, int i, uint64_t first, uint64_t n, uint64_t* out) {
+    return ctx ? ctx_read_words(ctx, i, first, n, out) : CRO_ERR_INVALID_ARG;
+}
+int cro_device_seed(cro_ctx* ctx, int i, uint64_t* seed) {
+    if (!ctx || !seed || i < 0 || i >= (int)ctx->devs.size()) return CRO_ERR_INVALID_ARG;
+    *seed = ctx->devs[(size_t)i]->seed;
+    return CRO_OK;
+}
+uint64_t cro_launch_count(cro_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+// ---- emitters --------------------------------------------------------------
+
+int cro_emit_status_json(const char* state, const char* error, const char* device_id,
+                         const char* cdi_device_id, char* buf, size_t cap, size_t* len) {
+    controller::ComposableResourceStatus st;
+    st.State = S(state);
+    st.Error = S(error);
+    st.DeviceID = S(device_id);
+    st.CDIDeviceID = S(cdi_device_id);
+    return copy_out(st.MarshalJSON(), buf, cap, len);
+}
+
+int cro_emit_scalar_status_json(const char* state, const char* device_id, const char* cdi_device_id,
+                                const char* node_name, const char* error, char* buf, size_t cap,
+                                size_t* len) {
+    // api/v1alpha1/composabilityrequest_types.go:74-80 (declaration order)
+    gojson::Writer w;
+    w.begin_object();
+    w.field("state", S(state));
+    w.field_omitempty("device_id", S(device_id));
+    w.field_omitempty("cdi_device_id", S(cdi_device_id));
+    w.field_omitempty("node_name", S(node_name));
+    w.field_omitempty("error", S(error));
+    w.end_object();
+    return copy_out(w.str(), buf, cap, len);
+}
+
+int cro_emit_fm_scale_up(const char* tenant_uuid, const char* mach_uuid, const char* res_type,
+                         const char* model, char* buf, size_t cap, size_t* len) {
+    // internal/cdi/fti/fm/api/scale_up.go:19-41, built at fti/fm/client.go:115-143
+    gojson::Writer w;
+    w.begin_object().key("tenants").begin_object();
+    w.field("tenant_uuid", S(tenant_uuid));
+    w.key("machines").begin_array().begin_object();
+    w.field("mach_uuid", S(mach_uuid));
+    w.key("resources").begin_array().begin_object();
+    w.key("res_specs").begin_array().begin_object();
+    w.field("res_type", S(res_type));
+    w.key("res_spec").begin_object().key("condition").begin_array().begin_object();
+    w.field("column", std::string("model")).field("operator", std::string("eq")).field("value", S(model));
+    w.end_object().end_array().end_object();
+    w.field("res_num", 1);
+    w.end_object().end_array();      // res_specs
+    w.end_object().end_array();      // resources
+    w.end_object().end_array();      // machines
+    w.end_object().end_object();
+    return copy_out(w.str(), buf, cap, len);
+}
+
+int cro_emit_fm_scale_down(const char* tenant_uuid, const char* mach_uuid, const char* res_type,
+                           const char* res_uuid, char* buf, size_t cap, size_t* len) {
+    // internal/cdi/fti/fm/api/scale_down.go:19-41, built at fti/fm/client.go:247-270
+    gojson::Writer w;
+    w.begin_object().key("tenants").begin_object();
+    w.field("tenant_uuid", S(tenant_uuid));
+    w.key("machines").begin_array().begin_object();
+    w.field("mach_uuid", S(mach_uuid));
+    w.key("resources").begin_array().begin_object();
+    w.key("res_specs").begin_array().begin_object();
+    w.field("res_type", S(res_type));
+    w.field("res_uuid", S(res_uuid));
+    w.field("res_num", 1);
+    w.end_object().end_array();
+    w.end_object().end_array();
+    w.end_object().end_array();
+    w.end_object().end_object();
+    return copy_out(w.str(), buf, cap, len);
+}
+
+int cro_emit_cm_scale_up(const char* spec_uuid, int device_count, char* buf, size_t cap, size_t* len) {
+    // internal/cdi/fti/cm/client.go:62-69
+    gojson::Writer w;
+    w.begin_object().key("increase_resource_count").begin_object();
+    w.field("spec_uuid", S(spec_uuid)).field("device_count", device_count);
+    w.end_object().end_object();
+    return copy_out(w.str(), buf, cap, len);
+}
+
+int cro_emit_cm_scale_down(const char* spec_uuid, int device_count, const char* device_id, char* buf,
+                           size_t cap, size_t* len) {
+    // internal/cdi/fti/cm/client.go:71-79
+    gojson::Writer w;
+    w.begin_object().key("remove_resources").begin_object();
+    w.field("spec_uuid", S(spec_uuid)).field("device_count", device_count);
+    w.key("devices").begin_array().value(S(device_id)).end_array();
+    w.end_object().end_object();
+    return copy_out(w.str(), buf, cap, len);
+}
+
+int cro_emit_sunfish_request(const char* name, long long count, const char* proc_type, const char* model,
+                             char* buf, size_t cap, size_t* len) {
+    // internal/cdi/sunfish/client.go:48-61
+    gojson::Writer w;
+    w.begin_object();
+    w.field("Name", S(name));
+    w.key("Processors").begin_object().key("Members").begin_array().begin_object();
+    w.field("@Redfish.RequestCount", count);
+    w.field("ProcessorType", S(proc_type));
+    w.field("Model", S(model));
+    w.end_object().end_array().end_object();
+    w.end_object();
+    return copy_out(w.str(), buf, cap, len);
+}
+
+static std::map<std::string, std::string> probe_annotations(const cro_probe_result& r) {
+    std::map<std::string, std::string> m;
+    m["cohdi.io/probe-status"] = cro_strerror(r.status);
+    m["cohdi.io/probe-device-id"] = fixed_str(r.gpu_uuid, sizeof r.gpu_uuid);
+    m["cohdi.io/probe-pci-bus-id"] = fixed_str(r.pci_bus_id, sizeof r.pci_bus_id);
+    m["cohdi.io/probe-device-minor"] = std::to_string(r.device_minor);
+    m["cohdi.io/probe-sweep-bytes"] = std::to_string(r.sweep_bytes);
+    m["cohdi.io/probe-checksum"] = hex16(r.checksum_xor) + ":" + hex16(r.checksum_sum);
+    m["cohdi.io/probe-hbm-fill-gbs"] = gbs_x10(r.sweep_bytes, r.fill_ns);
+    m["cohdi.io/probe-hbm-read-gbs"] = gbs_x10(r.sweep_bytes, r.read_best_ns);
+    if (r.copy_sweeps) m["cohdi.io/probe-hbm-copy-gbs"] = gbs_x10(2 * r.sweep_bytes, r.copy_best_ns);
+    std::string bw, lat;
+    for (int j = 0; j < 8; ++j) {
+        if (!r.p2p_read_ns[j]) continue;
+        if (!bw.empty()) { bw += ","; lat += ","; }
+        bw += std::to_string(j) + ":" + gbs_x10(r.p2p_bytes, r.p2p_read_ns[j]);
+        lat += std::to_string(j) + ":" + std::to_string(r.p2p_latency_ns_x16[j] / 16);
+    }
+    if (!bw.empty()) {
+        m["cohdi.io/probe-nvlink-read-gbs"] = bw;
+        m["cohdi.io/probe-nvlink-latency-ns"] = lat;
+    }
+    return m;
+}
+
+int cro_emit_probe_annotations_json(const cro_probe_result* r, char* buf, size_t cap, size_t* len) {
+    if (!r) return CRO_ERR_INVALID_ARG;
+    gojson::Writer w;
+    w.string_map(probe_annotations(*r));
+    return copy_out(w.str(), buf, cap, len);
+}
+
+int cro_fm_parse_scale_up_response(const char* body, const char* resource_name, const char* res_type,
+                                   const char* model, char* device_id, size_t device_id_cap,
+                                   char* cdi_device_id, size_t cdi_cap, char* err_buf, size_t err_cap) {
+    if (!body) return CRO_ERR_INVALID_ARG;
+    std::string dev, cdi;
+    controller::Error e = controller::FMScaleUpResponseToIDs(body, S(resource_name), S(res_type), S(model), &dev, &cdi);
+    if (!e.ok()) {
+        copy_out(e.msg, err_buf, err_cap, nullptr);
+        return CRO_ERR_PARSE;
+    }
+    int rc = copy_out(dev, device_id, device_id_cap, nullptr);
+    if (rc) return rc;
+    return copy_out(cdi, cdi_device_id, cdi_cap, nullptr);
+}
+
+// ---- reconcile step ---------------------------------------------------------
+
+namespace {
+
+class JsonProvider : public controller::CdiProvider {
+public:
+    explicit JsonProvider(const gojson::Value* p) : p_(p) {}
+    controller::Error AddResource(const controller::ComposableResource& inst, std::string* dev,
+                                  std::string* cdi) override {
+        if (!p_) return controller::Error::New("no provider configured");
+        if (p_->get_bool("waiting")) return controller::Error::New(controller::ErrWaitingDeviceAttaching);
+        const std::string err = p_->get_string("error");
+        if (!err.empty()) return controller::Error::New(err);
+        const gojson::Value* body = p_->get("fm_response_body");
+        if (body && body->kind == gojson::Value::String)
+            return controller::FMScaleUpResponseToIDs(body->str, inst.Name, inst.Spec.Type, inst.Spec.Model, dev, cdi);
+        *dev = p_->get_string("device_id");
+        *cdi = p_->get_string("cdi_device_id");
+        return controller::Error::Nil();
+    }
+
+private:
+    const gojson::Value* p_;
+};
+
+class ProbeNodeOps : public controller::NodeOps {
+public:
+    ProbeNodeOps(cro_ctx* ctx, const gojson::Value* in) : ctx_(ctx), in_(in) {}
+    bool probed = false;
+    cro_probe_result probe_result{};
+
+    controller::Error CheckNoGPULoads(const std::string&) override { return controller::Error::Nil(); }
+    controller::Error RestartDaemonset(const std::string& ns, const std::string& name) override {
+        const gojson::Value* errs = in_->get("daemonset_errors");
+        if (errs && errs->kind == gojson::Value::Object) {
+            const std::string e = errs->get_string(ns + "/" + name);
+            if (!e.empty()) return controller::Error::New(e);
+        }
+        return controller::Error::Nil();
+    }
+    controller::Error RunNvidiaSmi(const std::string& node) override {
+        std::vector<std::string> uuids;
+        return enumerate(node, &uuids);
+    }
+    controller::Error CheckGPUVisible(const std::string& type, const controller::ComposableResource& r,
+                                      bool* visible) override {
+        *visible = false;
+        bool listed = false;
+        const gojson::Value* slices = in_->get("resource_slices");
+        if (type == "DRA" && slices && slices->kind == gojson::Value::Array) {
+            // internal/utils/gpus.go:55-71
+            for (const auto& rs : slices->arr) {
+                const gojson::Value* devs = rs->get("devices");
+                if (!devs || devs->kind != gojson::Value::Array) continue;
+                for (const auto& d : devs->arr) {
+                    const gojson::Value* attrs = d->get("attributes");
+                    if (attrs && attrs->get_string("uuid") == r.Status.DeviceID && attrs->get("uuid")) listed = true;
+                }
+            }
+        } else {
+            std::vector<std::string> uuids;
+            controller::Error e = enumerate(r.Spec.TargetNode, &uuids);
+            if (!e.ok()) return e;
+            for (const std::string& u : uuids)
+                if (u == r.Status.DeviceID) listed = true;   // gpus.go:78-82
+        }
+        if (!listed) return controller::Error::Nil();
+        if (in_->get_bool("probe") && ctx_) {
+            // the strong check: the device must also deliver its HBM pattern
+            int idx = -1;
+            for (size_t i = 0; i < ctx_->devs.size(); ++i)
+                if (fixed_str(ctx_->devs[i]->info.gpu_uuid, 48) == r.Status.DeviceID) idx = (int)i;
+            if (idx < 0) return controller::Error::Nil();
+            int rc = ctx_probe_device(ctx_, idx, &probe_result);
+            probed = true;
+            if (rc != CRO_OK) {
+                char msg[512] = {0};
+                cro_last_error(ctx_, msg, sizeof msg);
+                return controller::Error::New(std::string("cuda probe failed: ") + cro_strerror(rc) +
+                                              (msg[0] ? std::string(": ") + msg : std::string()));
+            }
+        }
+        *visible = true;
+        return controller::Error::Nil();
+    }
+
+private:
+    controller::Error enumerate(const std::string& node, std::vector<std::string>* uuids) {
+        if (in_->get_bool("driver_pod_missing"))   // gpus.go:835
+            return controller::Error::New(
+                "no Pod with label 'app.kubernetes.io/component=nvidia-driver' found on node " + node);
+        std::string out, err;
+        const char* exec_err = nullptr;
+        std::string exec_err_s;
+        const gojson::Value* en = in_->get("enumeration");
+        if (en && en->kind == gojson::Value::Object) {
+            out = en->get_string("stdout");
+            err = en->get_string("stderr");
+            const gojson::Value* ee = en->get("exec_err");
+            if (ee && ee->kind == gojson::Value::String) { exec_err_s = ee->str; exec_err = exec_err_s.c_str(); }
+        } else if (ctx_) {
+            std::vector<cro_dev_info> infos;
+            for (auto& d : ctx_->devs) infos.push_back(d->info);
+            identity::EmitCsv(infos.data(), (int)infos.size(), "gpu_uuid", &out, nullptr);
+        } else {
+            return controller::Error::New("no probe context and no enumeration text");
+        }
+        identity::GpuInfoResult r = identity::getGPUInfoFromNvidiaSmiOutput(out, err, exec_err, "gpu_uuid");
+        if (r.code != CRO_OK) return controller::Error::New(r.error);
+        for (const auto& g : r.infos) {
+            auto it = g.find("gpu_uuid");
+            if (it != g.end()) uuids->push_back(it->second);
+        }
+        return controller::Error::Nil();
+    }
+    cro_ctx* ctx_;
+    const gojson::Value* in_;
+};
+
+}  // namespace
+
+int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t cap, size_t* len) {
+    if (!in_json) return CRO_ERR_INVALID_ARG;
+    std::string perr;
+    gojson::ValuePtr in = gojson::parse(in_json, &perr);
+    if (!in || in->kind != gojson::Value::Object) {
+        copy_out("bad reconcile request: " + perr, buf, cap, len);
+        return CRO_ERR_PARSE;
+    }
+    controller::ComposableResource res;
+    res.Name = in->get_string("name", "test-composable-resource");
+    res.DeletionTimestampSet = in->get_bool("deleting");
+    if (const gojson::Value* sp = in->get("spec")) {
+        res.Spec.Type = sp->get_string("type");
+        res.Spec.Model = sp->get_string("model");
+        res.Spec.TargetNode = sp->get_string("target_node");
+        res.Spec.ForceDetach = sp->get_bool("force_detach");
+    }
+    if (const gojson::Value* st = in->get("status")) {
+        res.Status.State = st->get_string("state");
+        res.Status.Error = st->get_string("error");
+        res.Status.DeviceID = st->get_string("device_id");
+        res.Status.CDIDeviceID = st->get_string("cdi_device_id");
+    }
+    if (const gojson::Value* lb = in->get("labels"))
+        if (lb->kind == gojson::Value::Object)
+            for (const auto& kv : lb->obj)
+                if (kv.second->kind == gojson::Value::String) res.Labels[kv.first] = kv.second->str;
+    const std::string type = in->get_string("device_resource_type", "DEVICE_PLUGIN");
+
+    JsonProvider provider(in->get("provider"));
+    ProbeNodeOps node(ctx, in.get());
+    controller::ComposableResourceReconciler rec(&provider, &node);
+    controller::Result result;
+    controller::Error err;
+    if (type != "DEVICE_PLUGIN" && type != "DRA") {
+        // composableresource_adapter.go:42-45
+        err = rec.requeueOnErr(&res, controller::Error::New(
+                                         "the env variable DEVICE_RESOURCE_TYPE has an invalid value: '" + type + "'"));
+    } else if (res.Status.State.empty()) {
+        err = rec.handleNoneState(&res, &result);
+    } else if (res.Status.State == "Attaching") {
+        err = rec.handleAttachingState(&res, type, &result);
+    }
+
+    gojson::Writer w;
+    w.begin_object();
+    w.key("status").raw(res.Status.MarshalJSON());
+    w.field("requeue_after_s", result.RequeueAfterSeconds);
+    w.field("error", err.ok() ? std::string() : err.msg);
+    w.key("status_updates").begin_array();
+    for (const auto& s : rec.statusUpdates) w.raw(s.MarshalJSON());
+    w.end_array();
+    if (node.probed) w.key("probe").string_map(probe_annotations(node.probe_result));
+    w.end_object();
+    return copy_out(w.str(), buf, cap, len);
+}
+
+}  // extern "C"

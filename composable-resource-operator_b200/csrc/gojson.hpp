@@ -1,0 +1,84 @@
+// gojson.hpp — byte-compatible writer for Go's encoding/json (go1.24, HTML
+// escaping on, as json.Marshal uses it) plus a small strict JSON reader.
+//
+// The reference marshals its wire structs with json.Marshal
+// (internal/cdi/fti/fm/client.go:144,271; fti/cm/client.go:139,218;
+// sunfish/client.go:78) and its CR status through the apimachinery JSON codec,
+// which is encoding/json as well.  "Bit-exact CDI JSON" therefore means:
+// struct-declaration field order, omitempty rules, sorted map keys, and the
+// stdlib's string escaping table — all restated here.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace cro {
+namespace gojson {
+
+// Appends the Go-escaped, quoted form of `s` to `out`.
+void append_string(std::string& out, const std::string& s);
+
+// Streaming writer for struct-shaped output.  Field order is the caller's
+// (Go emits struct fields in declaration order).
+class Writer {
+public:
+    Writer& begin_object();
+    Writer& end_object();
+    Writer& begin_array();
+    Writer& end_array();
+    Writer& key(const char* k);
+    Writer& value(const std::string& s);
+    Writer& value(const char* s);
+    Writer& value(long long v);
+    Writer& value(int v) { return value((long long)v); }
+    Writer& value_u64(unsigned long long v);
+    Writer& value(bool v);
+    Writer& null();
+    // key + value, skipped when the value is Go's zero value (omitempty).
+    Writer& field_omitempty(const char* k, const std::string& s);
+    Writer& field_omitempty(const char* k, bool v);
+    Writer& field_omitempty(const char* k, long long v);
+    Writer& field(const char* k, const std::string& s) { return key(k).value(s); }
+    Writer& field(const char* k, long long v) { return key(k).value(v); }
+    Writer& field(const char* k, int v) { return key(k).value((long long)v); }
+    Writer& field(const char* k, bool v) { return key(k).value(v); }
+    // map[string]string: Go sorts keys bytewise.
+    Writer& string_map(const std::map<std::string, std::string>& m);
+    Writer& raw(const std::string& json);
+    const std::string& str() const { return out_; }
+    std::string take() { return std::move(out_); }
+
+private:
+    void comma();
+    std::string out_;
+    std::vector<bool> first_;  // per nesting level: no element written yet
+    bool after_key_ = false;
+};
+
+// ---- reader ---------------------------------------------------------------
+struct Value;
+using ValuePtr = std::shared_ptr<Value>;
+struct Value {
+    enum Kind { Null, Bool, Number, String, Array, Object } kind = Null;
+    bool b = false;
+    double num = 0;
+    long long inum = 0;
+    bool is_int = false;
+    std::string str;
+    std::vector<ValuePtr> arr;
+    std::vector<std::pair<std::string, ValuePtr>> obj;  // insertion order
+
+    const Value* get(const std::string& k) const;  // last duplicate wins (Go)
+    std::string get_string(const std::string& k, const std::string& dflt = "") const;
+    bool get_bool(const std::string& k, bool dflt = false) const;
+    long long get_int(const std::string& k, long long dflt = 0) const;
+};
+
+// Returns nullptr and fills *err on malformed input.
+ValuePtr parse(const std::string& text, std::string* err);
+
+}  // namespace gojson
+}  // namespace cro

@@ -1,0 +1,162 @@
+// reconcile.cpp — see reconcile.hpp.
+#include "reconcile.hpp"
+
+namespace cro {
+namespace controller {
+
+const std::string ErrWaitingDeviceAttaching = "device is attaching to the cluster";
+const std::string ErrWaitingDeviceDetaching = "device is detaching from the cluster";
+
+std::string ComposableResourceStatus::MarshalJSON() const {
+    // api/v1alpha1/composableresource_types.go:36-41 — `state` is always
+    // present, the other three are omitempty.
+    gojson::Writer w;
+    w.begin_object();
+    w.field("state", State);
+    w.field_omitempty("error", Error);
+    w.field_omitempty("device_id", DeviceID);
+    w.field_omitempty("cdi_device_id", CDIDeviceID);
+    w.end_object();
+    return w.take();
+}
+
+Error FMScaleUpResponseToIDs(const std::string& body, const std::string& instanceName,
+                             const std::string& specType, const std::string& specModel,
+                             std::string* deviceID, std::string* CDIDeviceID) {
+    deviceID->clear();
+    CDIDeviceID->clear();
+    std::string perr;
+    gojson::ValuePtr root = gojson::parse(body, &perr);
+    if (!root || root->kind != gojson::Value::Object)
+        return Error::New(
+            "failed to unmarshal FM scaleup response body into scaleUpResponse. Original error: " + perr);
+    const gojson::Value* data = root->get("data");
+    const gojson::Value* machines = data ? data->get("machines") : nullptr;
+    if (machines && machines->kind == gojson::Value::Array && !machines->arr.empty()) {
+        const gojson::Value* m0 = machines->arr[0].get();
+        const gojson::Value* resources = m0->get("resources");
+        if (resources && resources->kind == gojson::Value::Array && !resources->arr.empty()) {
+            const gojson::Value* r0 = resources->arr[0].get();
+            if (r0->get_string("res_type") == specType) {
+                const gojson::Value* spec = r0->get("res_spec");
+                const gojson::Value* cond = spec ? spec->get("condition") : nullptr;
+                if (cond && cond->kind == gojson::Value::Array) {
+                    for (const auto& it : cond->arr) {
+                        if (it->get_string("column") == "model" && it->get_string("operator") == "eq" &&
+                            it->get_string("value") == specModel) {
+                            const std::string op = r0->get_string("res_op_status");
+                            if (op.empty())  // Go: OptionStatus[:1] on "" panics
+                                return Error::New("runtime error: slice bounds out of range [:1] with length 0");
+                            const char c = op[0];
+                            if (c == '0' || c == '1') {
+                                *deviceID = r0->get_string("res_serial_num");
+                                *CDIDeviceID = r0->get_string("res_uuid");
+                                return Error::Nil();
+                            }
+                            if (c == '2')
+                                return Error::New("the FM attached device called by " + instanceName +
+                                                  " is in Critical state in FM");
+                            return Error::New("the FM attached device called by " + instanceName +
+                                              " is in unknown state '" + op + "' in FM");
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return Error::New("can not find the added gpu when using FM to add gpu");
+}
+
+Error ComposableResourceReconciler::requeueOnErr(ComposableResource* resource, const Error& err) {
+    if (resource) {
+        resource->Status.Error = err.msg;
+        statusUpdate(*resource);
+    }
+    return err;
+}
+
+Error ComposableResourceReconciler::handleNoneState(ComposableResource* resource, Result* result) {
+    *result = Result();
+    auto it = resource->Labels.find("cohdi.io/ready-to-detach-device-id");
+    if (it != resource->Labels.end() && !it->second.empty()) {
+        resource->Status.DeviceID = it->second;
+        auto jt = resource->Labels.find("cohdi.io/ready-to-detach-cdi-device-id");
+        if (jt != resource->Labels.end() && !jt->second.empty()) resource->Status.CDIDeviceID = jt->second;
+    }
+    resource->Status.State = "Attaching";
+    resource->Status.Error = "";
+    statusUpdate(*resource);
+    return Error::Nil();
+}
+
+Error ComposableResourceReconciler::handleAttachingState(ComposableResource* resource,
+                                                         const std::string& deviceResourceType,
+                                                         Result* result) {
+    *result = Result();
+    if (resource->DeletionTimestampSet) {
+        if (resource->Status.DeviceID.empty()) {
+            resource->Status.State = "Deleting";
+            statusUpdate(*resource);
+            return Error::Nil();
+        }
+        if (!resource->Status.Error.empty()) {
+            resource->Status.State = "Detaching";
+            statusUpdate(*resource);
+            return Error::Nil();
+        }
+        // DeviceID set, no error: keeps attaching
+    }
+
+    if (resource->Status.DeviceID.empty()) {
+        std::string deviceID, cdiDeviceID;
+        Error err = provider_->AddResource(*resource, &deviceID, &cdiDeviceID);
+        if (!err.ok()) {
+            if (err.msg == ErrWaitingDeviceAttaching) {  // errors.Is on the sentinel
+                result->RequeueAfterSeconds = 30;
+                return Error::Nil();
+            }
+            return requeueOnErr(resource, err);
+        }
+        resource->Status.Error = "";
+        resource->Status.DeviceID = deviceID;
+        resource->Status.CDIDeviceID = cdiDeviceID;
+        statusUpdate(*resource);
+    }
+
+    if (deviceResourceType == "DEVICE_PLUGIN") {
+        (void)node_->CheckNoGPULoads(resource->Spec.TargetNode);  // logged only
+        for (const char* ds : {"nvidia-device-plugin-daemonset", "nvidia-dcgm"}) {
+            Error err = node_->RestartDaemonset("nvidia-gpu-operator", ds);
+            if (!err.ok()) {
+                resource->Status.Error = err.msg;
+                statusUpdate(*resource);
+            }
+        }
+    } else if (deviceResourceType == "DRA") {
+        Error err = node_->RunNvidiaSmi(resource->Spec.TargetNode);
+        if (!err.ok()) {
+            resource->Status.Error = err.msg;
+            statusUpdate(*resource);
+        }
+        err = node_->RestartDaemonset("nvidia-dra-driver-gpu", "nvidia-dra-driver-gpu-kubelet-plugin");
+        if (!err.ok()) {
+            resource->Status.Error = err.msg;
+            statusUpdate(*resource);
+        }
+    }
+
+    bool visible = false;
+    Error err = node_->CheckGPUVisible(deviceResourceType, *resource, &visible);
+    if (!err.ok()) return requeueOnErr(resource, err);
+    if (visible) {
+        resource->Status.State = "Online";
+        resource->Status.Error = "";
+        statusUpdate(*resource);
+        return Error::Nil();
+    }
+    result->RequeueAfterSeconds = 30;
+    return Error::Nil();
+}
+
+}  // namespace controller
+}  // namespace cro

@@ -1,0 +1,98 @@
+// reconcile.hpp — host-side mirror of the reference's attach step, the caller
+// of the probe.  Names, argument meaning and error strings follow
+//   internal/controller/composableresource_controller.go:176-287,423-441
+//   internal/cdi/client.go:25-44            (CdiProvider, sentinel errors)
+//   internal/cdi/fti/fm/client.go:184-213   (FM res_op_status gate)
+//   api/v1alpha1/composableresource_types.go:27-41
+// so the parity tests read like the reference's Ginkgo entries.  (The Go
+// toolchain is absent in the build image, hence C++ above the C ABI.)
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "gojson.hpp"
+
+namespace cro {
+namespace controller {
+
+// Go `error`: ok() == (err == nil)
+struct Error {
+    bool set = false;
+    std::string msg;
+    static Error Nil() { return Error(); }
+    static Error New(const std::string& m) { Error e; e.set = true; e.msg = m; return e; }
+    bool ok() const { return !set; }
+};
+
+extern const std::string ErrWaitingDeviceAttaching;  // "device is attaching to the cluster"
+extern const std::string ErrWaitingDeviceDetaching;  // "device is detaching from the cluster"
+
+struct ComposableResourceSpec {
+    std::string Type, Model, TargetNode;
+    bool ForceDetach = false;
+};
+struct ComposableResourceStatus {
+    std::string State, Error, DeviceID, CDIDeviceID;
+    std::string MarshalJSON() const;   // bytes of json.Marshal(status)
+};
+struct ComposableResource {
+    std::string Name;
+    std::map<std::string, std::string> Labels;
+    bool DeletionTimestampSet = false;
+    ComposableResourceSpec Spec;
+    ComposableResourceStatus Status;
+};
+
+struct Result {
+    long long RequeueAfterSeconds = 0;
+};
+
+// internal/cdi/client.go:34-39 (only AddResource is on the attach path)
+class CdiProvider {
+public:
+    virtual ~CdiProvider() {}
+    virtual Error AddResource(const ComposableResource& instance, std::string* deviceID,
+                              std::string* CDIDeviceID) = 0;
+};
+
+// The FM gate (fti/fm/client.go:184-213) over a ScaleUpResponse body.
+Error FMScaleUpResponseToIDs(const std::string& body, const std::string& instanceName,
+                             const std::string& specType, const std::string& specModel,
+                             std::string* deviceID, std::string* CDIDeviceID);
+
+// Node-side operations the attach step calls (internal/utils): the CUDA probe
+// backs RunNvidiaSmi / CheckGPUVisible; the daemonset restarts and the load
+// check are cluster bookkeeping, injected.
+class NodeOps {
+public:
+    virtual ~NodeOps() {}
+    virtual Error CheckNoGPULoads(const std::string& node) = 0;
+    virtual Error RestartDaemonset(const std::string& ns, const std::string& name) = 0;
+    virtual Error RunNvidiaSmi(const std::string& node) = 0;
+    virtual Error CheckGPUVisible(const std::string& deviceResourceType,
+                                  const ComposableResource& resource, bool* visible) = 0;
+};
+
+class ComposableResourceReconciler {
+public:
+    ComposableResourceReconciler(CdiProvider* provider, NodeOps* node) : provider_(provider), node_(node) {}
+    // composableresource_controller.go:176-198
+    Error handleNoneState(ComposableResource* resource, Result* result);
+    // composableresource_controller.go:200-287
+    Error handleAttachingState(ComposableResource* resource, const std::string& deviceResourceType,
+                               Result* result);
+    // Every Status().Update the reference would issue, in order.
+    std::vector<ComposableResourceStatus> statusUpdates;
+    // composableresource_controller.go:423-433
+    Error requeueOnErr(ComposableResource* resource, const Error& err);
+
+private:
+    void statusUpdate(const ComposableResource& r) { statusUpdates.push_back(r.Status); }
+    CdiProvider* provider_;
+    NodeOps* node_;
+};
+
+}  // namespace controller
+}  // namespace cro

@@ -1,0 +1,325 @@
+/*
+ * croprobe.h — C ABI of libcroprobe, the B200-native post-attach device probe
+ * and spec-emit path for the composable-resource operator.
+ *
+ * This header is the drop-in boundary.  Everything here is
+ * plain C: opaque context pointer, caller-allocated output buffers, integer
+ * return codes.  No torch / C++ types cross it.  A Go host binds it with cgo
+ * (see INTEGRATION.md and composable-resource-operator_b200/go/internal/cuda);
+ * the tests and bench.py bind it with ctypes.
+ *
+ * Each entry point names the reference interface (path:line under the
+ * reference tree) whose slot in the reconcile loop it fills or replaces.
+ *
+ * Threading: every entry point is re-entrant.  Calls that touch a device take
+ * that device's mutex and call cudaSetDevice themselves, so they may be issued
+ * from any OS thread (cgo migrates goroutines between threads).  No callbacks.
+ * Ownership: cro_ctx is library-owned (cro_probe_destroy frees it); every
+ * other buffer is caller-owned and is not retained after the call returns.
+ */
+#ifndef CROPROBE_H_
+#define CROPROBE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRO_ABI_VERSION 1u
+
+/* ---- return codes (0 ok, <0 error; text via cro_strerror) ---------------- */
+#define CRO_OK                  0
+#define CRO_ERR_INVALID_ARG    -1
+#define CRO_ERR_ABI_MISMATCH   -2
+#define CRO_ERR_NO_DEVICE      -3   /* zero CUDA devices: not an error for enumerate (n=0) */
+#define CRO_ERR_CUDA           -4   /* a CUDA runtime call failed; see cro_last_error */
+#define CRO_ERR_OOM            -5   /* sweep buffer could not be allocated (device busy) */
+#define CRO_ERR_CHECKSUM       -6   /* HBM sweep checksum differs from the closed form   */
+#define CRO_ERR_BUFFER_SMALL   -7   /* caller buffer too small; *len holds the need      */
+#define CRO_ERR_NCCL           -8
+#define CRO_ERR_DEADLINE       -9
+#define CRO_ERR_UNSUPPORTED   -10   /* e.g. unsupported field in a query string          */
+#define CRO_ERR_PARSE         -11   /* malformed CSV / JSON handed to a parser           */
+#define CRO_ERR_EXEC          -12   /* the enumerate command reported stderr / exec error */
+#define CRO_ERR_P2P           -13
+#define CRO_ERR_INTERNAL      -14
+
+/* ---- option flags -------------------------------------------------------- */
+#define CRO_F_SKIP_COPY       0x0001u  /* do not run the hbm_copy sweeps           */
+#define CRO_F_SKIP_P2P        0x0002u  /* cro_probe_all: no NVLink rounds          */
+#define CRO_F_SKIP_NCCL       0x0004u  /* cro_probe_all: host gather, no NCCL      */
+#define CRO_F_NO_NVML         0x0008u  /* identity from /proc + CUDA runtime only  */
+#define CRO_F_VERIFY_COPY     0x0010u  /* re-checksum the copy destination         */
+#define CRO_F_LAZY_ALLOC      0x0020u  /* allocate sweep buffers at first probe    */
+
+/* read-sweep kernel variants */
+#define CRO_READ_AUTO   0u
+#define CRO_READ_LDG    1u   /* ld.global.nc.L1::no_allocate 128-bit, unrolled      */
+#define CRO_READ_TMA    2u   /* cp.async.bulk (1-D TMA) smem ring + LDS.128 reduce  */
+#define CRO_COPY_AUTO   0u
+#define CRO_COPY_LDG    1u
+#define CRO_COPY_TMA    2u   /* bulk load -> smem -> bulk store, no register pass   */
+
+#define CRO_MAX_DEVICES 16
+
+typedef struct cro_ctx cro_ctx;
+
+/* Options for cro_probe_init.  Zero means "default" for every field. */
+typedef struct cro_opts {
+    uint32_t abi_version;          /* must be CRO_ABI_VERSION                               */
+    uint32_t flags;                /* CRO_F_*                                               */
+    uint64_t sweep_bytes;          /* S, per-device sweep region; default 4 GiB             */
+    uint64_t p2p_bytes;            /* S_p2p per directed pair; default 1 GiB (<= S)         */
+    uint64_t seed_base;            /* default 0x00C0FFEE00000000; seed = base | minor       */
+    uint32_t read_sweeps;          /* default 5                                             */
+    uint32_t copy_sweeps;          /* default 5                                             */
+    uint32_t latency_hops;         /* pointer-chase hops; default 65536                     */
+    uint32_t read_variant;         /* CRO_READ_*                                            */
+    uint32_t copy_variant;         /* CRO_COPY_*                                            */
+    int32_t  deadline_ms;          /* per-call deadline, 0 = none (Go ctx cannot cross cgo) */
+    int32_t  n_devices;            /* 0 = every visible CUDA device                         */
+    int32_t  devices[CRO_MAX_DEVICES]; /* CUDA ordinals to manage                           */
+    uint32_t reserved[8];
+} cro_opts;
+
+/*
+ * Identity of one device in the spellings the reference consumes
+ * (internal/utils/gpus.go:878-919 parses `nvidia-smi --query-gpu=...` CSV;
+ * :1014-1089 parses /proc/driver/nvidia/gpus/<bus>/information).
+ */
+typedef struct cro_dev_info {
+    int32_t  cuda_ordinal;
+    int32_t  device_minor;         /* -1 if no source could supply it                       */
+    char     gpu_uuid[48];         /* "GPU-xxxxxxxx-xxxx-xxxx-xxxx-xxxxxxxxxxxx", NUL padded */
+    char     pci_bus_id[24];       /* nvidia-smi spelling "00000000:1F:00.0"                */
+    char     name[64];
+    uint64_t hbm_bytes_total;
+    uint32_t sm_count;
+    uint32_t cc_major, cc_minor;
+    uint32_t identity_source;      /* 1 NVML, 2 /proc, 3 CUDA runtime only                  */
+    uint32_t reserved[4];
+} cro_dev_info;
+
+/*
+ * Fixed-size, pointer-free, integer-only per-device result: the payload of the
+ * single NCCL all-gather.  512 bytes, little-endian.
+ */
+typedef struct cro_probe_result {
+    uint32_t abi_version;          /*   0 */
+    int32_t  status;               /*   4  CRO_OK or a CRO_ERR_* */
+    int32_t  cuda_ordinal;         /*   8 */
+    int32_t  device_minor;         /*  12 */
+    char     gpu_uuid[48];         /*  16 */
+    char     pci_bus_id[24];       /*  64 */
+    uint64_t hbm_bytes_total;      /*  88 */
+    uint64_t sweep_bytes;          /*  96 */
+    uint64_t seed;                 /* 104 */
+    uint64_t checksum_xor;         /* 112  XOR of all 64-bit pattern words read back */
+    uint64_t checksum_sum;         /* 120  wrapping sum of the same words            */
+    uint64_t fill_ns;              /* 128 */
+    uint64_t read_best_ns;         /* 136 */
+    uint64_t read_median_ns;       /* 144 */
+    uint64_t copy_best_ns;         /* 152 */
+    uint64_t copy_median_ns;       /* 160 */
+    uint32_t sm_count;             /* 168 */
+    uint32_t sm_clock_mhz;         /* 172 */
+    uint32_t mem_clock_mhz;        /* 176 */
+    uint32_t ecc_errors;           /* 180 */
+    uint64_t p2p_read_ns[8];       /* 184  best time to read p2p_bytes from peer j   */
+    uint64_t p2p_checksum_xor[8];  /* 248 */
+    uint32_t p2p_latency_ns_x16[8];/* 312  mean hop latency x16 (fixed point)        */
+    uint8_t  p2p_access[8];        /* 344  cudaDeviceCanAccessPeer                   */
+    uint64_t p2p_bytes;            /* 352 */
+    uint64_t expect_xor;           /* 360  closed-form checksum computed on the device
+                                           by an independent generator kernel        */
+    uint64_t expect_sum;           /* 368 */
+    uint32_t read_variant;         /* 376  CRO_READ_* actually used                  */
+    uint32_t copy_variant;         /* 380 */
+    uint32_t read_sweeps;          /* 384 */
+    uint32_t copy_sweeps;          /* 388 */
+    uint64_t copy_checksum_xor;    /* 392  checksum of the copy destination (if verified) */
+    uint64_t copy_checksum_sum;    /* 400 */
+    uint32_t rank;                 /* 408  index in the minor-sorted device list      */
+    uint32_t world;                /* 412 */
+    uint8_t  reserved[96];         /* 416..511 */
+} cro_probe_result;
+
+/* Result of one timed sweep (bench / parity entry points). */
+typedef struct cro_sweep_result {
+    uint64_t bytes;                /* algorithmic bytes of the sweep (S, or 2S for copy) */
+    uint64_t ns;                   /* CUDA-event duration of the kernel launch(es)       */
+    uint64_t checksum_xor;
+    uint64_t checksum_sum;
+    uint32_t variant;
+    uint32_t launches;             /* kernels launched by this call                      */
+} cro_sweep_result;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+
+/* Creates the long-lived probe context (CUDA primary contexts, sweep buffers,
+ * streams, events).  The reference has no counterpart: it re-execs nvidia-smi
+ * every reconcile (internal/utils/gpus.go:886).  A warm context is what makes
+ * the storm / churn configs meaningful (SURVEY.md §7 "cold-start cost"). */
+int  cro_probe_init(const cro_opts *opts, cro_ctx **out);
+void cro_probe_destroy(cro_ctx *ctx);
+
+/* ---- enumeration: replaces the exec of nvidia-smi ------------------------ */
+
+/* Replaces `nvidia-smi --query-gpu=gpu_uuid` run for its side effect by
+ * utils.RunNvidiaSmi (internal/utils/gpus.go:666-689). */
+int  cro_device_count(cro_ctx *ctx, int *n);
+
+/* Replaces getGPUInfoFromNvidiaPod / getGPUInfoFromCroNodeAgentPod /
+ * getGPUInfoFromProcInCroNodeAgentPod (internal/utils/gpus.go:878-919,
+ * 921-962, 1014-1089).  Rows are sorted by device_minor (nvidia-smi order). */
+int  cro_enumerate(cro_ctx *ctx, cro_dev_info *out, int cap, int *n);
+
+/* Text that `nvidia-smi --query-gpu=<query> --format=csv,noheader,nounits`
+ * would print for these devices, so the unchanged Go parser at
+ * internal/utils/gpus.go:903-916 can consume it.  n == 0 emits
+ * "No devices were found\n" (gpus.go:896).  query fields: device_minor,
+ * gpu_uuid, pci.bus_id, name, index, memory.total. */
+int  cro_emit_csv(const cro_dev_info *devs, int n, const char *query,
+                  char *buf, size_t cap, size_t *len);
+
+/* The reference's CSV parse rule (internal/utils/gpus.go:896-916), kept
+ * quirk-for-quirk.  Output: Go encoding/json of the []map[string]string the
+ * reference would build.  exec_err NULL means a nil error.  Returns
+ * CRO_ERR_EXEC with the reference's formatted message in buf on the error
+ * path, CRO_ERR_PARSE where the reference would panic (short row). */
+int  cro_parse_gpu_csv(const char *std_out, const char *std_err, const char *exec_err,
+                       const char *query, char *buf, size_t cap, size_t *len);
+
+/* /proc flavour (internal/utils/gpus.go:1045-1089): input is the script's
+ * "minor,uuid,bus" lines. */
+int  cro_parse_proc_csv(const char *std_out, const char *std_err, const char *exec_err,
+                        const char *query, char *buf, size_t cap, size_t *len);
+
+/* Turns one /proc/driver/nvidia/gpus/<bus>/information text into the
+ * "minor,uuid,bus" line of the awk script at gpus.go:1017-1037 ("" if any
+ * of the three keys is missing). */
+int  cro_proc_information_to_line(const char *information_text,
+                                  char *buf, size_t cap, size_t *len);
+
+/* Membership decision of utils.CheckGPUVisible, DEVICE_PLUGIN branch
+ * (internal/utils/gpus.go:73-84): is device_id among the enumerated UUIDs. */
+int  cro_check_gpu_visible(const cro_dev_info *devs, int n, const char *device_id,
+                           int *visible);
+
+/* Bus-id / device-path spellings the reference derives
+ * (internal/utils/gpus.go:218,326,406,567,238,480).  kind:
+ * 0 upper(trim), 1 lower(trim), 2 TrimPrefix("0000") of upper,
+ * 3 "/dev/nvidia"+minor, 4 "/run/nvidia/driver/dev/nvidia"+minor. */
+int  cro_normalize(int kind, const char *in, char *buf, size_t cap, size_t *len);
+
+/* ---- the probe: new work in the slot of RunNvidiaSmi + CheckGPUVisible --- */
+
+/* Full per-device probe (fill, read sweeps, copy sweeps, closed-form check).
+ * Sits at internal/controller/composableresource_controller.go:259 and feeds
+ * the decision at :275.  dev_index indexes the cro_enumerate order. */
+int  cro_probe_device(cro_ctx *ctx, int dev_index, cro_probe_result *out);
+
+/* Concurrent probe of every managed device, NVLink P2P rounds, then ONE
+ * ncclAllGather of the 512-byte result structs.  out[] receives the gathered
+ * array as rank 0 holds it (asserted byte-identical on every rank). */
+int  cro_probe_all(cro_ctx *ctx, cro_probe_result *out, int cap, int *n);
+
+/* Device address of this device's result struct (the all-gather send buffer),
+ * for hosts that run their own collective (bench.py under torchrun). */
+int  cro_result_device_ptr(cro_ctx *ctx, int dev_index, uint64_t *dptr);
+
+/* Single sweeps, timed with CUDA events on the launching stream. */
+int  cro_hbm_fill(cro_ctx *ctx, int dev_index, cro_sweep_result *out);
+int  cro_hbm_read_checksum(cro_ctx *ctx, int dev_index, uint32_t variant, cro_sweep_result *out);
+int  cro_hbm_copy(cro_ctx *ctx, int dev_index, uint32_t variant, cro_sweep_result *out);
+/* Checksum of the copy destination region (same kernel, other half). */
+int  cro_hbm_read_checksum_dst(cro_ctx *ctx, int dev_index, uint32_t variant, cro_sweep_result *out);
+/* Closed-form expected checksum computed on the device without touching HBM. */
+int  cro_hbm_expected_checksum(cro_ctx *ctx, int dev_index, cro_sweep_result *out);
+/* Fault injection for tests: XOR `mask` into the 64-bit word at word_index. */
+int  cro_inject_fault(cro_ctx *ctx, int dev_index, uint64_t word_index, uint64_t mask);
+/* Copies [word_first, word_first+n_words) of the sweep region to host memory. */
+int  cro_read_words(cro_ctx *ctx, int dev_index, uint64_t word_first, uint64_t n_words, uint64_t *out);
+/* Repeats the read sweep `iters` times back to back under one event pair. */
+int  cro_hbm_read_loop(cro_ctx *ctx, int dev_index, uint32_t variant, uint32_t iters, cro_sweep_result *out);
+int  cro_hbm_copy_loop(cro_ctx *ctx, int dev_index, uint32_t variant, uint32_t iters, cro_sweep_result *out);
+int  cro_hbm_fill_loop(cro_ctx *ctx, int dev_index, uint32_t iters, cro_sweep_result *out);
+/* Seed used for a device (seed_base | minor). */
+int  cro_device_seed(cro_ctx *ctx, int dev_index, uint64_t *seed);
+/* Kernel launches issued by this context so far (bench "gpu_launches"). */
+uint64_t cro_launch_count(cro_ctx *ctx);
+
+/* ---- emit: encoding/json-compatible writers ------------------------------ */
+
+/* ComposableResourceStatus (api/v1alpha1/composableresource_types.go:36-41):
+ * {"state":..,"error":..,"device_id":..,"cdi_device_id":..} with Go omitempty
+ * rules; bytes identical to json.Marshal. */
+int  cro_emit_status_json(const char *state, const char *error, const char *device_id,
+                          const char *cdi_device_id, char *buf, size_t cap, size_t *len);
+
+/* ScalarResourceStatus (api/v1alpha1/composabilityrequest_types.go:74-80). */
+int  cro_emit_scalar_status_json(const char *state, const char *device_id,
+                                 const char *cdi_device_id, const char *node_name,
+                                 const char *error, char *buf, size_t cap, size_t *len);
+
+/* FM ScaleUpBody / ScaleDownBody (internal/cdi/fti/fm/api/scale_up.go:19-41,
+ * scale_down.go:19-41; built at fti/fm/client.go:115-144, :240-271). */
+int  cro_emit_fm_scale_up(const char *tenant_uuid, const char *mach_uuid, const char *res_type,
+                          const char *model, char *buf, size_t cap, size_t *len);
+int  cro_emit_fm_scale_down(const char *tenant_uuid, const char *mach_uuid, const char *res_type,
+                            const char *res_uuid, char *buf, size_t cap, size_t *len);
+/* CM resize bodies (internal/cdi/fti/cm/client.go:62-79, :133-139, :211-218). */
+int  cro_emit_cm_scale_up(const char *spec_uuid, int device_count,
+                          char *buf, size_t cap, size_t *len);
+int  cro_emit_cm_scale_down(const char *spec_uuid, int device_count, const char *device_id,
+                            char *buf, size_t cap, size_t *len);
+/* Sunfish CompositionRequest (internal/cdi/sunfish/client.go:48-61, :78). */
+int  cro_emit_sunfish_request(const char *name, long long count, const char *proc_type,
+                              const char *model, char *buf, size_t cap, size_t *len);
+
+/* Additive probe annotations (cohdi.io/probe-*), a Go-marshalled
+ * map[string]string (keys sorted).  Never mixed into the status bytes. */
+int  cro_emit_probe_annotations_json(const cro_probe_result *r, char *buf, size_t cap, size_t *len);
+
+/* (deviceID, CDIDeviceID) from an FM ScaleUpResponse body, with the
+ * res_op_status gate of internal/cdi/fti/fm/client.go:184-213.  On the error
+ * branches the reference's message is written to err_buf. */
+int  cro_fm_parse_scale_up_response(const char *body, const char *resource_name,
+                                    const char *res_type, const char *model,
+                                    char *device_id, size_t device_id_cap,
+                                    char *cdi_device_id, size_t cdi_cap,
+                                    char *err_buf, size_t err_cap);
+
+/* ---- reconcile step: the caller of the hot path -------------------------- */
+
+/*
+ * One pass of ComposableResourceReconciler.handleAttachingState
+ * (internal/controller/composableresource_controller.go:200-287) with the
+ * CUDA probe in the RunNvidiaSmi / CheckGPUVisible slots.
+ *
+ * in_json:  {"name":..,"spec":{type,model,target_node,force_detach},
+ *            "status":{state,error,device_id,cdi_device_id},
+ *            "deleting":bool,
+ *            "provider":{"device_id":..,"cdi_device_id":..,"error":..,"waiting":bool},
+ *            "device_resource_type":"DEVICE_PLUGIN"|"DRA",
+ *            "probe":bool}
+ * out_json: {"status":{...},"requeue_after_s":N,"error":"..","probe":{...}}
+ * The status object inside out_json is byte-identical to json.Marshal of the
+ * reference's ComposableResourceStatus after the same step.
+ */
+int  cro_reconcile_attach(cro_ctx *ctx, const char *in_json,
+                          char *buf, size_t cap, size_t *len);
+
+/* ---- diagnostics --------------------------------------------------------- */
+const char *cro_strerror(int code);
+/* Last error text recorded on this context by the calling thread's most
+ * recent failing call (thread-safe copy-out). */
+int  cro_last_error(cro_ctx *ctx, char *buf, size_t cap);
+const char *cro_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROPROBE_H_ */

@@ -1,0 +1,763 @@
+/*
+ * cro_oracle.c — CPU restatement of the reference's post-attach enumerate →
+ * parse → decide → emit path, plus the closed form of the probe pattern.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under composable-resource-operator_b200/
+ * may include, link or call this file.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs use it, as the checker
+ * and as the timed CPU baseline.
+ *
+ * Parity status: the reference (Go) cannot be compiled in this image (no Go
+ * toolchain), so oracle/_ref does not exist.  This restatement is pinned
+ * against every known-answer string the reference's own tests hold for the
+ * path (tests/golden/reference_kats.json, transcribed from
+ * internal/controller/composableresource_controller_test.go — see SURVEY.md
+ * §8c).  The JSON request bodies are "parity unpinned": no reference test reads
+ * a request body, so those vectors are derived from the struct tags and the
+ * Go encoding/json rules.
+ *
+ * Each function cites the reference lines it follows (paths relative to the
+ * reference tree).
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORACLE_OK 0
+#define ORACLE_ERR_EXEC -12
+#define ORACLE_ERR_PARSE -11
+#define ORACLE_ERR_UNSUPPORTED -10
+#define ORACLE_ERR_SMALL -7
+
+/* ------------------------------------------------------------------------ */
+/* probe pattern (new work)                          */
+/* ------------------------------------------------------------------------ */
+
+/* w[i] = one splitmix64 step of state (seed + i) */
+uint64_t oracle_pattern_word(uint64_t seed, uint64_t i) {
+    uint64_t z = seed + i + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+void oracle_fill(uint64_t *buf, uint64_t seed, uint64_t first, uint64_t n_words) {
+    for (uint64_t i = 0; i < n_words; ++i) buf[i] = oracle_pattern_word(seed, first + i);
+}
+
+/* (XOR-fold, wrapping sum) of words [first, first+n_words) */
+void oracle_checksum(uint64_t seed, uint64_t first, uint64_t n_words, uint64_t *x_out, uint64_t *s_out) {
+    uint64_t x = 0, s = 0;
+    for (uint64_t i = 0; i < n_words; ++i) {
+        const uint64_t w = oracle_pattern_word(seed, first + i);
+        x ^= w;
+        s += w;
+    }
+    *x_out = x;
+    *s_out = s;
+}
+
+/* checksum of a buffer that is already in memory (what a CPU "read sweep" does) */
+void oracle_checksum_buffer(const uint64_t *buf, uint64_t n_words, uint64_t *x_out, uint64_t *s_out) {
+    uint64_t x = 0, s = 0;
+    for (uint64_t i = 0; i < n_words; ++i) {
+        x ^= buf[i];
+        s += buf[i];
+    }
+    *x_out = x;
+    *s_out = s;
+}
+
+typedef struct {
+    uint64_t seed, first, n, x, s;
+} ck_job;
+static void *ck_worker(void *p) {
+    ck_job *j = (ck_job *)p;
+    oracle_checksum(j->seed, j->first, j->n, &j->x, &j->s);
+    return NULL;
+}
+/* same result with `threads` host threads (XOR / wrapping add are associative) */
+void oracle_checksum_mt(uint64_t seed, uint64_t n_words, int threads, uint64_t *x_out, uint64_t *s_out) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t th[256];
+    ck_job jobs[256];
+    const uint64_t per = n_words / (uint64_t)threads;
+    for (int t = 0; t < threads; ++t) {
+        jobs[t].seed = seed;
+        jobs[t].first = per * (uint64_t)t;
+        jobs[t].n = (t == threads - 1) ? n_words - per * (uint64_t)t : per;
+        pthread_create(&th[t], NULL, ck_worker, &jobs[t]);
+    }
+    uint64_t x = 0, s = 0;
+    for (int t = 0; t < threads; ++t) {
+        pthread_join(th[t], NULL);
+        x ^= jobs[t].x;
+        s += jobs[t].s;
+    }
+    *x_out = x;
+    *s_out = s;
+}
+
+/* mt19937_64 (Matsumoto & Nishimura 2004), the generator std::mt19937_64 names */
+typedef struct {
+    uint64_t mt[312];
+    int idx;
+} mt64;
+static void mt64_seed(mt64 *m, uint64_t seed) {
+    m->mt[0] = seed;
+    for (int i = 1; i < 312; ++i) m->mt[i] = 6364136223846793005ull * (m->mt[i - 1] ^ (m->mt[i - 1] >> 62)) + (uint64_t)i;
+    m->idx = 312;
+}
+static uint64_t mt64_next(mt64 *m) {
+    if (m->idx >= 312) {
+        for (int i = 0; i < 312; ++i) {
+            const uint64_t x = (m->mt[i] & 0xFFFFFFFF80000000ull) | (m->mt[(i + 1) % 312] & 0x7FFFFFFFull);
+            m->mt[i] = m->mt[(i + 156) % 312] ^ (x >> 1) ^ ((x & 1ull) ? 0xB5026F5AA96619E9ull : 0ull);
+        }
+        m->idx = 0;
+    }
+    uint64_t y = m->mt[m->idx++];
+    y ^= (y >> 29) & 0x5555555555555555ull;
+    y ^= (y << 17) & 0x71D67FFFEDA60000ull;
+    y ^= (y << 37) & 0xFFF7EEE000000000ull;
+    y ^= y >> 43;
+    return y;
+}
+/* index reached after `hops` steps from slot 0 of the latency permutation the
+ * probe places on device `minor` (Sattolo cycle, 16384 slots) */
+uint32_t oracle_chase_end(int minor, uint32_t hops) {
+    enum { N = 16384 };
+    static uint32_t perm[N];
+    mt64 m;
+    mt64_seed(&m, 0x5A77011000000000ull + (uint64_t)minor);
+    for (uint32_t i = 0; i < N; ++i) perm[i] = i;
+    for (uint32_t i = N - 1; i > 0; --i) {
+        const uint32_t j = (uint32_t)(mt64_next(&m) % i);
+        const uint32_t t = perm[i];
+        perm[i] = perm[j];
+        perm[j] = t;
+    }
+    uint32_t idx = 0;
+    for (uint32_t h = 0; h < hops; ++h) idx = perm[idx];
+    return idx;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Go string helpers                                                         */
+/* ------------------------------------------------------------------------ */
+
+/* unicode.IsSpace for the code points that can occur; strings.TrimSpace */
+static int is_space_cp(uint32_t r) {
+    if (r == '\t' || r == '\n' || r == '\v' || r == '\f' || r == '\r' || r == ' ' || r == 0x85 || r == 0xA0) return 1;
+    if (r == 0x1680 || (r >= 0x2000 && r <= 0x200A) || r == 0x2028 || r == 0x2029 || r == 0x202F || r == 0x205F || r == 0x3000) return 1;
+    return 0;
+}
+static size_t rune_at(const char *s, size_t n, size_t i, uint32_t *r) {
+    const unsigned char c = (unsigned char)s[i];
+    if (c < 0x80) { *r = c; return 1; }
+    if (c >= 0xC2 && c <= 0xDF && i + 1 < n && ((unsigned char)s[i + 1] & 0xC0) == 0x80) {
+        *r = ((uint32_t)(c & 0x1F) << 6) | ((unsigned char)s[i + 1] & 0x3F);
+        return 2;
+    }
+    if (c >= 0xE0 && c <= 0xEF && i + 2 < n && ((unsigned char)s[i + 1] & 0xC0) == 0x80 && ((unsigned char)s[i + 2] & 0xC0) == 0x80) {
+        *r = ((uint32_t)(c & 0x0F) << 12) | ((uint32_t)((unsigned char)s[i + 1] & 0x3F) << 6) | ((unsigned char)s[i + 2] & 0x3F);
+        if (*r >= 0x800 && !(*r >= 0xD800 && *r <= 0xDFFF)) return 3;
+    }
+    *r = 0xFFFD;
+    return 1;
+}
+/* returns [b,e) of TrimSpace(s[0..n)) */
+static void trim_space(const char *s, size_t n, size_t *b_out, size_t *e_out) {
+    size_t b = 0, e = n;
+    while (b < e) {
+        uint32_t r;
+        size_t k = rune_at(s, n, b, &r);
+        if (!is_space_cp(r)) break;
+        b += k;
+    }
+    while (e > b) {
+        size_t k = e - 1;
+        int back = 0;
+        while (k > b && ((unsigned char)s[k] & 0xC0) == 0x80 && back < 2) { --k; ++back; }
+        uint32_t r;
+        size_t len = rune_at(s, e, k, &r);
+        if (k + len != e) {
+            k = e - 1;
+            r = ((unsigned char)s[k] < 0x80) ? (unsigned char)s[k] : 0xFFFD;
+        }
+        if (!is_space_cp(r)) break;
+        e = k;
+    }
+    *b_out = b;
+    *e_out = e;
+}
+
+typedef struct {
+    char *p;
+    size_t cap, len;
+    int overflow;
+} sbuf;
+static void sb_init(sbuf *b, char *p, size_t cap) { b->p = p; b->cap = cap; b->len = 0; b->overflow = 0; if (cap) p[0] = 0; }
+static void sb_putn(sbuf *b, const char *s, size_t n) {
+    if (b->len + n + 1 > b->cap) { b->overflow = 1; return; }
+    memcpy(b->p + b->len, s, n);
+    b->len += n;
+    b->p[b->len] = 0;
+}
+static void sb_puts(sbuf *b, const char *s) { sb_putn(b, s, strlen(s)); }
+static void sb_putc(sbuf *b, char c) { sb_putn(b, &c, 1); }
+
+/* encoding/json appendString, escapeHTML=true (Go 1.24 encode.go) */
+static void sb_json_string(sbuf *b, const char *s, size_t n) {
+    static const char hex[] = "0123456789abcdef";
+    sb_putc(b, '"');
+    size_t i = 0;
+    while (i < n) {
+        const unsigned char c = (unsigned char)s[i];
+        if (c < 0x80) {
+            if (c >= 0x20 && c != '"' && c != '\\' && c != '<' && c != '>' && c != '&') sb_putc(b, (char)c);
+            else if (c == '"') sb_puts(b, "\\\"");
+            else if (c == '\\') sb_puts(b, "\\\\");
+            else if (c == '\b') sb_puts(b, "\\b");
+            else if (c == '\f') sb_puts(b, "\\f");
+            else if (c == '\n') sb_puts(b, "\\n");
+            else if (c == '\r') sb_puts(b, "\\r");
+            else if (c == '\t') sb_puts(b, "\\t");
+            else { char u[7] = {'\\', 'u', '0', '0', hex[c >> 4], hex[c & 15], 0}; sb_puts(b, u); }
+            ++i;
+            continue;
+        }
+        /* utf8.DecodeRune acceptance */
+        size_t len = 0;
+        uint32_t r = 0;
+        if (c >= 0xC2 && c <= 0xDF) {
+            if (i + 1 < n && ((unsigned char)s[i + 1] & 0xC0) == 0x80) { len = 2; r = ((uint32_t)(c & 0x1F) << 6) | ((unsigned char)s[i + 1] & 0x3F); }
+        } else if (c >= 0xE0 && c <= 0xEF) {
+            unsigned lo = c == 0xE0 ? 0xA0 : 0x80, hi = c == 0xED ? 0x9F : 0xBF;
+            if (i + 2 < n && (unsigned char)s[i + 1] >= lo && (unsigned char)s[i + 1] <= hi && ((unsigned char)s[i + 2] & 0xC0) == 0x80) {
+                len = 3;
+                r = ((uint32_t)(c & 0x0F) << 12) | ((uint32_t)((unsigned char)s[i + 1] & 0x3F) << 6) | ((unsigned char)s[i + 2] & 0x3F);
+            }
+        } else if (c >= 0xF0 && c <= 0xF4) {
+            unsigned lo = c == 0xF0 ? 0x90 : 0x80, hi = c == 0xF4 ? 0x8F : 0xBF;
+            if (i + 3 < n && (unsigned char)s[i + 1] >= lo && (unsigned char)s[i + 1] <= hi && ((unsigned char)s[i + 2] & 0xC0) == 0x80 &&
+                ((unsigned char)s[i + 3] & 0xC0) == 0x80)
+                len = 4;
+        }
+        if (len == 0) { sb_puts(b, "\\ufffd"); ++i; continue; }
+        if (r == 0x2028) sb_puts(b, "\\u2028");
+        else if (r == 0x2029) sb_puts(b, "\\u2029");
+        else sb_putn(b, s + i, len);
+        i += len;
+    }
+    sb_putc(b, '"');
+}
+static void sb_json_cstr(sbuf *b, const char *s) { sb_json_string(b, s ? s : "", s ? strlen(s) : 0); }
+static void sb_key(sbuf *b, const char *k) { sb_json_cstr(b, k); sb_putc(b, ':'); }
+
+int oracle_json_string(const char *s, char *out, size_t cap) {
+    sbuf b;
+    sb_init(&b, out, cap);
+    sb_json_cstr(&b, s);
+    return b.overflow ? ORACLE_ERR_SMALL : (int)b.len;
+}
+
+/* ------------------------------------------------------------------------ */
+/* CSV parse rule: internal/utils/gpus.go:880,896-916                        */
+/* ------------------------------------------------------------------------ */
+#define MAX_FIELDS 16
+typedef struct { const char *p; size_t n; } span;
+
+static size_t split_spans(const char *s, size_t n, char sep, span *out, size_t max) {
+    size_t cnt = 0, start = 0;
+    for (size_t i = 0; i <= n; ++i) {
+        if (i == n || s[i] == sep) {
+            if (cnt < max) { out[cnt].p = s + start; out[cnt].n = i - start; }
+            ++cnt;
+            start = i + 1;
+        }
+    }
+    return cnt;
+}
+static int span_cmp(const span *a, const span *b) {
+    const size_t m = a->n < b->n ? a->n : b->n;
+    const int c = memcmp(a->p, b->p, m);
+    if (c) return c;
+    return a->n < b->n ? -1 : (a->n > b->n ? 1 : 0);
+}
+
+/* Writes one map[string]string as Go marshals it: keys sorted bytewise; a key
+ * assigned twice keeps the last value. */
+static void emit_map(sbuf *b, const span *keys, const span *vals, size_t n) {
+    size_t order[MAX_FIELDS], m = 0;
+    for (size_t i = 0; i < n; ++i) {
+        int later = 0;
+        for (size_t j = i + 1; j < n; ++j)
+            if (span_cmp(&keys[i], &keys[j]) == 0) later = 1;
+        if (!later) order[m++] = i;
+    }
+    for (size_t i = 1; i < m; ++i)
+        for (size_t j = i; j > 0 && span_cmp(&keys[order[j]], &keys[order[j - 1]]) < 0; --j) {
+            size_t t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
+        }
+    sb_putc(b, '{');
+    for (size_t i = 0; i < m; ++i) {
+        if (i) sb_putc(b, ',');
+        sb_json_string(b, keys[order[i]].p, keys[order[i]].n);
+        sb_putc(b, ':');
+        sb_json_string(b, vals[order[i]].p, vals[order[i]].n);
+    }
+    sb_putc(b, '}');
+}
+
+static void exec_error_text(sbuf *b, const char *so, const char *se, const char *ee) {
+    sb_puts(b, "get gpu info command failed: err: '");
+    sb_puts(b, ee ? ee : "<nil>");
+    sb_puts(b, "', stderr: '");
+    sb_puts(b, se);
+    sb_puts(b, "', stdout: '");
+    sb_puts(b, so);
+    sb_puts(b, "'");
+}
+
+/* out: Go JSON of the []map[string]string, or the error text. */
+int oracle_parse_gpu_csv(const char *std_out, const char *std_err, const char *exec_err, const char *query,
+                         char *out, size_t cap) {
+    sbuf b;
+    sb_init(&b, out, cap);
+    const char *so = std_out ? std_out : "", *se = std_err ? std_err : "";
+    span fields[MAX_FIELDS];
+    const size_t nf = split_spans(query, strlen(query), ',', fields, MAX_FIELDS);
+    if (nf > MAX_FIELDS) return ORACLE_ERR_UNSUPPORTED;
+    size_t tb, te;
+    trim_space(so, strlen(so), &tb, &te);
+    /* gpus.go:896 — stdout test comes first */
+    if (te - tb == 21 && memcmp(so + tb, "No devices were found", 21) == 0) {
+        sb_puts(&b, "[]");
+        return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK;
+    }
+    if (se[0] != 0 || exec_err != NULL) { /* gpus.go:899 */
+        exec_error_text(&b, so, se, exec_err);
+        return b.overflow ? ORACLE_ERR_SMALL : ORACLE_ERR_EXEC;
+    }
+    int any = 0;
+    size_t pos = tb;
+    sbuf body;
+    char *tmp = (char *)malloc(cap ? cap : 1);
+    sb_init(&body, tmp, cap);
+    while (pos <= te) { /* strings.Split(TrimSpace(stdout), "\n") */
+        size_t eol = pos;
+        while (eol < te && so[eol] != '\n') ++eol;
+        if (eol > pos) { /* gpus.go:905 skips empty lines */
+            span parts[64];
+            const size_t np = split_spans(so + pos, eol - pos, ',', parts, 64);
+            span vals[MAX_FIELDS];
+            for (size_t i = 0; i < nf; ++i) {
+                if (i >= np) { /* gpus.go:913 parts[i] unguarded: Go panics */
+                    free(tmp);
+                    sb_init(&b, out, cap);
+                    char msg[96];
+                    snprintf(msg, sizeof msg, "runtime error: index out of range [%zu] with length %zu", i, np);
+                    sb_puts(&b, msg);
+                    return ORACLE_ERR_PARSE;
+                }
+                size_t vb, ve;
+                trim_space(parts[i].p, parts[i].n, &vb, &ve);
+                vals[i].p = parts[i].p + vb;
+                vals[i].n = ve - vb;
+            }
+            if (any) sb_putc(&body, ',');
+            emit_map(&body, fields, vals, nf);
+            any = 1;
+        }
+        if (eol >= te) break;
+        pos = eol + 1;
+    }
+    if (!any) sb_puts(&b, "null"); /* nil slice */
+    else { sb_putc(&b, '['); sb_putn(&b, body.p, body.len); sb_putc(&b, ']'); }
+    const int of = b.overflow || body.overflow;
+    free(tmp);
+    return of ? ORACLE_ERR_SMALL : ORACLE_OK;
+}
+
+/* /proc flavour: internal/utils/gpus.go:1045-1089 */
+int oracle_parse_proc_csv(const char *std_out, const char *std_err, const char *exec_err, const char *query,
+                          char *out, size_t cap) {
+    sbuf b;
+    sb_init(&b, out, cap);
+    const char *so = std_out ? std_out : "", *se = std_err ? std_err : "";
+    span fields[MAX_FIELDS];
+    const size_t nf = split_spans(query, strlen(query), ',', fields, MAX_FIELDS);
+    if (nf > MAX_FIELDS) return ORACLE_ERR_UNSUPPORTED;
+    if (se[0] != 0 || exec_err != NULL) {
+        exec_error_text(&b, so, se, exec_err);
+        return b.overflow ? ORACLE_ERR_SMALL : ORACLE_ERR_EXEC;
+    }
+    size_t tb, te;
+    trim_space(so, strlen(so), &tb, &te);
+    if (tb == te) { sb_puts(&b, "[]"); return ORACLE_OK; }
+    static const char *names[3] = {"device_minor", "gpu_uuid", "pci.bus_id"};
+    int any = 0;
+    sbuf body;
+    char *tmp = (char *)malloc(cap ? cap : 1);
+    sb_init(&body, tmp, cap);
+    size_t pos = tb;
+    while (pos <= te) {
+        size_t eol = pos;
+        while (eol < te && so[eol] != '\n') ++eol;
+        if (eol > pos) {
+            span parts[64];
+            const size_t np = split_spans(so + pos, eol - pos, ',', parts, 64);
+            if (np < 3) {
+                free(tmp);
+                sb_init(&b, out, cap);
+                sb_puts(&b, "unexpected GPU information format: '");
+                sb_putn(&b, so + pos, eol - pos);
+                sb_puts(&b, "'");
+                return ORACLE_ERR_PARSE;
+            }
+            span keys[MAX_FIELDS], vals[MAX_FIELDS];
+            for (size_t f = 0; f < nf; ++f) {
+                size_t kb, ke;
+                trim_space(fields[f].p, fields[f].n, &kb, &ke);
+                keys[f].p = fields[f].p + kb;
+                keys[f].n = ke - kb;
+                int hit = -1;
+                for (int k = 0; k < 3; ++k)
+                    if (strlen(names[k]) == keys[f].n && memcmp(names[k], keys[f].p, keys[f].n) == 0) hit = k;
+                if (hit < 0) {
+                    free(tmp);
+                    sb_init(&b, out, cap);
+                    sb_puts(&b, "unsupported field '");
+                    sb_putn(&b, keys[f].p, keys[f].n);
+                    sb_puts(&b, "' requested in queryArgs");
+                    return ORACLE_ERR_UNSUPPORTED;
+                }
+                size_t vb, ve;
+                trim_space(parts[hit].p, parts[hit].n, &vb, &ve);
+                vals[f].p = parts[hit].p + vb;
+                vals[f].n = ve - vb;
+            }
+            if (any) sb_putc(&body, ',');
+            emit_map(&body, keys, vals, nf);
+            any = 1;
+        }
+        if (eol >= te) break;
+        pos = eol + 1;
+    }
+    if (!any) sb_puts(&b, "null");
+    else { sb_putc(&b, '['); sb_putn(&b, body.p, body.len); sb_putc(&b, ']'); }
+    const int of = b.overflow || body.overflow;
+    free(tmp);
+    return of ? ORACLE_ERR_SMALL : ORACLE_OK;
+}
+
+/* awk '/^<key>/ {print $3; exit}' — internal/utils/gpus.go:1030-1032 */
+static int awk_field3(const char *text, const char *key, char *out, size_t cap) {
+    const size_t kl = strlen(key);
+    const char *line = text;
+    out[0] = 0;
+    while (*line) {
+        const char *eol = strchr(line, '\n');
+        const size_t ln = eol ? (size_t)(eol - line) : strlen(line);
+        if (ln >= kl && memcmp(line, key, kl) == 0) {
+            int field = 0;
+            size_t i = 0;
+            while (i < ln) {
+                while (i < ln && (line[i] == ' ' || line[i] == '\t')) ++i;
+                size_t j = i;
+                while (j < ln && line[j] != ' ' && line[j] != '\t') ++j;
+                if (j > i && ++field == 3) {
+                    const size_t n = j - i < cap - 1 ? j - i : cap - 1;
+                    memcpy(out, line + i, n);
+                    out[n] = 0;
+                    return 1;
+                }
+                i = j;
+            }
+            return 0; /* first match only ("exit") */
+        }
+        if (!eol) break;
+        line = eol + 1;
+    }
+    return 0;
+}
+/* the printf at gpus.go:1034; "" when any of the three is empty */
+int oracle_proc_information_to_line(const char *text, char *out, size_t cap) {
+    char minor[64], uuid[96], bus[64];
+    sbuf b;
+    sb_init(&b, out, cap);
+    awk_field3(text, "Device Minor:", minor, sizeof minor);
+    awk_field3(text, "GPU UUID:", uuid, sizeof uuid);
+    awk_field3(text, "Bus Location:", bus, sizeof bus);
+    if (!minor[0] || !uuid[0] || !bus[0]) return ORACLE_OK;
+    sb_puts(&b, minor); sb_putc(&b, ','); sb_puts(&b, uuid); sb_putc(&b, ','); sb_puts(&b, bus); sb_putc(&b, '\n');
+    return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK;
+}
+
+/* CheckGPUVisible, DEVICE_PLUGIN branch (gpus.go:73-84): 1 visible, 0 not,
+ * <0 error (text in err). */
+int oracle_check_gpu_visible(const char *std_out, const char *std_err, const char *exec_err, const char *device_id,
+                             char *err, size_t err_cap) {
+    const char *so = std_out ? std_out : "", *se = std_err ? std_err : "";
+    sbuf eb;
+    sb_init(&eb, err, err_cap);
+    size_t tb, te;
+    trim_space(so, strlen(so), &tb, &te);
+    if (te - tb == 21 && memcmp(so + tb, "No devices were found", 21) == 0) return 0;
+    if (se[0] != 0 || exec_err != NULL) {
+        exec_error_text(&eb, so, se, exec_err);
+        return ORACLE_ERR_EXEC;
+    }
+    const size_t dl = strlen(device_id);
+    size_t pos = tb;
+    while (pos <= te) {
+        size_t eol = pos;
+        while (eol < te && so[eol] != '\n') ++eol;
+        if (eol > pos) {
+            /* field 0 of the line, trimmed (query is the single field gpu_uuid) */
+            size_t c = pos;
+            while (c < eol && so[c] != ',') ++c;
+            size_t vb, ve;
+            trim_space(so + pos, c - pos, &vb, &ve);
+            if (ve - vb == dl && memcmp(so + pos + vb, device_id, dl) == 0) return 1;
+        }
+        if (eol >= te) break;
+        pos = eol + 1;
+    }
+    return 0;
+}
+
+/* bus-id / dev-path spellings: gpus.go:218 (0), :326 (1), :406,567 (2), :238 (3), :480 (4) */
+int oracle_normalize(int kind, const char *in, char *out, size_t cap) {
+    sbuf b;
+    sb_init(&b, out, cap);
+    if (kind == 3) { sb_puts(&b, "/dev/nvidia"); sb_puts(&b, in); return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK; }
+    if (kind == 4) { sb_puts(&b, "/run/nvidia/driver/dev/nvidia"); sb_puts(&b, in); return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK; }
+    size_t tb, te;
+    trim_space(in, strlen(in), &tb, &te);
+    char tmp[256];
+    size_t n = te - tb < sizeof tmp - 1 ? te - tb : sizeof tmp - 1;
+    for (size_t i = 0; i < n; ++i) {
+        char c = in[tb + i];
+        if (kind == 1) { if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a'); }
+        else if (c >= 'a' && c <= 'z') c = (char)(c - 'a' + 'A');
+        tmp[i] = c;
+    }
+    tmp[n] = 0;
+    const char *p = tmp;
+    if (kind == 2 && n >= 4 && memcmp(tmp, "0000", 4) == 0) p = tmp + 4;
+    sb_puts(&b, p);
+    return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK;
+}
+
+/* ------------------------------------------------------------------------ */
+/* emitters — json.Marshal of the wire structs                               */
+/* ------------------------------------------------------------------------ */
+
+/* api/v1alpha1/composableresource_types.go:36-41 */
+int oracle_emit_status(const char *state, const char *error, const char *device_id, const char *cdi_device_id,
+                       char *out, size_t cap) {
+    sbuf b;
+    sb_init(&b, out, cap);
+    sb_putc(&b, '{');
+    sb_key(&b, "state"); sb_json_cstr(&b, state);
+    if (error && error[0]) { sb_putc(&b, ','); sb_key(&b, "error"); sb_json_cstr(&b, error); }
+    if (device_id && device_id[0]) { sb_putc(&b, ','); sb_key(&b, "device_id"); sb_json_cstr(&b, device_id); }
+    if (cdi_device_id && cdi_device_id[0]) { sb_putc(&b, ','); sb_key(&b, "cdi_device_id"); sb_json_cstr(&b, cdi_device_id); }
+    sb_putc(&b, '}');
+    return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK;
+}
+
+/* api/v1alpha1/composabilityrequest_types.go:74-80 */
+int oracle_emit_scalar_status(const char *state, const char *device_id, const char *cdi_device_id,
+                              const char *node_name, const char *error, char *out, size_t cap) {
+    sbuf b;
+    sb_init(&b, out, cap);
+    sb_putc(&b, '{');
+    sb_key(&b, "state"); sb_json_cstr(&b, state);
+    if (device_id && device_id[0]) { sb_putc(&b, ','); sb_key(&b, "device_id"); sb_json_cstr(&b, device_id); }
+    if (cdi_device_id && cdi_device_id[0]) { sb_putc(&b, ','); sb_key(&b, "cdi_device_id"); sb_json_cstr(&b, cdi_device_id); }
+    if (node_name && node_name[0]) { sb_putc(&b, ','); sb_key(&b, "node_name"); sb_json_cstr(&b, node_name); }
+    if (error && error[0]) { sb_putc(&b, ','); sb_key(&b, "error"); sb_json_cstr(&b, error); }
+    sb_putc(&b, '}');
+    return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK;
+}
+
+/* internal/cdi/fti/fm/api/scale_up.go:19-41 + common.go:21-29; built at fti/fm/client.go:115-143 */
+int oracle_emit_fm_scale_up(const char *tenant, const char *mach, const char *type, const char *model, char *out, size_t cap) {
+    sbuf b;
+    sb_init(&b, out, cap);
+    sb_puts(&b, "{\"tenants\":{\"tenant_uuid\":"); sb_json_cstr(&b, tenant);
+    sb_puts(&b, ",\"machines\":[{\"mach_uuid\":"); sb_json_cstr(&b, mach);
+    sb_puts(&b, ",\"resources\":[{\"res_specs\":[{\"res_type\":"); sb_json_cstr(&b, type);
+    sb_puts(&b, ",\"res_spec\":{\"condition\":[{\"column\":\"model\",\"operator\":\"eq\",\"value\":"); sb_json_cstr(&b, model);
+    sb_puts(&b, "}]},\"res_num\":1}]}]}]}}");
+    return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK;
+}
+
+/* internal/cdi/fti/fm/api/scale_down.go:19-41; built at fti/fm/client.go:247-270 */
+int oracle_emit_fm_scale_down(const char *tenant, const char *mach, const char *type, const char *res_uuid, char *out, size_t cap) {
+    sbuf b;
+    sb_init(&b, out, cap);
+    sb_puts(&b, "{\"tenants\":{\"tenant_uuid\":"); sb_json_cstr(&b, tenant);
+    sb_puts(&b, ",\"machines\":[{\"mach_uuid\":"); sb_json_cstr(&b, mach);
+    sb_puts(&b, ",\"resources\":[{\"res_specs\":[{\"res_type\":"); sb_json_cstr(&b, type);
+    sb_puts(&b, ",\"res_uuid\":"); sb_json_cstr(&b, res_uuid);
+    sb_puts(&b, ",\"res_num\":1}]}]}]}}");
+    return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK;
+}
+
+/* internal/cdi/fti/cm/client.go:62-69 */
+int oracle_emit_cm_scale_up(const char *spec_uuid, int device_count, char *out, size_t cap) {
+    sbuf b;
+    char num[32];
+    sb_init(&b, out, cap);
+    snprintf(num, sizeof num, "%d", device_count);
+    sb_puts(&b, "{\"increase_resource_count\":{\"spec_uuid\":"); sb_json_cstr(&b, spec_uuid);
+    sb_puts(&b, ",\"device_count\":"); sb_puts(&b, num); sb_puts(&b, "}}");
+    return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK;
+}
+
+/* internal/cdi/fti/cm/client.go:71-79 */
+int oracle_emit_cm_scale_down(const char *spec_uuid, int device_count, const char *device_id, char *out, size_t cap) {
+    sbuf b;
+    char num[32];
+    sb_init(&b, out, cap);
+    snprintf(num, sizeof num, "%d", device_count);
+    sb_puts(&b, "{\"remove_resources\":{\"spec_uuid\":"); sb_json_cstr(&b, spec_uuid);
+    sb_puts(&b, ",\"device_count\":"); sb_puts(&b, num);
+    sb_puts(&b, ",\"devices\":["); sb_json_cstr(&b, device_id); sb_puts(&b, "]}}");
+    return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK;
+}
+
+/* internal/cdi/sunfish/client.go:48-61 */
+int oracle_emit_sunfish(const char *name, long long count, const char *proc_type, const char *model, char *out, size_t cap) {
+    sbuf b;
+    char num[32];
+    sb_init(&b, out, cap);
+    snprintf(num, sizeof num, "%lld", count);
+    sb_puts(&b, "{\"Name\":"); sb_json_cstr(&b, name);
+    sb_puts(&b, ",\"Processors\":{\"Members\":[{\"@Redfish.RequestCount\":"); sb_puts(&b, num);
+    sb_puts(&b, ",\"ProcessorType\":"); sb_json_cstr(&b, proc_type);
+    sb_puts(&b, ",\"Model\":"); sb_json_cstr(&b, model);
+    sb_puts(&b, "}]}}");
+    return b.overflow ? ORACLE_ERR_SMALL : ORACLE_OK;
+}
+
+/* ------------------------------------------------------------------------ */
+/* attach step: internal/controller/composableresource_controller.go:200-287 */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+    char state[32];
+    char error[1024];
+    char device_id[128];
+    char cdi_device_id[128];
+} oracle_status;
+
+typedef struct {
+    const char *name, *target_node;
+    int deleting;                          /* DeletionTimestamp != nil */
+    const char *device_resource_type;      /* "DEVICE_PLUGIN" | "DRA" */
+    int provider_waiting;                  /* AddResource returns ErrWaitingDeviceAttaching */
+    const char *provider_error;            /* AddResource error text or NULL */
+    const char *provider_device_id, *provider_cdi_device_id;
+    const char *std_out, *std_err, *exec_err; /* what the exec of nvidia-smi produced */
+    int driver_pod_missing;                /* gpus.go:835 */
+    const char *ds_err[3];                 /* restart errors: device-plugin, dcgm, dra-kubelet-plugin */
+    const char *slice_uuids;               /* DRA: '\n'-joined ResourceSlice uuid attributes, or NULL */
+} oracle_attach_in;
+
+static void set_str(char *dst, size_t cap, const char *s) {
+    snprintf(dst, cap, "%s", s ? s : "");
+}
+
+/* returns 0 (nil error) or 1 (error text in err); *n_updates counts Status().Update calls */
+int oracle_attach_step(const oracle_attach_in *in, oracle_status *st, int *requeue_after_s, char *err, size_t err_cap,
+                       int *n_updates) {
+    *requeue_after_s = 0;
+    *n_updates = 0;
+    err[0] = 0;
+    if (in->deleting) { /* :203-213 */
+        if (st->device_id[0] == 0) { set_str(st->state, sizeof st->state, "Deleting"); ++*n_updates; return 0; }
+        if (st->error[0] != 0) { set_str(st->state, sizeof st->state, "Detaching"); ++*n_updates; return 0; }
+    }
+    if (st->device_id[0] == 0) { /* :217-237 */
+        if (in->provider_waiting) { *requeue_after_s = 30; return 0; }
+        if (in->provider_error && in->provider_error[0]) {
+            set_str(err, err_cap, in->provider_error);
+            set_str(st->error, sizeof st->error, err); /* requeueOnErr :423-433 */
+            ++*n_updates;
+            return 1;
+        }
+        st->error[0] = 0;
+        set_str(st->device_id, sizeof st->device_id, in->provider_device_id);
+        set_str(st->cdi_device_id, sizeof st->cdi_device_id, in->provider_cdi_device_id);
+        ++*n_updates;
+    }
+    const int dra = strcmp(in->device_resource_type, "DRA") == 0;
+    const int dp = strcmp(in->device_resource_type, "DEVICE_PLUGIN") == 0;
+    char pod_err[256];
+    snprintf(pod_err, sizeof pod_err, "no Pod with label 'app.kubernetes.io/component=nvidia-driver' found on node %s",
+             in->target_node ? in->target_node : "");
+    if (dp) { /* :239-257 */
+        for (int k = 0; k < 2; ++k)
+            if (in->ds_err[k] && in->ds_err[k][0]) { set_str(st->error, sizeof st->error, in->ds_err[k]); ++*n_updates; }
+    } else if (dra) { /* :258-273 */
+        char e2[1024];
+        int failed = 0;
+        if (in->driver_pod_missing) { set_str(e2, sizeof e2, pod_err); failed = 1; }
+        else {
+            char js[4096];
+            int rc = oracle_parse_gpu_csv(in->std_out, in->std_err, in->exec_err, "gpu_uuid", js, sizeof js);
+            if (rc == ORACLE_ERR_EXEC || rc == ORACLE_ERR_PARSE) { set_str(e2, sizeof e2, js); failed = 1; }
+        }
+        if (failed) { set_str(st->error, sizeof st->error, e2); ++*n_updates; }
+        if (in->ds_err[2] && in->ds_err[2][0]) { set_str(st->error, sizeof st->error, in->ds_err[2]); ++*n_updates; }
+    }
+    /* :275-286 CheckGPUVisible */
+    int visible = 0;
+    if (dra && in->slice_uuids) { /* gpus.go:55-71 */
+        const char *p = in->slice_uuids;
+        const size_t dl = strlen(st->device_id);
+        while (*p) {
+            const char *e = strchr(p, '\n');
+            const size_t n = e ? (size_t)(e - p) : strlen(p);
+            if (n == dl && memcmp(p, st->device_id, dl) == 0) visible = 1;
+            if (!e) break;
+            p = e + 1;
+        }
+    } else {
+        if (in->driver_pod_missing) {
+            set_str(err, err_cap, pod_err);
+            set_str(st->error, sizeof st->error, err);
+            ++*n_updates;
+            return 1;
+        }
+        int v = oracle_check_gpu_visible(in->std_out, in->std_err, in->exec_err, st->device_id, err, err_cap);
+        if (v < 0) { set_str(st->error, sizeof st->error, err); ++*n_updates; return 1; }
+        visible = v;
+    }
+    if (visible) {
+        set_str(st->state, sizeof st->state, "Online");
+        st->error[0] = 0;
+        ++*n_updates;
+        return 0;
+    }
+    *requeue_after_s = 30;
+    return 0;
+}
+
+/* FM res_op_status gate: internal/cdi/fti/fm/client.go:195-208 (given the
+ * already-decoded first resource).  0 ok, 1 error (text in err). */
+int oracle_fm_gate(const char *instance_name, const char *op_status, char *err, size_t err_cap) {
+    err[0] = 0;
+    if (!op_status || !op_status[0]) { snprintf(err, err_cap, "runtime error: slice bounds out of range [:1] with length 0"); return 1; }
+    if (op_status[0] == '0' || op_status[0] == '1') return 0;
+    if (op_status[0] == '2') { snprintf(err, err_cap, "the FM attached device called by %s is in Critical state in FM", instance_name); return 1; }
+    snprintf(err, err_cap, "the FM attached device called by %s is in unknown state '%s' in FM", instance_name, op_status);
+    return 1;
+}

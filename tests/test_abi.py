@@ -1,0 +1,75 @@
+"""The C-ABI library loads, exports every symbol include/croprobe.h declares,
+keeps the 512-byte result layout, and fails loudly without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "croprobe.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cro_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(cro):
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(cro.lib, s), "declared in croprobe.h but not exported: " + s
+    assert sorted(cro.EXPORTS) == syms, set(cro.EXPORTS) ^ set(syms)
+
+
+def test_result_struct_layout(cro):
+    R = cro.ProbeResult
+    assert ctypes.sizeof(R) == 512
+    offs = {"gpu_uuid": 16, "pci_bus_id": 64, "hbm_bytes_total": 88, "checksum_xor": 112, "fill_ns": 128,
+            "sm_count": 168, "p2p_read_ns": 184, "p2p_checksum_xor": 248, "p2p_latency_ns_x16": 312,
+            "p2p_access": 344, "p2p_bytes": 352, "rank": 408}
+    for k, v in offs.items():
+        assert getattr(R, k).offset == v, k
+
+
+def test_library_has_sm100a_code_and_blackwell_instructions():
+    so = os.path.join(ROOT, "composable-resource-operator_b200", "libcroprobe.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass, "1-D TMA bulk copies must be present (cp.async.bulk)"
+    assert "SYNCS" in sass, "mbarrier instructions must be present"
+    assert "LDG.E" in sass and ".256" in sass, "256-bit global loads must be present"
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="a GPU is present")
+def test_no_gpu_fails_loudly(cro):
+    """There is no CPU fallback: without a device the probe context refuses to exist."""
+    with pytest.raises(cro.ProbeError) as e:
+        cro.ProbeContext(sweep_bytes=1 << 20)
+    assert e.value.code in (cro.ERR_NO_DEVICE, cro.ERR_CUDA)
+
+
+def test_strerror_and_version(cro):
+    assert cro.strerror(0) == "ok"
+    assert cro.strerror(cro.ERR_CHECKSUM) == "hbm checksum mismatch"
+    assert "sm_100a" in cro.version()
+
+
+def test_product_never_touches_the_oracle():
+    """The shipped path must not include, link or import anything under oracle/."""
+    pkg = os.path.join(ROOT, "composable-resource-operator_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".cu", ".cpp", ".hpp", ".cuh", ".py", ".go", ".h")):
+                t = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "cro_oracle" not in t and "liboracle" not in t and "import oracle" not in t, os.path.join(dirpath, f)
+    so = os.path.join(pkg, "libcroprobe.so")
+    out = subprocess.run(["nm", "-D", so], capture_output=True, text=True).stdout
+    assert "oracle_" not in out
