@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — composed-GPU probes/sec for the post-attach probe + spec path.
+
+A "step" is one pass of the hot path for one freshly composed GPU: the attach
+reconcile step (enumerate -> HBM probe -> visibility decision -> status / CDI
+JSON emit), BASELINE.json config 2 ("1xB200 attach: sm_100a HBM probe + CDI
+emit").  One probe = 1 fill + 5 read sweeps + 5 copy sweeps over S = 4 GiB
+(algorithmic bytes 16*S, DESIGN.md "Measurement").
+
+  value      probes/s with everything resident in HBM: K probes divided by the
+             CUDA-event time of their kernels (events recorded by libcroprobe
+             on the stream the kernels run on), max over ranks.
+  e2e        probes/s through the public C-ABI call (cro_reconcile_attach):
+             host JSON in, host JSON out, host<->device copies inside,
+             wall clock bracketed by barrier + synchronize.
+  roofline   the kernel with the largest share of the step (hbm_copy) against
+             MEASURED_PEAKS.json; roofline_kernels lists fill / read / copy.
+  cpu_baseline / --impl reference
+             the reference's CPU path for the same step (exec nvidia-smi,
+             parse, decide, emit) from the oracle port, timed on this host.
+
+N > 1 (torchrun): one rank per GPU, each probes its own device (weak scaling,
+no data-path collective) and the 512-byte result structs are all-gathered over
+NCCL — the one exchange step the path has.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SWEEP_BYTES = 4 << 30
+METRIC = "composed-GPU probes/sec"
+UNIT = "probes/s"
+WORKLOAD = "configs[1]: 1xB200 attach — HBM probe (fill + 5 read + 5 copy sweeps, S=4 GiB) + CDI/status JSON emit"
+CANNED_UUID = "GPU-device00-uuid-temp-0000-000000000000"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        smi = shutil.which("nvidia-smi")
+        if not smi:
+            return
+        try:
+            self.proc = subprocess.Popen([smi, "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for k, name in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path
+# ---------------------------------------------------------------------------
+def reference_step_factory():
+    """Returns (step_fn, description).  One step = what handleAttachingState does on the CPU for one CR:
+    exec `nvidia-smi --query-gpu=gpu_uuid` (internal/utils/gpus.go:886), parse (:896-916), decide (:73-84),
+    emit status JSON + the FM scale-up body.  The SPDY/kubelet hop of the reference is NOT included, so this
+    is a lower bound on the reference's latency."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    co = oracle.COracle()
+    smi = shutil.which("nvidia-smi")
+    canned = CANNED_UUID + "\n"
+    if smi:
+        first = subprocess.run([smi, "--query-gpu=gpu_uuid", "--format=csv,noheader,nounits"], capture_output=True, text=True)
+        dev = first.stdout.strip().split("\n")[0].strip() if first.returncode == 0 and first.stdout.strip() else CANNED_UUID
+    else:
+        dev = CANNED_UUID
+
+    def step():
+        if smi:
+            p = subprocess.run([smi, "--query-gpu=gpu_uuid", "--format=csv,noheader,nounits"], capture_output=True, text=True)
+            so, se, ee = p.stdout, p.stderr, (None if p.returncode == 0 else "exit status %d" % p.returncode)
+        else:
+            so, se, ee = canned, "", None
+        inp = oracle.AttachInput(name="cr", target_node="worker-0", device_resource_type="DEVICE_PLUGIN",
+                                 provider_device_id=dev, provider_cdi_device_id="res-0-0", std_out=so, std_err=se, exec_err=ee)
+        st, rq, err, _n = co.attach_step(inp, oracle.Status("Attaching"))
+        js = co.emit_status(st.state, st.error, st.device_id, st.cdi_device_id)
+        body = co.emit_fm_scale_up("tenant", "machine", "gpu", "NVIDIA-B200")
+        return st.state, len(js) + len(body)
+
+    how = ("exec nvidia-smi --query-gpu=gpu_uuid per step + oracle parse/decide/emit" if smi else
+           "nvidia-smi absent: canned enumeration text + oracle parse/decide/emit (process spawn NOT included)")
+    return step, how, co
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    step, how, _co = reference_step_factory()
+    cores = os.cpu_count() or 1
+    per_step = max(1, cores)          # one step = `cores` concurrent reconciles, every host thread busy
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        for _ in range(args.steps):
+            list(ex.map(lambda _i: step(), range(per_step)))
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_path": "oracle port (Go reference cannot be compiled here: no Go toolchain)",
+                   "reconciles_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": how},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(budget_s: float = 12.0):
+    step, how, co = reference_step_factory()
+    step()
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and n < 2000:
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    # context: what the same integer sweep costs on the host (closed form, all cores), bounded to 256 MiB
+    cores = os.cpu_count() or 1
+    words = (256 << 20) // 8
+    t1 = time.perf_counter()
+    co.checksum(0x00C0FFEE00000000, 0, words, threads=cores)
+    sweep_s = time.perf_counter() - t1
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d sequential steps in %.1f s; %s" % (n, dt, how),
+            "host_pattern_checksum_gbs_all_cores": (256 << 20) / sweep_s / 1e9, "host_cores": cores}
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+class _DevBuf:
+    """Zero-copy view of a device pointer for torch (the all-gather send buffer lives in libcroprobe)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    cro = importlib.import_module("composable-resource-operator_b200")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    t_init = time.perf_counter()
+    ctx = cro.ProbeContext(sweep_bytes=args.sweep_bytes, devices=[local_rank], read_variant=args.read_variant,
+                           copy_variant=args.copy_variant)
+    info = ctx.enumerate()[0]
+    uuid = info.gpu_uuid.decode()
+    cold_init_s = time.perf_counter() - t_init
+
+    send = gathered = None
+    if world > 1:
+        send = torch.as_tensor(_DevBuf(ctx.result_device_ptr(0), 512), device=dev)
+        gathered = torch.empty(world * 512, dtype=torch.uint8, device=dev)
+
+    request = {"name": "cr-%d" % rank, "spec": {"type": "gpu", "model": "NVIDIA-B200", "target_node": "worker-%d" % rank},
+               "status": {"state": "Attaching"}, "device_resource_type": "DEVICE_PLUGIN", "probe": True,
+               "provider": {"device_id": uuid, "cdi_device_id": "res-%d-0" % rank}}
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ag_start, ag_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def all_gather_results():
+        """The path's one exchange step: 512-byte result structs over NCCL; returns its device time in ns."""
+        if not dist:
+            return 0
+        ag_start.record()
+        dist.all_gather_into_tensor(gathered, send)
+        ag_end.record()
+        ag_end.synchronize()
+        return int(ag_start.elapsed_time(ag_end) * 1e6)
+
+    # ---- warm-up -----------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        ctx.probe_device(0)
+        all_gather_results()
+        cro.reconcile_attach(ctx, request)
+
+    # ---- device-resident timing: `value` ------------------------------------
+    sampler = ClockSampler(info.cuda_ordinal)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = ctx.launch_count()
+    barrier()
+    dev_ns = 0
+    fill_ns = read_ns = copy_ns = 0
+    n_read = n_copy = 0
+    best_read = None
+    results = []
+    for _ in range(args.steps):
+        r = ctx.probe_device(0)
+        dev_ns += r.total_ns + all_gather_results()
+        fill_ns += r.fill_ns
+        read_ns += r.read_total_ns
+        copy_ns += r.copy_total_ns
+        n_read += r.read_sweeps
+        n_copy += r.copy_sweeps
+        best_read = r.read_best_ns if best_read is None else min(best_read, r.read_best_ns)
+        results.append(r)
+    barrier()
+    launches = ctx.launch_count() - launches0
+
+    # ---- end to end through the reference-facing call: `e2e` ----------------
+    barrier()
+    t0 = time.perf_counter()
+    specs = 0
+    last = None
+    for _ in range(args.steps):
+        last = cro.reconcile_attach(ctx, request)       # host JSON in -> probe -> host JSON out
+        all_gather_results()
+        specs += 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop()
+    time.sleep(0.05)
+    clocks = sampler.summary()
+
+    # max over ranks
+    if dist:
+        t = torch.tensor([float(dev_ns), e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ns, e2e_s = float(t[0]), float(t[1])
+        gl = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(gl)
+        launches = int(gl[0])
+
+    ok = all(r.status == 0 for r in results) and last["status"]["state"] == "Online"
+    if world > 1:
+        got = bytes(gathered.cpu().numpy().tobytes())
+        mine = bytes(ctypes.string_at(ctypes.addressof(results[-1]), 512))
+        # rank r's slot must hold the struct rank r published last (the e2e loop republished an equal-shape one)
+        ok = ok and got[rank * 512 + 16: rank * 512 + 64] == mine[16:64]
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        S = args.sweep_bytes
+        value = world * args.steps / (dev_ns * 1e-9)
+        e2e = world * args.steps / e2e_s
+        fill_avg, read_avg, copy_avg = fill_ns / args.steps, read_ns / max(1, n_read), copy_ns / max(1, n_copy)
+        step_ns = fill_ns + read_ns + copy_ns
+
+        def roof(name, alg_bytes, avg_ns, share):
+            ach = alg_bytes / avg_ns   # bytes per ns == GB/s
+            return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "frac_of_nominal_8000": ach / 8000.0, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                    "avg_launch_ms": avg_ns * 1e-6, "share_of_step": share, "peak_source": peak_src}
+        kernels = [roof("hbm_fill", S, fill_avg, fill_ns / step_ns),
+                   roof("hbm_read_checksum", S, read_avg, read_ns / step_ns),
+                   roof("hbm_copy", 2 * S, copy_avg, copy_ns / step_ns)]
+        dominant = max(kernels, key=lambda k: k["share_of_step"])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": dev_ns * 1e-6 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sweep_bytes": S, "read_sweeps": results[-1].read_sweeps,
+                       "copy_sweeps": results[-1].copy_sweeps, "algorithmic_bytes_per_probe": 16 * S,
+                       "read_variant": results[-1].read_variant, "copy_variant": results[-1].copy_variant,
+                       "l2": "inputs (4 GiB per sweep) are larger than the 126 MB L2; no flush needed",
+                       "parallelism": "1 rank per GPU, independent devices, one 512 B all-gather per step" if world > 1 else "1 GPU"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 512 + len(json.dumps(request)),
+                    "d2h_bytes_per_step": 32 * (results[-1].read_sweeps + 1) + len(last["_raw"]),
+                    "ms_per_step": e2e_s * 1e3 / args.steps, "call": "cro_reconcile_attach (C ABI) with host JSON buffers"},
+            "specs_per_s": world * specs / e2e_s,
+            "probe_gbs_best_read": S / best_read, "probe_frac_of_8000": S / best_read / 8000.0,
+            "roofline": dominant, "roofline_kernels": kernels,
+            "gpu_launches": launches, "clocks": clocks, "parity_ok": bool(ok),
+            "cold_init_s": cold_init_s, "device": uuid,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sweep-bytes", type=int, default=SWEEP_BYTES)
+    ap.add_argument("--read-variant", type=int, default=0)
+    ap.add_argument("--copy-variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import __graft_entry__ as g
+    if rank == 0 or not os.path.exists(os.path.join(ROOT, "composable-resource-operator_b200", "libcroprobe.so")):
+        try:
+            g.build()
+        except Exception as e:   # the GPU box may lack nothing, but never hide a stale library behind a build error
+            print("build() failed: %s" % e, file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

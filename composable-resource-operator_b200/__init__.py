@@ -86,7 +86,9 @@ class ProbeResult(ctypes.Structure):
         ("read_variant", ctypes.c_uint32), ("copy_variant", ctypes.c_uint32),
         ("read_sweeps", ctypes.c_uint32), ("copy_sweeps", ctypes.c_uint32),
         ("copy_checksum_xor", ctypes.c_uint64), ("copy_checksum_sum", ctypes.c_uint64),
-        ("rank", ctypes.c_uint32), ("world", ctypes.c_uint32), ("reserved", ctypes.c_uint8 * 96),
+        ("rank", ctypes.c_uint32), ("world", ctypes.c_uint32),
+        ("total_ns", ctypes.c_uint64), ("read_total_ns", ctypes.c_uint64), ("copy_total_ns", ctypes.c_uint64),
+        ("reserved", ctypes.c_uint8 * 72),
     ]
 
 

@@ -292,10 +292,12 @@ hbm_read_ldg_kernel(const uint4* __restrict__ base, unsigned long long n_vec, Sw
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 hbm_read_tma_kernel(const unsigned char* __restrict__ base, unsigned long long bytes,
-                    unsigned tile_bytes, unsigned stages, SweepScratch sc, SweepOut* out) {
+                    unsigned tile_bytes, unsigned stages, unsigned chunk,
+                    unsigned long long* tile_ctr, SweepScratch sc, SweepOut* out) {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) uint64_t full_bar[16];
     __shared__ __align__(8) uint64_t empty_bar[16];
+    __shared__ unsigned long long tile_of[16];
     const unsigned long long t_start = globaltimer_ns();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned n_cons_warps = (blockDim.x >> 5) - 1;
@@ -311,15 +313,33 @@ hbm_read_tma_kernel(const unsigned char* __restrict__ base, unsigned long long b
     __syncthreads();
 
     unsigned long long x0 = 0, x1 = 0, s0 = 0, s1 = 0;
+    constexpr unsigned long long kEnd = ~0ull;
     if (warp == 0) {
         if (lane == 0) {
+            // Producer.  Tiles come from a device-wide atomic counter (dynamic:
+            // fast SMs take more tiles, the in-flight window stays compact) or
+            // from static striding when tile_ctr is null.
             unsigned stage = 0, phase = 0;
-            for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            unsigned long long cur = 0, end = 0;   // claimed-but-unissued tiles [cur, end)
+            for (unsigned long long k = 0;; ++k) {
+                unsigned long long tile;
+                if (tile_ctr) {
+                    if (cur == end) { cur = atomicAdd(tile_ctr, (unsigned long long)chunk); end = cur + chunk; }
+                    tile = cur++;
+                } else {
+                    tile = blockIdx.x + k * (unsigned long long)gridDim.x;
+                }
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
+                if (tile >= n_tiles) {
+                    tile_of[stage] = kEnd;
+                    mbar_arrive(&full_bar[stage]);      // completes the phase with no bytes
+                    break;
+                }
+                tile_of[stage] = tile;
                 const unsigned long long off = tile * tile_bytes;
                 const unsigned long long left = bytes - off;
                 const unsigned nb = left < tile_bytes ? (unsigned)left : tile_bytes;
-                mbar_expect_tx(&full_bar[stage], nb);
+                mbar_expect_tx(&full_bar[stage], nb);  // release: publishes tile_of[stage]
                 tma_load_1d(ring + (size_t)stage * tile_bytes, base + off, nb, &full_bar[stage]);
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
@@ -328,8 +348,10 @@ hbm_read_tma_kernel(const unsigned char* __restrict__ base, unsigned long long b
         const unsigned ctid = threadIdx.x - 32;
         const unsigned n_cons = n_cons_warps * 32;
         unsigned stage = 0, phase = 0;
-        for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (;;) {
             mbar_wait(&full_bar[stage], phase);
+            const unsigned long long tile = *reinterpret_cast<volatile unsigned long long*>(&tile_of[stage]);
+            if (tile == kEnd) break;
             const unsigned long long off = tile * tile_bytes;
             const unsigned long long left = bytes - off;
             const unsigned nvec = (left < tile_bytes ? (unsigned)left : tile_bytes) >> 4;
@@ -389,44 +411,63 @@ hbm_copy_ldg_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(32, 1)
 hbm_copy_tma_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src,
-                    unsigned long long bytes, unsigned tile_bytes, unsigned stages) {
+                    unsigned long long bytes, unsigned tile_bytes, unsigned stages, unsigned chunk,
+                    unsigned long long* tile_ctr) {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) uint64_t full_bar[16];
+    __shared__ unsigned long long tile_of[16];
     if (threadIdx.x != 0) return;
     for (unsigned s = 0; s < stages; ++s) mbar_init(&full_bar[s], 1);
     mbar_fence_init();
 
     const unsigned long long n_tiles = (bytes + tile_bytes - 1) / tile_bytes;
-    // number of tiles this CTA owns
-    const unsigned long long mine =
-        blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    auto tile_off = [&](unsigned long long k) {
-        return (blockIdx.x + k * (unsigned long long)gridDim.x) * tile_bytes;
+    unsigned long long fetched = 0;   // tiles this CTA has asked for
+    bool dry = false;                 // the counter ran past the last tile
+    unsigned long long cur = 0, end = 0;   // claimed-but-unissued tiles [cur, end)
+    auto fetch = [&]() -> unsigned long long {
+        unsigned long long t;
+        if (tile_ctr) {
+            if (cur == end) { cur = atomicAdd(tile_ctr, (unsigned long long)chunk); end = cur + chunk; }
+            t = cur++;
+        } else {
+            t = blockIdx.x + fetched * (unsigned long long)gridDim.x;
+        }
+        ++fetched;
+        if (t >= n_tiles) dry = true;
+        return t;
     };
     auto tile_len = [&](unsigned long long off) {
         const unsigned long long left = bytes - off;
         return left < tile_bytes ? (unsigned)left : tile_bytes;
     };
-    auto issue_load = [&](unsigned long long k) {
-        const unsigned st = (unsigned)(k % stages);
-        const unsigned long long off = tile_off(k);
+    auto issue_load = [&](unsigned st, unsigned long long tile) {
+        const unsigned long long off = tile * tile_bytes;
         const unsigned nb = tile_len(off);
+        tile_of[st] = tile;
         mbar_expect_tx(&full_bar[st], nb);
         tma_load_1d(ring + (size_t)st * tile_bytes, src + off, nb, &full_bar[st]);
     };
     // prologue: fill the ring
-    for (unsigned long long k = 0; k < mine && k < stages; ++k) issue_load(k);
-    for (unsigned long long k = 0; k < mine; ++k) {
+    unsigned long long loaded = 0;
+    for (unsigned s = 0; s < stages && !dry; ++s) {
+        const unsigned long long t = fetch();
+        if (!dry) { issue_load(s, t); ++loaded; }
+    }
+    for (unsigned long long k = 0; k < loaded; ++k) {
         const unsigned st = (unsigned)(k % stages);
         const unsigned phase = (unsigned)((k / stages) & 1ull);
         mbar_wait(&full_bar[st], phase);
-        const unsigned long long off = tile_off(k);
+        const unsigned long long off = tile_of[st] * tile_bytes;
         tma_store_1d(dst + off, ring + (size_t)st * tile_bytes, tile_len(off));
         tma_commit();
         // refill the slot whose store was issued one trip ago
-        if (k >= 1 && k - 1 + stages < mine) {
-            tma_wait_read<1>();   // all but the newest store have finished reading smem
-            issue_load(k - 1 + stages);
+        if (k >= 1 && !dry) {
+            const unsigned long long t = fetch();
+            if (!dry) {
+                tma_wait_read<1>();   // all but the newest store have finished reading smem
+                issue_load((unsigned)((k - 1) % stages), t);
+                ++loaded;
+            }
         }
     }
     tma_wait_all();
@@ -489,20 +530,25 @@ int env_int(const char* name, int dflt) {
     return atoi(v);
 }
 
-struct TmaTune { unsigned tile, stages, threads; };
+struct TmaTune { unsigned tile, stages, threads, chunk; };
 TmaTune read_tma_tune() {
     TmaTune t;
+    // defaults = best point of the sweeps in profiles/r01_sweeps.md
     t.tile = (unsigned)env_int("CRO_TMA_READ_TILE", 32768);
-    t.stages = (unsigned)env_int("CRO_TMA_READ_STAGES", 6);
-    t.threads = (unsigned)env_int("CRO_TMA_READ_THREADS", 288);  // 1 producer + 8 consumer warps
+    t.stages = (unsigned)env_int("CRO_TMA_READ_STAGES", 4);
+    t.threads = (unsigned)env_int("CRO_TMA_READ_THREADS", 160);  // 1 producer + 4 consumer warps
+    t.chunk = (unsigned)env_int("CRO_TMA_READ_CHUNK", 1);
+    if (t.chunk < 1) t.chunk = 1;
     if (t.stages > 16) t.stages = 16;
     return t;
 }
 TmaTune copy_tma_tune() {
     TmaTune t;
     t.tile = (unsigned)env_int("CRO_TMA_COPY_TILE", 32768);
-    t.stages = (unsigned)env_int("CRO_TMA_COPY_STAGES", 6);
+    t.stages = (unsigned)env_int("CRO_TMA_COPY_STAGES", 4);
     t.threads = 32;
+    t.chunk = (unsigned)env_int("CRO_TMA_COPY_CHUNK", 1);
+    if (t.chunk < 1) t.chunk = 1;
     if (t.stages > 16) t.stages = 16;
     return t;
 }
@@ -519,7 +565,7 @@ cudaError_t plan_kernels(int device, KernelPlan* plan) {
     auto fill = hbm_fill_kernel<kFillThreads, kFillUnroll>;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fill, kFillThreads, 0)) != cudaSuccess)
         return e;
-    plan->fill = {sms * (occ > 0 ? occ : 1) * env_int("CRO_FILL_WAVES", 1), kFillThreads, 0};
+    plan->fill = {sms * (occ > 0 ? occ : 1) * env_int("CRO_FILL_WAVES", 64), kFillThreads, 0};
 
     auto rd = hbm_read_ldg_kernel<kReadThreads, false>;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rd, kReadThreads, 0)) != cudaSuccess)
@@ -533,7 +579,7 @@ cudaError_t plan_kernels(int device, KernelPlan* plan) {
     auto cp = hbm_copy_ldg_kernel<kCopyThreads, kCopyUnroll>;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cp, kCopyThreads, 0)) != cudaSuccess)
         return e;
-    plan->copy_ldg = {sms * (occ > 0 ? occ : 1) * env_int("CRO_COPY_WAVES", 1), kCopyThreads, 0};
+    plan->copy_ldg = {sms * (occ > 0 ? occ : 1) * env_int("CRO_COPY_WAVES", 128), kCopyThreads, 0};
 
     {
         const TmaTune t = read_tma_tune();
@@ -544,7 +590,7 @@ cudaError_t plan_kernels(int device, KernelPlan* plan) {
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hbm_read_tma_kernel,
                                                                (int)t.threads, smem)) != cudaSuccess)
             return e;
-        plan->read_tma = {sms * (occ > 0 ? occ : 1), (int)t.threads, smem};
+        plan->read_tma = {sms * (occ > 0 ? occ : 1) * env_int("CRO_TMA_READ_WAVES", 1), (int)t.threads, smem};
     }
     {
         const TmaTune t = copy_tma_tune();
@@ -555,7 +601,7 @@ cudaError_t plan_kernels(int device, KernelPlan* plan) {
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hbm_copy_tma_kernel, 32, smem)) !=
             cudaSuccess)
             return e;
-        plan->copy_tma = {sms * (occ > 0 ? occ : 1), 32, smem};
+        plan->copy_tma = {sms * (occ > 0 ? occ : 1) * env_int("CRO_TMA_COPY_WAVES", 1), 32, smem};
     }
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hbm_expected_kernel, 256, 0)) !=
         cudaSuccess)
@@ -575,8 +621,14 @@ cudaError_t launch_read(const KernelPlan& p, unsigned variant, const void* base,
                         const SweepScratch& sc, SweepOut* out, cudaStream_t st) {
     if (variant == READ_TMA) {
         const TmaTune t = read_tma_tune();
+        unsigned long long* ctr = nullptr;
+        if (env_int("CRO_TMA_READ_DYN", 1) && sc.tile_ctr) {
+            ctr = sc.tile_ctr;
+            cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st);
+            if (e != cudaSuccess) return e;
+        }
         hbm_read_tma_kernel<<<p.read_tma.grid, p.read_tma.block, p.read_tma.smem, st>>>(
-            static_cast<const unsigned char*>(base), bytes, t.tile, t.stages, sc, out);
+            static_cast<const unsigned char*>(base), bytes, t.tile, t.stages, t.chunk, ctr, sc, out);
     } else if (variant == READ_LDG256) {
         hbm_read_ldg_kernel<kReadThreads, true><<<p.read_ldg256.grid, p.read_ldg256.block, 0, st>>>(
             static_cast<const uint4*>(base), bytes >> 4, sc, out);
@@ -588,12 +640,18 @@ cudaError_t launch_read(const KernelPlan& p, unsigned variant, const void* base,
 }
 
 cudaError_t launch_copy(const KernelPlan& p, unsigned variant, void* dst, const void* src,
-                        uint64_t bytes, cudaStream_t st) {
+                        uint64_t bytes, const SweepScratch& sc, cudaStream_t st) {
     if (variant == COPY_TMA) {
         const TmaTune t = copy_tma_tune();
+        unsigned long long* ctr = nullptr;
+        if (env_int("CRO_TMA_COPY_DYN", 1) && sc.tile_ctr) {
+            ctr = sc.tile_ctr;
+            cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st);
+            if (e != cudaSuccess) return e;
+        }
         hbm_copy_tma_kernel<<<p.copy_tma.grid, p.copy_tma.block, p.copy_tma.smem, st>>>(
             static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), bytes, t.tile,
-            t.stages);
+            t.stages, t.chunk, ctr);
     } else {
         hbm_copy_ldg_kernel<kCopyThreads, kCopyUnroll><<<p.copy_ldg.grid, p.copy_ldg.block, 0, st>>>(
             static_cast<uint4*>(dst), static_cast<const uint4*>(src), bytes >> 4);

@@ -24,6 +24,7 @@ struct SweepScratch {
     unsigned int* counter;     // self-resetting "CTAs done" counter
     unsigned long long* tmin;  // per-sweep timers, reset by the last CTA
     unsigned long long* tmax;
+    unsigned long long* tile_ctr;  // dynamic tile counter of the TMA kernels (zeroed per launch)
 };
 
 struct LaunchCfg {
@@ -54,7 +55,7 @@ cudaError_t launch_fill(const KernelPlan&, void* base, uint64_t bytes, uint64_t 
 cudaError_t launch_read(const KernelPlan&, unsigned variant, const void* base, uint64_t bytes,
                         const SweepScratch&, SweepOut* out, cudaStream_t);
 cudaError_t launch_copy(const KernelPlan&, unsigned variant, void* dst, const void* src,
-                        uint64_t bytes, cudaStream_t);
+                        uint64_t bytes, const SweepScratch&, cudaStream_t);
 cudaError_t launch_expected(const KernelPlan&, uint64_t bytes, uint64_t seed,
                             const SweepScratch&, SweepOut* out, cudaStream_t);
 cudaError_t launch_xor_word(void* base, uint64_t word_index, uint64_t mask, cudaStream_t);

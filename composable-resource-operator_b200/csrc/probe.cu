@@ -243,6 +243,8 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
         CU_TRY(c.get(), cudaMalloc(&d->scratch.counter, sizeof(unsigned)));
         CU_TRY(c.get(), cudaMalloc(&d->scratch.tmin, sizeof(unsigned long long)));
         CU_TRY(c.get(), cudaMalloc(&d->scratch.tmax, sizeof(unsigned long long)));
+        CU_TRY(c.get(), cudaMalloc(&d->scratch.tile_ctr, sizeof(unsigned long long)));
+        CU_TRY(c.get(), cudaMemset(d->scratch.tile_ctr, 0, sizeof(unsigned long long)));
         CU_TRY(c.get(), cudaMemset(d->scratch.counter, 0, sizeof(unsigned)));
         CU_TRY(c.get(), cudaMemset(d->scratch.tmin, 0xFF, sizeof(unsigned long long)));
         CU_TRY(c.get(), cudaMemset(d->scratch.tmax, 0, sizeof(unsigned long long)));
@@ -279,6 +281,7 @@ void ctx_destroy(cro_ctx* c) {
         cudaFree(d->scratch.counter);
         cudaFree(d->scratch.tmin);
         cudaFree(d->scratch.tmax);
+        cudaFree(d->scratch.tile_ctr);
         cudaFree(d->d_out);
         cudaFreeHost(d->h_out);
         cudaFree(d->d_result);
@@ -365,7 +368,7 @@ int ctx_copy(cro_ctx* c, int idx, uint32_t variant, uint32_t iters, cro_sweep_re
     CU_TRY(c, cudaEventRecord(d->ev0, d->stream));
     for (uint32_t i = 0; i < iters; ++i)
         CU_TRY(c, launch_copy(d->plan, variant, d->region + d->sweep_bytes, d->region, d->sweep_bytes,
-                              d->stream));
+                              d->scratch, d->stream));
     CU_TRY(c, cudaEventRecord(d->ev1, d->stream));
     c->launches += iters;
     if ((rc = wait_stream(c, d))) return rc;
@@ -487,7 +490,7 @@ static int probe_locked(cro_ctx* c, Device* d, cro_probe_result* r) {
         CU_TRY(c, cudaEventRecord(ev[k++], d->stream));
     }
     for (uint32_t i = 0; i < r->copy_sweeps; ++i) {
-        CU_TRY(c, launch_copy(d->plan, cv, d->region + d->sweep_bytes, d->region, d->sweep_bytes, d->stream));
+        CU_TRY(c, launch_copy(d->plan, cv, d->region + d->sweep_bytes, d->region, d->sweep_bytes, d->scratch, d->stream));
         CU_TRY(c, cudaEventRecord(ev[k++], d->stream));
     }
     const bool verify = (o.flags & CRO_F_VERIFY_COPY) && r->copy_sweeps > 0;
@@ -512,6 +515,10 @@ static int probe_locked(cro_ctx* c, Device* d, cro_probe_result* r) {
         CU_TRY(c, cudaEventElapsedTime(&ms, ev[1 + o.read_sweeps + i], ev[2 + o.read_sweeps + i]));
         ct.push_back(ms_to_ns(ms));
     }
+    CU_TRY(c, cudaEventElapsedTime(&ms, ev[0], ev[k - 1]));
+    r->total_ns = ms_to_ns(ms);
+    for (uint64_t t : rt) r->read_total_ns += t;
+    for (uint64_t t : ct) r->copy_total_ns += t;
     r->read_best_ns = *std::min_element(rt.begin(), rt.end());
     r->read_median_ns = median_of(rt);
     if (!ct.empty()) {

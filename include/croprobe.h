@@ -143,7 +143,10 @@ typedef struct cro_probe_result {
     uint64_t copy_checksum_sum;    /* 400 */
     uint32_t rank;                 /* 408  index in the minor-sorted device list      */
     uint32_t world;                /* 412 */
-    uint8_t  reserved[96];         /* 416..511 */
+    uint64_t total_ns;             /* 416  CUDA-event time of the whole probe (fill..last copy) */
+    uint64_t read_total_ns;        /* 424  sum over the read sweeps  */
+    uint64_t copy_total_ns;        /* 432  sum over the copy sweeps  */
+    uint8_t  reserved[72];         /* 440..511 */
 } cro_probe_result;
 
 /* Result of one timed sweep (bench / parity entry points). */
