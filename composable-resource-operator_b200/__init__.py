@@ -55,7 +55,8 @@ class Opts(ctypes.Structure):
         ("sweep_bytes", ctypes.c_uint64), ("p2p_bytes", ctypes.c_uint64), ("seed_base", ctypes.c_uint64),
         ("read_sweeps", ctypes.c_uint32), ("copy_sweeps", ctypes.c_uint32), ("latency_hops", ctypes.c_uint32),
         ("read_variant", ctypes.c_uint32), ("copy_variant", ctypes.c_uint32), ("deadline_ms", ctypes.c_int32),
-        ("n_devices", ctypes.c_int32), ("devices", ctypes.c_int32 * MAX_DEVICES), ("reserved", ctypes.c_uint32 * 8),
+        ("n_devices", ctypes.c_int32), ("devices", ctypes.c_int32 * MAX_DEVICES),
+        ("rank_base", ctypes.c_uint32), ("world_override", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 6),
     ]
 
 
@@ -305,7 +306,7 @@ class ProbeContext:
     def __init__(self, sweep_bytes: int = 0, devices: Optional[List[int]] = None, flags: int = 0,
                  read_sweeps: int = 0, copy_sweeps: int = 0, read_variant: int = READ_AUTO,
                  copy_variant: int = COPY_AUTO, p2p_bytes: int = 0, latency_hops: int = 0,
-                 deadline_ms: int = 0, seed_base: int = 0) -> None:
+                 deadline_ms: int = 0, seed_base: int = 0, rank_base: int = 0, world: int = 0) -> None:
         o = Opts()
         o.abi_version = ABI_VERSION
         o.flags = flags
@@ -316,6 +317,7 @@ class ProbeContext:
         o.latency_hops = latency_hops
         o.read_variant, o.copy_variant = read_variant, copy_variant
         o.deadline_ms = deadline_ms
+        o.rank_base, o.world_override = rank_base, world
         if devices:
             o.n_devices = len(devices)
             for i, d in enumerate(devices):

@@ -454,8 +454,8 @@ static int probe_locked(cro_ctx* c, Device* d, cro_probe_result* r) {
     r->sm_count = d->info.sm_count;
     r->sm_clock_mhz = d->sm_clock_mhz;
     r->mem_clock_mhz = d->mem_clock_mhz;
-    r->rank = (uint32_t)d->index;
-    r->world = (uint32_t)c->devs.size();
+    r->rank = c->opts.rank_base + (uint32_t)d->index;
+    r->world = c->opts.world_override ? c->opts.world_override : (uint32_t)c->devs.size();
     r->p2p_bytes = o.p2p_bytes;
     const uint32_t rv = resolve_read_variant(o.read_variant);
     const uint32_t cv = resolve_copy_variant(o.copy_variant);

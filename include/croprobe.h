@@ -81,7 +81,9 @@ typedef struct cro_opts {
     int32_t  deadline_ms;          /* per-call deadline, 0 = none (Go ctx cannot cross cgo) */
     int32_t  n_devices;            /* 0 = every visible CUDA device                         */
     int32_t  devices[CRO_MAX_DEVICES]; /* CUDA ordinals to manage                           */
-    uint32_t reserved[8];
+    uint32_t rank_base;            /* one-process-per-GPU hosts: this process's first rank  */
+    uint32_t world_override;       /* ... and the job's world size (0 = devices managed)    */
+    uint32_t reserved[6];
 } cro_opts;
 
 /*
