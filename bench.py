@@ -319,10 +319,18 @@ def run_ours(args, rank, local_rank, world):
         fill_avg, read_avg, copy_avg = fill_ns / args.steps, read_ns / max(1, n_read), copy_ns / max(1, n_copy)
         step_ns = fill_ns + read_ns + copy_ns
 
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            ncu = None
+
         def roof(name, alg_bytes, avg_ns, share):
             ach = alg_bytes / avg_ns   # bytes per ns == GB/s
+            traffic = None
+            if ncu and name in ncu:    # dram bytes per launch from the committed ncu --set full capture, scaled to S
+                traffic = (ncu[name]["dram_read"] + ncu[name]["dram_write"]) * (S / ncu["sweep_bytes"])
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "frac_of_nominal_8000": ach / 8000.0, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                    "frac_of_nominal_8000": ach / 8000.0, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": avg_ns * 1e-6, "share_of_step": share, "peak_source": peak_src}
         kernels = [roof("hbm_fill", S, fill_avg, fill_ns / step_ns),
                    roof("hbm_read_checksum", S, read_avg, read_ns / step_ns),

@@ -110,7 +110,7 @@ EXPORTS = [
     "cro_device_seed", "cro_launch_count", "cro_emit_status_json", "cro_emit_scalar_status_json",
     "cro_emit_fm_scale_up", "cro_emit_fm_scale_down", "cro_emit_cm_scale_up", "cro_emit_cm_scale_down",
     "cro_emit_sunfish_request", "cro_emit_probe_annotations_json", "cro_fm_parse_scale_up_response",
-    "cro_reconcile_attach", "cro_strerror", "cro_last_error", "cro_version",
+    "cro_reconcile_attach", "cro_strerror", "cro_last_error", "cro_version", "cro_cm_check_adding_resources",
 ]
 
 
@@ -160,6 +160,7 @@ def _load() -> ctypes.CDLL:
         "cro_emit_probe_annotations_json": (i32, [ctypes.POINTER(ProbeResult)] + out),
         "cro_fm_parse_scale_up_response": (i32, [c, c, c, c, c, sz, c, sz, c, sz]),
         "cro_reconcile_attach": (i32, [vp, c] + out),
+        "cro_cm_check_adding_resources": (i32, [c, c, c, c, c, sz, ctypes.POINTER(i32), c, sz, c, sz, c, sz]),
         "cro_strerror": (c, [i32]),
         "cro_last_error": (i32, [vp, c, sz]),
         "cro_version": (c, []),
@@ -282,6 +283,16 @@ def fm_parse_scale_up_response(body: str, name: str, res_type: str, model: str) 
     if rc != OK:
         return "", "", err.value.decode()
     return dev.value.decode(), cdi.value.decode(), ""
+
+
+def cm_check_adding_resources(machine_body: str, existing_device_ids: List[str], res_type: str, model: str):
+    """(specUUID, deviceCount, deviceID, CDIDeviceID, err) per internal/cdi/fti/cm/client.go:432-459."""
+    spec, dev, cdi = (ctypes.create_string_buffer(256) for _ in range(3))
+    err = ctypes.create_string_buffer(1024)
+    n = ctypes.c_int(0)
+    lib.cro_cm_check_adding_resources(_b(machine_body), _b("\n".join(existing_device_ids)), _b(res_type), _b(model),
+                                      spec, 256, ctypes.byref(n), dev, 256, cdi, 256, err, 1024)
+    return spec.value.decode(), n.value, dev.value.decode(), cdi.value.decode(), err.value.decode()
 
 
 def reconcile_attach(ctx: Optional["ProbeContext"], request: Dict) -> Dict:

@@ -352,6 +352,23 @@ int cro_fm_parse_scale_up_response(const char* body, const char* resource_name, 
     return copy_out(cdi, cdi_device_id, cdi_cap, nullptr);
 }
 
+int cro_cm_check_adding_resources(const char* machine_body, const char* existing_device_ids,
+                                  const char* res_type, const char* model, char* spec_uuid, size_t spec_cap,
+                                  int* device_count, char* device_id, size_t device_id_cap,
+                                  char* cdi_device_id, size_t cdi_cap, char* err_buf, size_t err_cap) {
+    if (!machine_body) return CRO_ERR_INVALID_ARG;
+    std::vector<std::string> existing;
+    if (existing_device_ids) existing = identity::Split(existing_device_ids, "\n");
+    controller::CMAddingResult r = controller::CMCheckAddingResources(machine_body, existing, S(res_type), S(model));
+    if (device_count) *device_count = (int)r.deviceCount;
+    int rc = copy_out(r.specUUID, spec_uuid, spec_cap, nullptr);
+    if (rc) return rc;
+    if ((rc = copy_out(r.deviceID, device_id, device_id_cap, nullptr))) return rc;
+    if ((rc = copy_out(r.CDIDeviceID, cdi_device_id, cdi_cap, nullptr))) return rc;
+    copy_out(r.err.ok() ? std::string() : r.err.msg, err_buf, err_cap, nullptr);
+    return r.err.ok() ? CRO_OK : CRO_ERR_PARSE;
+}
+
 // ---- reconcile step ---------------------------------------------------------
 
 namespace {
@@ -368,6 +385,23 @@ public:
         const gojson::Value* body = p_->get("fm_response_body");
         if (body && body->kind == gojson::Value::String)
             return controller::FMScaleUpResponseToIDs(body->str, inst.Name, inst.Spec.Type, inst.Spec.Model, dev, cdi);
+        const gojson::Value* cm = p_->get("cm_machine_body");
+        if (cm && cm->kind == gojson::Value::String) {
+            // CM AddResource (fti/cm/client.go:107-182): unused device -> ids (+ error); none -> POST resize, wait
+            std::vector<std::string> existing;
+            const gojson::Value* ex = p_->get("existing_device_ids");
+            if (ex && ex->kind == gojson::Value::Array)
+                for (const auto& e : ex->arr)
+                    if (e->kind == gojson::Value::String) existing.push_back(e->str);
+            controller::CMAddingResult r = controller::CMCheckAddingResources(cm->str, existing, inst.Spec.Type, inst.Spec.Model);
+            if (!r.deviceID.empty()) {
+                *dev = r.deviceID;
+                *cdi = r.CDIDeviceID;
+                return r.err;
+            }
+            if (!r.err.ok()) return r.err;
+            return controller::Error::New(controller::ErrWaitingDeviceAttaching);
+        }
         *dev = p_->get_string("device_id");
         *cdi = p_->get_string("cdi_device_id");
         return controller::Error::Nil();

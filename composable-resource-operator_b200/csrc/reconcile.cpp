@@ -67,6 +67,68 @@ Error FMScaleUpResponseToIDs(const std::string& body, const std::string& instanc
     return Error::New("can not find the added gpu when using FM to add gpu");
 }
 
+CMAddingResult CMCheckAddingResources(const std::string& machineBody,
+                                      const std::vector<std::string>& existingDeviceIDs,
+                                      const std::string& specType, const std::string& specModel) {
+    CMAddingResult out;
+    std::string perr;
+    gojson::ValuePtr root = gojson::parse(machineBody, &perr);
+    if (!root || root->kind != gojson::Value::Object) {
+        out.err = Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
+        return out;
+    }
+    const gojson::Value* data = root->get("data");
+    const gojson::Value* cluster = data ? data->get("cluster") : nullptr;
+    const gojson::Value* machine = cluster ? cluster->get("machine") : nullptr;
+    const gojson::Value* specs = machine ? machine->get("resspecs") : nullptr;
+    if (!specs || specs->kind != gojson::Value::Array) return out;
+    for (const auto& spec : specs->arr) {
+        // isSpecMatch (cm/client.go:485-499)
+        if (spec->get_string("type") != specType) continue;
+        bool match = false;
+        const gojson::Value* sel = spec->get("selector");
+        const gojson::Value* expr = sel ? sel->get("expression") : nullptr;
+        const gojson::Value* conds = expr ? expr->get("conditions") : nullptr;
+        if (conds && conds->kind == gojson::Value::Array)
+            for (const auto& c : conds->arr)
+                if (c->get_string("column") == "model" && c->get_string("operator") == "eq" &&
+                    c->get_string("value") == specModel)
+                    match = true;
+        if (!match) continue;
+        // findAvailableDevice (cm/client.go:501-509): first device no CR owns
+        const gojson::Value* devices = spec->get("devices");
+        if (devices && devices->kind == gojson::Value::Array) {
+            for (const auto& dev : devices->arr) {
+                const std::string id = dev->get_string("device_id");
+                bool owned = false;
+                for (const std::string& e : existingDeviceIDs)
+                    if (e == id) owned = true;
+                if (owned) continue;
+                const std::string status = dev->get_string("status");
+                const gojson::Value* detail = dev->get("detail");
+                const std::string res = detail ? detail->get_string("res_uuid") : std::string();
+                if (status == "ADD_COMPLETE") {
+                    out.deviceID = id;
+                    out.CDIDeviceID = res;
+                    return out;
+                }
+                if (status == "ADD_FAILED") {
+                    out.deviceID = id;
+                    out.CDIDeviceID = res;
+                    out.err = Error::New("an error occurred with the resource in CM: '" +
+                                         dev->get_string("status_reason") + "'");
+                    return out;
+                }
+                break;  // an unowned device in any other state: fall through to the resize request
+            }
+        }
+        out.specUUID = spec->get_string("spec_uuid");
+        out.deviceCount = spec->get_int("device_count");
+        break;
+    }
+    return out;
+}
+
 Error ComposableResourceReconciler::requeueOnErr(ComposableResource* resource, const Error& err) {
     if (resource) {
         resource->Status.Error = err.msg;

@@ -62,6 +62,20 @@ Error FMScaleUpResponseToIDs(const std::string& body, const std::string& instanc
                              const std::string& specType, const std::string& specModel,
                              std::string* deviceID, std::string* CDIDeviceID);
 
+// CM flavour: checkAddingResources + isSpecMatch + findAvailableDevice
+// (internal/cdi/fti/cm/client.go:432-459, 485-509) over the machine JSON of
+// GET .../machines/<id> (internal/cdi/fti/cm/api/machine.go:19-93).
+// existingDeviceIDs = Status.DeviceID of every ComposableResource in the cluster.
+struct CMAddingResult {
+    std::string specUUID;
+    long long deviceCount = 0;
+    std::string deviceID, CDIDeviceID;
+    Error err;
+};
+CMAddingResult CMCheckAddingResources(const std::string& machineBody,
+                                      const std::vector<std::string>& existingDeviceIDs,
+                                      const std::string& specType, const std::string& specModel);
+
 // Node-side operations the attach step calls (internal/utils): the CUDA probe
 // backs RunNvidiaSmi / CheckGPUVisible; the daemonset restarts and the load
 // check are cluster bookkeeping, injected.

@@ -297,6 +297,20 @@ int  cro_fm_parse_scale_up_response(const char *body, const char *resource_name,
                                     char *cdi_device_id, size_t cdi_cap,
                                     char *err_buf, size_t err_cap);
 
+/* CM flavour of the ID production: checkAddingResources
+ * (internal/cdi/fti/cm/client.go:432-459,485-509) over the GET-machine JSON.
+ * existing_device_ids: '\n'-joined Status.DeviceID of every ComposableResource.
+ * Outputs: spec_uuid + *device_count for the resize request, or the unused
+ * device's (device_id, cdi_device_id).  Returns CRO_ERR_PARSE with the
+ * reference's message in err_buf on the ADD_FAILED / malformed branches (the
+ * ids are still filled, as the reference returns them with the error). */
+int  cro_cm_check_adding_resources(const char *machine_body, const char *existing_device_ids,
+                                   const char *res_type, const char *model,
+                                   char *spec_uuid, size_t spec_cap, int *device_count,
+                                   char *device_id, size_t device_id_cap,
+                                   char *cdi_device_id, size_t cdi_cap,
+                                   char *err_buf, size_t err_cap);
+
 /* ---- reconcile step: the caller of the hot path -------------------------- */
 
 /*

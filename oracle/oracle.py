@@ -316,6 +316,31 @@ def fm_scale_up_response_to_ids(body: str, name: str, spec_type: str, spec_model
     return "", "", "can not find the added gpu when using FM to add gpu"
 
 
+def cm_check_adding_resources(machine_body: str, existing_device_ids: List[str], spec_type: str, spec_model: str):
+    """internal/cdi/fti/cm/client.go:432-459 (checkAddingResources), :485-499 (isSpecMatch),
+    :501-509 (findAvailableDevice).  Returns (specUUID, deviceCount, deviceID, CDIDeviceID, err)."""
+    data = json.loads(machine_body)
+    specs = ((((data.get("data") or {}).get("cluster") or {}).get("machine") or {}).get("resspecs")) or []
+    for spec in specs:
+        if spec.get("type", "") != spec_type:
+            continue
+        conds = (((spec.get("selector") or {}).get("expression") or {}).get("conditions")) or []
+        if not any(c.get("column") == "model" and c.get("operator") == "eq" and c.get("value") == spec_model for c in conds):
+            continue
+        for dev in (spec.get("devices") or []):
+            if dev.get("device_id", "") in existing_device_ids:
+                continue
+            res = (dev.get("detail") or {}).get("res_uuid", "")
+            if dev.get("status") == "ADD_COMPLETE":
+                return "", 0, dev.get("device_id", ""), res, ""
+            if dev.get("status") == "ADD_FAILED":
+                return "", 0, dev.get("device_id", ""), res, \
+                    "an error occurred with the resource in CM: '%s'" % dev.get("status_reason", "")
+            break
+        return spec.get("spec_uuid", ""), int(spec.get("device_count", 0)), "", "", ""
+    return "", 0, "", "", ""
+
+
 @dataclass
 class Status:
     state: str = ""
