@@ -111,6 +111,8 @@ EXPORTS = [
     "cro_emit_fm_scale_up", "cro_emit_fm_scale_down", "cro_emit_cm_scale_up", "cro_emit_cm_scale_down",
     "cro_emit_sunfish_request", "cro_emit_probe_annotations_json", "cro_fm_parse_scale_up_response",
     "cro_reconcile_attach", "cro_strerror", "cro_last_error", "cro_version", "cro_cm_check_adding_resources",
+    "cro_sim_create", "cro_sim_destroy", "cro_sim_apply", "cro_sim_delete", "cro_sim_plant", "cro_sim_run",
+    "cro_sim_reconcile_request", "cro_sim_dump",
 ]
 
 
@@ -161,6 +163,14 @@ def _load() -> ctypes.CDLL:
         "cro_fm_parse_scale_up_response": (i32, [c, c, c, c, c, sz, c, sz, c, sz]),
         "cro_reconcile_attach": (i32, [vp, c] + out),
         "cro_cm_check_adding_resources": (i32, [c, c, c, c, c, sz, ctypes.POINTER(i32), c, sz, c, sz, c, sz]),
+        "cro_sim_create": (i32, [vp, c, ctypes.POINTER(vp)]),
+        "cro_sim_destroy": (None, [vp]),
+        "cro_sim_apply": (i32, [vp, c, c, sz]),
+        "cro_sim_plant": (i32, [vp, c, c, sz]),
+        "cro_sim_delete": (i32, [vp, c]),
+        "cro_sim_run": (i32, [vp, ctypes.c_longlong] + out),
+        "cro_sim_reconcile_request": (i32, [vp, c, c, sz]),
+        "cro_sim_dump": (i32, [vp] + out),
         "cro_strerror": (c, [i32]),
         "cro_last_error": (i32, [vp, c, sz]),
         "cro_version": (c, []),
@@ -425,3 +435,60 @@ class ProbeContext:
 
     def launch_count(self) -> int:
         return int(lib.cro_launch_count(self.handle))
+
+
+class Cluster:
+    """In-memory API server + both reconcilers (cro_sim_*): the caller of the hot path.
+
+    Mirrors ComposabilityRequestReconciler / ComposableResourceReconciler
+    (internal/controller/*.go); drives the storm / churn configs."""
+
+    def __init__(self, config: Dict, ctx: Optional[ProbeContext] = None) -> None:
+        h = ctypes.c_void_p()
+        rc = lib.cro_sim_create(ctx.handle if ctx is not None else None, _b(json.dumps(config)), ctypes.byref(h))
+        if rc != OK:
+            raise ProbeError(rc, "cro_sim_create")
+        self.handle = h
+        self._ctx = ctx   # keep the probe context alive
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            lib.cro_sim_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self) -> "Cluster":
+        return self
+
+    def __exit__(self, *a) -> None:
+        self.close()
+
+    def _err_call(self, fn, arg: str) -> str:
+        err = ctypes.create_string_buffer(1024)
+        fn(self.handle, _b(arg), err, 1024)
+        return err.value.decode("utf-8", "replace")
+
+    def apply(self, name: str, resource: Dict) -> str:
+        """kubectl apply of a ComposabilityRequest; returns "" or the admission error."""
+        return self._err_call(lib.cro_sim_apply, json.dumps({"name": name, "resource": resource}))
+
+    def plant(self, obj: Dict) -> str:
+        return self._err_call(lib.cro_sim_plant, json.dumps(obj))
+
+    def delete(self, name: str) -> bool:
+        return lib.cro_sim_delete(self.handle, _b(name)) == OK
+
+    def reconcile_request(self, name: str) -> str:
+        """One Reconcile of the request controller; returns the reconcile error ("" = nil)."""
+        return self._err_call(lib.cro_sim_reconcile_request, name)
+
+    def run(self, max_reconciles: int = 0) -> Dict:
+        rc, raw = _text_call(lib.cro_sim_run, self.handle, max_reconciles, cap=1 << 16)
+        if rc != OK:
+            raise ProbeError(rc)
+        return json.loads(raw.decode())
+
+    def dump(self) -> Dict:
+        rc, raw = _text_call(lib.cro_sim_dump, self.handle, cap=1 << 22)
+        if rc != OK:
+            raise ProbeError(rc)
+        return json.loads(raw.decode())

@@ -9,6 +9,7 @@
 #include "identity.hpp"
 #include "probe.hpp"
 #include "reconcile.hpp"
+#include "cluster.hpp"
 
 using namespace cro;
 
@@ -562,6 +563,69 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
     if (node.probed) w.key("probe").string_map(probe_annotations(node.probe_result));
     w.end_object();
     return copy_out(w.str(), buf, cap, len);
+}
+
+// ---- in-memory cluster -----------------------------------------------------------
+
+struct cro_sim {
+    std::unique_ptr<sim::Cluster> cluster;
+    std::mutex mu;
+};
+
+int cro_sim_create(cro_ctx* ctx, const char* config_json, cro_sim** out) {
+    if (!out) return CRO_ERR_INVALID_ARG;
+    std::string perr;
+    gojson::ValuePtr cfg = gojson::parse(config_json ? config_json : "{}", &perr);
+    if (!cfg || cfg->kind != gojson::Value::Object) return CRO_ERR_PARSE;
+    cro_sim* s = new cro_sim;
+    s->cluster.reset(new sim::Cluster(ctx, *cfg));
+    *out = s;
+    return CRO_OK;
+}
+void cro_sim_destroy(cro_sim* s) { delete s; }
+
+static int sim_json_call(cro_sim* s, const char* json, char* err_buf, size_t err_cap,
+                         controller::Error (sim::Cluster::*fn)(const gojson::Value&)) {
+    if (!s || !json) return CRO_ERR_INVALID_ARG;
+    std::string perr;
+    gojson::ValuePtr v = gojson::parse(json, &perr);
+    if (!v || v->kind != gojson::Value::Object) {
+        copy_out(perr, err_buf, err_cap, nullptr);
+        return CRO_ERR_PARSE;
+    }
+    std::lock_guard<std::mutex> g(s->mu);
+    controller::Error e = (s->cluster.get()->*fn)(*v);
+    copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
+    return e.ok() ? CRO_OK : CRO_ERR_INVALID_ARG;
+}
+int cro_sim_apply(cro_sim* s, const char* json, char* err_buf, size_t err_cap) {
+    return sim_json_call(s, json, err_buf, err_cap, &sim::Cluster::Apply);
+}
+int cro_sim_plant(cro_sim* s, const char* json, char* err_buf, size_t err_cap) {
+    return sim_json_call(s, json, err_buf, err_cap, &sim::Cluster::Plant);
+}
+int cro_sim_delete(cro_sim* s, const char* name) {
+    if (!s || !name) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(s->mu);
+    return s->cluster->Delete(name).ok() ? CRO_OK : CRO_ERR_INVALID_ARG;
+}
+int cro_sim_run(cro_sim* s, long long max_reconciles, char* buf, size_t cap, size_t* len) {
+    if (!s) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(s->mu);
+    s->cluster->Run(max_reconciles > 0 ? max_reconciles : (1ll << 40));
+    return copy_out(s->cluster->StatsJSON(), buf, cap, len);
+}
+int cro_sim_reconcile_request(cro_sim* s, const char* name, char* err_buf, size_t err_cap) {
+    if (!s || !name) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(s->mu);
+    controller::Error e = s->cluster->ReconcileRequestOnce(name);
+    copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
+    return e.ok() ? CRO_OK : CRO_ERR_EXEC;
+}
+int cro_sim_dump(cro_sim* s, char* buf, size_t cap, size_t* len) {
+    if (!s) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(s->mu);
+    return copy_out(s->cluster->DumpJSON(), buf, cap, len);
 }
 
 }  // extern "C"

@@ -331,6 +331,32 @@ int  cro_cm_check_adding_resources(const char *machine_body, const char *existin
 int  cro_reconcile_attach(cro_ctx *ctx, const char *in_json,
                           char *buf, size_t cap, size_t *len);
 
+/* ---- the caller of the hot path: both reconcilers over an in-memory API --- */
+
+/*
+ * In-memory cluster (nodes, ComposabilityRequests, ComposableResources with
+ * Kubernetes finalizer / deletionTimestamp semantics) driven by restatements of
+ * ComposabilityRequestReconciler (internal/controller/composabilityrequest_controller.go:72-625)
+ * and ComposableResourceReconciler (internal/controller/composableresource_controller.go:73-441).
+ * Drives BASELINE configs 4 (reconcile storm) and 5 (attach/detach churn);
+ * every attach runs the CUDA probe when config.probe is true.
+ * config_json: {"nodes":["worker-0",...] | [{"name","cpu","memory","ephemeral_storage","pods"}],
+ *               "device_resource_type":"DEVICE_PLUGIN"|"DRA","probe":bool,"seed":N,"uuids":[...]}
+ */
+typedef struct cro_sim cro_sim;
+int  cro_sim_create(cro_ctx *ctx /* may be NULL when probe is false */, const char *config_json, cro_sim **out);
+void cro_sim_destroy(cro_sim *sim);
+/* kubectl apply: {"name":..,"resource":{type,model,size,force_detach,allocation_policy,target_node,other_spec}} */
+int  cro_sim_apply(cro_sim *sim, const char *request_json, char *err_buf, size_t err_cap);
+int  cro_sim_delete(cro_sim *sim, const char *request_name);
+/* test hook: place an object in a given state ({"kind":"ComposabilityRequest"|"ComposableResource",...}) */
+int  cro_sim_plant(cro_sim *sim, const char *object_json, char *err_buf, size_t err_cap);
+/* run both controllers until quiescent (or max_reconciles); stats JSON out */
+int  cro_sim_run(cro_sim *sim, long long max_reconciles, char *buf, size_t cap, size_t *len);
+/* exactly one Reconcile of the request controller (how the reference's tests drive it) */
+int  cro_sim_reconcile_request(cro_sim *sim, const char *name, char *err_buf, size_t err_cap);
+int  cro_sim_dump(cro_sim *sim, char *buf, size_t cap, size_t *len);
+
 /* ---- diagnostics --------------------------------------------------------- */
 const char *cro_strerror(int code);
 /* Last error text recorded on this context by the calling thread's most
