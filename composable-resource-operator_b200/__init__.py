@@ -112,7 +112,7 @@ EXPORTS = [
     "cro_emit_sunfish_request", "cro_emit_probe_annotations_json", "cro_fm_parse_scale_up_response",
     "cro_reconcile_attach", "cro_strerror", "cro_last_error", "cro_version", "cro_cm_check_adding_resources",
     "cro_sim_create", "cro_sim_destroy", "cro_sim_apply", "cro_sim_delete", "cro_sim_plant", "cro_sim_run",
-    "cro_sim_reconcile_request", "cro_sim_dump",
+    "cro_sim_reconcile_request", "cro_sim_dump", "cro_probe_begin", "cro_probe_end",
 ]
 
 
@@ -139,6 +139,8 @@ def _load() -> ctypes.CDLL:
         "cro_normalize": (i32, [i32, c] + out),
         "cro_probe_device": (i32, [vp, i32, ctypes.POINTER(ProbeResult)]),
         "cro_probe_all": (i32, [vp, ctypes.POINTER(ProbeResult), i32, ctypes.POINTER(i32)]),
+        "cro_probe_begin": (i32, [vp, i32]),
+        "cro_probe_end": (i32, [vp, i32, ctypes.POINTER(ProbeResult)]),
         "cro_result_device_ptr": (i32, [vp, i32, ctypes.POINTER(u64)]),
         "cro_hbm_fill": (i32, [vp, i32, ctypes.POINTER(SweepResult)]),
         "cro_hbm_fill_loop": (i32, [vp, i32, u32, ctypes.POINTER(SweepResult)]),
@@ -393,6 +395,14 @@ class ProbeContext:
         r = ProbeResult()
         self._check(lib.cro_probe_device(self.handle, dev, ctypes.byref(r)),
                     allow=(ERR_CHECKSUM,) if allow_checksum_error else ())
+        return r
+
+    def probe_begin(self, dev: int = 0) -> None:
+        self._check(lib.cro_probe_begin(self.handle, dev))
+
+    def probe_end(self, dev: int = 0) -> ProbeResult:
+        r = ProbeResult()
+        self._check(lib.cro_probe_end(self.handle, dev, ctypes.byref(r)))
         return r
 
     def probe_all(self) -> List[ProbeResult]:

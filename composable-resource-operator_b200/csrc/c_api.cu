@@ -157,6 +157,11 @@ int cro_probe_device(cro_ctx* ctx, int dev_index, cro_probe_result* out) {
     return ctx_probe_device(ctx, dev_index, out);
 }
 
+int cro_probe_begin(cro_ctx* ctx, int dev_index) { return ctx ? ctx_probe_begin(ctx, dev_index) : CRO_ERR_INVALID_ARG; }
+int cro_probe_end(cro_ctx* ctx, int dev_index, cro_probe_result* out) {
+    return ctx ? ctx_probe_end(ctx, dev_index, out) : CRO_ERR_INVALID_ARG;
+}
+
 int cro_probe_all(cro_ctx* ctx, cro_probe_result* out, int cap, int* n) {
     return ctx_probe_all(ctx, out, cap, n);
 }

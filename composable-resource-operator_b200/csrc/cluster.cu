@@ -740,7 +740,8 @@ public:
             if (idx < 0) return Error::Nil();
             cro_probe_result pr;
             ++c_->stats.probes;
-            int rc = ctx_probe_device(c_->ctx_, idx, &pr);
+            int rc = ctx_probe_end(c_->ctx_, idx, &pr);   // collects the prefetched probe (or probes now)
+            c_->prefetchProbes(idx);                       // keep this device busy with the next queued attach
             if (rc != CRO_OK) {
                 ++c_->stats.probe_failures;
                 return Error::New(std::string("cuda probe failed: ") + cro_strerror(rc));
@@ -880,6 +881,39 @@ Error Cluster::ReconcileRequestOnce(const std::string& name) {
     return reconcileRequest(name, &rq);
 }
 
+// Device (index in the probe context) that backs a node, as SimProvider maps it.
+int Cluster::deviceOfNode(const std::string& node) const {
+    if (!ctx_) return -1;
+    size_t idx = 0;
+    bool found = false;
+    for (size_t i = 0; i < nodes_.size(); ++i)
+        if (nodes_[i].Name == node) { idx = i; found = true; }
+    if (!found) return -1;
+    const std::string& uuid = uuids_[idx % uuids_.size()];
+    for (size_t i = 0; i < ctx_->devs.size(); ++i)
+        if (std::string(ctx_->devs[i]->info.gpu_uuid, strnlen(ctx_->devs[i]->info.gpu_uuid, 48)) == uuid) return (int)i;
+    return -1;
+}
+
+// One reconcile worker, many GPUs: look ahead in the resource queue and begin
+// (asynchronously) the probe every queued attach will need, at most one per
+// device.  only_dev >= 0 restricts the look-ahead to that device.
+void Cluster::prefetchProbes(int only_dev) {
+    if (!probe_) return;
+    std::set<int> begun;
+    for (const std::string& key : res_queue_) {
+        auto it = resources_.find(key);
+        if (it == resources_.end()) continue;
+        const controller::ComposableResource& r = it->second.obj;
+        if (!(r.Status.State.empty() || r.Status.State == "Attaching") || r.DeletionTimestampSet) continue;
+        const int dev = deviceOfNode(r.Spec.TargetNode);
+        if (dev < 0 || (only_dev >= 0 && dev != only_dev) || begun.count(dev)) continue;
+        begun.insert(dev);
+        if (ctx_probe_begin(ctx_, dev) == CRO_OK) ++stats.prefetches;
+        if (only_dev >= 0 || begun.size() == ctx_->devs.size()) break;
+    }
+}
+
 // ---- event loop ----------------------------------------------------------------------
 void Cluster::Run(long long max_reconciles) {
     using clk = std::chrono::steady_clock;
@@ -890,6 +924,7 @@ void Cluster::Run(long long max_reconciles) {
         bool worked = false;
         while ((!req_queue_.empty() || !res_queue_.empty()) && n < max_reconciles) {
             worked = true;
+            if ((n & 15) == 0) prefetchProbes(-1);
             // one worker per controller (MaxConcurrentReconciles default 1), interleaved
             if (!res_queue_.empty()) {
                 const std::string key = res_queue_.front();
@@ -976,7 +1011,7 @@ std::string Cluster::StatsJSON() const {
     w.field("resources", (long long)resources_.size()).field("resources_online", online);
     w.field("request_reconciles", stats.request_reconciles).field("resource_reconciles", stats.resource_reconciles);
     w.field("status_updates", stats.status_updates).field("spec_bytes", stats.spec_bytes);
-    w.field("probes", stats.probes).field("probe_failures", stats.probe_failures);
+    w.field("probes", stats.probes).field("probe_failures", stats.probe_failures).field("probe_prefetches", stats.prefetches);
     w.field("reconcile_errors", stats.reconcile_errors).field("timer_rounds", stats.timer_rounds);
     w.field("reconcile_p50_ns", pct(0.50)).field("reconcile_p99_ns", pct(0.99));
     w.field("wall_us", (long long)(stats.wall_s * 1e6));

@@ -98,7 +98,7 @@ struct StoredResource {
 
 struct Stats {
     long long request_reconciles = 0, resource_reconciles = 0, status_updates = 0, spec_bytes = 0;
-    long long probes = 0, probe_failures = 0, timer_rounds = 0, reconcile_errors = 0;
+    long long probes = 0, probe_failures = 0, timer_rounds = 0, reconcile_errors = 0, prefetches = 0;
     std::vector<long long> reconcile_ns;   // one entry per Reconcile call
     double wall_s = 0;
 };
@@ -142,6 +142,8 @@ private:
     std::string GenerateComposableResourceName(const std::string& typeName);
     Error CheckNodeCapacitySufficient(const std::string& nodeName, const NodeSpec& spec, bool* ok) const;
 
+    int deviceOfNode(const std::string& node) const;
+    void prefetchProbes(int only_dev);
     Error reconcileRequest(const std::string& key, long long* requeue_after_s);
     Error reconcileResource(const std::string& key, long long* requeue_after_s);
 

@@ -27,7 +27,7 @@ constexpr int kMaxSweeps = 64;
 constexpr uint64_t kDefaultSweep = 4ull << 30;
 constexpr uint64_t kDefaultP2P = 1ull << 30;
 constexpr uint64_t kDefaultSeedBase = 0x00C0FFEE00000000ull;
-constexpr uint32_t kDefaultHops = 16384;
+constexpr uint32_t kDefaultHops = 4096;
 constexpr uint32_t kChaseSlots = 16384;      // one 8-byte slot per 128-byte line → 2 MiB
 
 #define CU_TRY(ctx, expr)                                                              \
@@ -296,6 +296,8 @@ void ctx_destroy(cro_ctx* c) {
     delete c;
 }
 
+static void drain_pending_fwd(cro_ctx* c, Device* d);
+
 static Device* dev_at(cro_ctx* c, int idx) {
     if (!c || idx < 0 || idx >= (int)c->devs.size()) return nullptr;
     return c->devs[(size_t)idx].get();
@@ -308,6 +310,7 @@ int ctx_fill(cro_ctx* c, int idx, uint32_t iters, cro_sweep_result* out) {
     Device* d = dev_at(c, idx);
     if (!d || !out || iters == 0) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
+    drain_pending_fwd(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
     int rc = ensure_region(c, d);
     if (rc) return rc;
@@ -333,6 +336,7 @@ int ctx_read(cro_ctx* c, int idx, uint32_t variant, uint32_t iters, bool dst_hal
     if (!d || !out || iters == 0) return CRO_ERR_INVALID_ARG;
     variant = resolve_read_variant(variant);
     std::lock_guard<std::mutex> g(d->mu);
+    drain_pending_fwd(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
     int rc = ensure_filled(c, d);
     if (rc) return rc;
@@ -362,6 +366,7 @@ int ctx_copy(cro_ctx* c, int idx, uint32_t variant, uint32_t iters, cro_sweep_re
     if (!d || !out || iters == 0) return CRO_ERR_INVALID_ARG;
     variant = resolve_copy_variant(variant);
     std::lock_guard<std::mutex> g(d->mu);
+    drain_pending_fwd(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
     int rc = ensure_filled(c, d);
     if (rc) return rc;
@@ -386,6 +391,7 @@ int ctx_expected(cro_ctx* c, int idx, cro_sweep_result* out) {
     Device* d = dev_at(c, idx);
     if (!d || !out) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
+    drain_pending_fwd(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
     d->have_expected = false;
     CU_TRY(c, cudaEventRecord(d->ev0, d->stream));
@@ -409,6 +415,7 @@ int ctx_inject(cro_ctx* c, int idx, uint64_t word, uint64_t mask) {
     if (!d) return CRO_ERR_INVALID_ARG;
     if (word >= d->sweep_bytes / 8) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
+    drain_pending_fwd(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
     int rc = ensure_filled(c, d);
     if (rc) return rc;
@@ -423,6 +430,7 @@ int ctx_read_words(cro_ctx* c, int idx, uint64_t first, uint64_t n, uint64_t* ou
     if (!d || !out) return CRO_ERR_INVALID_ARG;
     if (first + n > 2 * d->sweep_bytes / 8) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
+    drain_pending_fwd(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
     int rc = ensure_filled(c, d);
     if (rc) return rc;
@@ -439,8 +447,9 @@ static uint64_t median_of(std::vector<uint64_t> v) {
     return v.empty() ? 0 : v[v.size() / 2];
 }
 
-// Caller holds d->mu.
-static int probe_locked(cro_ctx* c, Device* d, cro_probe_result* r) {
+// Caller holds d->mu.  Enqueues one whole probe (fill, reads, copies, result
+// copy-back) on the device's stream and returns without waiting.
+static int probe_enqueue(cro_ctx* c, Device* d, cro_probe_result* r) {
     const cro_opts& o = c->opts;
     memset(r, 0, sizeof *r);
     r->abi_version = CRO_ABI_VERSION;
@@ -501,6 +510,19 @@ static int probe_locked(cro_ctx* c, Device* d, cro_probe_result* r) {
     c->launches += 1 + o.read_sweeps + r->copy_sweeps + (verify ? 1 : 0);
     CU_TRY(c, cudaMemcpyAsync(d->h_out, d->d_out, sizeof(SweepOut) * (o.read_sweeps + 1),
                               cudaMemcpyDeviceToHost, d->stream));
+    d->pending_events = k;
+    return CRO_OK;
+}
+
+// Caller holds d->mu.  Waits for the probe enqueued by probe_enqueue and
+// evaluates it into *r (which probe_enqueue started filling).
+static int probe_finish(cro_ctx* c, Device* d, cro_probe_result* r) {
+    const cro_opts& o = c->opts;
+    std::vector<cudaEvent_t>& ev = d->evpool;
+    const size_t k = d->pending_events;
+    const bool verify = (o.flags & CRO_F_VERIFY_COPY) && r->copy_sweeps > 0;
+    CU_TRY(c, cudaSetDevice(d->ordinal));
+    int rc;
     if ((rc = wait_stream(c, d))) { r->status = rc; return rc; }
 
     float ms = 0;
@@ -552,6 +574,23 @@ static int probe_locked(cro_ctx* c, Device* d, cro_probe_result* r) {
     return status;
 }
 
+static int probe_locked(cro_ctx* c, Device* d, cro_probe_result* r) {
+    int rc = probe_enqueue(c, d, r);
+    if (rc) { r->status = rc; return rc; }
+    return probe_finish(c, d, r);
+}
+
+// Drains a probe begun with ctx_probe_begin whose result nobody has collected
+// yet, so another operation may use the stream / result slots.  Caller holds d->mu.
+static void drain_pending(cro_ctx* c, Device* d) {
+    if (!d->pending) return;
+    d->pending_rc = probe_finish(c, d, &d->pending_result);
+    d->pending = false;
+    d->have_pending_result = true;
+}
+
+static void drain_pending_fwd(cro_ctx* c, Device* d) { drain_pending(c, d); }
+
 static int publish_result(cro_ctx* c, Device* d, const cro_probe_result* r) {
     CU_TRY(c, cudaSetDevice(d->ordinal));
     CU_TRY(c, cudaMemcpyAsync(d->d_result, r, sizeof *r, cudaMemcpyHostToDevice, d->stream));
@@ -563,7 +602,49 @@ int ctx_probe_device(cro_ctx* c, int idx, cro_probe_result* out) {
     Device* d = dev_at(c, idx);
     if (!d || !out) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
+    drain_pending(c, d);
+    d->have_pending_result = false;   // a synchronous probe supersedes an uncollected asynchronous one
     int rc = probe_locked(c, d, out);
+    if (rc == CRO_OK || rc == CRO_ERR_CHECKSUM) {
+        int prc = publish_result(c, d, out);
+        if (prc) return prc;
+    }
+    return rc;
+}
+
+// Asynchronous form: begin enqueues the probe and returns; end waits and
+// evaluates.  Lets ONE host thread (the reference's single reconcile worker)
+// keep every attached GPU busy: probes of different devices overlap.
+int ctx_probe_begin(cro_ctx* c, int idx) {
+    Device* d = dev_at(c, idx);
+    if (!d) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(d->mu);
+    if (d->pending || d->have_pending_result) return CRO_OK;   // one in flight (or waiting to be collected)
+    int rc = probe_enqueue(c, d, &d->pending_result);
+    if (rc) return rc;
+    d->pending = true;
+    d->pending_since = std::chrono::steady_clock::now();
+    return CRO_OK;
+}
+
+int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out) {
+    Device* d = dev_at(c, idx);
+    if (!d || !out) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(d->mu);
+    // a prefetched result nobody collected for more than a second says nothing about the device NOW
+    if (d->have_pending_result && !d->pending &&
+        std::chrono::steady_clock::now() - d->pending_since > std::chrono::seconds(1))
+        d->have_pending_result = false;
+    if (!d->pending && !d->have_pending_result) {   // nothing begun: behave like the synchronous call
+        int rc = probe_enqueue(c, d, &d->pending_result);
+        if (rc) return rc;
+        d->pending = true;
+        d->pending_since = std::chrono::steady_clock::now();
+    }
+    drain_pending(c, d);
+    d->have_pending_result = false;
+    *out = d->pending_result;
+    int rc = d->pending_rc;
     if (rc == CRO_OK || rc == CRO_ERR_CHECKSUM) {
         int prc = publish_result(c, d, out);
         if (prc) return prc;
@@ -688,6 +769,8 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
             th.emplace_back([&, i] {
                 Device* d = c->devs[(size_t)i].get();
                 std::lock_guard<std::mutex> g(d->mu);
+                drain_pending(c, d);
+                d->have_pending_result = false;
                 rcs[(size_t)i] = probe_locked(c, d, &res[(size_t)i]);
             });
         for (auto& t : th) t.join();

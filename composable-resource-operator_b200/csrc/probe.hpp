@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -39,6 +40,12 @@ struct Device {
     cro_probe_result* d_gather = nullptr;  // all-gather receive buffer (world entries)
     unsigned long long* d_chase_next = nullptr;  // latency permutation (peers read it)
     unsigned long long* d_chase_out = nullptr;
+    // asynchronous probe (ctx_probe_begin / ctx_probe_end)
+    bool pending = false, have_pending_result = false;
+    int pending_rc = 0;
+    size_t pending_events = 0;
+    std::chrono::steady_clock::time_point pending_since{};
+    cro_probe_result pending_result{};
     bool have_expected = false;
     uint64_t expect_x = 0, expect_s = 0;
     unsigned sm_clock_mhz = 0, mem_clock_mhz = 0;
@@ -70,6 +77,8 @@ int ctx_create(const cro_opts* o, cro_ctx** out);
 void ctx_destroy(cro_ctx* c);
 int ctx_probe_device(cro_ctx* c, int idx, cro_probe_result* out);
 int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n);
+int ctx_probe_begin(cro_ctx* c, int idx);
+int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out);
 
 // single sweeps (each takes the device mutex)
 int ctx_fill(cro_ctx* c, int idx, uint32_t iters, cro_sweep_result* out);

@@ -75,7 +75,7 @@ typedef struct cro_opts {
     uint64_t seed_base;            /* default 0x00C0FFEE00000000; seed = base | minor       */
     uint32_t read_sweeps;          /* default 5                                             */
     uint32_t copy_sweeps;          /* default 5                                             */
-    uint32_t latency_hops;         /* pointer-chase hops; default 65536                     */
+    uint32_t latency_hops;         /* pointer-chase hops; default 4096                      */
     uint32_t read_variant;         /* CRO_READ_*                                            */
     uint32_t copy_variant;         /* CRO_COPY_*                                            */
     int32_t  deadline_ms;          /* per-call deadline, 0 = none (Go ctx cannot cross cgo) */
@@ -225,6 +225,14 @@ int  cro_normalize(int kind, const char *in, char *buf, size_t cap, size_t *len)
  * Sits at internal/controller/composableresource_controller.go:259 and feeds
  * the decision at :275.  dev_index indexes the cro_enumerate order. */
 int  cro_probe_device(cro_ctx *ctx, int dev_index, cro_probe_result *out);
+
+/* Asynchronous form of cro_probe_device: begin enqueues the whole probe on the
+ * device's stream and returns at once; end waits and evaluates.  One host
+ * thread (the reference's single reconcile worker, MaxConcurrentReconciles=1)
+ * can keep every attached GPU busy this way.  At most one probe per device is
+ * in flight; a second begin is a no-op; end without begin probes synchronously. */
+int  cro_probe_begin(cro_ctx *ctx, int dev_index);
+int  cro_probe_end(cro_ctx *ctx, int dev_index, cro_probe_result *out);
 
 /* Concurrent probe of every managed device, NVLink P2P rounds, then ONE
  * ncclAllGather of the 512-byte result structs.  out[] receives the gathered

@@ -205,3 +205,47 @@ def test_multi_device_probe_all(cro, coracle):
                     continue
                 assert r.p2p_read_ns[j] > 0 and r.p2p_latency_ns_x16[j] > 0
                 assert r.p2p_checksum_xor[j] == coracle.checksum(res[j].seed, 0, (64 << 20) // 8)[0]
+
+
+def test_async_probe_begin_end(cro, coracle):
+    """cro_probe_begin / cro_probe_end: same result as the synchronous probe; a sweep in between drains it."""
+    with cro.ProbeContext(sweep_bytes=32 << 20, devices=[0], read_sweeps=2, copy_sweeps=1) as c:
+        want = coracle.checksum(c.seed(0), 0, (32 << 20) // 8)
+        c.probe_begin(0)
+        c.probe_begin(0)                       # second begin is a no-op
+        r = c.probe_end(0)
+        assert r.status == 0 and (r.checksum_xor, r.checksum_sum) == want
+        r2 = c.probe_end(0)                    # end without begin probes synchronously
+        assert r2.status == 0 and (r2.checksum_xor, r2.checksum_sum) == want
+        c.probe_begin(0)
+        s = c.hbm_read_checksum(0, 1)          # another op first drains the in-flight probe
+        assert (s.checksum_xor, s.checksum_sum) == want
+        r3 = c.probe_end(0)
+        assert r3.status == 0 and r3.read_best_ns > 0
+
+
+def test_storm_and_churn_with_live_probe(cro):
+    """BASELINE configs 4 / 5 in miniature with the CUDA probe in the attach slot (all GPUs of the box)."""
+    import random
+    with cro.ProbeContext(sweep_bytes=64 << 20, read_sweeps=2, copy_sweeps=1) as ctx:
+        n = ctx.device_count()
+        uuids = [d.gpu_uuid.decode() for d in ctx.enumerate()]
+        with cro.Cluster({"nodes": ["worker-%d" % i for i in range(n)], "probe": True}, ctx) as c:
+            rng = random.Random(1)
+            sizes = {}
+            for i in range(24):
+                sizes["req-%02d" % i] = rng.randint(1, 3)
+                assert c.apply("req-%02d" % i, {"type": "gpu", "model": "NVIDIA-B200-%d" % (i // n), "size": sizes["req-%02d" % i],
+                                                "target_node": "worker-%d" % (i % n)}) == ""
+            st = c.run()
+            assert st["requests_running"] == 24 and st["reconcile_errors"] == 0 and st["probe_failures"] == 0
+            assert st["probes"] == sum(sizes.values())          # every attach was probed exactly once
+            d = c.dump()
+            for name, req in d["requests"].items():
+                node = int(req["spec"]["target_node"].split("-")[1])
+                assert all(cs["state"] == "Online" and cs["device_id"] == uuids[node] for cs in req["status"]["resources"].values())
+            for name in sizes:
+                c.delete(name)
+            c.run()
+            d = c.dump()
+            assert d["requests"] == {} and d["resources"] == {}
