@@ -738,10 +738,31 @@ public:
                     r.Status.DeviceID)
                     idx = (int)i;
             if (idx < 0) return Error::Nil();
+            // Non-blocking reconcile: the first pass begins the probe on the device's stream and
+            // asks for a requeue; a later pass collects it.  One reconcile worker therefore keeps
+            // every GPU of the box busy (a device serves one attach at a time, in arrival order).
+            auto owner = c_->probe_owner_.find(idx);
+            if (owner == c_->probe_owner_.end()) {
+                if (ctx_probe_begin(c_->ctx_, idx) != CRO_OK)
+                    return Error::New("cuda probe failed: could not start the probe");
+                c_->probe_owner_[idx] = r.Name;
+                probePending = true;
+                return Error::Nil();
+            }
+            if (owner->second != r.Name) {   // the device is serving another attach: queue behind it
+                if (c_->probe_waiting_.insert(r.Name).second) c_->dev_waiters_[idx].push_back(r.Name);
+                probePending = true;
+                return Error::Nil();
+            }
+            if (!ctx_probe_poll(c_->ctx_, idx)) {   // ours, still running
+                c_->probe_notified_.erase(idx);
+                probePending = true;
+                return Error::Nil();
+            }
             cro_probe_result pr;
             ++c_->stats.probes;
-            int rc = ctx_probe_end(c_->ctx_, idx, &pr);   // collects the prefetched probe (or probes now)
-            c_->prefetchProbes(idx);                       // keep this device busy with the next queued attach
+            int rc = ctx_probe_end(c_->ctx_, idx, &pr);
+            c_->releaseDevice(idx);
             if (rc != CRO_OK) {
                 ++c_->stats.probe_failures;
                 return Error::New(std::string("cuda probe failed: ") + cro_strerror(rc));
@@ -750,6 +771,7 @@ public:
         *visible = true;
         return Error::Nil();
     }
+    bool probePending = false;   // set when CheckGPUVisible is waiting on a probe rather than on the cluster
 
 private:
     Cluster* c_;
@@ -808,7 +830,7 @@ public:
         // object; persist once (the count of updates is what the stats report)
         c_->stats.status_updates += rec.statusUpdates.empty() ? 0 : (long long)rec.statusUpdates.size() - 1;
         c_->updateResource(s);
-        *requeue = result.RequeueAfterSeconds;
+        *requeue = node_.probePending ? -1 : result.RequeueAfterSeconds;
         return err;
     }
 
@@ -881,36 +903,53 @@ Error Cluster::ReconcileRequestOnce(const std::string& name) {
     return reconcileRequest(name, &rq);
 }
 
-// Device (index in the probe context) that backs a node, as SimProvider maps it.
-int Cluster::deviceOfNode(const std::string& node) const {
-    if (!ctx_) return -1;
-    size_t idx = 0;
-    bool found = false;
-    for (size_t i = 0; i < nodes_.size(); ++i)
-        if (nodes_[i].Name == node) { idx = i; found = true; }
-    if (!found) return -1;
-    const std::string& uuid = uuids_[idx % uuids_.size()];
-    for (size_t i = 0; i < ctx_->devs.size(); ++i)
-        if (std::string(ctx_->devs[i]->info.gpu_uuid, strnlen(ctx_->devs[i]->info.gpu_uuid, 48)) == uuid) return (int)i;
-    return -1;
+// Requeues the attaches whose probe has finished (called between reconciles), and drops the
+// ownership of devices whose attach disappeared meanwhile.
+void Cluster::pollProbes(bool block) {
+    if (probe_owner_.empty()) return;
+    std::vector<int> orphaned;
+    bool woke = false;
+    for (const auto& kv : probe_owner_) {
+        auto it = resources_.find(kv.second);
+        if (it == resources_.end() || it->second.obj.Status.State != "Attaching") {
+            orphaned.push_back(kv.first);
+        } else if (!probe_notified_.count(kv.first) && ctx_probe_poll(ctx_, kv.first)) {
+            probe_notified_.insert(kv.first);
+            enqueueResource(kv.second);   // its owner can collect now
+            woke = true;
+        }
+    }
+    for (int dev : orphaned) {   // the attach vanished: discard its probe, hand the device on
+        cro_probe_result discard;
+        ctx_probe_end(ctx_, dev, &discard);
+        releaseDevice(dev);
+        woke = true;
+    }
+    if (!woke && block && !probe_owner_.empty()) {
+        for (const auto& kv : probe_owner_) {
+            if (probe_notified_.count(kv.first)) continue;
+            ctx_probe_wait(ctx_, kv.first);   // the other devices keep running meanwhile
+            probe_notified_.insert(kv.first);
+            enqueueResource(kv.second);
+            break;
+        }
+    }
 }
 
-// One reconcile worker, many GPUs: look ahead in the resource queue and begin
-// (asynchronously) the probe every queued attach will need, at most one per
-// device.  only_dev >= 0 restricts the look-ahead to that device.
-void Cluster::prefetchProbes(int only_dev) {
-    if (!probe_) return;
-    std::set<int> begun;
-    for (const std::string& key : res_queue_) {
-        auto it = resources_.find(key);
-        if (it == resources_.end()) continue;
-        const controller::ComposableResource& r = it->second.obj;
-        if (!(r.Status.State.empty() || r.Status.State == "Attaching") || r.DeletionTimestampSet) continue;
-        const int dev = deviceOfNode(r.Spec.TargetNode);
-        if (dev < 0 || (only_dev >= 0 && dev != only_dev) || begun.count(dev)) continue;
-        begun.insert(dev);
-        if (ctx_probe_begin(ctx_, dev) == CRO_OK) ++stats.prefetches;
-        if (only_dev >= 0 || begun.size() == ctx_->devs.size()) break;
+// The attach that owned `dev` is done with it: the next one queued behind it gets a turn.
+void Cluster::releaseDevice(int dev) {
+    probe_owner_.erase(dev);
+    probe_notified_.erase(dev);
+    auto q = dev_waiters_.find(dev);
+    if (q == dev_waiters_.end()) return;
+    while (!q->second.empty()) {
+        const std::string next = q->second.front();
+        q->second.pop_front();
+        probe_waiting_.erase(next);
+        if (resources_.count(next)) {
+            enqueueResource(next);
+            break;
+        }
     }
 }
 
@@ -924,7 +963,7 @@ void Cluster::Run(long long max_reconciles) {
         bool worked = false;
         while ((!req_queue_.empty() || !res_queue_.empty()) && n < max_reconciles) {
             worked = true;
-            if ((n & 15) == 0) prefetchProbes(-1);
+            if ((n & 15) == 0) pollProbes(false);
             // one worker per controller (MaxConcurrentReconciles default 1), interleaved
             if (!res_queue_.empty()) {
                 const std::string key = res_queue_.front();
@@ -937,6 +976,7 @@ void Cluster::Run(long long max_reconciles) {
                 ++stats.resource_reconciles;
                 ++n;
                 if (!e.ok()) { ++stats.reconcile_errors; res_timers_.insert(key); }   // back-off requeue
+                else if (rq < 0) { /* parked on a GPU (owner or queued behind one): pollProbes wakes it */ }
                 else if (rq > 0) res_timers_.insert(key);
             }
             if (!req_queue_.empty()) {
@@ -955,6 +995,10 @@ void Cluster::Run(long long max_reconciles) {
         }
         (void)worked;
         if (n >= max_reconciles) break;
+        if (!probe_owner_.empty()) {   // nothing else to do: wait for the next probe to finish
+            pollProbes(true);
+            continue;
+        }
         // queue drained: fire the RequeueAfter timers, unless the last round changed nothing
         if ((req_timers_.empty() && res_timers_.empty()) || changes_ == changes_at_flush) break;
         changes_at_flush = changes_;
@@ -1011,7 +1055,7 @@ std::string Cluster::StatsJSON() const {
     w.field("resources", (long long)resources_.size()).field("resources_online", online);
     w.field("request_reconciles", stats.request_reconciles).field("resource_reconciles", stats.resource_reconciles);
     w.field("status_updates", stats.status_updates).field("spec_bytes", stats.spec_bytes);
-    w.field("probes", stats.probes).field("probe_failures", stats.probe_failures).field("probe_prefetches", stats.prefetches);
+    w.field("probes", stats.probes).field("probe_failures", stats.probe_failures);
     w.field("reconcile_errors", stats.reconcile_errors).field("timer_rounds", stats.timer_rounds);
     w.field("reconcile_p50_ns", pct(0.50)).field("reconcile_p99_ns", pct(0.99));
     w.field("wall_us", (long long)(stats.wall_s * 1e6));

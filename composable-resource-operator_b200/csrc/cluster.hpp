@@ -98,7 +98,7 @@ struct StoredResource {
 
 struct Stats {
     long long request_reconciles = 0, resource_reconciles = 0, status_updates = 0, spec_bytes = 0;
-    long long probes = 0, probe_failures = 0, timer_rounds = 0, reconcile_errors = 0, prefetches = 0;
+    long long probes = 0, probe_failures = 0, timer_rounds = 0, reconcile_errors = 0;
     std::vector<long long> reconcile_ns;   // one entry per Reconcile call
     double wall_s = 0;
 };
@@ -142,8 +142,8 @@ private:
     std::string GenerateComposableResourceName(const std::string& typeName);
     Error CheckNodeCapacitySufficient(const std::string& nodeName, const NodeSpec& spec, bool* ok) const;
 
-    int deviceOfNode(const std::string& node) const;
-    void prefetchProbes(int only_dev);
+    void pollProbes(bool block);
+    void releaseDevice(int dev);
     Error reconcileRequest(const std::string& key, long long* requeue_after_s);
     Error reconcileResource(const std::string& key, long long* requeue_after_s);
 
@@ -159,6 +159,10 @@ private:
     std::deque<std::string> req_queue_, res_queue_;
     std::set<std::string> req_queued_, res_queued_;
     std::set<std::string> req_timers_, res_timers_;
+    std::map<int, std::string> probe_owner_;                    // device -> the attach whose probe is in flight on it
+    std::set<int> probe_notified_;                              // devices whose owner has been told "done"
+    std::map<int, std::deque<std::string>> dev_waiters_;        // attaches queued behind a device's owner
+    std::set<std::string> probe_waiting_;                       // names present in some dev_waiters_ queue
     long long changes_ = 0, seq_ = 0;
     std::mt19937_64 rng_;
 };

@@ -627,6 +627,27 @@ int ctx_probe_begin(cro_ctx* c, int idx) {
     return CRO_OK;
 }
 
+// 1 when a probe begun on this device has finished (or none is in flight), 0 while it runs.
+int ctx_probe_poll(cro_ctx* c, int idx) {
+    Device* d = dev_at(c, idx);
+    if (!d) return 1;
+    std::lock_guard<std::mutex> g(d->mu);
+    if (!d->pending) return 1;
+    cudaSetDevice(d->ordinal);
+    return cudaStreamQuery(d->stream) == cudaSuccess ? 1 : 0;
+}
+
+// Blocks until the probe in flight on this device (if any) has finished; does not collect it.
+int ctx_probe_wait(cro_ctx* c, int idx) {
+    Device* d = dev_at(c, idx);
+    if (!d) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(d->mu);
+    if (!d->pending) return CRO_OK;
+    CU_TRY(c, cudaSetDevice(d->ordinal));
+    CU_TRY(c, cudaStreamSynchronize(d->stream));
+    return CRO_OK;
+}
+
 int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out) {
     Device* d = dev_at(c, idx);
     if (!d || !out) return CRO_ERR_INVALID_ARG;

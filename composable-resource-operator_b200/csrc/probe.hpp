@@ -79,6 +79,8 @@ int ctx_probe_device(cro_ctx* c, int idx, cro_probe_result* out);
 int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n);
 int ctx_probe_begin(cro_ctx* c, int idx);
 int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out);
+int ctx_probe_poll(cro_ctx* c, int idx);
+int ctx_probe_wait(cro_ctx* c, int idx);
 
 // single sweeps (each takes the device mutex)
 int ctx_fill(cro_ctx* c, int idx, uint32_t iters, cro_sweep_result* out);
