@@ -183,6 +183,13 @@ void Cluster::enqueueRequest(const std::string& key) {
 void Cluster::enqueueResource(const std::string& key) {
     if (res_queued_.insert(key).second) res_queue_.push_back(key);
 }
+// GPU wake-ups jump the queue: a finished probe (or a freed device) should not idle behind
+// thousands of unrelated reconciles.
+void Cluster::enqueueResourceFront(const std::string& key) {
+    if (res_queued_.insert(key).second) { res_queue_.push_front(key); return; }
+    auto it = std::find(res_queue_.begin(), res_queue_.end(), key);
+    if (it != res_queue_.end() && it != res_queue_.begin()) { res_queue_.erase(it); res_queue_.push_front(key); }
+}
 
 void Cluster::updateRequest(const ComposabilityRequest& r) {
     auto it = requests_.find(r.Name);
@@ -915,7 +922,7 @@ void Cluster::pollProbes(bool block) {
             orphaned.push_back(kv.first);
         } else if (!probe_notified_.count(kv.first) && ctx_probe_poll(ctx_, kv.first)) {
             probe_notified_.insert(kv.first);
-            enqueueResource(kv.second);   // its owner can collect now
+            enqueueResourceFront(kv.second);   // its owner can collect now
             woke = true;
         }
     }
@@ -930,7 +937,7 @@ void Cluster::pollProbes(bool block) {
             if (probe_notified_.count(kv.first)) continue;
             ctx_probe_wait(ctx_, kv.first);   // the other devices keep running meanwhile
             probe_notified_.insert(kv.first);
-            enqueueResource(kv.second);
+            enqueueResourceFront(kv.second);
             break;
         }
     }
@@ -947,7 +954,7 @@ void Cluster::releaseDevice(int dev) {
         q->second.pop_front();
         probe_waiting_.erase(next);
         if (resources_.count(next)) {
-            enqueueResource(next);
+            enqueueResourceFront(next);
             break;
         }
     }
@@ -963,7 +970,7 @@ void Cluster::Run(long long max_reconciles) {
         bool worked = false;
         while ((!req_queue_.empty() || !res_queue_.empty()) && n < max_reconciles) {
             worked = true;
-            if ((n & 15) == 0) pollProbes(false);
+            if ((n & 3) == 0) pollProbes(false);
             // one worker per controller (MaxConcurrentReconciles default 1), interleaved
             if (!res_queue_.empty()) {
                 const std::string key = res_queue_.front();

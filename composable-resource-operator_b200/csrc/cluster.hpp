@@ -139,6 +139,7 @@ private:
     void deleteResource(const std::string& name);
     void enqueueRequest(const std::string& key);
     void enqueueResource(const std::string& key);
+    void enqueueResourceFront(const std::string& key);
     std::string GenerateComposableResourceName(const std::string& typeName);
     Error CheckNodeCapacitySufficient(const std::string& nodeName, const NodeSpec& spec, bool* ok) const;
 
