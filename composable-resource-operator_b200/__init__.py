@@ -113,6 +113,8 @@ EXPORTS = [
     "cro_reconcile_attach", "cro_strerror", "cro_last_error", "cro_version", "cro_cm_check_adding_resources",
     "cro_sim_create", "cro_sim_destroy", "cro_sim_apply", "cro_sim_delete", "cro_sim_plant", "cro_sim_run",
     "cro_sim_reconcile_request", "cro_sim_dump", "cro_probe_begin", "cro_probe_end",
+    "cro_check_no_gpu_loads", "cro_check_gpu_drain_status", "cro_check_device_file_scan",
+    "cro_scan_device_file_holders",
 ]
 
 
@@ -173,6 +175,10 @@ def _load() -> ctypes.CDLL:
         "cro_sim_run": (i32, [vp, ctypes.c_longlong] + out),
         "cro_sim_reconcile_request": (i32, [vp, c, c, sz]),
         "cro_sim_dump": (i32, [vp] + out),
+        "cro_check_no_gpu_loads": (i32, [c, c, c, c, c, c, i32, c, sz]),
+        "cro_check_gpu_drain_status": (i32, [c, c, c, c, c, ctypes.POINTER(i32), c, sz]),
+        "cro_check_device_file_scan": (i32, [c, c, c, i32, c, sz]),
+        "cro_scan_device_file_holders": (i32, [c, c, i32] + out),
         "cro_strerror": (c, [i32]),
         "cro_last_error": (i32, [vp, c, sz]),
         "cro_version": (c, []),
@@ -445,6 +451,35 @@ class ProbeContext:
 
     def launch_count(self) -> int:
         return int(lib.cro_launch_count(self.handle))
+
+
+def CheckNoGPULoadsFromOutput(std_out: str, std_err: str, exec_err: Optional[str], pod_name: str, node_name: str,
+                              target_uuid: Optional[str], driver_enabled: bool) -> str:
+    """utils.CheckNoGPULoads parse + decision (internal/utils/gpus.go:145-186); returns the error text ("" = nil)."""
+    err = ctypes.create_string_buffer(4096)
+    lib.cro_check_no_gpu_loads(_b(std_out), _b(std_err), _b(exec_err), _b(pod_name), _b(node_name), _b(target_uuid),
+                               int(driver_enabled), err, 4096)
+    return err.value.decode("utf-8", "surrogateescape")
+
+
+def checkGPUDrainStatusFromOutput(std_out: str, std_err: str, exec_err: Optional[str], node_name: str,
+                                  bus_id: str) -> Tuple[bool, str]:
+    """checkGPUDrainStatus (internal/utils/gpus.go:964-1012); returns (draining, error text)."""
+    err = ctypes.create_string_buffer(4096)
+    d = ctypes.c_int(0)
+    lib.cro_check_gpu_drain_status(_b(std_out), _b(std_err), _b(exec_err), _b(node_name), _b(bus_id), ctypes.byref(d), err, 4096)
+    return bool(d.value), err.value.decode("utf-8", "surrogateescape")
+
+
+def CheckDeviceFileScanResult(std_out: str, std_err: str, exec_err: Optional[str], rke2: bool = False) -> str:
+    err = ctypes.create_string_buffer(4096)
+    lib.cro_check_device_file_scan(_b(std_out), _b(std_err), _b(exec_err), int(rke2), err, 4096)
+    return err.value.decode("utf-8", "surrogateescape")
+
+
+def scan_device_file_holders(target: str, proc_root: Optional[str] = None, rke2: bool = False) -> str:
+    """Native fd scan (replaces the shell scripts at internal/utils/gpus.go:236-260, 441-457)."""
+    return _text(lib.cro_scan_device_file_holders, _b(proc_root), _b(target), int(rke2))
 
 
 class Cluster:

@@ -10,6 +10,7 @@
 #include "probe.hpp"
 #include "reconcile.hpp"
 #include "cluster.hpp"
+#include "detach.hpp"
 
 using namespace cro;
 
@@ -568,6 +569,40 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
     if (node.probed) w.key("probe").string_map(probe_annotations(node.probe_result));
     w.end_object();
     return copy_out(w.str(), buf, cap, len);
+}
+
+// ---- detach-side pre-flight -------------------------------------------------------
+
+static int finish_err(const controller::Error& e, char* err_buf, size_t err_cap) {
+    copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
+    return e.ok() ? CRO_OK : CRO_ERR_EXEC;
+}
+
+int cro_check_no_gpu_loads(const char* std_out, const char* std_err, const char* exec_err, const char* pod_name,
+                           const char* node_name, const char* target_uuid, int driver_enabled, char* err_buf,
+                           size_t err_cap) {
+    std::string uuid = S(target_uuid);
+    return finish_err(detach::CheckNoGPULoadsFromOutput(S(std_out), S(std_err), exec_err, S(pod_name), S(node_name),
+                                                        target_uuid ? &uuid : nullptr, driver_enabled != 0),
+                      err_buf, err_cap);
+}
+
+int cro_check_gpu_drain_status(const char* std_out, const char* std_err, const char* exec_err, const char* node_name,
+                               const char* bus_id, int* draining, char* err_buf, size_t err_cap) {
+    bool d = false;
+    controller::Error e = detach::checkGPUDrainStatusFromOutput(S(std_out), S(std_err), exec_err, S(node_name), S(bus_id), &d);
+    if (draining) *draining = d ? 1 : 0;
+    return finish_err(e, err_buf, err_cap);
+}
+
+int cro_check_device_file_scan(const char* std_out, const char* std_err, const char* exec_err, int rke2, char* err_buf,
+                               size_t err_cap) {
+    return finish_err(detach::CheckDeviceFileScanResult(S(std_out), S(std_err), exec_err, rke2 != 0), err_buf, err_cap);
+}
+
+int cro_scan_device_file_holders(const char* proc_root, const char* target, int rke2, char* buf, size_t cap, size_t* len) {
+    if (!target) return CRO_ERR_INVALID_ARG;
+    return copy_out(detach::ScanDeviceFileHolders(S(proc_root), target, rke2 != 0), buf, cap, len);
 }
 
 // ---- in-memory cluster -----------------------------------------------------------

@@ -3,6 +3,8 @@
 #include "cluster.hpp"
 
 #include <algorithm>
+#include <unistd.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -933,12 +935,18 @@ void Cluster::pollProbes(bool block) {
         woke = true;
     }
     if (!woke && block && !probe_owner_.empty()) {
-        for (const auto& kv : probe_owner_) {
-            if (probe_notified_.count(kv.first)) continue;
-            ctx_probe_wait(ctx_, kv.first);   // the other devices keep running meanwhile
-            probe_notified_.insert(kv.first);
-            enqueueResourceFront(kv.second);
-            break;
+        // nothing else to reconcile: wait for WHICHEVER device finishes first (blocking on one
+        // particular stream would leave the others idle once they drift apart)
+        bool any_unnotified = false;
+        for (const auto& kv : probe_owner_) any_unnotified |= !probe_notified_.count(kv.first);
+        while (any_unnotified && !woke) {
+            for (const auto& kv : probe_owner_) {
+                if (probe_notified_.count(kv.first) || !ctx_probe_poll(ctx_, kv.first)) continue;
+                probe_notified_.insert(kv.first);
+                enqueueResourceFront(kv.second);
+                woke = true;
+            }
+            if (!woke) usleep(20);
         }
     }
 }

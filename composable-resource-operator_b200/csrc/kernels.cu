@@ -132,6 +132,31 @@ __device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, u
                  "r"(smem_u32(smem_src)), "r"(bytes)
                  : "memory");
 }
+// L2 eviction-priority policies for the bulk copies (streaming data is touched once).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                                 uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_1d_hint(void* gdst, const void* smem_src, uint32_t bytes,
+                                                  uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_commit() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -302,6 +327,8 @@ hbm_read_tma_kernel(const unsigned char* __restrict__ base, unsigned long long b
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned n_cons_warps = (blockDim.x >> 5) - 1;
     const unsigned long long n_tiles = (bytes + tile_bytes - 1) / tile_bytes;
+    const unsigned hint = chunk >> 16;   // bit 0: L2 evict_first on the loads
+    chunk &= 0xFFFFu;
 
     if (threadIdx.x == 0) {
         for (unsigned s = 0; s < stages; ++s) {
@@ -340,7 +367,11 @@ hbm_read_tma_kernel(const unsigned char* __restrict__ base, unsigned long long b
                 const unsigned long long left = bytes - off;
                 const unsigned nb = left < tile_bytes ? (unsigned)left : tile_bytes;
                 mbar_expect_tx(&full_bar[stage], nb);  // release: publishes tile_of[stage]
-                tma_load_1d(ring + (size_t)stage * tile_bytes, base + off, nb, &full_bar[stage]);
+                if (hint & 1u)
+                    tma_load_1d_hint(ring + (size_t)stage * tile_bytes, base + off, nb, &full_bar[stage],
+                                     l2_policy_evict_first());
+                else
+                    tma_load_1d(ring + (size_t)stage * tile_bytes, base + off, nb, &full_bar[stage]);
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -419,6 +450,10 @@ hbm_copy_tma_kernel(unsigned char* __restrict__ dst, const unsigned char* __rest
     if (threadIdx.x != 0) return;
     for (unsigned s = 0; s < stages; ++s) mbar_init(&full_bar[s], 1);
     mbar_fence_init();
+    // bit 0: evict_first loads, bit 1: evict_first stores, bit 2: evict_last stores
+    const unsigned hint = chunk >> 16;
+    chunk &= 0xFFFFu;
+    const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
 
     const unsigned long long n_tiles = (bytes + tile_bytes - 1) / tile_bytes;
     unsigned long long fetched = 0;   // tiles this CTA has asked for
@@ -445,7 +480,8 @@ hbm_copy_tma_kernel(unsigned char* __restrict__ dst, const unsigned char* __rest
         const unsigned nb = tile_len(off);
         tile_of[st] = tile;
         mbar_expect_tx(&full_bar[st], nb);
-        tma_load_1d(ring + (size_t)st * tile_bytes, src + off, nb, &full_bar[st]);
+        if (hint & 1u) tma_load_1d_hint(ring + (size_t)st * tile_bytes, src + off, nb, &full_bar[st], pol_first);
+        else tma_load_1d(ring + (size_t)st * tile_bytes, src + off, nb, &full_bar[st]);
     };
     // prologue: fill the ring
     unsigned long long loaded = 0;
@@ -458,7 +494,10 @@ hbm_copy_tma_kernel(unsigned char* __restrict__ dst, const unsigned char* __rest
         const unsigned phase = (unsigned)((k / stages) & 1ull);
         mbar_wait(&full_bar[st], phase);
         const unsigned long long off = tile_of[st] * tile_bytes;
-        tma_store_1d(dst + off, ring + (size_t)st * tile_bytes, tile_len(off));
+        if (hint & 6u)
+            tma_store_1d_hint(dst + off, ring + (size_t)st * tile_bytes, tile_len(off), (hint & 2u) ? pol_first : pol_last);
+        else
+            tma_store_1d(dst + off, ring + (size_t)st * tile_bytes, tile_len(off));
         tma_commit();
         // refill the slot whose store was issued one trip ago
         if (k >= 1 && !dry) {
@@ -539,6 +578,7 @@ TmaTune read_tma_tune() {
     t.threads = (unsigned)env_int("CRO_TMA_READ_THREADS", 160);  // 1 producer + 4 consumer warps
     t.chunk = (unsigned)env_int("CRO_TMA_READ_CHUNK", 1);
     if (t.chunk < 1) t.chunk = 1;
+    t.chunk = (t.chunk & 0xFFFFu) | ((unsigned)env_int("CRO_TMA_READ_HINT", 0) << 16);
     if (t.stages > 16) t.stages = 16;
     return t;
 }
@@ -549,6 +589,7 @@ TmaTune copy_tma_tune() {
     t.threads = 32;
     t.chunk = (unsigned)env_int("CRO_TMA_COPY_CHUNK", 1);
     if (t.chunk < 1) t.chunk = 1;
+    t.chunk = (t.chunk & 0xFFFFu) | ((unsigned)env_int("CRO_TMA_COPY_HINT", 0) << 16);
     if (t.stages > 16) t.stages = 16;
     return t;
 }

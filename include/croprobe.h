@@ -339,6 +339,29 @@ int  cro_cm_check_adding_resources(const char *machine_body, const char *existin
 int  cro_reconcile_attach(cro_ctx *ctx, const char *in_json,
                           char *buf, size_t cap, size_t *len);
 
+/* ---- detach-side pre-flight (the step on the other side of the path) ------ */
+
+/* Parse + decision of utils.CheckNoGPULoads (internal/utils/gpus.go:145-186)
+ * over the output of `nvidia-smi --query-compute-apps=gpu_uuid,process_name`.
+ * driver_enabled != 0: OCP branch (any load on the node); 0: RKE2 branch (only
+ * loads on target_uuid).  CRO_OK = no load; CRO_ERR_EXEC = the reference's
+ * error text in err_buf. */
+int  cro_check_no_gpu_loads(const char *std_out, const char *std_err, const char *exec_err,
+                            const char *pod_name, const char *node_name, const char *target_uuid,
+                            int driver_enabled, char *err_buf, size_t err_cap);
+/* checkGPUDrainStatus (internal/utils/gpus.go:964-1012) over `nvidia-smi drain -p <bus> -q`. */
+int  cro_check_gpu_drain_status(const char *std_out, const char *std_err, const char *exec_err,
+                                const char *node_name, const char *bus_id, int *draining,
+                                char *err_buf, size_t err_cap);
+/* Decision after the open-file scan (gpus.go:468-473, :629-634; RKE2 flavour :286-291). */
+int  cro_check_device_file_scan(const char *std_out, const char *std_err, const char *exec_err, int rke2,
+                                char *err_buf, size_t err_cap);
+/* Native replacement of the fd-scan shell scripts (gpus.go:236-260, 441-457):
+ * prints what the script would print for `target` (e.g. "/dev/nvidia0").
+ * proc_root NULL = "/proc". */
+int  cro_scan_device_file_holders(const char *proc_root, const char *target, int rke2,
+                                  char *buf, size_t cap, size_t *len);
+
 /* ---- the caller of the hot path: both reconcilers over an in-memory API --- */
 
 /*

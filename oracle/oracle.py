@@ -316,6 +316,78 @@ def fm_scale_up_response_to_ids(body: str, name: str, spec_type: str, spec_model
     return "", "", "can not find the added gpu when using FM to add gpu"
 
 
+def check_no_gpu_loads(std_out: str, std_err: str, exec_err: Optional[str], pod_name: str, node_name: str,
+                       target_uuid: Optional[str], driver_enabled: bool) -> str:
+    """internal/utils/gpus.go:145-186 (parse + decision of CheckNoGPULoads).  Returns the error text."""
+    if go_trim_space(std_out) == "No devices were found":
+        return ""
+    if std_err != "" or exec_err is not None:
+        return "run nvidia-smi in pod '%s' to check gpu loads failed: '%s', stderr: '%s', stdout: '%s'" % (
+            pod_name, exec_err if exec_err is not None else "<nil>", std_err, std_out)
+    apps = []
+    for line in go_trim_space(std_out).split("\n"):
+        if line == "":
+            continue
+        parts = line.split(",")
+        if len(parts) < 2:
+            return "runtime error: index out of range [1] with length %d" % len(parts)
+        apps.append((go_trim_space(parts[0]), go_trim_space(parts[1])))
+    listed = "[" + " ".join("GPUUUID: '%s', ProcessName: '%s'" % a for a in apps) + "]"   # %v + String() :50-52
+    if not driver_enabled:
+        if target_uuid is None:
+            return "runtime error: invalid memory address or nil pointer dereference"
+        if any(a[0] == target_uuid for a in apps):
+            return "found gpu load on gpu '%s': %s" % (target_uuid, listed)
+        return ""
+    if apps:
+        return "found gpu loads on node '%s': '%s'" % (node_name, listed)
+    return ""
+
+
+def check_gpu_drain_status(std_out: str, std_err: str, exec_err: Optional[str], node_name: str, bus_id: str):
+    """internal/utils/gpus.go:964-1012.  Returns (draining, error text)."""
+    def low(t: str) -> str:
+        return "".join(chr(ord(c) + 32) if "A" <= c <= "Z" else c for c in t)
+    bus = go_trim_space(bus_id)
+    if bus == "":
+        return False, "target GPU bus ID is empty"
+    if exec_err is not None or std_err != "":
+        return False, "check gpu drain status command failed: '%s', stderr: '%s', stdout: '%s'" % (
+            exec_err if exec_err is not None else "<nil>", std_err, std_out)
+    trimmed = go_trim_space(std_out)
+    if trimmed == "":
+        return False, "nvidia-smi drain query returned empty output (node=%s, busID=%s)" % (node_name, bus)
+    for line in trimmed.split("\n"):
+        lower = low(go_trim_space(line))
+        if "drain" not in lower:
+            continue
+        idx = lower.find(":")
+        if idx >= 0:
+            status = go_trim_space(lower[idx + 1:]).strip(".")
+            if "not draining" in status:
+                return False, ""
+            if "draining" in status:
+                return True, ""
+    return False, "nvidia-smi drain query did not contain recognizable drain state (node=%s, busID=%s, raw=%s)" % (
+        node_name, bus, trimmed)
+
+
+def check_device_file_scan(std_out: str, std_err: str, exec_err: Optional[str], rke2: bool = False) -> str:
+    """internal/utils/gpus.go:468-473 / :629-634 (OCP), :286-291 (RKE2)."""
+    e = exec_err if exec_err is not None else "<nil>"
+    if rke2:
+        if exec_err is not None or std_err != "":
+            return "deatch command 'check /dev/nvidiaX' failed: '%s', stderr: '%s', stdout: '%s'" % (e, std_err, std_out)
+        if std_out != "":
+            return "check /dev/nvidiaX command failed: /dev/nvidiaX is in use by one or more processes: %s" % std_out
+        return ""
+    if std_err != "" or exec_err is not None:
+        return "check /dev/nvidiaX command failed: '%s', stderr: '%s'" % (e, std_err)
+    if std_out != "":
+        return "check /dev/nvidiaX command failed: there is a process %s occupied the nvidiaX file" % std_out
+    return ""
+
+
 def cm_check_adding_resources(machine_body: str, existing_device_ids: List[str], spec_type: str, spec_model: str):
     """internal/cdi/fti/cm/client.go:432-459 (checkAddingResources), :485-499 (isSpecMatch),
     :501-509 (findAvailableDevice).  Returns (specUUID, deviceCount, deviceID, CDIDeviceID, err)."""
