@@ -1,0 +1,33 @@
+"""NVLink peer-read bandwidth by read-kernel variant (needs >= 2 GPUs).
+Runs cro_probe_all with CRO_P2P_READ_VARIANT = 1 (LDG.128), 3 (LDG.256), 2 (TMA bulk from peer memory)
+and unidirectional vs bidirectional peer copies through torch for context."""
+import importlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g
+
+g.build()
+cro = importlib.import_module("composable-resource-operator_b200")
+
+for variant, extra in ((3, {}), (1, {}), (2, {}), (2, {"CRO_TMA_READ_STAGES": 6, "CRO_TMA_READ_TILE": 32768}),
+                       (2, {"CRO_TMA_READ_STAGES": 3, "CRO_TMA_READ_TILE": 65536}), (1, {"CRO_READ_WAVES": 2})):
+    os.environ["CRO_P2P_READ_VARIANT"] = str(variant)
+    for k, v in extra.items():
+        os.environ[k] = str(v)
+    try:
+        with cro.ProbeContext(sweep_bytes=1 << 30, p2p_bytes=1 << 30, read_sweeps=1, copy_sweeps=1, latency_hops=1024) as c:
+            c.probe_all()
+            res = c.probe_all()
+            n = len(res)
+            bw = [[round(r.p2p_bytes / r.p2p_read_ns[j], 1) if r.p2p_read_ns[j] else None for j in range(n)] for r in res]
+            flat = [x for row in bw for x in row if x]
+            print(json.dumps({"variant": variant, "env": extra, "min": min(flat), "max": max(flat), "mean": round(sum(flat) / len(flat), 1),
+                              "status": [r.status for r in res]}), flush=True)
+    except Exception as e:
+        print(json.dumps({"variant": variant, "env": extra, "error": str(e)}), flush=True)
+    for k in extra:
+        os.environ.pop(k, None)
