@@ -114,7 +114,7 @@ EXPORTS = [
     "cro_sim_create", "cro_sim_destroy", "cro_sim_apply", "cro_sim_delete", "cro_sim_plant", "cro_sim_run",
     "cro_sim_reconcile_request", "cro_sim_dump", "cro_probe_begin", "cro_probe_end",
     "cro_check_no_gpu_loads", "cro_check_gpu_drain_status", "cro_check_device_file_scan",
-    "cro_scan_device_file_holders",
+    "cro_scan_device_file_holders", "cro_sim_reconcile_resource", "cro_sim_sync_upstream",
 ]
 
 
@@ -175,6 +175,8 @@ def _load() -> ctypes.CDLL:
         "cro_sim_run": (i32, [vp, ctypes.c_longlong] + out),
         "cro_sim_reconcile_request": (i32, [vp, c, c, sz]),
         "cro_sim_dump": (i32, [vp] + out),
+        "cro_sim_reconcile_resource": (i32, [vp, c, c, sz]),
+        "cro_sim_sync_upstream": (i32, [vp, c, ctypes.c_longlong, c, sz]),
         "cro_check_no_gpu_loads": (i32, [c, c, c, c, c, c, i32, c, sz]),
         "cro_check_gpu_drain_status": (i32, [c, c, c, c, c, ctypes.POINTER(i32), c, sz]),
         "cro_check_device_file_scan": (i32, [c, c, c, i32, c, sz]),
@@ -525,6 +527,16 @@ class Cluster:
     def reconcile_request(self, name: str) -> str:
         """One Reconcile of the request controller; returns the reconcile error ("" = nil)."""
         return self._err_call(lib.cro_sim_reconcile_request, name)
+
+    def reconcile_resource(self, name: str) -> str:
+        """One Reconcile of the ComposableResource controller; returns the reconcile error ("" = nil)."""
+        return self._err_call(lib.cro_sim_reconcile_resource, name)
+
+    def sync_upstream(self, devices: List[Dict], now_s: int) -> str:
+        """One UpstreamSyncer tick (upstreamsyncer_controller.go:77-136) at time now_s."""
+        err = ctypes.create_string_buffer(1024)
+        lib.cro_sim_sync_upstream(self.handle, _b(json.dumps(devices)), now_s, err, 1024)
+        return err.value.decode("utf-8", "replace")
 
     def run(self, max_reconciles: int = 0) -> Dict:
         rc, raw = _text_call(lib.cro_sim_run, self.handle, max_reconciles, cap=1 << 16)

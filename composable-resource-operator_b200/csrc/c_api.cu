@@ -662,6 +662,26 @@ int cro_sim_reconcile_request(cro_sim* s, const char* name, char* err_buf, size_
     copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
     return e.ok() ? CRO_OK : CRO_ERR_EXEC;
 }
+int cro_sim_reconcile_resource(cro_sim* s, const char* name, char* err_buf, size_t err_cap) {
+    if (!s || !name) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(s->mu);
+    controller::Error e = s->cluster->ReconcileResourceOnce(name);
+    copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
+    return e.ok() ? CRO_OK : CRO_ERR_EXEC;
+}
+int cro_sim_sync_upstream(cro_sim* s, const char* devices_json, long long now_s, char* err_buf, size_t err_cap) {
+    if (!s || !devices_json) return CRO_ERR_INVALID_ARG;
+    std::string perr;
+    gojson::ValuePtr v = gojson::parse(devices_json, &perr);
+    if (!v) {
+        copy_out("failed to fetch data from upstream server: " + perr, err_buf, err_cap, nullptr);
+        return CRO_ERR_PARSE;
+    }
+    std::lock_guard<std::mutex> g(s->mu);
+    controller::Error e = s->cluster->SyncUpstream(*v, now_s);
+    copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
+    return e.ok() ? CRO_OK : CRO_ERR_EXEC;
+}
 int cro_sim_dump(cro_sim* s, char* buf, size_t cap, size_t* len) {
     if (!s) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(s->mu);

@@ -968,6 +968,58 @@ void Cluster::releaseDevice(int dev) {
     }
 }
 
+// =====================================================================================
+// UpstreamSyncer  (internal/controller/upstreamsyncer_controller.go:77-159)
+// =====================================================================================
+// devices: what CdiProvider.GetResources() returned ([]cdi.DeviceInfo, internal/cdi/client.go:25-32) —
+// or, on a node-local agent, the gathered probe results: a device the node can enumerate and probe
+// but no ComposableResource owns is exactly the drift this loop repairs.
+Error Cluster::SyncUpstream(const gojson::Value& devices, long long now_s) {
+    if (devices.kind != gojson::Value::Array) return Error::New("failed to fetch data from upstream server: not a device list");
+    std::set<std::string> existingDeviceIDs;                                   // :88-93
+    for (const auto& kv : resources_)
+        if (!kv.second.obj.Status.DeviceID.empty()) existingDeviceIDs.insert(kv.second.obj.Status.DeviceID);
+    std::set<std::string> upstream;
+    for (const auto& d : devices.arr) {                                        // :95-121
+        const std::string deviceID = d->get_string("device_id");
+        upstream.insert(deviceID);
+        if (existingDeviceIDs.count(deviceID)) {
+            missing_devices_.erase(deviceID);
+            continue;
+        }
+        auto it = missing_devices_.find(deviceID);
+        if (it == missing_devices_.end()) {
+            missing_devices_[deviceID] = now_s;                                // start tracking
+        } else if (now_s - it->second > 10 * 60) {                             // missingDeviceGracePeriod :37
+            // createDetachCR :138-159.  GenerateName is a full "gpu-<uuid4>", so the API server
+            // appends 5 more characters.
+            StoredResource s;
+            static const char alnum[] = "bcdfghjklmnpqrstvwxz2456789";
+            std::string name = GenerateComposableResourceName("gpu");
+            for (int k = 0; k < 5; ++k) name.push_back(alnum[rng_() % (sizeof alnum - 1)]);
+            s.obj.Name = name;
+            s.obj.Labels["cohdi.io/ready-to-detach-device-id"] = deviceID;
+            s.obj.Labels["cohdi.io/ready-to-detach-cdi-device-id"] = d->get_string("cdi_device_id");
+            s.obj.Spec.Type = d->get_string("device_type");
+            s.obj.Spec.Model = d->get_string("model");
+            s.obj.Spec.TargetNode = d->get_string("node_name");
+            s.obj.Spec.ForceDetach = false;
+            attached_.insert(name);   // the device IS on the node: that is the premise of the repair
+            createResource(s);
+            missing_devices_.erase(deviceID);
+        }
+    }
+    for (auto it = missing_devices_.begin(); it != missing_devices_.end();)   // :123-133
+        it = upstream.count(it->first) ? std::next(it) : missing_devices_.erase(it);
+    return Error::Nil();
+}
+
+Error Cluster::ReconcileResourceOnce(const std::string& name) {
+    long long rq = 0;
+    ++stats.resource_reconciles;
+    return reconcileResource(name, &rq);
+}
+
 // ---- event loop ----------------------------------------------------------------------
 void Cluster::Run(long long max_reconciles) {
     using clk = std::chrono::steady_clock;
@@ -1040,6 +1092,9 @@ std::string Cluster::DumpJSON() const {
         w.end_array();
         w.end_object();
     }
+    w.end_object();
+    w.key("missing_devices").begin_object();
+    for (const auto& kv : missing_devices_) w.key(kv.first.c_str()).value(kv.second);
     w.end_object();
     w.key("resources").begin_object();
     for (const auto& kv : resources_) {

@@ -119,6 +119,9 @@ public:
     void Run(long long max_reconciles);
     // exactly one Reconcile of the request controller on `name` (the reference's tests drive it this way)
     Error ReconcileRequestOnce(const std::string& name);
+    Error ReconcileResourceOnce(const std::string& name);
+    // one tick of the UpstreamSyncer (upstreamsyncer_controller.go:77-136) at time now_s
+    Error SyncUpstream(const gojson::Value& devices, long long now_s);
 
     std::string DumpJSON() const;
     std::string StatsJSON() const;
@@ -156,6 +159,7 @@ private:
     std::map<std::string, StoredResource> resources_;
     std::vector<std::string> uuids_;
     std::set<std::string> attached_;                            // resource names the fake fabric has attached
+    std::map<std::string, long long> missing_devices_;          // UpstreamSyncer.missingDevices: id -> first seen (s)
     std::map<std::string, long long> cdi_serial_;               // per request: next res-<req>-<k>
     std::deque<std::string> req_queue_, res_queue_;
     std::set<std::string> req_queued_, res_queued_;

@@ -386,6 +386,12 @@ int  cro_sim_plant(cro_sim *sim, const char *object_json, char *err_buf, size_t 
 int  cro_sim_run(cro_sim *sim, long long max_reconciles, char *buf, size_t cap, size_t *len);
 /* exactly one Reconcile of the request controller (how the reference's tests drive it) */
 int  cro_sim_reconcile_request(cro_sim *sim, const char *name, char *err_buf, size_t err_cap);
+int  cro_sim_reconcile_resource(cro_sim *sim, const char *name, char *err_buf, size_t err_cap);
+/* One tick of the UpstreamSyncer (internal/controller/upstreamsyncer_controller.go:77-159) at time
+ * now_s.  devices_json: [{"node_name","machine_uuid","device_type","model","device_id","cdi_device_id"}]
+ * (cdi.DeviceInfo, internal/cdi/client.go:25-32) — from the fabric, or from the gathered probe
+ * results: a device the node can probe but no ComposableResource owns is the drift it repairs. */
+int  cro_sim_sync_upstream(cro_sim *sim, const char *devices_json, long long now_s, char *err_buf, size_t err_cap);
 int  cro_sim_dump(cro_sim *sim, char *buf, size_t cap, size_t *len);
 
 /* ---- diagnostics --------------------------------------------------------- */
