@@ -115,6 +115,7 @@ EXPORTS = [
     "cro_sim_reconcile_request", "cro_sim_dump", "cro_probe_begin", "cro_probe_end",
     "cro_check_no_gpu_loads", "cro_check_gpu_drain_status", "cro_check_device_file_scan",
     "cro_scan_device_file_holders", "cro_sim_reconcile_resource", "cro_sim_sync_upstream",
+    "cro_fabric_check_resource", "cro_fabric_get_resources",
 ]
 
 
@@ -175,6 +176,8 @@ def _load() -> ctypes.CDLL:
         "cro_sim_run": (i32, [vp, ctypes.c_longlong] + out),
         "cro_sim_reconcile_request": (i32, [vp, c, c, sz]),
         "cro_sim_dump": (i32, [vp] + out),
+        "cro_fabric_check_resource": (i32, [c, c, c, c, c, c, sz]),
+        "cro_fabric_get_resources": (i32, [c, c, c, c] + out),
         "cro_sim_reconcile_resource": (i32, [vp, c, c, sz]),
         "cro_sim_sync_upstream": (i32, [vp, c, ctypes.c_longlong, c, sz]),
         "cro_check_no_gpu_loads": (i32, [c, c, c, c, c, c, i32, c, sz]),
@@ -453,6 +456,18 @@ class ProbeContext:
 
     def launch_count(self) -> int:
         return int(lib.cro_launch_count(self.handle))
+
+
+def fabric_check_resource(kind: str, machine_body: str, res_type: str, model: str, device_id: str) -> str:
+    """CdiProvider.CheckResource decision (fm/client.go:314-359, cm/client.go:262-304); "" = healthy."""
+    err = ctypes.create_string_buffer(2048)
+    lib.cro_fabric_check_resource(_b(kind), _b(machine_body), _b(res_type), _b(model), _b(device_id), err, 2048)
+    return err.value.decode("utf-8", "surrogateescape")
+
+
+def fabric_get_resources(kind: str, machine_body: str, node_name: str, machine_uuid: str) -> List[Dict]:
+    """CdiProvider.GetResources decode for one node (fm/client.go:385-410, cm/client.go:335-343)."""
+    return json.loads(_text(lib.cro_fabric_get_resources, _b(kind), _b(machine_body), _b(node_name), _b(machine_uuid)))
 
 
 def CheckNoGPULoadsFromOutput(std_out: str, std_err: str, exec_err: Optional[str], pod_name: str, node_name: str,

@@ -11,6 +11,7 @@
 #include "reconcile.hpp"
 #include "cluster.hpp"
 #include "detach.hpp"
+#include "fabric.hpp"
 
 using namespace cro;
 
@@ -569,6 +570,34 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
     if (node.probed) w.key("probe").string_map(probe_annotations(node.probe_result));
     w.end_object();
     return copy_out(w.str(), buf, cap, len);
+}
+
+// ---- fabric wire codec ---------------------------------------------------------------
+
+int cro_fabric_check_resource(const char* kind, const char* machine_body, const char* res_type, const char* model,
+                              const char* device_id, char* err_buf, size_t err_cap) {
+    if (!kind || !machine_body) return CRO_ERR_INVALID_ARG;
+    controller::Error e;
+    if (S(kind) == "fm") e = fabric::FMCheckResource(machine_body, S(res_type), S(model), S(device_id));
+    else if (S(kind) == "cm") e = fabric::CMCheckResource(machine_body, S(res_type), S(model), S(device_id));
+    else return CRO_ERR_INVALID_ARG;
+    copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
+    return e.ok() ? CRO_OK : CRO_ERR_EXEC;
+}
+
+int cro_fabric_get_resources(const char* kind, const char* machine_body, const char* node_name, const char* machine_uuid,
+                             char* buf, size_t cap, size_t* len) {
+    if (!kind || !machine_body) return CRO_ERR_INVALID_ARG;
+    std::vector<fabric::DeviceInfo> v;
+    controller::Error e;
+    if (S(kind) == "fm") e = fabric::FMGetResources(machine_body, S(node_name), S(machine_uuid), &v);
+    else if (S(kind) == "cm") e = fabric::CMGetResources(machine_body, S(node_name), S(machine_uuid), &v);
+    else return CRO_ERR_INVALID_ARG;
+    if (!e.ok()) {
+        copy_out(e.msg, buf, cap, len);
+        return CRO_ERR_PARSE;
+    }
+    return copy_out(fabric::DeviceInfosToJson(v), buf, cap, len);
 }
 
 // ---- detach-side pre-flight -------------------------------------------------------

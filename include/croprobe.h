@@ -339,6 +339,19 @@ int  cro_cm_check_adding_resources(const char *machine_body, const char *existin
 int  cro_reconcile_attach(cro_ctx *ctx, const char *in_json,
                           char *buf, size_t cap, size_t *len);
 
+/* ---- fabric wire codec (response side) ------------------------------------ */
+
+/* CdiProvider.CheckResource decision over the GET-machine body.  kind "fm":
+ * internal/cdi/fti/fm/client.go:314-359; kind "cm": internal/cdi/fti/cm/client.go:262-304.
+ * CRO_OK = healthy; CRO_ERR_EXEC = the reference's error text in err_buf. */
+int  cro_fabric_check_resource(const char *kind, const char *machine_body, const char *res_type,
+                               const char *model, const char *device_id, char *err_buf, size_t err_cap);
+/* CdiProvider.GetResources decode for one node's machine (fm/client.go:385-410,
+ * cm/client.go:335-343): JSON array of cdi.DeviceInfo
+ * {"node_name","machine_uuid","device_type","model","device_id","cdi_device_id"}. */
+int  cro_fabric_get_resources(const char *kind, const char *machine_body, const char *node_name,
+                              const char *machine_uuid, char *buf, size_t cap, size_t *len);
+
 /* ---- detach-side pre-flight (the step on the other side of the path) ------ */
 
 /* Parse + decision of utils.CheckNoGPULoads (internal/utils/gpus.go:145-186)

@@ -316,6 +316,76 @@ def fm_scale_up_response_to_ids(body: str, name: str, spec_type: str, spec_model
     return "", "", "can not find the added gpu when using FM to add gpu"
 
 
+def _op_status(op: str, device_id: str, where: str) -> str:
+    if op == "":
+        return "runtime error: slice bounds out of range [:1] with length 0"
+    if op[:1] == "0":
+        return ""
+    if op[:1] == "1":
+        return "the target gpu '%s' is showing a Warning status in %s" % (device_id, where)
+    if op[:1] == "2":
+        return "the target gpu '%s' is showing a Critical status in %s" % (device_id, where)
+    return "the target gpu '%s' has unknown status '%s' in %s" % (device_id, op, where)
+
+
+def fabric_check_resource(kind: str, body: str, spec_type: str, spec_model: str, device_id: str) -> str:
+    """FM: internal/cdi/fti/fm/client.go:314-359.  CM: internal/cdi/fti/cm/client.go:262-304."""
+    data = json.loads(body)
+    if kind == "fm":
+        machines = (data.get("data") or {}).get("machines") or []
+        if not machines:
+            return "runtime error: index out of range [0] with length 0"
+        for r in machines[0].get("resources") or []:
+            if r.get("res_type", "") != spec_type:
+                continue
+            for c in ((r.get("res_spec") or {}).get("condition") or []):
+                if c.get("column") != "model" or c.get("operator") != "eq" or c.get("value") != spec_model:
+                    continue
+                if r.get("res_serial_num", "") == device_id:
+                    return _op_status(r.get("res_op_status", ""), device_id, "FM")
+    else:
+        specs = ((((data.get("data") or {}).get("cluster") or {}).get("machine") or {}).get("resspecs")) or []
+        for s in specs:
+            if s.get("type", "") != spec_type:
+                continue
+            for c in ((((s.get("selector") or {}).get("expression") or {}).get("conditions")) or []):
+                if c.get("column") != "model" or c.get("operator") != "eq" or c.get("value") != spec_model:
+                    continue
+                for d in s.get("devices") or []:
+                    if d.get("device_id", "") == device_id:
+                        return _op_status((d.get("detail") or {}).get("res_op_status", ""), device_id, "CM")
+    return "the target device '%s' cannot be found in CDI system" % device_id
+
+
+def fabric_get_resources(kind: str, body: str, node: str, machine_uuid: str) -> List[Dict[str, str]]:
+    """FM: internal/cdi/fti/fm/client.go:385-410.  CM: internal/cdi/fti/cm/client.go:335-343."""
+    data = json.loads(body)
+    out = []
+    if kind == "fm":
+        machines = (data.get("data") or {}).get("machines") or []
+        if not machines:
+            return out
+        for r in machines[0].get("resources") or []:
+            if r.get("res_type", "") != "gpu":
+                continue
+            model = ""
+            for c in ((r.get("res_spec") or {}).get("condition") or []):
+                if c.get("column") == "model" and c.get("operator") == "eq":
+                    model = c.get("value", "")
+                    break
+            out.append({"node_name": node, "machine_uuid": machine_uuid, "device_type": "gpu", "model": model,
+                        "device_id": r.get("res_serial_num", ""), "cdi_device_id": r.get("res_uuid", "")})
+    else:
+        specs = ((((data.get("data") or {}).get("cluster") or {}).get("machine") or {}).get("resspecs")) or []
+        for s in specs:
+            if s.get("type", "") != "gpu":
+                continue
+            for d in s.get("devices") or []:
+                out.append({"node_name": node, "machine_uuid": machine_uuid, "device_type": "gpu", "model": "",
+                            "device_id": d.get("device_id", ""), "cdi_device_id": (d.get("detail") or {}).get("res_uuid", "")})
+    return out
+
+
 def check_no_gpu_loads(std_out: str, std_err: str, exec_err: Optional[str], pod_name: str, node_name: str,
                        target_uuid: Optional[str], driver_enabled: bool) -> str:
     """internal/utils/gpus.go:145-186 (parse + decision of CheckNoGPULoads).  Returns the error text."""
