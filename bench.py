@@ -377,8 +377,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     # NCCL prints "NCCL version ..." on STDOUT when NCCL_DEBUG >= VERSION; stdout must carry the JSON line only
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-        os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
+    # (an /etc/nccl.conf can switch that on even with the variable unset; the environment wins over the file)
+    if "NCCL_DEBUG" not in os.environ:
+        os.environ["NCCL_DEBUG"] = "WARN"
+    elif os.environ["NCCL_DEBUG"].upper() in ("VERSION", "INFO", "TRACE"):
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

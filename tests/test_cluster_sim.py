@@ -96,6 +96,46 @@ def test_size_shrink_evicts_by_priority(cro):
         assert st["state"] == "Updating" and list(st["resources"]) == ["gpu-a"]
 
 
+CR0, CR1 = "gpu-00000000-temp-uuid-0000-000000000000", "gpu-00000000-temp-uuid-0000-000000000001"
+SPEC_CHANGE_KATS = [  # (cite, base policy, spec overrides, children must be dropped?, expected used nodes)
+    (":1019 type, samenode", "samenode", {"type": "cxlmemory"}, True, ["worker-0", "worker-0"]),
+    (":1033 model, samenode", "samenode", {"model": "NVIDIA-H100-PCIE-80GB"}, True, ["worker-0", "worker-0"]),
+    (":1047 size 3, samenode", "samenode", {"size": 3}, False, ["worker-0", "worker-0", "worker-0"]),
+    (":1060 ForceDetach, samenode", "samenode", {"force_detach": True}, True, ["worker-0", "worker-0"]),
+    (":1074 policy -> differentnode", "samenode", {"allocation_policy": "differentnode"}, False, ["worker-0", "worker-1"]),
+    (":1087 TargetNode -> worker-1", "samenode", {"target_node": "worker-1"}, True, ["worker-1", "worker-1"]),
+    (":1101 OtherSpec, samenode", "samenode", {"other_spec": BIG}, True, ["worker-6", "worker-6"]),
+    (":1121 type, differentnode", "differentnode", {"type": "cxlmemory"}, True, ["worker-0", "worker-1"]),
+    (":1135 model, differentnode", "differentnode", {"model": "NVIDIA-H100-PCIE-80GB"}, True, ["worker-0", "worker-1"]),
+    (":1149 size 3, differentnode", "differentnode", {"size": 3}, False, ["worker-0", "worker-1", "worker-2"]),
+    (":1162 ForceDetach, differentnode", "differentnode", {"force_detach": True}, True, ["worker-0", "worker-1"]),
+    (":1176 policy -> samenode", "differentnode", {"allocation_policy": "samenode"}, False, ["worker-0", "worker-0"]),
+    (":1189 OtherSpec, differentnode", "differentnode", {"other_spec": BIG}, True, ["worker-6", "worker-7"]),
+]
+
+
+@pytest.mark.parametrize("cite,policy,over,dropped,expect", SPEC_CHANGE_KATS, ids=[k[0] for k in SPEC_CHANGE_KATS])
+def test_spec_change_kats(cro, cite, policy, over, dropped, expect):
+    """'should succeed when user changes the ...' (composabilityrequest_controller_test.go:1019-1205): two children
+    exist from the old spec; after one NodeAllocating reconcile the listed nodes are used and, where the change
+    invalidates them, neither old child survives in Status.Resources."""
+    with cro.Cluster({"nodes": NODES}) as c:
+        old = dict(BASE, allocation_policy=policy)
+        nodes = ["worker-0", "worker-0"] if policy == "samenode" else ["worker-0", "worker-1"]
+        c.plant({"kind": "ComposabilityRequest", "name": "r", "resource": dict(old, **over),
+                 "status": {"state": "NodeAllocating", "scalarResource": old,
+                            "resources": {CR0: {"node_name": nodes[0]}, CR1: {"node_name": nodes[1]}}}})
+        for name, node in zip((CR0, CR1), nodes):
+            c.plant({"kind": "ComposableResource", "name": name, "labels": {"app.kubernetes.io/managed-by": "r"},
+                     "spec": {"type": old["type"], "model": old["model"], "target_node": node}, "status": {"state": ""}})
+        assert c.reconcile_request("r") == ""
+        st = c.dump()["requests"]["r"]["status"]
+        assert st["state"] == "Updating"
+        assert sorted(x["node_name"] for x in st["resources"].values()) == sorted(expect)
+        if dropped:
+            assert CR0 not in st["resources"] and CR1 not in st["resources"]
+
+
 def test_admission_rules(cro):
     with cro.Cluster({"nodes": NODES}) as c:
         assert c.apply("a", dict(BASE, allocation_policy="differentnode", target_node="worker-0")) == \
