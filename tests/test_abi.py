@@ -60,6 +60,23 @@ def test_strerror_and_version(cro):
     assert "sm_100a" in cro.version()
 
 
+def build_c_harness():
+    """gcc (plain C, not nvcc / g++) against include/croprobe.h, linked to the shared library like cgo does."""
+    exe = os.path.join(ROOT, "tests", "_c_abi_harness")
+    src = os.path.join(ROOT, "tests", "c_abi_harness.c")
+    pkg = os.path.join(ROOT, "composable-resource-operator_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L" + pkg, "-lcroprobe", "-Wl,-rpath," + pkg])
+    return exe
+
+
+def test_c_harness_links_and_runs_like_cgo(cro):
+    exe = build_c_harness()
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "c abi harness ok" in out.stdout
+
+
 def test_product_never_touches_the_oracle():
     """The shipped path must not include, link or import anything under oracle/."""
     pkg = os.path.join(ROOT, "composable-resource-operator_b200")

@@ -207,6 +207,14 @@ def test_multi_device_probe_all(cro, coracle):
                 assert r.p2p_checksum_xor[j] == coracle.checksum(res[j].seed, 0, (64 << 20) // 8)[0]
 
 
+def test_c_harness_on_gpu(cro):
+    """The plain-C caller (what cgo compiles to) runs a probe + emit through the same ABI."""
+    from test_abi import build_c_harness
+    out = subprocess.run([build_c_harness(), "gpu"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "gpu ok: GPU-" in out.stdout and "cohdi.io/probe-status" in out.stdout
+
+
 def test_async_probe_begin_end(cro, coracle):
     """cro_probe_begin / cro_probe_end: same result as the synchronous probe; a sweep in between drains it."""
     with cro.ProbeContext(sweep_bytes=32 << 20, devices=[0], read_sweeps=2, copy_sweeps=1) as c:
