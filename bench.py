@@ -46,6 +46,19 @@ WORKLOAD = "configs[1]: 1xB200 attach — HBM probe (fill + 5 read + 5 copy swee
 CANNED_UUID = "GPU-device00-uuid-temp-0000-000000000000"
 
 
+_REAL_STDOUT = None
+
+
+def emit(line) -> None:
+    """Writes the one JSON line to the process's real stdout (see main())."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -176,7 +189,7 @@ def run_reference(args, rank, world):
         "all_threads": all_threads,
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(budget_s: float = 12.0):
@@ -356,7 +369,7 @@ def run_ours(args, rank, local_rank, world):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if dist:
         dist.barrier()
@@ -376,12 +389,13 @@ def main():
     ap.add_argument("--copy-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    # NCCL prints "NCCL version ..." on STDOUT when NCCL_DEBUG >= VERSION; stdout must carry the JSON line only
-    # (an /etc/nccl.conf can switch that on even with the variable unset; the environment wins over the file)
-    if "NCCL_DEBUG" not in os.environ:
-        os.environ["NCCL_DEBUG"] = "WARN"
-    elif os.environ["NCCL_DEBUG"].upper() in ("VERSION", "INFO", "TRACE"):
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout must carry the ONE JSON line and nothing else, but libraries print there too (NCCL writes
+    # "NCCL version ..." with printf at init).  Keep the real stdout aside and point fd 1 at stderr for
+    # everything else; emit() writes the JSON line to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
