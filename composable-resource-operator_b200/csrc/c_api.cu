@@ -414,6 +414,26 @@ public:
         *cdi = p_->get_string("cdi_device_id");
         return controller::Error::Nil();
     }
+    // Online state: the health decision over the GET-machine body (fabric codec), or a canned error
+    controller::Error CheckResource(const controller::ComposableResource& inst) override {
+        if (!p_) return controller::Error::Nil();
+        const std::string canned = p_->get_string("check_resource_error");
+        if (!canned.empty()) return controller::Error::New(canned);
+        const gojson::Value* fm = p_->get("fm_machine_body");
+        if (fm && fm->kind == gojson::Value::String)
+            return fabric::FMCheckResource(fm->str, inst.Spec.Type, inst.Spec.Model, inst.Status.DeviceID);
+        const gojson::Value* cm = p_->get("cm_check_body");
+        if (cm && cm->kind == gojson::Value::String)
+            return fabric::CMCheckResource(cm->str, inst.Spec.Type, inst.Spec.Model, inst.Status.DeviceID);
+        return controller::Error::Nil();
+    }
+    controller::Error RemoveResource(const controller::ComposableResource&) override {
+        const gojson::Value* rm = p_ ? p_->get("remove") : nullptr;
+        if (!rm) return controller::Error::Nil();
+        if (rm->get_bool("waiting")) return controller::Error::New(controller::ErrWaitingDeviceDetaching);
+        const std::string err = rm->get_string("error");
+        return err.empty() ? controller::Error::Nil() : controller::Error::New(err);
+    }
 
 private:
     const gojson::Value* p_;
@@ -438,11 +458,50 @@ public:
         std::vector<std::string> uuids;
         return enumerate(node, &uuids);
     }
+    // ---- detach side: the text rules of csrc/detach.cpp over injected command output ----
+    static bool io(const gojson::Value* v, std::string* so, std::string* se, std::string* ee_s, const char** ee) {
+        if (!v || v->kind != gojson::Value::Object) return false;
+        *so = v->get_string("stdout");
+        *se = v->get_string("stderr");
+        const gojson::Value* e = v->get("exec_err");
+        *ee = nullptr;
+        if (e && e->kind == gojson::Value::String) { *ee_s = e->str; *ee = ee_s->c_str(); }
+        return true;
+    }
+    controller::Error CheckNoGPULoadsFor(const std::string& node, const std::string* uuid) override {
+        std::string so, se, ee_s;
+        const char* ee;
+        const gojson::Value* lc = in_->get("load_check");
+        if (!io(lc, &so, &se, &ee_s, &ee)) return controller::Error::Nil();
+        return detach::CheckNoGPULoadsFromOutput(so, se, ee, lc->get_string("pod_name", "nvidia-driver-daemonset-test"), node, uuid,
+                                                 lc->get_bool("driver_enabled", true));
+    }
+    controller::Error CreateDeviceTaint(const controller::ComposableResource&) override {
+        const std::string e = in_->get_string("create_taint_error");
+        return e.empty() ? controller::Error::Nil() : controller::Error::New(e);
+    }
+    controller::Error DeleteDeviceTaint(const controller::ComposableResource&) override {
+        const std::string e = in_->get_string("delete_taint_error");
+        return e.empty() ? controller::Error::Nil() : controller::Error::New(e);
+    }
+    controller::Error DrainGPU(const std::string&, const std::string&, const std::string&) override {
+        const gojson::Value* dr = in_->get("drain");
+        if (!dr) return controller::Error::Nil();
+        const std::string canned = dr->get_string("error");
+        if (!canned.empty()) return controller::Error::New(canned);
+        std::string so, se, ee_s;
+        const char* ee;
+        if (io(dr->get("fd_scan"), &so, &se, &ee_s, &ee))
+            return detach::CheckDeviceFileScanResult(so, se, ee, dr->get_bool("rke2"));
+        return controller::Error::Nil();
+    }
     controller::Error CheckGPUVisible(const std::string& type, const controller::ComposableResource& r,
                                       bool* visible) override {
         *visible = false;
         bool listed = false;
-        const gojson::Value* slices = in_->get("resource_slices");
+        // while detaching, the cluster is looked at AFTER the fabric removed the device
+        const bool after = r.Status.State == "Detaching";
+        const gojson::Value* slices = in_->get(after && in_->get("resource_slices_after_remove") ? "resource_slices_after_remove" : "resource_slices");
         if (type == "DRA" && slices && slices->kind == gojson::Value::Array) {
             // internal/utils/gpus.go:55-71
             for (const auto& rs : slices->arr) {
@@ -455,13 +514,13 @@ public:
             }
         } else {
             std::vector<std::string> uuids;
-            controller::Error e = enumerate(r.Spec.TargetNode, &uuids);
+            controller::Error e = enumerate(r.Spec.TargetNode, &uuids, after && in_->get("enumeration_after_remove") ? "enumeration_after_remove" : "enumeration");
             if (!e.ok()) return e;
             for (const std::string& u : uuids)
                 if (u == r.Status.DeviceID) listed = true;   // gpus.go:78-82
         }
         if (!listed) return controller::Error::Nil();
-        if (in_->get_bool("probe") && ctx_) {
+        if (in_->get_bool("probe") && ctx_ && !after) {
             // the strong check: the device must also deliver its HBM pattern
             int idx = -1;
             for (size_t i = 0; i < ctx_->devs.size(); ++i)
@@ -481,14 +540,14 @@ public:
     }
 
 private:
-    controller::Error enumerate(const std::string& node, std::vector<std::string>* uuids) {
+    controller::Error enumerate(const std::string& node, std::vector<std::string>* uuids, const char* key = "enumeration") {
         if (in_->get_bool("driver_pod_missing"))   // gpus.go:835
             return controller::Error::New(
                 "no Pod with label 'app.kubernetes.io/component=nvidia-driver' found on node " + node);
         std::string out, err;
         const char* exec_err = nullptr;
         std::string exec_err_s;
-        const gojson::Value* en = in_->get("enumeration");
+        const gojson::Value* en = in_->get(key);
         if (en && en->kind == gojson::Value::Object) {
             out = en->get_string("stdout");
             err = en->get_string("stderr");
@@ -557,12 +616,17 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
         err = rec.handleNoneState(&res, &result);
     } else if (res.Status.State == "Attaching") {
         err = rec.handleAttachingState(&res, type, &result);
+    } else if (res.Status.State == "Online") {
+        err = rec.handleOnlineState(&res, &result);
+    } else if (res.Status.State == "Detaching") {
+        err = rec.handleDetachingState(&res, type, &result);
     }
 
     gojson::Writer w;
     w.begin_object();
     w.key("status").raw(res.Status.MarshalJSON());
     w.field("requeue_after_s", result.RequeueAfterSeconds);
+    w.field("delete_requested", res.DeleteRequested);
     w.field("error", err.ok() ? std::string() : err.msg);
     w.key("status_updates").begin_array();
     for (const auto& s : rec.statusUpdates) w.raw(s.MarshalJSON());

@@ -718,7 +718,7 @@ public:
         c_->attached_.insert(inst.Name);
         return Error::Nil();
     }
-    Error RemoveResource(const controller::ComposableResource& inst) {
+    Error RemoveResource(const controller::ComposableResource& inst) override {
         c_->attached_.erase(inst.Name);
         return Error::Nil();
     }
@@ -829,9 +829,14 @@ public:
         } else if (st == "Attaching") {
             err = rec.handleAttachingState(&res, c_->deviceResourceType_, &result);
         } else if (st == "Online") {
-            err = handleOnlineState(&s, &result);
+            err = rec.handleOnlineState(&res, &result);
+            if (res.DeleteRequested) {   // r.Delete(resource) on itself (:298)
+                res.DeleteRequested = false;
+                c_->deleteResource(res.Name);
+                res.DeletionTimestampSet = true;
+            }
         } else if (st == "Detaching") {
-            err = handleDetachingState(&s, &result);
+            err = rec.handleDetachingState(&res, c_->deviceResourceType_, &result);
         } else if (st == "Deleting") {
             removeStr(&s.Finalizers, kFinalizer);   // :409-421
         }
@@ -844,54 +849,6 @@ public:
     }
 
 private:
-    Error handleOnlineState(StoredResource* s, controller::Result* result) {   // :289-318
-        controller::ComposableResource& res = s->obj;
-        if (res.DeletionTimestampSet) {
-            res.Status.State = "Detaching";
-            return Error::Nil();
-        }
-        auto lb = res.Labels.find(kReadyToDetach);
-        if (lb != res.Labels.end() && !lb->second.empty()) {
-            c_->deleteResource(res.Name);
-            s->obj.DeletionTimestampSet = true;
-            return Error::Nil();
-        }
-        res.Status.Error = "";   // CheckResource of the fake fabric reports nothing
-        result->RequeueAfterSeconds = 30;
-        return Error::Nil();
-    }
-
-    Error handleDetachingState(StoredResource* s, controller::Result* result) {   // :320-407
-        controller::ComposableResource& res = s->obj;
-        if (!res.Status.DeviceID.empty()) {
-            // CheckNoGPULoads / CreateDeviceTaint / DrainGPU: node-side shell orchestration, nil here
-            Error e = provider_.RemoveResource(res);
-            if (!e.ok()) {
-                if (e.msg == controller::ErrWaitingDeviceDetaching) {
-                    result->RequeueAfterSeconds = 30;
-                    return Error::Nil();
-                }
-                res.Status.Error = e.msg;
-                return e;
-            }
-            bool visible = false;
-            e = node_.CheckGPUVisible(c_->deviceResourceType_, res, &visible);
-            if (!e.ok()) {
-                res.Status.Error = e.msg;
-                return e;
-            }
-            if (visible) {
-                result->RequeueAfterSeconds = 3;
-                return Error::Nil();
-            }
-            res.Status.Error = "";
-            res.Status.DeviceID = "";
-            res.Status.CDIDeviceID = "";
-        }
-        res.Status.State = "Deleting";
-        return Error::Nil();
-    }
-
     Cluster* c_;
     SimProvider provider_;
     SimNodeOps node_;

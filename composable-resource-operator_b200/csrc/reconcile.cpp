@@ -220,5 +220,79 @@ Error ComposableResourceReconciler::handleAttachingState(ComposableResource* res
     return Error::Nil();
 }
 
+Error ComposableResourceReconciler::handleOnlineState(ComposableResource* resource, Result* result) {
+    *result = Result();
+    if (resource->DeletionTimestampSet) {   // :292-295
+        resource->Status.State = "Detaching";
+        statusUpdate(*resource);
+        return Error::Nil();
+    }
+    auto lb = resource->Labels.find("cohdi.io/ready-to-detach-device-id");
+    if (lb != resource->Labels.end() && !lb->second.empty()) {   // :297-302
+        resource->DeleteRequested = true;
+        return Error::Nil();
+    }
+    Error err = provider_->CheckResource(*resource);   // :305-315: recorded, never returned
+    resource->Status.Error = err.ok() ? std::string() : err.msg;
+    statusUpdate(*resource);
+    result->RequeueAfterSeconds = 30;
+    return Error::Nil();
+}
+
+Error ComposableResourceReconciler::handleDetachingState(ComposableResource* resource,
+                                                         const std::string& deviceResourceType,
+                                                         Result* result) {
+    *result = Result();
+    if (!resource->Status.DeviceID.empty()) {
+        if (!resource->Spec.ForceDetach) {   // :327-341
+            Error err = deviceResourceType == "DEVICE_PLUGIN"
+                            ? node_->CheckNoGPULoadsFor(resource->Spec.TargetNode, nullptr)
+                            : node_->CheckNoGPULoadsFor(resource->Spec.TargetNode, &resource->Status.DeviceID);
+            if (!err.ok()) return requeueOnErr(resource, err);
+        }
+        if (deviceResourceType == "DRA") {   // :344-348
+            Error err = node_->CreateDeviceTaint(*resource);
+            if (!err.ok()) return requeueOnErr(resource, err);
+        }
+        Error err = node_->DrainGPU(resource->Spec.TargetNode, resource->Status.DeviceID, deviceResourceType);   // :351
+        if (!err.ok()) return requeueOnErr(resource, err);
+        err = provider_->RemoveResource(*resource);   // :355-364
+        if (!err.ok()) {
+            if (err.msg == ErrWaitingDeviceDetaching) {
+                result->RequeueAfterSeconds = 30;
+                return Error::Nil();
+            }
+            return requeueOnErr(resource, err);
+        }
+        if (deviceResourceType == "DEVICE_PLUGIN") {   // :369-380: restart failures are fatal here
+            for (const char* ds : {"nvidia-device-plugin-daemonset", "nvidia-dcgm"}) {
+                err = node_->RestartDaemonset("nvidia-gpu-operator", ds);
+                if (!err.ok()) return requeueOnErr(resource, err);
+            }
+        } else {
+            err = node_->RestartDaemonset("nvidia-dra-driver-gpu", "nvidia-dra-driver-gpu-kubelet-plugin");
+            if (!err.ok()) return requeueOnErr(resource, err);
+        }
+        bool visible = false;   // :383-390
+        err = node_->CheckGPUVisible(deviceResourceType, *resource, &visible);
+        if (!err.ok()) return requeueOnErr(resource, err);
+        if (visible) {
+            result->RequeueAfterSeconds = 3;
+            return Error::Nil();
+        }
+        if (deviceResourceType == "DRA") {   // :393-397
+            err = node_->DeleteDeviceTaint(*resource);
+            if (!err.ok()) return requeueOnErr(resource, err);
+        }
+        resource->Status.Error = "";
+        resource->Status.DeviceID = "";
+        resource->Status.CDIDeviceID = "";
+        statusUpdate(*resource);
+    }
+    resource->Status.State = "Deleting";   // :405-406
+    statusUpdate(*resource);
+    return Error::Nil();
+}
+
 }  // namespace controller
 }  // namespace cro

@@ -41,6 +41,7 @@ struct ComposableResource {
     std::string Name;
     std::map<std::string, std::string> Labels;
     bool DeletionTimestampSet = false;
+    bool DeleteRequested = false;      // the reconciler called r.Delete(resource) on itself (:298)
     ComposableResourceSpec Spec;
     ComposableResourceStatus Status;
 };
@@ -49,12 +50,14 @@ struct Result {
     long long RequeueAfterSeconds = 0;
 };
 
-// internal/cdi/client.go:34-39 (only AddResource is on the attach path)
+// internal/cdi/client.go:34-39
 class CdiProvider {
 public:
     virtual ~CdiProvider() {}
     virtual Error AddResource(const ComposableResource& instance, std::string* deviceID,
                               std::string* CDIDeviceID) = 0;
+    virtual Error RemoveResource(const ComposableResource&) { return Error::Nil(); }
+    virtual Error CheckResource(const ComposableResource&) { return Error::Nil(); }
 };
 
 // The FM gate (fti/fm/client.go:184-213) over a ScaleUpResponse body.
@@ -87,6 +90,12 @@ public:
     virtual Error RunNvidiaSmi(const std::string& node) = 0;
     virtual Error CheckGPUVisible(const std::string& deviceResourceType,
                                   const ComposableResource& resource, bool* visible) = 0;
+    // detach side (internal/utils/gpus.go:88, 188, 691, 756); targetGPUUUID null = whole node
+    virtual Error CheckNoGPULoadsFor(const std::string& /*node*/, const std::string* /*targetGPUUUID*/) { return Error::Nil(); }
+    virtual Error CreateDeviceTaint(const ComposableResource&) { return Error::Nil(); }
+    virtual Error DeleteDeviceTaint(const ComposableResource&) { return Error::Nil(); }
+    virtual Error DrainGPU(const std::string& /*node*/, const std::string& /*deviceID*/,
+                           const std::string& /*deviceResourceType*/) { return Error::Nil(); }
 };
 
 class ComposableResourceReconciler {
@@ -96,6 +105,11 @@ public:
     Error handleNoneState(ComposableResource* resource, Result* result);
     // composableresource_controller.go:200-287
     Error handleAttachingState(ComposableResource* resource, const std::string& deviceResourceType,
+                               Result* result);
+    // composableresource_controller.go:289-318
+    Error handleOnlineState(ComposableResource* resource, Result* result);
+    // composableresource_controller.go:320-407
+    Error handleDetachingState(ComposableResource* resource, const std::string& deviceResourceType,
                                Result* result);
     // Every Status().Update the reference would issue, in order.
     std::vector<ComposableResourceStatus> statusUpdates;

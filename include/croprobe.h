@@ -322,17 +322,30 @@ int  cro_cm_check_adding_resources(const char *machine_body, const char *existin
 /* ---- reconcile step: the caller of the hot path -------------------------- */
 
 /*
- * One pass of ComposableResourceReconciler.handleAttachingState
- * (internal/controller/composableresource_controller.go:200-287) with the
- * CUDA probe in the RunNvidiaSmi / CheckGPUVisible slots.
+ * One Reconcile pass of ComposableResourceReconciler for the state in
+ * status.state: "" (handleNoneState :176-198), "Attaching" (handleAttachingState
+ * :200-287, the hot path, with the CUDA probe in the RunNvidiaSmi /
+ * CheckGPUVisible slots), "Online" (:289-318), "Detaching" (:320-407)
+ * (all in internal/controller/composableresource_controller.go).
  *
- * in_json:  {"name":..,"spec":{type,model,target_node,force_detach},
+ * in_json:  {"name":..,"spec":{type,model,target_node,force_detach},"labels":{..},
  *            "status":{state,error,device_id,cdi_device_id},
  *            "deleting":bool,
- *            "provider":{"device_id":..,"cdi_device_id":..,"error":..,"waiting":bool},
  *            "device_resource_type":"DEVICE_PLUGIN"|"DRA",
- *            "probe":bool}
- * out_json: {"status":{...},"requeue_after_s":N,"error":"..","probe":{...}}
+ *            "probe":bool,
+ *            "provider":{"device_id","cdi_device_id","error","waiting",          AddResource
+ *                        "fm_response_body" | "cm_machine_body"+"existing_device_ids",
+ *                        "check_resource_error" | "fm_machine_body" | "cm_check_body",   CheckResource
+ *                        "remove":{"waiting","error"}},                                   RemoveResource
+ *            what the node would have answered, when there is no live context:
+ *            "enumeration":{"stdout","stderr","exec_err"}, "enumeration_after_remove":{..},
+ *            "resource_slices":[..], "resource_slices_after_remove":[..],
+ *            "driver_pod_missing":bool, "daemonset_errors":{"ns/name":"error"},
+ *            "load_check":{"stdout","stderr","exec_err","pod_name","driver_enabled"},
+ *            "drain":{"error" | "fd_scan":{"stdout","stderr","exec_err"},"rke2":bool},
+ *            "create_taint_error","delete_taint_error"}
+ * out_json: {"status":{...},"requeue_after_s":N,"delete_requested":bool,"error":"..",
+ *            "status_updates":[...],"probe":{...}}
  * The status object inside out_json is byte-identical to json.Marshal of the
  * reference's ComposableResourceStatus after the same step.
  */

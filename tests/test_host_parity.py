@@ -26,7 +26,7 @@ def _request(kats, v):
         req["provider"] = {"fm_response_body": fx["fm_update_body"][v["fm_update"]]}
     else:
         req["provider"] = v.get("provider", {})
-    for k in ("enumeration", "driver_pod_missing", "resource_slices"):
+    for k in ("enumeration", "driver_pod_missing", "resource_slices", "daemonset_errors"):
         if k in v:
             req[k] = v[k]
     if "enumeration" not in req and not v.get("driver_pod_missing"):

@@ -44,6 +44,7 @@ def _attach_inputs(oracle, kats, v):
     en = v.get("enumeration", {})
     inp.std_out, inp.std_err, inp.exec_err = en.get("stdout", ""), en.get("stderr", ""), en.get("exec_err")
     inp.driver_pod_missing = v.get("driver_pod_missing", False)
+    inp.ds_err = dict(v.get("daemonset_errors", {}))
     if "resource_slices" in v:
         inp.slice_uuids = [d["attributes"]["uuid"] for rs in v["resource_slices"] for d in rs.get("devices", [])
                            if "uuid" in d.get("attributes", {})]
