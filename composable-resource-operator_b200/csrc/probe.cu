@@ -288,6 +288,7 @@ void ctx_destroy(cro_ctx* c) {
         cudaFree(d->d_gather);
         cudaFree(d->d_chase_next);
         cudaFree(d->d_chase_out);
+        if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
         for (cudaEvent_t e : d->evpool) cudaEventDestroy(e);
         cudaEventDestroy(d->ev0);
         cudaEventDestroy(d->ev1);
@@ -489,27 +490,69 @@ static int probe_enqueue(cro_ctx* c, Device* d, cro_probe_result* r) {
     }
     std::vector<cudaEvent_t>& ev = d->evpool;
 
-    size_t k = 0;
-    CU_TRY(c, cudaEventRecord(ev[k++], d->stream));
-    CU_TRY(c, launch_fill(d->plan, d->region, d->sweep_bytes, d->seed, d->stream));
-    d->filled = true;
-    CU_TRY(c, cudaEventRecord(ev[k++], d->stream));
-    for (uint32_t i = 0; i < o.read_sweeps; ++i) {
-        CU_TRY(c, launch_read(d->plan, rv, d->region, d->sweep_bytes, d->scratch, &d->d_out[i], d->stream));
-        CU_TRY(c, cudaEventRecord(ev[k++], d->stream));
-    }
-    for (uint32_t i = 0; i < r->copy_sweeps; ++i) {
-        CU_TRY(c, launch_copy(d->plan, cv, d->region + d->sweep_bytes, d->region, d->sweep_bytes, d->scratch, d->stream));
-        CU_TRY(c, cudaEventRecord(ev[k++], d->stream));
-    }
     const bool verify = (o.flags & CRO_F_VERIFY_COPY) && r->copy_sweeps > 0;
-    if (verify) {
-        CU_TRY(c, launch_read(d->plan, rv, d->region + d->sweep_bytes, d->sweep_bytes, d->scratch,
-                              &d->d_out[o.read_sweeps], d->stream));
+    size_t k = 0;
+    // The whole probe as one sequence; `external` records the timing events as external event-record
+    // nodes so that the same sequence can be stream-captured into a CUDA graph once and replayed.
+    auto issue = [&](bool external) -> int {
+        const unsigned flag = external ? cudaEventRecordExternal : cudaEventRecordDefault;
+        k = 0;
+        CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
+        CU_TRY(c, launch_fill(d->plan, d->region, d->sweep_bytes, d->seed, d->stream));
+        CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
+        for (uint32_t i = 0; i < o.read_sweeps; ++i) {
+            CU_TRY(c, launch_read(d->plan, rv, d->region, d->sweep_bytes, d->scratch, &d->d_out[i], d->stream));
+            CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
+        }
+        for (uint32_t i = 0; i < r->copy_sweeps; ++i) {
+            CU_TRY(c, launch_copy(d->plan, cv, d->region + d->sweep_bytes, d->region, d->sweep_bytes, d->scratch, d->stream));
+            CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
+        }
+        if (verify)
+            CU_TRY(c, launch_read(d->plan, rv, d->region + d->sweep_bytes, d->sweep_bytes, d->scratch,
+                                  &d->d_out[o.read_sweeps], d->stream));
+        CU_TRY(c, cudaMemcpyAsync(d->h_out, d->d_out, sizeof(SweepOut) * (o.read_sweeps + 1),
+                                  cudaMemcpyDeviceToHost, d->stream));
+        return CRO_OK;
+    };
+    // One graph launch instead of ~35 runtime calls per probe (matters when one host thread feeds 8 GPUs).
+    // The graph is tied to the options it was captured with; any capture problem falls back to direct launches.
+    const uint64_t graph_key = ((uint64_t)rv << 48) ^ ((uint64_t)cv << 40) ^ ((uint64_t)o.read_sweeps << 24) ^
+                               ((uint64_t)r->copy_sweeps << 8) ^ (verify ? 1u : 0u);
+    if (env_u32("CRO_USE_GRAPH", 1) && !d->graph_failed) {
+        if (d->graph_exec && d->graph_key != graph_key) {
+            cudaGraphExecDestroy(d->graph_exec);
+            d->graph_exec = nullptr;
+        }
+        if (!d->graph_exec) {
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                const int irc = issue(true);
+                const cudaError_t ec = cudaStreamEndCapture(d->stream, &graph);
+                ok = irc == CRO_OK && ec == cudaSuccess && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&d->graph_exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (!ok) {
+                cudaGetLastError();
+                d->graph_exec = nullptr;
+                d->graph_failed = true;
+            } else {
+                d->graph_key = graph_key;
+                d->graph_events = k;
+            }
+        }
     }
+    if (d->graph_exec) {
+        CU_TRY(c, cudaGraphLaunch(d->graph_exec, d->stream));
+        k = d->graph_events;
+    } else {
+        int irc = issue(false);
+        if (irc) return irc;
+    }
+    d->filled = true;
     c->launches += 1 + o.read_sweeps + r->copy_sweeps + (verify ? 1 : 0);
-    CU_TRY(c, cudaMemcpyAsync(d->h_out, d->d_out, sizeof(SweepOut) * (o.read_sweeps + 1),
-                              cudaMemcpyDeviceToHost, d->stream));
     d->pending_events = k;
     return CRO_OK;
 }

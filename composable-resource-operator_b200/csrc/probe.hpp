@@ -46,6 +46,11 @@ struct Device {
     size_t pending_events = 0;
     std::chrono::steady_clock::time_point pending_since{};
     cro_probe_result pending_result{};
+    // the whole probe captured as one CUDA graph (timing events are external event-record nodes)
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_key = 0;
+    size_t graph_events = 0;
+    bool graph_failed = false;
     bool have_expected = false;
     uint64_t expect_x = 0, expect_s = 0;
     unsigned sm_clock_mhz = 0, mem_clock_mhz = 0;
