@@ -38,7 +38,7 @@ ERR_INVALID_ARG, ERR_ABI_MISMATCH, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM = -1, -2, -3
 ERR_CHECKSUM, ERR_BUFFER_SMALL, ERR_NCCL, ERR_DEADLINE, ERR_UNSUPPORTED = -6, -7, -8, -9, -10
 ERR_PARSE, ERR_EXEC, ERR_P2P, ERR_INTERNAL = -11, -12, -13, -14
 
-F_SKIP_COPY, F_SKIP_P2P, F_SKIP_NCCL, F_NO_NVML, F_VERIFY_COPY, F_LAZY_ALLOC = 1, 2, 4, 8, 16, 32
+F_SKIP_COPY, F_SKIP_P2P, F_SKIP_NCCL, F_NO_NVML, F_VERIFY_COPY, F_LAZY_ALLOC, F_DEGRADE_ON_OOM = 1, 2, 4, 8, 16, 32, 64
 READ_AUTO, READ_LDG, READ_TMA, READ_LDG256 = 0, 1, 2, 3
 COPY_AUTO, COPY_LDG, COPY_TMA = 0, 1, 2
 

@@ -49,13 +49,28 @@ int env_u32(const char* name, int dflt) {
 int ensure_region(cro_ctx* c, Device* d) {
     if (d->region) return CRO_OK;
     CU_TRY(c, cudaSetDevice(d->ordinal));
-    cudaError_t e = cudaMalloc(&d->region, 2 * d->sweep_bytes);
-    if (e != cudaSuccess) {
+    // A device that is already in use may not have 2*S free (the reference's own pre-check for that
+    // is CheckNoGPULoads, internal/utils/gpus.go:88).  Degrade: halve S down to 64 MiB — still far
+    // beyond the 126 MB L2 when doubled — and report the size actually swept in the result.
+    const uint64_t asked = d->sweep_bytes;
+    cudaError_t e = cudaErrorMemoryAllocation;
+    for (uint64_t s = asked;; s = (s / 2) & ~(uint64_t)15) {
+        e = cudaMalloc(&d->region, 2 * s);
+        if (e == cudaSuccess) {
+            if (s != d->sweep_bytes) {
+                d->sweep_bytes = s;
+                d->have_expected = false;   // the closed form depends on S
+                if (d->graph_exec) { cudaGraphExecDestroy(d->graph_exec); d->graph_exec = nullptr; }
+            }
+            break;
+        }
         cudaGetLastError();
         d->region = nullptr;
-        c->set_error("cudaMalloc of sweep region (" + std::to_string(2 * d->sweep_bytes) +
-                     " bytes) failed: " + cudaGetErrorString(e));
-        return CRO_ERR_OOM;
+        if (e != cudaErrorMemoryAllocation || s <= (64ull << 20) || !(c->opts.flags & CRO_F_DEGRADE_ON_OOM)) {
+            c->set_error("cudaMalloc of sweep region (" + std::to_string(2 * s) + " bytes, asked for " +
+                         std::to_string(2 * asked) + ") failed: " + cudaGetErrorString(e));
+            return CRO_ERR_OOM;
+        }
     }
     d->filled = false;
     return CRO_OK;
@@ -116,8 +131,10 @@ void copy_cstr(char* dst, size_t cap, const std::string& s) {
 
 }  // namespace
 
-uint32_t resolve_read_variant(uint32_t v) {
-    if (v == CRO_READ_AUTO) v = (uint32_t)env_u32("CRO_READ_VARIANT", CRO_READ_TMA);
+uint32_t resolve_read_variant(uint32_t v, uint64_t bytes) {
+    // AUTO: the TMA ring wins from ~1 GiB up (7.46 vs 7.31 TB/s at 4 GiB); for small sweeps its fixed
+    // cost (one CTA per SM, atomic tile claims) loses to plain LDG (profiles/r01_size_sweep.jsonl).
+    if (v == CRO_READ_AUTO) v = (uint32_t)env_u32("CRO_READ_VARIANT", bytes <= (128ull << 20) ? CRO_READ_LDG : CRO_READ_TMA);
     return (v == READ_LDG || v == READ_TMA || v == READ_LDG256) ? v : (uint32_t)READ_TMA;
 }
 uint32_t resolve_copy_variant(uint32_t v) {
@@ -335,7 +352,7 @@ int ctx_read(cro_ctx* c, int idx, uint32_t variant, uint32_t iters, bool dst_hal
              cro_sweep_result* out) {
     Device* d = dev_at(c, idx);
     if (!d || !out || iters == 0) return CRO_ERR_INVALID_ARG;
-    variant = resolve_read_variant(variant);
+    variant = resolve_read_variant(variant, d->sweep_bytes);
     std::lock_guard<std::mutex> g(d->mu);
     drain_pending_fwd(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
@@ -467,7 +484,7 @@ static int probe_enqueue(cro_ctx* c, Device* d, cro_probe_result* r) {
     r->rank = c->opts.rank_base + (uint32_t)d->index;
     r->world = c->opts.world_override ? c->opts.world_override : (uint32_t)c->devs.size();
     r->p2p_bytes = o.p2p_bytes;
-    const uint32_t rv = resolve_read_variant(o.read_variant);
+    const uint32_t rv = resolve_read_variant(o.read_variant, d->sweep_bytes);
     const uint32_t cv = resolve_copy_variant(o.copy_variant);
     r->read_variant = rv;
     r->copy_variant = cv;
@@ -478,6 +495,7 @@ static int probe_enqueue(cro_ctx* c, Device* d, cro_probe_result* r) {
     int rc = ensure_region(c, d);
     if (rc) { r->status = rc; return rc; }
     if ((rc = ensure_expected(c, d))) { r->status = rc; return rc; }
+    r->sweep_bytes = d->sweep_bytes;   // ensure_region may have degraded it (CRO_F_DEGRADE_ON_OOM)
     r->expect_xor = d->expect_x;
     r->expect_sum = d->expect_s;
 
@@ -856,7 +874,7 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
             Device* d = c->devs[(size_t)i].get();
             CU_TRY(c, cudaSetDevice(d->ordinal));
             if ((rc = ensure_chase(c, d))) return rc;
-            CU_TRY(c, launch_expected(d->plan, o.p2p_bytes, d->seed, d->scratch, &d->d_out[kMaxSweeps - 2], d->stream));
+            CU_TRY(c, launch_expected(d->plan, std::min<uint64_t>(o.p2p_bytes, d->sweep_bytes), d->seed, d->scratch, &d->d_out[kMaxSweeps - 2], d->stream));
             c->launches++;
             CU_TRY(c, cudaMemcpyAsync(&d->h_out[kMaxSweeps - 2], &d->d_out[kMaxSweeps - 2], sizeof(SweepOut),
                                       cudaMemcpyDeviceToHost, d->stream));
@@ -888,7 +906,7 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
                     // address) into this GPU's shared memory, checksummed as they land: 669 GB/s per
                     // direction with all pairs running both ways, vs 632 GB/s for LDG.128/256
                     CU_TRY(c, launch_read(a->plan, (unsigned)env_u32("CRO_P2P_READ_VARIANT", READ_TMA), b->region,
-                                          o.p2p_bytes, a->scratch, &a->d_out[0], a->stream));
+                                          std::min<uint64_t>(o.p2p_bytes, b->sweep_bytes), a->scratch, &a->d_out[0], a->stream));
                     CU_TRY(c, cudaEventRecord(a->ev1, a->stream));
                     c->launches++;
                     CU_TRY(c, cudaMemcpyAsync(&a->h_out[0], &a->d_out[0], sizeof(SweepOut), cudaMemcpyDeviceToHost, a->stream));

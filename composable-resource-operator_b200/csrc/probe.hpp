@@ -95,7 +95,7 @@ int ctx_expected(cro_ctx* c, int idx, cro_sweep_result* out);
 int ctx_inject(cro_ctx* c, int idx, uint64_t word, uint64_t mask);
 int ctx_read_words(cro_ctx* c, int idx, uint64_t first, uint64_t n, uint64_t* out);
 
-uint32_t resolve_read_variant(uint32_t v);
+uint32_t resolve_read_variant(uint32_t v, uint64_t bytes);
 uint32_t resolve_copy_variant(uint32_t v);
 
 }  // namespace cro

@@ -53,6 +53,8 @@ extern "C" {
 #define CRO_F_NO_NVML         0x0008u  /* identity from /proc + CUDA runtime only  */
 #define CRO_F_VERIFY_COPY     0x0010u  /* re-checksum the copy destination         */
 #define CRO_F_LAZY_ALLOC      0x0020u  /* allocate sweep buffers at first probe    */
+#define CRO_F_DEGRADE_ON_OOM  0x0040u  /* busy device: halve S (>= 64 MiB) instead of failing;
+                                          the result's sweep_bytes says what was swept  */
 
 /* read-sweep kernel variants */
 #define CRO_READ_AUTO   0u

@@ -207,6 +207,19 @@ def test_multi_device_probe_all(cro, coracle):
                 assert r.p2p_checksum_xor[j] == coracle.checksum(res[j].seed, 0, (64 << 20) // 8)[0]
 
 
+def test_oom_fails_loudly_or_degrades(cro, coracle):
+    """A sweep region that does not fit (2*S = 192 GiB > 180 GB): CRO_ERR_OOM by default; with
+    CRO_F_DEGRADE_ON_OOM the probe halves S until it fits and says so in the result."""
+    S = 96 << 30
+    with pytest.raises(cro.ProbeError) as e:
+        cro.ProbeContext(sweep_bytes=S, devices=[0])
+    assert e.value.code == cro.ERR_OOM
+    with cro.ProbeContext(sweep_bytes=S, devices=[0], flags=cro.F_DEGRADE_ON_OOM, read_sweeps=1, copy_sweeps=1) as c:
+        r = c.probe_device(0)
+        assert r.status == 0 and r.sweep_bytes == 48 << 30
+        assert (r.checksum_xor, r.checksum_sum) == coracle.checksum(r.seed, 0, r.sweep_bytes // 8, threads=os.cpu_count() or 1)
+
+
 def test_c_harness_on_gpu(cro):
     """The plain-C caller (what cgo compiles to) runs a probe + emit through the same ABI."""
     from test_abi import build_c_harness
