@@ -32,7 +32,6 @@ void removeStr(std::vector<std::string>* v, const std::string& s) {
 // time.Parse(time.RFC3339, s) reduced to a sortable integer (seconds since epoch).
 bool parseRFC3339(const std::string& s, long long* out) {
     int Y, M, D, h, m, sec;
-    char tz[8] = {0};
     int n = 0;
     if (sscanf(s.c_str(), "%4d-%2d-%2dT%2d:%2d:%2d%n", &Y, &M, &D, &h, &m, &sec, &n) != 6) return false;
     std::string rest = s.substr((size_t)n);
@@ -48,7 +47,6 @@ bool parseRFC3339(const std::string& s, long long* out) {
         off = ((rest[1] - '0') * 10 + (rest[2] - '0')) * 3600 + ((rest[4] - '0') * 10 + (rest[5] - '0')) * 60;
         if (rest[0] == '-') off = -off;
     } else return false;
-    (void)tz;
     // days from civil (Howard Hinnant)
     long long y = Y - (M <= 2);
     const long long era = (y >= 0 ? y : y - 399) / 400;
@@ -426,7 +424,7 @@ private:
         const std::string parent = mb == child.obj.Labels.end() ? std::string() : mb->second;
         auto it = c_->requests_.find(parent);
         if (it == c_->requests_.end())
-            return Error::New("ComposabilityRequest.cro.hpsys.ibm.ie.com \"" + parent + "\" not found");
+            return Error::New("composabilityrequests.cro.hpsys.ibm.ie.com \"" + parent + "\" not found");
         ComposabilityRequest r = it->second;
         auto slot = r.Status.Resources.find(child.obj.Name);
         if (slot != r.Status.Resources.end()) {
@@ -984,9 +982,7 @@ void Cluster::Run(long long max_reconciles) {
     long long n = 0;
     long long changes_at_flush = -1;
     for (;;) {
-        bool worked = false;
         while ((!req_queue_.empty() || !res_queue_.empty()) && n < max_reconciles) {
-            worked = true;
             if ((n & 3) == 0) pollProbes(false);
             // one worker per controller (MaxConcurrentReconciles default 1), interleaved
             if (!res_queue_.empty()) {
@@ -1017,7 +1013,6 @@ void Cluster::Run(long long max_reconciles) {
                 else if (rq > 0) req_timers_.insert(key);
             }
         }
-        (void)worked;
         if (n >= max_reconciles) break;
         if (!probe_owner_.empty()) {   // nothing else to do: wait for the next probe to finish
             pollProbes(true);
