@@ -208,7 +208,48 @@ def cpu_baseline(budget_s: float = 12.0):
     sweep_s = time.perf_counter() - t1
     return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "%d sequential steps in %.1f s; %s" % (n, dt, how),
+            "enumerate_ms": cpu_enumerate_ms(),
             "host_pattern_checksum_gbs_all_cores": (256 << 20) / sweep_s / 1e9, "host_cores": cores}
+
+
+def cpu_enumerate_ms():
+    """Best-case CPU enumeration next to the reference's exec of nvidia-smi: NVML in
+    process, and the /proc scan the RKE2 branch scripts (internal/utils/gpus.go:1017-1037).  Median of 10, ms."""
+    out = {}
+
+    def med(fn, n=10):
+        ts = []
+        for _ in range(n):
+            t = time.perf_counter()
+            fn()
+            ts.append((time.perf_counter() - t) * 1e3)
+        ts.sort()
+        return round(ts[len(ts) // 2], 3)
+    smi = shutil.which("nvidia-smi")
+    if smi:
+        out["nvidia_smi_exec"] = med(lambda: subprocess.run([smi, "--query-gpu=gpu_uuid", "--format=csv,noheader,nounits"],
+                                                            capture_output=True), 5)
+    try:
+        import pynvml
+
+        def nvml():
+            pynvml.nvmlInit()
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                pynvml.nvmlDeviceGetUUID(h), pynvml.nvmlDeviceGetMinorNumber(h), pynvml.nvmlDeviceGetPciInfo(h)
+            pynvml.nvmlShutdown()
+        out["nvml_in_process"] = med(nvml)
+    except Exception as e:   # noqa: BLE001
+        out["nvml_in_process"] = "unavailable: %s" % type(e).__name__
+    base = "/proc/driver/nvidia/gpus"
+    if os.path.isdir(base):
+        def proc():
+            for name in sorted(os.listdir(base)):
+                p = os.path.join(base, name, "information")
+                if os.path.isfile(p):
+                    open(p).read()
+        out["proc_scan"] = med(proc)
+    return out
 
 
 # ---------------------------------------------------------------------------

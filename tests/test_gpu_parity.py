@@ -220,6 +220,37 @@ def test_oom_fails_loudly_or_degrades(cro, coracle):
         assert (r.checksum_xor, r.checksum_sum) == coracle.checksum(r.seed, 0, r.sweep_bytes // 8, threads=os.cpu_count() or 1)
 
 
+def test_concurrent_callers_are_serialised_per_device(cro, coracle):
+    """Reconciles for different CRs may probe the same GPU from different OS threads (cgo migrates
+    goroutines): every entry point takes the device mutex and calls cudaSetDevice itself."""
+    import threading
+    with cro.ProbeContext(sweep_bytes=32 << 20, devices=[0], read_sweeps=2, copy_sweeps=1) as c:
+        want = coracle.checksum(c.seed(0), 0, (32 << 20) // 8)
+        errors, results = [], []
+
+        def worker(k):
+            try:
+                for i in range(4):
+                    if (k + i) % 3 == 0:
+                        s = c.hbm_read_checksum(0, 1 + (k + i) % 3)
+                        results.append((s.checksum_xor, s.checksum_sum))
+                    elif (k + i) % 3 == 1:
+                        r = c.probe_device(0)
+                        results.append((r.checksum_xor, r.checksum_sum))
+                    else:
+                        out = cro.reconcile_attach(c, {"status": {"state": "Attaching"}, "probe": True, "spec": {"type": "gpu", "model": "m", "target_node": "n"},
+                                                       "provider": {"device_id": c.enumerate()[0].gpu_uuid.decode(), "cdi_device_id": "r"}})
+                        assert out["status"]["state"] == "Online"
+            except Exception as e:   # noqa: BLE001
+                errors.append(repr(e))
+        ts = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert errors == [] and results and all(r == want for r in results)
+
+
 def test_c_harness_on_gpu(cro):
     """The plain-C caller (what cgo compiles to) runs a probe + emit through the same ABI."""
     from test_abi import build_c_harness
