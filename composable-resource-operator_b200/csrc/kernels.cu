@@ -16,6 +16,7 @@
 // No tensor cores: there is no contraction anywhere on this path.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -651,9 +652,15 @@ cudaError_t plan_kernels(int device, KernelPlan* plan) {
     return cudaSuccess;
 }
 
+// No more CTAs than there are tiles: a small sweep should not pay for a grid sized for 4 GiB.
+static int clamp_grid(int planned, uint64_t bytes, uint64_t tile_bytes) {
+    const uint64_t tiles = (bytes + tile_bytes - 1) / tile_bytes;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)planned, tiles));
+}
+
 cudaError_t launch_fill(const KernelPlan& p, void* base, uint64_t bytes, uint64_t seed,
                         cudaStream_t st) {
-    hbm_fill_kernel<kFillThreads, kFillUnroll><<<p.fill.grid, p.fill.block, 0, st>>>(
+    hbm_fill_kernel<kFillThreads, kFillUnroll><<<clamp_grid(p.fill.grid, bytes, kFillThreads * kFillUnroll * 16), p.fill.block, 0, st>>>(
         static_cast<uint4*>(base), bytes >> 4, seed);
     return cudaGetLastError();
 }
@@ -668,13 +675,13 @@ cudaError_t launch_read(const KernelPlan& p, unsigned variant, const void* base,
             cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st);
             if (e != cudaSuccess) return e;
         }
-        hbm_read_tma_kernel<<<p.read_tma.grid, p.read_tma.block, p.read_tma.smem, st>>>(
+        hbm_read_tma_kernel<<<clamp_grid(p.read_tma.grid, bytes, t.tile), p.read_tma.block, p.read_tma.smem, st>>>(
             static_cast<const unsigned char*>(base), bytes, t.tile, t.stages, t.chunk, ctr, sc, out);
     } else if (variant == READ_LDG256) {
-        hbm_read_ldg_kernel<kReadThreads, true><<<p.read_ldg256.grid, p.read_ldg256.block, 0, st>>>(
+        hbm_read_ldg_kernel<kReadThreads, true><<<clamp_grid(p.read_ldg256.grid, bytes, kReadThreads * 128), p.read_ldg256.block, 0, st>>>(
             static_cast<const uint4*>(base), bytes >> 4, sc, out);
     } else {
-        hbm_read_ldg_kernel<kReadThreads, false><<<p.read_ldg.grid, p.read_ldg.block, 0, st>>>(
+        hbm_read_ldg_kernel<kReadThreads, false><<<clamp_grid(p.read_ldg.grid, bytes, kReadThreads * 128), p.read_ldg.block, 0, st>>>(
             static_cast<const uint4*>(base), bytes >> 4, sc, out);
     }
     return cudaGetLastError();
@@ -690,11 +697,11 @@ cudaError_t launch_copy(const KernelPlan& p, unsigned variant, void* dst, const 
             cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st);
             if (e != cudaSuccess) return e;
         }
-        hbm_copy_tma_kernel<<<p.copy_tma.grid, p.copy_tma.block, p.copy_tma.smem, st>>>(
+        hbm_copy_tma_kernel<<<clamp_grid(p.copy_tma.grid, bytes, t.tile), p.copy_tma.block, p.copy_tma.smem, st>>>(
             static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), bytes, t.tile,
             t.stages, t.chunk, ctr);
     } else {
-        hbm_copy_ldg_kernel<kCopyThreads, kCopyUnroll><<<p.copy_ldg.grid, p.copy_ldg.block, 0, st>>>(
+        hbm_copy_ldg_kernel<kCopyThreads, kCopyUnroll><<<clamp_grid(p.copy_ldg.grid, bytes, kCopyThreads * kCopyUnroll * 16), p.copy_ldg.block, 0, st>>>(
             static_cast<uint4*>(dst), static_cast<const uint4*>(src), bytes >> 4);
     }
     return cudaGetLastError();

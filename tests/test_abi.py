@@ -77,6 +77,19 @@ def test_c_harness_links_and_runs_like_cgo(cro):
     assert "c abi harness ok" in out.stdout
 
 
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="a GPU is present")
+def test_cli_without_gpu(cro):
+    """The helper process: an empty box enumerates as nvidia-smi says it ("No devices were found"),
+    and a probe refuses loudly (no CPU fallback)."""
+    cli = os.path.join(ROOT, "composable-resource-operator_b200", "croprobe-cli")
+    out = subprocess.run([cli, "csv", "gpu_uuid"], capture_output=True, text=True)
+    assert (out.returncode, out.stdout) == (0, "No devices were found\n")
+    rc, js = cro.getGPUInfoFromNvidiaSmiOutput(out.stdout, "", None, "gpu_uuid")
+    assert (rc, js) == (0, "[]")                      # and the reference's parse rule turns that into an empty list
+    out = subprocess.run([cli, "probe", "0"], capture_output=True, text=True)
+    assert out.returncode == 2 and "no CUDA device" in out.stderr
+
+
 def test_product_never_touches_the_oracle():
     """The shipped path must not include, link or import anything under oracle/."""
     pkg = os.path.join(ROOT, "composable-resource-operator_b200")

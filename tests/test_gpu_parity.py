@@ -251,6 +251,28 @@ def test_concurrent_callers_are_serialised_per_device(cro, coracle):
         assert errors == [] and results and all(r == want for r in results)
 
 
+def test_cli_helper_process(cro):
+    """croprobe-cli: the fresh-process form (a hot-plugged GPU is invisible to an already initialised CUDA process)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "composable-resource-operator_b200", "croprobe-cli")
+    smi = shutil.which("nvidia-smi")
+    if smi:
+        want = subprocess.run([smi, "--query-gpu=gpu_uuid,pci.bus_id", "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout
+        got = subprocess.run([cli, "csv", "gpu_uuid,pci.bus_id"], capture_output=True, text=True)
+        assert got.returncode == 0 and got.stdout == want
+    devs = json.loads(subprocess.run([cli, "enumerate"], capture_output=True, text=True).stdout)
+    uuid = devs[0]["gpu_uuid"]
+    out = subprocess.run([cli, "probe", uuid, "256"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    ann = json.loads(out.stdout)
+    assert ann["cohdi.io/probe-status"] == "ok" and ann["cohdi.io/probe-device-id"] == uuid
+    assert subprocess.run([cli, "probe", "GPU-00000000-dead-beef-0000-000000000000"], capture_output=True).returncode == 3
+    cold = json.loads(subprocess.run([cli, "cold", "0", "4096"], capture_output=True, text=True).stdout)
+    assert cold["status"] == 0 and cold["cold_total_s"] > cold["warm_probe_s"] > 0
+    print("cold vs warm:", cold)
+
+
 def test_c_harness_on_gpu(cro):
     """The plain-C caller (what cgo compiles to) runs a probe + emit through the same ABI."""
     from test_abi import build_c_harness
