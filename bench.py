@@ -399,8 +399,11 @@ def run_ours(args, rank, local_rank, world):
                        "read_variant": results[-1].read_variant, "copy_variant": results[-1].copy_variant,
                        "l2": "inputs (4 GiB per sweep) are larger than the 126 MB L2; no flush needed",
                        "parallelism": "1 rank per GPU, independent devices, one 512 B all-gather per step" if world > 1 else "1 GPU"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 512 + len(json.dumps(request)),
-                    "d2h_bytes_per_step": 32 * (results[-1].read_sweeps + 1) + len(last["_raw"]),
+            # what actually crosses PCIe per step: the 512-byte result struct goes up (all-gather send buffer),
+            # the per-sweep (xor, sum, t0, t1) slots come down; the probe's inputs are options, not tensors
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 512,
+                    "d2h_bytes_per_step": 32 * (results[-1].read_sweeps + 1),
+                    "host_json_in_bytes": len(json.dumps(request)), "host_json_out_bytes": len(last["_raw"]),
                     "ms_per_step": e2e_s * 1e3 / args.steps, "call": "cro_reconcile_attach (C ABI) with host JSON buffers"},
             "specs_per_s": world * specs / e2e_s,
             "probe_gbs_best_read": S / best_read, "probe_frac_of_8000": S / best_read / 8000.0,
