@@ -38,7 +38,7 @@ ERR_INVALID_ARG, ERR_ABI_MISMATCH, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM = -1, -2, -3
 ERR_CHECKSUM, ERR_BUFFER_SMALL, ERR_NCCL, ERR_DEADLINE, ERR_UNSUPPORTED = -6, -7, -8, -9, -10
 ERR_PARSE, ERR_EXEC, ERR_P2P, ERR_INTERNAL = -11, -12, -13, -14
 
-F_SKIP_COPY, F_SKIP_P2P, F_SKIP_NCCL, F_NO_NVML, F_VERIFY_COPY, F_LAZY_ALLOC, F_DEGRADE_ON_OOM = 1, 2, 4, 8, 16, 32, 64
+F_SKIP_COPY, F_SKIP_P2P, F_SKIP_NCCL, F_NO_NVML, F_VERIFY_COPY, F_LAZY_ALLOC, F_DEGRADE_ON_OOM, F_SKIP_P2P_WRITE = 1, 2, 4, 8, 16, 32, 64, 128
 READ_AUTO, READ_LDG, READ_TMA, READ_LDG256 = 0, 1, 2, 3
 COPY_AUTO, COPY_LDG, COPY_TMA = 0, 1, 2
 
@@ -89,7 +89,7 @@ class ProbeResult(ctypes.Structure):
         ("copy_checksum_xor", ctypes.c_uint64), ("copy_checksum_sum", ctypes.c_uint64),
         ("rank", ctypes.c_uint32), ("world", ctypes.c_uint32),
         ("total_ns", ctypes.c_uint64), ("read_total_ns", ctypes.c_uint64), ("copy_total_ns", ctypes.c_uint64),
-        ("reserved", ctypes.c_uint8 * 72),
+        ("p2p_write_ns", ctypes.c_uint64 * 8), ("reserved", ctypes.c_uint8 * 8),
     ]
 
 

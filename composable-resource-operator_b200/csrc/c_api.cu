@@ -22,6 +22,7 @@ static_assert(offsetof(cro_probe_result, checksum_xor) == 112, "layout");
 static_assert(offsetof(cro_probe_result, p2p_read_ns) == 184, "layout");
 static_assert(offsetof(cro_probe_result, p2p_access) == 344, "layout");
 static_assert(offsetof(cro_probe_result, rank) == 408, "layout");
+static_assert(offsetof(cro_probe_result, p2p_write_ns) == 440, "layout");
 
 namespace {
 
@@ -335,6 +336,13 @@ static std::map<std::string, std::string> probe_annotations(const cro_probe_resu
         m["cohdi.io/probe-nvlink-read-gbs"] = bw;
         m["cohdi.io/probe-nvlink-latency-ns"] = lat;
     }
+    std::string wr;
+    for (int j = 0; j < 8; ++j) {
+        if (!r.p2p_write_ns[j]) continue;
+        if (!wr.empty()) wr += ",";
+        wr += std::to_string(j) + ":" + gbs_x10(r.p2p_bytes, r.p2p_write_ns[j]);
+    }
+    if (!wr.empty()) m["cohdi.io/probe-nvlink-write-gbs"] = wr;
     return m;
 }
 

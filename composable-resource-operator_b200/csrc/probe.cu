@@ -929,6 +929,67 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
                     }
                 }
             }
+            // push leg: posted NVLink writes.  a streams its own pattern prefix through shared memory
+            // (TMA bulk load from local HBM, TMA bulk store to the peer-mapped address) into the
+            // SCRATCH half of b's region; b then re-reads that half locally and must find a's checksum.
+            // The scratch half is rewritten by every probe's copy sweeps, so nothing needs restoring.
+            if (!(o.flags & CRO_F_SKIP_P2P_WRITE)) {
+                auto push_bytes = [&](const Device* a, const Device* b) {
+                    return std::min<uint64_t>(std::min<uint64_t>(o.p2p_bytes, a->sweep_bytes), b->sweep_bytes);
+                };
+                for (int rep = 0; rep < 2; ++rep) {   // rep 0 maps the peer pages (1/16 of the bytes), rep 1 is timed
+                    for (const auto& pr : directed) {
+                        Device* a = c->devs[(size_t)pr.first].get();
+                        Device* b = c->devs[(size_t)pr.second].get();
+                        if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
+                        uint64_t nb = push_bytes(a, b);
+                        if (rep == 0) nb = std::max<uint64_t>(nb / 16, std::min<uint64_t>(nb, 1u << 20)) & ~uint64_t(15);
+                        CU_TRY(c, cudaSetDevice(a->ordinal));
+                        CU_TRY(c, cudaEventRecord(a->ev0, a->stream));
+                        CU_TRY(c, launch_copy(a->plan, (unsigned)env_u32("CRO_P2P_WRITE_VARIANT", COPY_TMA),
+                                              b->region + b->sweep_bytes, a->region, nb, a->scratch, a->stream));
+                        CU_TRY(c, cudaEventRecord(a->ev1, a->stream));
+                        c->launches++;
+                    }
+                    for (const auto& pr : directed) {
+                        Device* a = c->devs[(size_t)pr.first].get();
+                        if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
+                        CU_TRY(c, cudaSetDevice(a->ordinal));
+                        CU_TRY(c, cudaStreamSynchronize(a->stream));
+                        if (rep == 0) continue;
+                        float ms = 0;
+                        CU_TRY(c, cudaEventElapsedTime(&ms, a->ev0, a->ev1));
+                        res[(size_t)pr.first].p2p_write_ns[pr.second] = ms_to_ns(ms);
+                    }
+                }
+                // every pusher has drained (stream syncs above): the receivers check what landed
+                for (const auto& pr : directed) {
+                    Device* a = c->devs[(size_t)pr.first].get();
+                    Device* b = c->devs[(size_t)pr.second].get();
+                    if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
+                    CU_TRY(c, cudaSetDevice(b->ordinal));
+                    CU_TRY(c, launch_read(b->plan, resolve_read_variant(CRO_READ_AUTO, push_bytes(a, b)), b->region + b->sweep_bytes,
+                                          push_bytes(a, b), b->scratch, &b->d_out[1], b->stream));
+                    c->launches++;
+                    CU_TRY(c, cudaMemcpyAsync(&b->h_out[1], &b->d_out[1], sizeof(SweepOut), cudaMemcpyDeviceToHost, b->stream));
+                }
+                for (const auto& pr : directed) {
+                    Device* a = c->devs[(size_t)pr.first].get();
+                    Device* b = c->devs[(size_t)pr.second].get();
+                    if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
+                    CU_TRY(c, cudaSetDevice(b->ordinal));
+                    CU_TRY(c, cudaStreamSynchronize(b->stream));
+                    // prefix[] holds the checksum of min(p2p_bytes, owner's S) words; a smaller receiver
+                    // region changes the byte count, in which case only the timing is reported
+                    if (push_bytes(a, b) != std::min<uint64_t>(o.p2p_bytes, a->sweep_bytes)) continue;
+                    if (b->h_out[1].x != prefix[(size_t)pr.first].x || b->h_out[1].s != prefix[(size_t)pr.first].s) {
+                        res[(size_t)pr.first].status = CRO_ERR_CHECKSUM;
+                        worst = CRO_ERR_CHECKSUM;
+                        c->set_error(std::string("NVLink push from ") + a->info.gpu_uuid + " into " + b->info.gpu_uuid +
+                                     " did not land the pattern checksum");
+                    }
+                }
+            }
             // latency: dependent loads into the peer's permutation
             for (const auto& pr : directed) {
                 Device* a = c->devs[(size_t)pr.first].get();

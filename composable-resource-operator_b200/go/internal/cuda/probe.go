@@ -39,6 +39,7 @@ type ProbeResult struct {
 	ReadBestNs   uint64
 	CopyBestNs   uint64
 	P2PReadNs    [8]uint64
+	P2PWriteNs   [8]uint64
 	P2PLatencyNs [8]uint32
 	Annotations  string // Go-marshalled map[string]string of cohdi.io/probe-* keys
 }
@@ -132,6 +133,7 @@ func convert(r *C.cro_probe_result) ProbeResult {
 	}
 	for j := 0; j < 8; j++ {
 		out.P2PReadNs[j] = uint64(r.p2p_read_ns[j])
+		out.P2PWriteNs[j] = uint64(r.p2p_write_ns[j])
 		out.P2PLatencyNs[j] = uint32(r.p2p_latency_ns_x16[j]) / 16
 	}
 	buf := (*C.char)(C.malloc(4096))

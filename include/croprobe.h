@@ -55,6 +55,7 @@ extern "C" {
 #define CRO_F_LAZY_ALLOC      0x0020u  /* allocate sweep buffers at first probe    */
 #define CRO_F_DEGRADE_ON_OOM  0x0040u  /* busy device: halve S (>= 64 MiB) instead of failing;
                                           the result's sweep_bytes says what was swept  */
+#define CRO_F_SKIP_P2P_WRITE  0x0080u  /* cro_probe_all: peer reads only, no push leg */
 
 /* read-sweep kernel variants */
 #define CRO_READ_AUTO   0u
@@ -150,7 +151,9 @@ typedef struct cro_probe_result {
     uint64_t total_ns;             /* 416  CUDA-event time of the whole probe (fill..last copy) */
     uint64_t read_total_ns;        /* 424  sum over the read sweeps  */
     uint64_t copy_total_ns;        /* 432  sum over the copy sweeps  */
-    uint8_t  reserved[72];         /* 440..511 */
+    uint64_t p2p_write_ns[8];      /* 440  best time to PUSH p2p_bytes into peer j's scratch half
+                                           (posted NVLink writes; the peer re-reads and checks them) */
+    uint8_t  reserved[8];          /* 504..511 */
 } cro_probe_result;
 
 /* Result of one timed sweep (bench / parity entry points). */

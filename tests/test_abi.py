@@ -29,7 +29,7 @@ def test_result_struct_layout(cro):
     assert ctypes.sizeof(R) == 512
     offs = {"gpu_uuid": 16, "pci_bus_id": 64, "hbm_bytes_total": 88, "checksum_xor": 112, "fill_ns": 128,
             "sm_count": 168, "p2p_read_ns": 184, "p2p_checksum_xor": 248, "p2p_latency_ns_x16": 312,
-            "p2p_access": 344, "p2p_bytes": 352, "rank": 408}
+            "p2p_access": 344, "p2p_bytes": 352, "rank": 408, "p2p_write_ns": 440}
     for k, v in offs.items():
         assert getattr(R, k).offset == v, k
 

@@ -203,8 +203,28 @@ def test_multi_device_probe_all(cro, coracle):
             for j in range(min(n, 8)):
                 if j == i or not r.p2p_access[j]:
                     continue
-                assert r.p2p_read_ns[j] > 0 and r.p2p_latency_ns_x16[j] > 0
+                assert r.p2p_read_ns[j] > 0 and r.p2p_latency_ns_x16[j] > 0 and r.p2p_write_ns[j] > 0
                 assert r.p2p_checksum_xor[j] == coracle.checksum(res[j].seed, 0, (64 << 20) // 8)[0]
+
+
+def test_peer_push_lands_the_pushers_pattern(cro, coracle):
+    """The push leg writes a's pattern prefix into the scratch half of b over NVLink; afterwards that half
+    must hold exactly a's words (read back through the C ABI and compared with the oracle's generator)."""
+    S, P = 64 << 20, 16 << 20
+    with cro.ProbeContext(sweep_bytes=S, p2p_bytes=P, read_sweeps=1, copy_sweeps=1, latency_hops=256, flags=cro.F_SKIP_COPY) as c:
+        n = c.device_count()
+        if n < 2:
+            pytest.skip("single-GPU box")
+        res = c.probe_all()
+        assert all(r.status == 0 for r in res)
+        # the LAST round of the 1-factorisation pairs each device with a known partner: find it by content
+        seeds = [r.seed for r in res]
+        for b in range(n):
+            words = c.read_words(b, S // 8, 4)                  # first words of b's scratch half
+            owners = [a for a in range(n) if a != b and list(words) == [coracle.pattern_word(seeds[a], i) for i in range(4)]]
+            assert len(owners) == 1, (b, words)
+            tail = c.read_words(b, S // 8 + P // 8 - 4, 4)       # ...and the last words of the pushed prefix
+            assert list(tail) == [coracle.pattern_word(seeds[owners[0]], P // 8 - 4 + i) for i in range(4)]
 
 
 def test_oom_fails_loudly_or_degrades(cro, coracle):

@@ -14,7 +14,9 @@ g.build()
 cro = importlib.import_module("composable-resource-operator_b200")
 
 for variant, extra in ((3, {}), (1, {}), (2, {}), (2, {"CRO_TMA_READ_STAGES": 6, "CRO_TMA_READ_TILE": 32768}),
-                       (2, {"CRO_TMA_READ_STAGES": 3, "CRO_TMA_READ_TILE": 65536}), (1, {"CRO_READ_WAVES": 2})):
+                       (2, {"CRO_TMA_READ_STAGES": 3, "CRO_TMA_READ_TILE": 65536}), (1, {"CRO_READ_WAVES": 2}),
+                       (2, {"CRO_P2P_WRITE_VARIANT": 1}), (2, {"CRO_TMA_COPY_TILE": 65536, "CRO_TMA_COPY_STAGES": 3}),
+                       (2, {"CRO_TMA_COPY_TILE": 16384, "CRO_TMA_COPY_STAGES": 8})):
     os.environ["CRO_P2P_READ_VARIANT"] = str(variant)
     for k, v in extra.items():
         os.environ[k] = str(v)
@@ -25,7 +27,9 @@ for variant, extra in ((3, {}), (1, {}), (2, {}), (2, {"CRO_TMA_READ_STAGES": 6,
             n = len(res)
             bw = [[round(r.p2p_bytes / r.p2p_read_ns[j], 1) if r.p2p_read_ns[j] else None for j in range(n)] for r in res]
             flat = [x for row in bw for x in row if x]
+            wr = [round(r.p2p_bytes / r.p2p_write_ns[j], 1) for r in res for j in range(n) if r.p2p_write_ns[j]]
             print(json.dumps({"variant": variant, "env": extra, "min": min(flat), "max": max(flat), "mean": round(sum(flat) / len(flat), 1),
+                              "write_min": min(wr) if wr else None, "write_max": max(wr) if wr else None,
                               "status": [r.status for r in res]}), flush=True)
     except Exception as e:
         print(json.dumps({"variant": variant, "env": extra, "error": str(e)}), flush=True)

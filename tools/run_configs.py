@@ -58,6 +58,7 @@ def config3(ctx):
         "hbm_read_gbs": [gbs(S, r.read_best_ns) for r in res], "hbm_copy_gbs": [gbs(2 * S, r.copy_best_ns) for r in res],
         "hbm_fill_gbs": [gbs(S, r.fill_ns) for r in res],
         "nvlink_read_gbs": [[gbs(r.p2p_bytes, r.p2p_read_ns[j]) if j < 8 and r.p2p_read_ns[j] else None for j in range(n)] for r in res],
+        "nvlink_write_gbs": [[gbs(r.p2p_bytes, r.p2p_write_ns[j]) if j < 8 and r.p2p_write_ns[j] else None for j in range(n)] for r in res],
         "nvlink_latency_ns": [[r.p2p_latency_ns_x16[j] // 16 if j < 8 and r.p2p_read_ns[j] else None for j in range(n)] for r in res],
     }
 
