@@ -1,0 +1,143 @@
+// Deterministic mutation fuzzer for the host-side parsers of libcroprobe,
+// built with -fsanitize=address,undefined by tests/test_host_sanitizers.py.
+// Everything these functions read comes from outside the operator (exec
+// output of nvidia-smi / awk, HTTP bodies of the fabric managers), so none of
+// them may read out of bounds, overflow or leak on arbitrary bytes.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "detach.hpp"
+#include "fabric.hpp"
+#include "gojson.hpp"
+#include "identity.hpp"
+#include "reconcile.hpp"
+
+using namespace cro;
+
+static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+static uint64_t rnd() {
+    rng_state ^= rng_state << 13;
+    rng_state ^= rng_state >> 7;
+    rng_state ^= rng_state << 17;
+    return rng_state;
+}
+
+static const char* kCorpus[] = {
+    // nvidia-smi csv,noheader
+    "0, GPU-7cc45b7b-2a6d-f0ac-1b02-6f8de09e1a6c, 00000000:1F:00.0\n1, GPU-aaaa, 00000000:20:00.0\n",
+    "No devices were found\n",
+    "GPU-1, python3\nGPU-2, pytorch\n",
+    "",
+    "\n\n , ,\n",
+    // awk over /proc/driver/nvidia/gpus/*/information
+    "Model: NVIDIA B200\nGPU UUID: GPU-7cc45b7b\nDevice Minor: 3\nBus Location: 0000:1f:00.0\n",
+    "3,GPU-7cc45b7b,0000:1f:00.0\n",
+    // drain status
+    "GPU 0000:1F:00.0 is currently: draining\n",
+    "GPU 0000:1F:00.0 is currently: not draining\n",
+    // FM scale-up response / machine
+    "{\"data\":{\"machines\":[{\"fabric_uuid\":\"f\",\"fabric_id\":1,\"mach_uuid\":\"m\",\"mach_id\":1,\"mach_name\":\"n\","
+    "\"tenant_uuid\":\"t\",\"resources\":[{\"res_uuid\":\"GPU-1\",\"res_name\":\"res-0\",\"res_type\":\"gpu\","
+    "\"res_status\":1,\"res_op_status\":\"0\",\"res_serial_num\":\"s\",\"res_spec\":{\"condition\":[{\"column\":\"model\","
+    "\"operator\":\"eq\",\"value\":\"NVIDIA-B200\"}]}}]}]}}",
+    // CM machine
+    "{\"data\":{\"cluster\":{\"cluster_uuid\":\"c\",\"machine\":{\"uuid\":\"m\",\"name\":\"n\",\"status\":\"s\","
+    "\"status_reason\":\"\",\"resspecs\":[{\"spec_uuid\":\"su\",\"type\":\"gpu\",\"selector\":{\"version\":\"1\","
+    "\"expression\":{\"conditions\":[{\"column\":\"model\",\"operator\":\"eq\",\"value\":\"NVIDIA-B200\"}]}},"
+    "\"min_resspec_count\":0,\"max_resspec_count\":2,\"device_count\":1,\"devices\":[{\"device_uuid\":\"GPU-1\","
+    "\"status\":\"ADD_COMPLETE\",\"status_reason\":\"\",\"detail\":{\"fabr_gid\":\"g\",\"res_uuid\":\"GPU-1\","
+    "\"fabr_uuid\":\"f\",\"res_type\":\"gpu\",\"res_name\":\"r\",\"res_status\":\"1\",\"res_op_status\":\"0\","
+    "\"res_spec\":[{\"name\":\"model\",\"value\":\"NVIDIA-B200\"}],\"tenant_id\":\"t\",\"mach_id\":\"m\"}}]}]}}}}",
+    "{\"a\":[1,2.5e3,-0,true,false,null,\"\\u00e9\\ud83d\\ude00\\n\"],\"b\":{\"c\":{}}}",
+    "[[[[[[[[[[[[[[[[[[[[[[[[[[[[[[[[]]]]]]]]]]]]]]]]]]]]]]]]]]]]]]]]",
+};
+
+static std::string mutate(std::string s) {
+    const int ops = 1 + (int)(rnd() % 4);
+    for (int k = 0; k < ops; ++k) {
+        const uint64_t r = rnd();
+        switch (r % 7) {
+        case 0: if (!s.empty()) s[(r >> 8) % s.size()] = (char)(r >> 40); break;                   // byte flip
+        case 1: if (!s.empty()) s.resize((r >> 8) % s.size()); break;                               // truncate
+        case 2: s.insert((r >> 8) % (s.size() + 1), 1, (char)(r >> 40)); break;                     // insert
+        case 3: if (!s.empty()) { size_t a = (r >> 8) % s.size(); s += s.substr(a, (r >> 32) % 64); } break;  // splice
+        case 4: if (!s.empty()) s.erase((r >> 8) % s.size(), (r >> 32) % 8); break;                 // delete
+        case 5: { static const char* tok[] = {"\"", "\\", "\\u", "\\ud800", "{", "[", ",", ":", "\n", "\r\n", ", ",
+                                               "\xc3", "\xe2\x80\xa8", "\xff", "1e999", "-", "0000", "null"};
+                  s.insert((r >> 8) % (s.size() + 1), tok[(r >> 40) % (sizeof tok / sizeof *tok)]); } break;
+        default: { const char* o = kCorpus[(r >> 8) % (sizeof kCorpus / sizeof *kCorpus)]; s += o; } break;
+        }
+    }
+    return s;
+}
+
+static size_t sink = 0;   // keeps results alive
+
+static void one(const std::string& in, const std::string& err_text) {
+    const char* exec_err = (rnd() & 7) == 0 ? "command terminated with exit code 1" : nullptr;
+    static const char* queries[] = {"device_minor,gpu_uuid,pci.bus_id", "gpu_uuid", "index,gpu_uuid,name,pci.bus_id", ""};
+    const std::string q = queries[rnd() % 4];
+    {
+        auto r = identity::getGPUInfoFromNvidiaSmiOutput(in, err_text, exec_err, q);
+        sink += identity::GpuInfosToJson(r).size() + r.error.size();
+        auto p = identity::getGPUInfoFromProcOutput(in, err_text, exec_err, q);
+        sink += identity::GpuInfosToJson(p).size() + p.error.size();
+        sink += identity::ProcInformationToLine(in).size();
+        std::string out;
+        for (int kind = 0; kind < 6; ++kind) sink += (size_t)identity::Normalize(kind, in, &out) + out.size();
+        sink += identity::TrimSpace(in).size() + identity::Split(in, q.empty() ? "," : ", ").size();
+    }
+    {
+        const std::string target = "GPU-1";
+        sink += detach::CheckNoGPULoadsFromOutput(in, err_text, exec_err, "pod", "node", (rnd() & 1) ? &target : nullptr,
+                                                  rnd() & 1).msg.size();
+        bool draining = false;
+        sink += detach::checkGPUDrainStatusFromOutput(in, err_text, exec_err, "node", "0000:1F:00.0", &draining).msg.size();
+        sink += detach::CheckDeviceFileScanResult(in, err_text, exec_err, rnd() & 1).msg.size();
+    }
+    {
+        std::string e;
+        auto v = gojson::parse(in, &e);
+        sink += e.size() + (v ? v->arr.size() + v->obj.size() : 0);
+        std::string quoted;
+        gojson::append_string(quoted, in);
+        std::string e2;
+        auto back = gojson::parse(quoted, &e2);          // whatever goes in must come back as a string value
+        if (!back || back->kind != gojson::Value::String) {
+            std::fprintf(stderr, "append_string produced unparsable JSON: %s\n", e2.c_str());
+            std::abort();
+        }
+    }
+    {
+        std::string id, cdi;
+        sink += controller::FMScaleUpResponseToIDs(in, "res-0", "gpu", "NVIDIA-B200", &id, &cdi).msg.size() + id.size();
+        auto a = controller::CMCheckAddingResources(in, {"GPU-0"}, "gpu", "NVIDIA-B200");
+        sink += sizeof a;
+        std::vector<fabric::DeviceInfo> devs;
+        sink += fabric::FMCheckResource(in, "gpu", "NVIDIA-B200", "GPU-1").msg.size();
+        sink += fabric::CMCheckResource(in, "gpu", "NVIDIA-B200", "GPU-1").msg.size();
+        sink += fabric::FMGetResources(in, "node", "m", &devs).msg.size();
+        sink += fabric::CMGetResources(in, "node", "m", &devs).msg.size();
+        sink += fabric::DeviceInfosToJson(devs).size();
+    }
+}
+
+int main(int argc, char** argv) {
+    const long iters = argc > 1 ? std::atol(argv[1]) : 20000;
+    const size_t n = sizeof kCorpus / sizeof *kCorpus;
+    for (size_t i = 0; i < n; ++i) one(kCorpus[i], "");
+    one(std::string(1 << 20, '['), "");                      // nesting bomb: must fail cleanly, not overflow the stack
+    one("{\"a\":" + std::string(1 << 18, '{'), "");
+    one(std::string(1 << 20, ','), "");                      // a million empty CSV fields
+    one(std::string(1 << 16, '\n'), "");
+    for (long i = 0; i < iters; ++i) {
+        std::string s = mutate(kCorpus[rnd() % n]);
+        if ((rnd() & 3) == 0) s = mutate(s);
+        one(s, (rnd() & 7) == 0 ? mutate("NVIDIA-SMI has failed") : "");
+    }
+    std::printf("host fuzz ok: %ld inputs, sink %zu\n", iters, sink);
+    return 0;
+}
