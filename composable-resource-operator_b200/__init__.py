@@ -115,7 +115,7 @@ EXPORTS = [
     "cro_sim_reconcile_request", "cro_sim_dump", "cro_probe_begin", "cro_probe_end",
     "cro_check_no_gpu_loads", "cro_check_gpu_drain_status", "cro_check_device_file_scan",
     "cro_scan_device_file_holders", "cro_sim_reconcile_resource", "cro_sim_sync_upstream",
-    "cro_fabric_check_resource", "cro_fabric_get_resources",
+    "cro_fabric_check_resource", "cro_fabric_get_resources", "cro_fabric_list_devices",
 ]
 
 
@@ -178,6 +178,7 @@ def _load() -> ctypes.CDLL:
         "cro_sim_dump": (i32, [vp] + out),
         "cro_fabric_check_resource": (i32, [c, c, c, c, c, c, sz]),
         "cro_fabric_get_resources": (i32, [c, c, c, c] + out),
+        "cro_fabric_list_devices": (i32, [c] + out),
         "cro_sim_reconcile_resource": (i32, [vp, c, c, sz]),
         "cro_sim_sync_upstream": (i32, [vp, c, ctypes.c_longlong, c, sz]),
         "cro_check_no_gpu_loads": (i32, [c, c, c, c, c, c, i32, c, sz]),
@@ -468,6 +469,12 @@ def fabric_check_resource(kind: str, machine_body: str, res_type: str, model: st
 def fabric_get_resources(kind: str, machine_body: str, node_name: str, machine_uuid: str) -> List[Dict]:
     """CdiProvider.GetResources decode for one node (fm/client.go:385-410, cm/client.go:335-343)."""
     return json.loads(_text(lib.cro_fabric_get_resources, _b(kind), _b(machine_body), _b(node_name), _b(machine_uuid)))
+
+
+def fabric_list_devices(request: Dict) -> Dict:
+    """CdiProvider.GetResources of the FM / CM client over a scripted fabric (what the UpstreamSyncer
+    tick reads: upstreamsyncer_controller.go:77-84).  request = {"env": {...}, "fabric": {...}}."""
+    return json.loads(_text(lib.cro_fabric_list_devices, _b(json.dumps(request))))
 
 
 def CheckNoGPULoadsFromOutput(std_out: str, std_err: str, exec_err: Optional[str], pod_name: str, node_name: str,

@@ -12,6 +12,9 @@
 #include "cluster.hpp"
 #include "detach.hpp"
 #include "fabric.hpp"
+#include "provider.hpp"
+#include "nodes.hpp"
+#include <memory>
 
 using namespace cro;
 
@@ -239,64 +242,21 @@ int cro_emit_scalar_status_json(const char* state, const char* device_id, const 
 
 int cro_emit_fm_scale_up(const char* tenant_uuid, const char* mach_uuid, const char* res_type,
                          const char* model, char* buf, size_t cap, size_t* len) {
-    // internal/cdi/fti/fm/api/scale_up.go:19-41, built at fti/fm/client.go:115-143
-    gojson::Writer w;
-    w.begin_object().key("tenants").begin_object();
-    w.field("tenant_uuid", S(tenant_uuid));
-    w.key("machines").begin_array().begin_object();
-    w.field("mach_uuid", S(mach_uuid));
-    w.key("resources").begin_array().begin_object();
-    w.key("res_specs").begin_array().begin_object();
-    w.field("res_type", S(res_type));
-    w.key("res_spec").begin_object().key("condition").begin_array().begin_object();
-    w.field("column", std::string("model")).field("operator", std::string("eq")).field("value", S(model));
-    w.end_object().end_array().end_object();
-    w.field("res_num", 1);
-    w.end_object().end_array();      // res_specs
-    w.end_object().end_array();      // resources
-    w.end_object().end_array();      // machines
-    w.end_object().end_object();
-    return copy_out(w.str(), buf, cap, len);
+    return copy_out(fabric::FMScaleUpBody(S(tenant_uuid), S(mach_uuid), S(res_type), S(model)), buf, cap, len);
 }
 
 int cro_emit_fm_scale_down(const char* tenant_uuid, const char* mach_uuid, const char* res_type,
                            const char* res_uuid, char* buf, size_t cap, size_t* len) {
-    // internal/cdi/fti/fm/api/scale_down.go:19-41, built at fti/fm/client.go:247-270
-    gojson::Writer w;
-    w.begin_object().key("tenants").begin_object();
-    w.field("tenant_uuid", S(tenant_uuid));
-    w.key("machines").begin_array().begin_object();
-    w.field("mach_uuid", S(mach_uuid));
-    w.key("resources").begin_array().begin_object();
-    w.key("res_specs").begin_array().begin_object();
-    w.field("res_type", S(res_type));
-    w.field("res_uuid", S(res_uuid));
-    w.field("res_num", 1);
-    w.end_object().end_array();
-    w.end_object().end_array();
-    w.end_object().end_array();
-    w.end_object().end_object();
-    return copy_out(w.str(), buf, cap, len);
+    return copy_out(fabric::FMScaleDownBody(S(tenant_uuid), S(mach_uuid), S(res_type), S(res_uuid)), buf, cap, len);
 }
 
 int cro_emit_cm_scale_up(const char* spec_uuid, int device_count, char* buf, size_t cap, size_t* len) {
-    // internal/cdi/fti/cm/client.go:62-69
-    gojson::Writer w;
-    w.begin_object().key("increase_resource_count").begin_object();
-    w.field("spec_uuid", S(spec_uuid)).field("device_count", device_count);
-    w.end_object().end_object();
-    return copy_out(w.str(), buf, cap, len);
+    return copy_out(fabric::CMScaleUpBody(S(spec_uuid), device_count), buf, cap, len);
 }
 
 int cro_emit_cm_scale_down(const char* spec_uuid, int device_count, const char* device_id, char* buf,
                            size_t cap, size_t* len) {
-    // internal/cdi/fti/cm/client.go:71-79
-    gojson::Writer w;
-    w.begin_object().key("remove_resources").begin_object();
-    w.field("spec_uuid", S(spec_uuid)).field("device_count", device_count);
-    w.key("devices").begin_array().value(S(device_id)).end_array();
-    w.end_object().end_object();
-    return copy_out(w.str(), buf, cap, len);
+    return copy_out(fabric::CMScaleDownBody(S(spec_uuid), device_count, S(device_id)), buf, cap, len);
 }
 
 int cro_emit_sunfish_request(const char* name, long long count, const char* proc_type, const char* model,
@@ -435,7 +395,7 @@ public:
             return fabric::CMCheckResource(cm->str, inst.Spec.Type, inst.Spec.Model, inst.Status.DeviceID);
         return controller::Error::Nil();
     }
-    controller::Error RemoveResource(const controller::ComposableResource&) override {
+    controller::Error RemoveResource(controller::ComposableResource&) override {
         const gojson::Value* rm = p_ ? p_->get("remove") : nullptr;
         if (!rm) return controller::Error::Nil();
         if (rm->get_bool("waiting")) return controller::Error::New(controller::ErrWaitingDeviceDetaching);
@@ -446,6 +406,130 @@ public:
 private:
     const gojson::Value* p_;
 };
+
+// ---- scripted fabric: the reference's httptest server + envtest objects, as data -------------
+// "fabric": {"http": [{"method": "GET", "path_contains": "/machines/", "status": 404, "body": "..."}, ...],
+//            "transport_error": "", "token_error": "",
+//            "objects": {"nodes": {"worker-0": {"annotations": {..}, "provider_id": ""}},
+//                        "metal3machines": {"ns/name": {"annotations": {..}}}, "baremetalhosts": {"ns/name": {..}},
+//                        "composable_resource_device_ids": ["GPU-.."], "status_update_error": ""}}
+class ScriptedTransport : public fabric::Transport {
+public:
+    explicit ScriptedTransport(const gojson::Value* f) : f_(f) {}
+    fabric::HttpReply Do(const fabric::HttpRequest& req) override {
+        fabric::HttpReply rep;
+        if (f_) {
+            const std::string terr = f_->get_string("transport_error");
+            if (!terr.empty()) { rep.transport_error = terr; return rep; }
+            const gojson::Value* rules = f_->get("http");
+            if (rules && rules->kind == gojson::Value::Array)
+                for (const auto& r : rules->arr) {
+                    if (r->kind != gojson::Value::Object) continue;
+                    const std::string m = r->get_string("method");
+                    if (!m.empty() && m != req.method) continue;
+                    const gojson::Value* exact = r->get("path");             // "path": whole path, like the
+                    if (exact && exact->kind == gojson::Value::String) {     // reference's `switch r.URL.Path`
+                        if (exact->str != req.path) continue;
+                    } else if (req.path.find(r->get_string("path_contains")) == std::string::npos) {
+                        continue;
+                    }
+                    rep.status = (int)r->get_int("status", 200);
+                    rep.body = r->get_string("body");
+                    return rep;
+                }
+        }
+        rep.transport_error = req.method + " \"https://fabric/" + req.path + "\": no route in the scripted fabric";
+        return rep;
+    }
+
+private:
+    const gojson::Value* f_;
+};
+
+class JsonObjectStore : public fabric::ObjectStore {
+public:
+    explicit JsonObjectStore(const gojson::Value* f) : o_(f ? f->get("objects") : nullptr) {}
+    std::vector<controller::ComposableResourceStatus>* updates = nullptr;
+
+    controller::Error GetNode(const std::string& name, fabric::K8sObject* out) override {
+        return get("nodes", "nodes", name, name, out);
+    }
+    controller::Error GetMetal3Machine(const std::string& ns, const std::string& name, fabric::K8sObject* out) override {
+        return get("metal3machines", "metal3machines.infrastructure.cluster.x-k8s.io", ns + "/" + name, name, out);
+    }
+    controller::Error GetBareMetalHost(const std::string& ns, const std::string& name, fabric::K8sObject* out) override {
+        return get("baremetalhosts", "baremetalhosts.metal3.io", ns + "/" + name, name, out);
+    }
+    controller::Error ListNodeNames(std::vector<std::string>* out) override {
+        const gojson::Value* c = o_ ? o_->get("nodes") : nullptr;
+        if (c && c->kind == gojson::Value::Object)
+            for (const auto& kv : c->obj) out->push_back(kv.first);
+        return controller::Error::Nil();
+    }
+    controller::Error ListComposableResourceDeviceIDs(std::vector<std::string>* out) override {
+        const gojson::Value* c = o_ ? o_->get("composable_resource_device_ids") : nullptr;
+        if (c && c->kind == gojson::Value::Array)
+            for (const auto& e : c->arr)
+                if (e->kind == gojson::Value::String) out->push_back(e->str);
+        return controller::Error::Nil();
+    }
+    controller::Error UpdateStatus(const controller::ComposableResource& instance) override {
+        const std::string e = o_ ? o_->get_string("status_update_error") : std::string();
+        if (!e.empty()) return controller::Error::New(e);
+        if (updates) updates->push_back(instance.Status);
+        return controller::Error::Nil();
+    }
+
+private:
+    controller::Error get(const char* coll, const char* resource, const std::string& key, const std::string& name,
+                          fabric::K8sObject* out) {
+        const gojson::Value* c = o_ ? o_->get(coll) : nullptr;
+        const gojson::Value* v = (c && c->kind == gojson::Value::Object) ? c->get(key) : nullptr;
+        if (!v || v->kind != gojson::Value::Object)   // apimachinery NewNotFound(gr, name).Error()
+            return controller::Error::New(std::string(resource) + " \"" + name + "\" not found");
+        out->name = name;
+        out->provider_id = v->get_string("provider_id");
+        const gojson::Value* a = v->get("annotations");
+        if (a && a->kind == gojson::Value::Object) {
+            out->has_annotations = true;
+            for (const auto& kv : a->obj)
+                if (kv.second->kind == gojson::Value::String) out->annotations[kv.first] = kv.second->str;
+        }
+        return controller::Error::Nil();
+    }
+    const gojson::Value* o_;
+};
+
+class JsonTokenSource : public fabric::TokenSource {
+public:
+    explicit JsonTokenSource(const gojson::Value* f) : f_(f) {}
+    controller::Error GetToken() override {
+        const std::string e = f_ ? f_->get_string("token_error") : std::string();
+        return e.empty() ? controller::Error::Nil() : controller::Error::New(e);
+    }
+
+private:
+    const gojson::Value* f_;
+};
+
+// NewComposableResourceAdapter (composableresource_adapter.go:39-72) over an env map: which
+// provider flavour, or the error the reconcile surfaces.  "" kind + nil error never happens.
+controller::Error SelectAdapter(const gojson::Value* env, std::string* kind) {
+    const std::string drt = env->get_string("DEVICE_RESOURCE_TYPE");
+    if (drt != "DEVICE_PLUGIN" && drt != "DRA")
+        return controller::Error::New("the env variable DEVICE_RESOURCE_TYPE has an invalid value: '" + drt + "'");
+    const std::string provider = env->get_string("CDI_PROVIDER_TYPE");
+    if (provider == "SUNFISH") { *kind = "sunfish"; return controller::Error::Nil(); }
+    if (provider == "FTI_CDI") {
+        if (env->get_string("FTI_CDI_CLUSTER_ID").empty() && drt == "DEVICE_PLUGIN")
+            return controller::Error::New("The cluster in RKE2 does not support DEVICE_PLUGIN, please use DRA");
+        const std::string api = env->get_string("FTI_CDI_API_TYPE");
+        if (api == "CM") { *kind = "cm"; return controller::Error::Nil(); }
+        if (api == "FM") { *kind = "fm"; return controller::Error::Nil(); }
+        return controller::Error::New("the env variable FTI_CDI_API_TYPE has an invalid value: '" + api + "'");
+    }
+    return controller::Error::New("the env variable CDI_PROVIDER_TYPE has an invalid value: '" + provider + "'");
+}
 
 class ProbeNodeOps : public controller::NodeOps {
 public:
@@ -460,8 +544,32 @@ public:
             const std::string e = errs->get_string(ns + "/" + name);
             if (!e.empty()) return controller::Error::New(e);
         }
-        return controller::Error::Nil();
+        // "daemonsets": {"ns/name": {"desired":1,"ready":1,"current":1,"unavailable":0,"misscheduled":0,
+        //                            "restarted_at":"2025-01-01T00:00:00Z"}}, "now": "<RFC3339>":
+        // the restart rule of internal/utils/nodes.go:35-76 decides; absent objects keep the old "restart ok".
+        const gojson::Value* sets = in_->get("daemonsets");
+        const gojson::Value* ds = (sets && sets->kind == gojson::Value::Object) ? sets->get(ns + "/" + name) : nullptr;
+        if (sets && sets->kind == gojson::Value::Object && !ds)     // client.Get NotFound
+            return controller::Error::New("daemonsets.apps \"" + name + "\" not found");
+        if (!ds || ds->kind != gojson::Value::Object) return controller::Error::Nil();
+        nodes::DaemonSetView v;
+        v.DesiredNumberScheduled = ds->get_int("desired");
+        v.NumberReady = ds->get_int("ready");
+        v.CurrentNumberScheduled = ds->get_int("current");
+        v.NumberUnavailable = ds->get_int("unavailable");
+        v.NumberMisscheduled = ds->get_int("misscheduled");
+        if (const gojson::Value* ra = ds->get("restarted_at"))
+            if (ra->kind == gojson::Value::String) { v.hasRestartedAt = true; v.restartedAt = ra->str; }
+        long long now = 0, nowNs = 0;
+        std::string perr;
+        const std::string nowText = in_->get_string("now", "2025-01-01T00:00:00Z");
+        if (!nodes::ParseRFC3339(nowText, &now, &nowNs, &perr)) return controller::Error::New("bad \"now\": " + perr);
+        nodes::Restart what;
+        controller::Error e = nodes::RestartDaemonsetDecision(ns, name, v, now, nowNs, &what);
+        if (e.ok() && what == nodes::Restart::Restarted) restarted.push_back(ns + "/" + name + "@" + nodes::FormatRFC3339UTC(now));
+        return e;
     }
+    std::vector<std::string> restarted;   // "ns/name@<restartedAt stamp>" for every Update the rule issued
     controller::Error RunNvidiaSmi(const std::string& node) override {
         std::vector<std::string> uuids;
         return enumerate(node, &uuids);
@@ -609,14 +717,37 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
         if (lb->kind == gojson::Value::Object)
             for (const auto& kv : lb->obj)
                 if (kv.second->kind == gojson::Value::String) res.Labels[kv.first] = kv.second->str;
-    const std::string type = in->get_string("device_resource_type", "DEVICE_PLUGIN");
+    std::string type = in->get_string("device_resource_type", "DEVICE_PLUGIN");
 
-    JsonProvider provider(in->get("provider"));
+    // With an "env" object the adapter is chosen the way the operator does it and the provider is
+    // the real FM / CM client over the scripted fabric; otherwise the canned JsonProvider.
+    const gojson::Value* env = in->get("env");
+    const gojson::Value* fab = in->get("fabric");
+    ScriptedTransport transport(fab);
+    JsonObjectStore store(fab);
+    JsonTokenSource tokens(fab);
+    std::unique_ptr<fabric::FTIClientBase> fti;
+    controller::Error adapterErr;
+    if (env && env->kind == gojson::Value::Object) {
+        type = env->get_string("DEVICE_RESOURCE_TYPE");
+        std::string kind;
+        adapterErr = SelectAdapter(env, &kind);
+        fabric::ClientConfig cfg{env->get_string("FTI_CDI_TENANT_ID"), env->get_string("FTI_CDI_CLUSTER_ID")};
+        if (kind == "fm") fti.reset(new fabric::FMClient(cfg, &transport, &store, &tokens));
+        else if (kind == "cm") fti.reset(new fabric::CMClient(cfg, &transport, &store, &tokens));
+        else if (adapterErr.ok()) adapterErr = controller::Error::New("provider kind '" + kind + "' is not scripted in this harness");
+    }
+
+    JsonProvider canned(in->get("provider"));
+    controller::CdiProvider* provider = fti ? static_cast<controller::CdiProvider*>(fti.get()) : &canned;
     ProbeNodeOps node(ctx, in.get());
-    controller::ComposableResourceReconciler rec(&provider, &node);
+    controller::ComposableResourceReconciler rec(provider, &node);
+    store.updates = &rec.statusUpdates;
     controller::Result result;
     controller::Error err;
-    if (type != "DEVICE_PLUGIN" && type != "DRA") {
+    if (!adapterErr.ok()) {
+        err = rec.requeueOnErr(&res, adapterErr);          // composableresource_controller.go:91-94
+    } else if (type != "DEVICE_PLUGIN" && type != "DRA") {
         // composableresource_adapter.go:42-45
         err = rec.requeueOnErr(&res, controller::Error::New(
                                          "the env variable DEVICE_RESOURCE_TYPE has an invalid value: '" + type + "'"));
@@ -640,6 +771,20 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
     for (const auto& s : rec.statusUpdates) w.raw(s.MarshalJSON());
     w.end_array();
     if (node.probed) w.key("probe").string_map(probe_annotations(node.probe_result));
+    if (!node.restarted.empty()) {
+        w.key("daemonset_restarts").begin_array();
+        for (const auto& r : node.restarted) w.value(r);
+        w.end_array();
+    }
+    if (fti) {
+        w.key("fabric_requests").begin_array();
+        for (const auto& r : fti->requests) {
+            w.begin_object();
+            w.field("method", r.method).field("path", r.path).field("query", r.query).field("body", r.body);
+            w.end_object();
+        }
+        w.end_array();
+    }
     w.end_object();
     return copy_out(w.str(), buf, cap, len);
 }
@@ -670,6 +815,45 @@ int cro_fabric_get_resources(const char* kind, const char* machine_body, const c
         return CRO_ERR_PARSE;
     }
     return copy_out(fabric::DeviceInfosToJson(v), buf, cap, len);
+}
+
+int cro_fabric_list_devices(const char* request_json, char* buf, size_t cap, size_t* len) {
+    if (!request_json) return CRO_ERR_INVALID_ARG;
+    std::string perr;
+    gojson::ValuePtr in = gojson::parse(request_json, &perr);
+    if (!in || in->kind != gojson::Value::Object) {
+        copy_out("bad request: " + perr, buf, cap, len);
+        return CRO_ERR_PARSE;
+    }
+    const gojson::Value* env = in->get("env");
+    const gojson::Value* fab = in->get("fabric");
+    if (!env || env->kind != gojson::Value::Object) return CRO_ERR_INVALID_ARG;
+    ScriptedTransport transport(fab);
+    JsonObjectStore store(fab);
+    JsonTokenSource tokens(fab);
+    std::string kind;
+    controller::Error e = SelectAdapter(env, &kind);
+    std::unique_ptr<fabric::FTIClientBase> fti;
+    fabric::ClientConfig cfg{env->get_string("FTI_CDI_TENANT_ID"), env->get_string("FTI_CDI_CLUSTER_ID")};
+    if (kind == "fm") fti.reset(new fabric::FMClient(cfg, &transport, &store, &tokens));
+    else if (kind == "cm") fti.reset(new fabric::CMClient(cfg, &transport, &store, &tokens));
+    else if (e.ok()) e = controller::Error::New("provider kind '" + kind + "' is not scripted in this harness");
+    std::vector<fabric::DeviceInfo> devs;
+    if (fti) e = fti->GetResources(&devs);
+    gojson::Writer w;
+    w.begin_object();
+    w.key("devices").raw(fabric::DeviceInfosToJson(devs));
+    w.field("error", e.ok() ? std::string() : e.msg);
+    w.key("fabric_requests").begin_array();
+    if (fti)
+        for (const auto& r : fti->requests) {
+            w.begin_object();
+            w.field("method", r.method).field("path", r.path).field("query", r.query).field("body", r.body);
+            w.end_object();
+        }
+    w.end_array();
+    w.end_object();
+    return copy_out(w.str(), buf, cap, len);
 }
 
 // ---- detach-side pre-flight -------------------------------------------------------

@@ -197,6 +197,9 @@ void Cluster::updateRequest(const ComposabilityRequest& r) {
     const ComposabilityRequest& old = it->second;
     const bool changed = !(old.Status == r.Status) || !(old.Spec == r.Spec) || old.Finalizers != r.Finalizers ||
                          old.DeletionTimestampSet != r.DeletionTimestampSet;
+    // r.Update (finalizers) comes before r.Status().Update in every handler that does both
+    if (!fault_update_.empty() && (old.Finalizers != r.Finalizers || !(old.Spec == r.Spec))) throw ApiFault{fault_update_};
+    if (!fault_status_update_.empty() && !(old.Status == r.Status)) throw ApiFault{fault_status_update_};
     if (!(old.Status == r.Status)) {   // Status().Update marshals the status: one emitted spec
         ++stats.status_updates;
         stats.spec_bytes += (long long)r.Status.MarshalJSON().size();
@@ -242,6 +245,9 @@ void Cluster::updateResource(const StoredResource& r) {
                                 old.obj.Status.CDIDeviceID != r.obj.Status.CDIDeviceID;
     const bool changed = status_changed || old.Finalizers != r.Finalizers || old.obj.Labels != r.obj.Labels ||
                          old.Annotations != r.Annotations || old.obj.DeletionTimestampSet != r.obj.DeletionTimestampSet;
+    if (!fault_update_.empty() && (old.Finalizers != r.Finalizers || old.obj.Labels != r.obj.Labels || old.Annotations != r.Annotations))
+        throw ApiFault{fault_update_};
+    if (!fault_status_update_.empty() && status_changed) throw ApiFault{fault_status_update_};
     if (status_changed) {
         ++stats.status_updates;
         stats.spec_bytes += (long long)r.obj.Status.MarshalJSON().size();
@@ -280,11 +286,40 @@ Error Cluster::Apply(const gojson::Value& v) {
     const gojson::Value* res = v.get("resource");
     ScalarResourceDetails d = detailsFromJson(res);
     // CRD validation (config/crd/bases/...composabilityrequests.yaml:45-90)
-    if (d.Type != "gpu" && d.Type != "cxlmemory") return Error::New("spec.resource.type: Unsupported value: \"" + d.Type + "\"");
-    if (d.Model.empty()) return Error::New("spec.resource.model: Invalid value: \"\"");
-    if (d.Size < 0) return Error::New("spec.resource.size: Invalid value");
-    if (d.AllocationPolicy != "samenode" && d.AllocationPolicy != "differentnode")
-        return Error::New("spec.resource.allocation_policy: Unsupported value: \"" + d.AllocationPolicy + "\"");
+    // The API server's words (apimachinery field.ErrorList -> StatusError), pinned one field at a time by
+    // composabilityrequest_controller_test.go:324-412; several bad fields aggregate as "[a, b]" (order unpinned).
+    {
+        std::vector<std::string> errs;
+        auto quoted = [](const std::string& s) { std::string o; gojson::append_string(o, s); return o; };
+        auto minimum = [&](const char* path, long long v) {
+            if (v < 0)
+                errs.push_back(std::string(path) + ": Invalid value: " + std::to_string(v) + ": " + path +
+                               " in body should be greater than or equal to 0");
+        };
+        if (d.Type != "gpu" && d.Type != "cxlmemory")
+            errs.push_back("spec.resource.type: Unsupported value: " + quoted(d.Type) + ": supported values: \"gpu\", \"cxlmemory\"");
+        if (d.Model.empty())
+            errs.push_back("spec.resource.model: Invalid value: \"\": spec.resource.model in body should be at least 1 chars long");
+        minimum("spec.resource.size", d.Size);
+        if (d.AllocationPolicy != "samenode" && d.AllocationPolicy != "differentnode")
+            errs.push_back("spec.resource.allocation_policy: Unsupported value: " + quoted(d.AllocationPolicy) +
+                           ": supported values: \"samenode\", \"differentnode\"");
+        if (d.HasOtherSpec) {
+            minimum("spec.resource.other_spec.milli_cpu", d.OtherSpec.MilliCPU);
+            minimum("spec.resource.other_spec.memory", d.OtherSpec.Memory);
+            minimum("spec.resource.other_spec.ephemeral_storage", d.OtherSpec.EphemeralStorage);
+            minimum("spec.resource.other_spec.allowed_pod_number", d.OtherSpec.AllowedPodNumber);
+        }
+        if (!errs.empty()) {
+            std::string all = errs[0];
+            if (errs.size() > 1) {
+                all = "[" + errs[0];
+                for (size_t i = 1; i < errs.size(); ++i) all += ", " + errs[i];
+                all += "]";
+            }
+            return Error::New("ComposabilityRequest.cro.hpsys.ibm.ie.com \"" + name + "\" is invalid: " + all);
+        }
+    }
     // admission webhook (internal/webhook/v1alpha1/composabilityrequest_webhook.go:107-110)
     if (d.AllocationPolicy == "differentnode" && !d.TargetNode.empty())
         return Error::New("TargetNode cannot be specified when AllocationPolicy is set to 'differentnode'");
@@ -314,6 +349,11 @@ Error Cluster::Delete(const std::string& name) {
 Error Cluster::Plant(const gojson::Value& v) {
     const std::string kind = v.get_string("kind");
     const std::string name = v.get_string("name");
+    if (kind == "Fault") {   // arm / clear the API-server faults
+        fault_update_ = v.get_string("update");
+        fault_status_update_ = v.get_string("status_update");
+        return Error::Nil();
+    }
     if (kind == "ComposabilityRequest") {
         ComposabilityRequest r;
         r.Name = name;
@@ -378,7 +418,7 @@ public:
     Error requeueOnErr(ComposabilityRequest* r, const Error& err) {   // :627-637
         if (r) {
             r->Status.Error = err.msg;
-            c_->updateRequest(*r);
+            try { c_->updateRequest(*r); } catch (const ApiFault&) {}   // best effort (:631-634): the original error wins
         }
         return err;
     }
@@ -716,7 +756,7 @@ public:
         c_->attached_.insert(inst.Name);
         return Error::Nil();
     }
-    Error RemoveResource(const controller::ComposableResource& inst) override {
+    Error RemoveResource(controller::ComposableResource& inst) override {
         c_->attached_.erase(inst.Name);
         return Error::Nil();
     }
@@ -852,13 +892,25 @@ private:
     SimNodeOps node_;
 };
 
+// A failed write ends the handler where it stands (Go: `if err := r.Update(...); err != nil { return requeueOnErr }`)
+// and the reconcile returns that error; nothing the handler did after the last good write survives.
 Error Cluster::reconcileRequest(const std::string& key, long long* requeue) {
     RequestReconciler r(this);
-    return r.Reconcile(key, requeue);
+    try {
+        return r.Reconcile(key, requeue);
+    } catch (const ApiFault& f) {
+        *requeue = 0;
+        return Error::New(f.msg);
+    }
 }
 Error Cluster::reconcileResource(const std::string& key, long long* requeue) {
     ResourceReconciler r(this);
-    return r.Reconcile(key, requeue);
+    try {
+        return r.Reconcile(key, requeue);
+    } catch (const ApiFault& f) {
+        *requeue = 0;
+        return Error::New(f.msg);
+    }
 }
 
 Error Cluster::ReconcileRequestOnce(const std::string& name) {
@@ -1057,6 +1109,9 @@ std::string Cluster::DumpJSON() const {
         w.key("status").raw(r.Status.MarshalJSON());
         w.key("labels").string_map(r.Labels);
         w.field("deleting", r.DeletionTimestampSet);
+        w.key("finalizers").begin_array();
+        for (const auto& f : kv.second.Finalizers) w.value(f);
+        w.end_array();
         w.end_object();
     }
     w.end_object();

@@ -89,6 +89,10 @@ struct ComposabilityRequest {
     ComposabilityRequestStatus Status;
 };
 
+struct ApiFault {   // thrown by a write the armed fault refuses; caught at the reconcile boundary
+    std::string msg;
+};
+
 struct StoredResource {
     controller::ComposableResource obj;
     std::map<std::string, std::string> Annotations;
@@ -153,6 +157,9 @@ private:
 
     cro_ctx* ctx_;
     std::string deviceResourceType_ = "DEVICE_PLUGIN";
+    // API-server fault injection (the reference's MockUpdate / MockStatusUpdate hooks): while armed,
+    // Update() resp. Status().Update() of either kind fails with this text and writes nothing.
+    std::string fault_update_, fault_status_update_;
     bool probe_ = false;
     std::vector<Node> nodes_;                                   // sorted by name (API list order)
     std::map<std::string, ComposabilityRequest> requests_;

@@ -32,7 +32,7 @@ Error FMCheckResource(const std::string& body, const std::string& specType, cons
                       const std::string& deviceID) {
     std::string perr;
     gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!root || root->kind != Value::Object)
+    if (!gojson::rootOk(root, &perr, "api.GetMachineResponse"))
         return Error::New("failed to unmarshal FM get machine response body into machineData: " + perr);
     const Value* machines = arr(root->get("data"), "machines");
     if (!machines || machines->arr.empty())   // fm/client.go:331 indexes Machines[0] unguarded
@@ -58,7 +58,7 @@ Error FMGetResources(const std::string& body, const std::string& nodeName, const
                      std::vector<DeviceInfo>* out) {
     std::string perr;
     gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!root || root->kind != Value::Object)
+    if (!gojson::rootOk(root, &perr, "api.GetMachineResponse"))
         return Error::New("failed to unmarshal FM get machine response body into machineData: " + perr);
     const Value* machines = arr(root->get("data"), "machines");
     if (!machines || machines->arr.empty()) return Error::Nil();   // fm/client.go:385-387
@@ -83,7 +83,7 @@ Error CMCheckResource(const std::string& body, const std::string& specType, cons
                       const std::string& deviceID) {
     std::string perr;
     gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!root || root->kind != Value::Object)
+    if (!gojson::rootOk(root, &perr, "api.MachineData"))
         return Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
     const Value* data = root->get("data");
     const Value* cluster = data ? data->get("cluster") : nullptr;
@@ -113,7 +113,7 @@ Error CMGetResources(const std::string& body, const std::string& nodeName, const
                      std::vector<DeviceInfo>* out) {
     std::string perr;
     gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!root || root->kind != Value::Object)
+    if (!gojson::rootOk(root, &perr, "api.MachineData"))
         return Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
     const Value* data = root->get("data");
     const Value* cluster = data ? data->get("cluster") : nullptr;

@@ -250,12 +250,13 @@ struct Parser {
         if (++depth > 512) { fail("nesting too deep"); return nullptr; }
         ws();
         ValuePtr v = std::make_shared<Value>();
+        v->raw_begin = i;
         if (i >= t.size()) { fail("unexpected end"); return nullptr; }
         const char c = t[i];
         if (c == '{') {
             v->kind = Value::Object;
             ++i; ws();
-            if (i < t.size() && t[i] == '}') { ++i; --depth; return v; }
+            if (i < t.size() && t[i] == '}') { ++i; --depth; v->raw_end = i; return v; }
             for (;;) {
                 ws();
                 std::string k;
@@ -275,7 +276,7 @@ struct Parser {
         } else if (c == '[') {
             v->kind = Value::Array;
             ++i; ws();
-            if (i < t.size() && t[i] == ']') { ++i; --depth; return v; }
+            if (i < t.size() && t[i] == ']') { ++i; --depth; v->raw_end = i; return v; }
             for (;;) {
                 ValuePtr e = value();
                 if (!e) return nullptr;
@@ -324,12 +325,221 @@ struct Parser {
             return nullptr;
         }
         --depth;
+        v->raw_end = i;
         return v;
     }
 };
 }  // namespace
 
+// ---- Go's validity scanner ----------------------------------------------------
+// json.Unmarshal runs checkValid over the whole input before it decodes anything,
+// so the text of every "invalid character ..." error the reference surfaces comes
+// from this byte-at-a-time state machine (Go stdlib encoding/json/scanner.go,
+// go1.24 per the reference's go.mod; restated from its published behaviour).
+namespace {
+enum class St {
+    BeginValue, BeginValueOrEmpty, BeginStringOrEmpty, BeginString, EndValue, EndTop,
+    InString, InStringEsc, EscU, EscU1, EscU12, EscU123,
+    Neg, Num1, Num0, Dot, Dot0, E, ESign, E0,
+    T, Tr, Tru, F, Fa, Fal, Fals, N, Nu, Nul
+};
+enum class Ps : unsigned char { ObjectKey, ObjectValue, ArrayValue };
+
+std::string quoteChar(unsigned char c) {
+    if (c == '\'') return "'\\''";
+    if (c == '"') return "'\"'";
+    // strconv.Quote(string(rune(c))) without its double quotes
+    std::string s = "'";
+    char buf[8];
+    switch (c) {
+        case '\a': s += "\\a"; break;
+        case '\b': s += "\\b"; break;
+        case '\f': s += "\\f"; break;
+        case '\n': s += "\\n"; break;
+        case '\r': s += "\\r"; break;
+        case '\t': s += "\\t"; break;
+        case '\v': s += "\\v"; break;
+        case '\\': s += "\\\\"; break;
+        default:
+            if (c < 0x20 || c == 0x7f) { snprintf(buf, sizeof buf, "\\x%02x", c); s += buf; }
+            else if (c < 0x80) s.push_back((char)c);
+            else if (c < 0xa1 || c == 0xad) { snprintf(buf, sizeof buf, "\\u%04x", c); s += buf; }  // not IsPrint
+            else { s.push_back((char)(0xC0 | (c >> 6))); s.push_back((char)(0x80 | (c & 0x3F))); }   // U+00A1..U+00FF
+    }
+    return s + "'";
+}
+inline bool isSpaceByte(unsigned char c) { return c <= ' ' && (c == ' ' || c == '\t' || c == '\r' || c == '\n'); }
+inline bool isHex(unsigned char c) {
+    return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'f') || (c >= 'A' && c <= 'F');
+}
+}  // namespace
+
+std::string SyntaxError(const std::string& text) {
+    constexpr size_t kMaxNestingDepth = 10000;
+    St st = St::BeginValue;
+    std::vector<Ps> stack;
+    bool endTop = false;
+    std::string err;
+    auto bad = [&](unsigned char c, const char* context) {
+        err = "invalid character " + quoteChar(c) + " " + context;
+    };
+    auto pop = [&]() {
+        stack.pop_back();
+        if (stack.empty()) { st = St::EndTop; endTop = true; }
+        else st = St::EndValue;
+    };
+    // one step of the machine; `again` re-dispatches the same byte in a new state
+    auto step = [&](unsigned char c) {
+        for (;;) {
+            switch (st) {
+                case St::BeginValueOrEmpty:
+                    if (isSpaceByte(c)) return;
+                    if (c == ']') { st = St::EndValue; continue; }
+                    st = St::BeginValue;
+                    continue;
+                case St::BeginValue:
+                    if (isSpaceByte(c)) return;
+                    switch (c) {
+                        case '{':
+                            st = St::BeginStringOrEmpty;
+                            stack.push_back(Ps::ObjectKey);
+                            if (stack.size() > kMaxNestingDepth) bad(c, "exceeded max depth");
+                            return;
+                        case '[':
+                            st = St::BeginValueOrEmpty;
+                            stack.push_back(Ps::ArrayValue);
+                            if (stack.size() > kMaxNestingDepth) bad(c, "exceeded max depth");
+                            return;
+                        case '"': st = St::InString; return;
+                        case '-': st = St::Neg; return;
+                        case '0': st = St::Num0; return;
+                        case 't': st = St::T; return;
+                        case 'f': st = St::F; return;
+                        case 'n': st = St::N; return;
+                    }
+                    if (c >= '1' && c <= '9') { st = St::Num1; return; }
+                    bad(c, "looking for beginning of value");
+                    return;
+                case St::BeginStringOrEmpty:
+                    if (isSpaceByte(c)) return;
+                    if (c == '}') { stack.back() = Ps::ObjectValue; st = St::EndValue; continue; }
+                    st = St::BeginString;
+                    continue;
+                case St::BeginString:
+                    if (isSpaceByte(c)) return;
+                    if (c == '"') { st = St::InString; return; }
+                    bad(c, "looking for beginning of object key string");
+                    return;
+                case St::EndValue:
+                    if (stack.empty()) { st = St::EndTop; endTop = true; continue; }
+                    if (isSpaceByte(c)) { st = St::EndValue; return; }
+                    switch (stack.back()) {
+                        case Ps::ObjectKey:
+                            if (c == ':') { stack.back() = Ps::ObjectValue; st = St::BeginValue; return; }
+                            bad(c, "after object key");
+                            return;
+                        case Ps::ObjectValue:
+                            if (c == ',') { stack.back() = Ps::ObjectKey; st = St::BeginString; return; }
+                            if (c == '}') { pop(); return; }
+                            bad(c, "after object key:value pair");
+                            return;
+                        case Ps::ArrayValue:
+                            if (c == ',') { st = St::BeginValue; return; }
+                            if (c == ']') { pop(); return; }
+                            bad(c, "after array element");
+                            return;
+                    }
+                    return;
+                case St::EndTop:
+                    if (!isSpaceByte(c)) bad(c, "after top-level value");
+                    return;
+                case St::InString:
+                    if (c == '"') { st = St::EndValue; return; }
+                    if (c == '\\') { st = St::InStringEsc; return; }
+                    if (c < 0x20) bad(c, "in string literal");
+                    return;
+                case St::InStringEsc:
+                    switch (c) {
+                        case 'b': case 'f': case 'n': case 'r': case 't': case '\\': case '/': case '"':
+                            st = St::InString; return;
+                        case 'u': st = St::EscU; return;
+                    }
+                    bad(c, "in string escape code");
+                    return;
+                case St::EscU: case St::EscU1: case St::EscU12: case St::EscU123:
+                    if (isHex(c)) {
+                        st = st == St::EscU ? St::EscU1 : st == St::EscU1 ? St::EscU12 : st == St::EscU12 ? St::EscU123 : St::InString;
+                        return;
+                    }
+                    bad(c, "in \\u hexadecimal character escape");
+                    return;
+                case St::Neg:
+                    if (c == '0') { st = St::Num0; return; }
+                    if (c >= '1' && c <= '9') { st = St::Num1; return; }
+                    bad(c, "in numeric literal");
+                    return;
+                case St::Num1:
+                    if (c >= '0' && c <= '9') return;
+                    st = St::Num0;
+                    continue;
+                case St::Num0:
+                    if (c == '.') { st = St::Dot; return; }
+                    if (c == 'e' || c == 'E') { st = St::E; return; }
+                    st = St::EndValue;
+                    continue;
+                case St::Dot:
+                    if (c >= '0' && c <= '9') { st = St::Dot0; return; }
+                    bad(c, "after decimal point in numeric literal");
+                    return;
+                case St::Dot0:
+                    if (c >= '0' && c <= '9') return;
+                    if (c == 'e' || c == 'E') { st = St::E; return; }
+                    st = St::EndValue;
+                    continue;
+                case St::E:
+                    if (c == '+' || c == '-') { st = St::ESign; return; }
+                    st = St::ESign;
+                    continue;
+                case St::ESign:
+                    if (c >= '0' && c <= '9') { st = St::E0; return; }
+                    bad(c, "in exponent of numeric literal");
+                    return;
+                case St::E0:
+                    if (c >= '0' && c <= '9') return;
+                    st = St::EndValue;
+                    continue;
+#define CRO_LIT(state, want, next, text)                                             \
+                case St::state:                                                      \
+                    if (c == want) { st = St::next; return; }                        \
+                    bad(c, "in literal " text " (expecting " #want ")");           \
+                    return;
+                CRO_LIT(T, 'r', Tr, "true") CRO_LIT(Tr, 'u', Tru, "true") CRO_LIT(Tru, 'e', EndValue, "true")
+                CRO_LIT(F, 'a', Fa, "false") CRO_LIT(Fa, 'l', Fal, "false") CRO_LIT(Fal, 's', Fals, "false")
+                CRO_LIT(Fals, 'e', EndValue, "false")
+                CRO_LIT(N, 'u', Nu, "null") CRO_LIT(Nu, 'l', Nul, "null") CRO_LIT(Nul, 'l', EndValue, "null")
+#undef CRO_LIT
+            }
+            return;
+        }
+    };
+    for (unsigned char c : text) {
+        step(c);
+        if (!err.empty()) return err;
+    }
+    // eof(): one virtual space lets a pending number / literal finish
+    if (endTop) return "";
+    step(' ');
+    if (!err.empty()) return err;
+    if (endTop) return "";
+    return "unexpected end of JSON input";
+}
+
 ValuePtr parse(const std::string& text, std::string* err) {
+    const std::string syntax = SyntaxError(text);
+    if (!syntax.empty()) {
+        if (err) *err = syntax;
+        return nullptr;
+    }
     Parser p(text);
     ValuePtr v = p.value();
     if (v) {
@@ -341,6 +551,14 @@ ValuePtr parse(const std::string& text, std::string* err) {
     }
     if (!v && err) *err = p.err;
     return v;
+}
+
+bool rootOk(const ValuePtr& root, std::string* perr, const char* goType) {
+    if (!root) return false;
+    if (root->kind == Value::Object || root->kind == Value::Null) return true;
+    static const char* kKind[] = {"null", "bool", "number", "string", "array", "object"};
+    *perr = std::string("json: cannot unmarshal ") + kKind[root->kind] + " into Go value of type " + goType;
+    return false;
 }
 
 }  // namespace gojson

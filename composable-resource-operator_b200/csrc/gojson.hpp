@@ -70,6 +70,7 @@ struct Value {
     std::string str;
     std::vector<ValuePtr> arr;
     std::vector<std::pair<std::string, ValuePtr>> obj;  // insertion order
+    size_t raw_begin = 0, raw_end = 0;                   // [begin, end) of this value in the parsed text (json.RawMessage)
 
     const Value* get(const std::string& k) const;  // last duplicate wins (Go)
     std::string get_string(const std::string& k, const std::string& dflt = "") const;
@@ -77,8 +78,22 @@ struct Value {
     long long get_int(const std::string& k, long long dflt = 0) const;
 };
 
-// Returns nullptr and fills *err on malformed input.
+// Go's json.Valid / checkValid as a message: "" when `text` is one valid JSON
+// value, else the text of the *json.SyntaxError Unmarshal would return
+// ("invalid character '<' looking for beginning of value", "unexpected end of
+// JSON input", ...).  Pinned by the reference's own expected strings
+// (composableresource_controller_test.go:1479,1674,1804,...).
+std::string SyntaxError(const std::string& text);
+
+// Returns nullptr and fills *err on malformed input; *err is SyntaxError(text).
+// Deviation: trees deeper than 512 are refused (Go allows 10000).
 ValuePtr parse(const std::string& text, std::string* err);
+
+// Can a parse() result be decoded into a Go struct of type `goType`?  False with
+// *perr = the message json.Unmarshal returns: the syntax error parse() left there,
+// or "json: cannot unmarshal array into Go value of type api.X" when the top-level
+// value is not an object.  JSON null decodes into the zero struct (true).
+bool rootOk(const ValuePtr& root, std::string* perr, const char* goType);
 
 }  // namespace gojson
 }  // namespace cro

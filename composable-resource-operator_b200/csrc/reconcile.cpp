@@ -27,7 +27,7 @@ Error FMScaleUpResponseToIDs(const std::string& body, const std::string& instanc
     CDIDeviceID->clear();
     std::string perr;
     gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!root || root->kind != gojson::Value::Object)
+    if (!gojson::rootOk(root, &perr, "api.ScaleUpResponse"))
         return Error::New(
             "failed to unmarshal FM scaleup response body into scaleUpResponse. Original error: " + perr);
     const gojson::Value* data = root->get("data");
@@ -73,7 +73,7 @@ CMAddingResult CMCheckAddingResources(const std::string& machineBody,
     CMAddingResult out;
     std::string perr;
     gojson::ValuePtr root = gojson::parse(machineBody, &perr);
-    if (!root || root->kind != gojson::Value::Object) {
+    if (!gojson::rootOk(root, &perr, "api.MachineData")) {
         out.err = Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
         return out;
     }

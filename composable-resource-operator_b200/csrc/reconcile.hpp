@@ -56,7 +56,7 @@ public:
     virtual ~CdiProvider() {}
     virtual Error AddResource(const ComposableResource& instance, std::string* deviceID,
                               std::string* CDIDeviceID) = 0;
-    virtual Error RemoveResource(const ComposableResource&) { return Error::Nil(); }
+    virtual Error RemoveResource(ComposableResource&) { return Error::Nil(); }   // CM records a reason in Status.Error (cm/client.go:201-207)
     virtual Error CheckResource(const ComposableResource&) { return Error::Nil(); }
 };
 

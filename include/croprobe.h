@@ -369,6 +369,13 @@ int  cro_fabric_check_resource(const char *kind, const char *machine_body, const
  * {"node_name","machine_uuid","device_type","model","device_id","cdi_device_id"}. */
 int  cro_fabric_get_resources(const char *kind, const char *machine_body, const char *node_name,
                               const char *machine_uuid, char *buf, size_t cap, size_t *len);
+/* CdiProvider.GetResources of the whole FM / CM client (internal/cdi/fti/fm/client.go:361-413,
+ * internal/cdi/fti/cm/client.go:306-346) over a scripted fabric: request_json =
+ * {"env": {"CDI_PROVIDER_TYPE","FTI_CDI_API_TYPE","DEVICE_RESOURCE_TYPE","FTI_CDI_TENANT_ID","FTI_CDI_CLUSTER_ID"},
+ *  "fabric": {"http": [...], "objects": {...}, "token_error": ""}} (the same "fabric" object
+ * cro_reconcile_attach takes).  Reply: {"devices": [DeviceInfo...], "error": "", "fabric_requests": [...]};
+ * the FM flavour skips nodes that fail, the CM flavour aborts with the first error. */
+int  cro_fabric_list_devices(const char *request_json, char *buf, size_t cap, size_t *len);
 
 /* ---- detach-side pre-flight (the step on the other side of the path) ------ */
 

@@ -1,0 +1,128 @@
+"""Extract the EXPECTATIONS of the reference's ComposableResource table tests into a fixture.
+(container only: reads /root/reference; the output tests/golden/reference_entries.json travels)
+
+For every Entry(...) of internal/controller/composableresource_controller_test.go this records
+  line, title, the Describe block it sits in, tenant/cluster uuid (they select the fake fabric's
+  routes), the secret's username (selects the token scenario), the initial Status fields the entry
+  sets, and what the entry expects: expectedReconcileError, the expected Status fields, or
+  expectedRequestDeleted.
+No Go code is copied: only string literals and field assignments the tests assert on.  The scenario
+INPUTS (which objects exist, what nvidia-smi prints) are written by hand in
+tests/test_reference_entries.py from the same entries."""
+import json
+import os
+import re
+import sys
+
+SRC = "/root/reference/internal/controller/composableresource_controller_test.go"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_entries.json")
+
+STR = r'"((?:[^"\\]|\\.)*)"'
+
+
+def unquote(s):
+    return json.loads('"' + s + '"')
+
+
+def block_assignments(block, opener):
+    """Field assignments inside `<opener>: func() ... }(),`."""
+    i = block.find(opener + ": func()")
+    if i < 0:
+        return None
+    j = block.find("}(),", i)
+    body = block[i:j]
+    out = {}
+    for m in re.finditer(r"composableResourceStatus\.(\w+) = " + STR, body):
+        out[m.group(1)] = unquote(m.group(2))
+    return out
+
+
+def main():
+    lines = open(SRC, errors="replace").read().split("\n")
+    describes = []       # (line, title)
+    entries = []
+    for n, l in enumerate(lines, 1):
+        m = re.search(r'\bDescribe\("((?:[^"\\]|\\.)*)"', l)
+        if m:
+            describes.append((n, l[:len(l) - len(l.lstrip())], unquote(m.group(1))))
+        m = re.search(r'\bEntry\(' + STR, l)
+        if m:
+            entries.append((n, unquote(m.group(1))))
+    out = []
+    for k, (n, title) in enumerate(entries):
+        end = entries[k + 1][0] - 1 if k + 1 < len(entries) else len(lines)
+        block = "\n".join(lines[n - 1:end])
+        # the enclosing Describe chain = the last Describe at each smaller indentation
+        chain, indent = [], None
+        for dn, dind, dtitle in reversed([d for d in describes if d[0] < n]):
+            if indent is None or len(dind) < indent:
+                chain.append(dtitle)
+                indent = len(dind)
+        e = {"line": n, "title": title, "context": list(reversed(chain))[1:]}
+        for key in ("tenant_uuid", "cluster_uuid", "resourceName"):
+            m = re.search(key + r":\s*" + STR, block)
+            if m:
+                e[key] = unquote(m.group(1))
+        m = re.search(r'"username":\s*\[\]byte\(' + STR + r"\)", block)
+        if m:
+            e["username"] = unquote(m.group(1))
+        m = re.search(r"expectedReconcileError:\s*(?:fmt\.Errorf\()?" + STR, block)
+        if m:
+            e["expected_error"] = unquote(m.group(1))
+        if re.search(r"expectedRequestDeleted:\s*true", block):
+            e["expected_deleted"] = True
+        init = block_assignments(block, "resourceStatus")
+        if init:
+            e["initial_status"] = init
+        exp = block_assignments(block, "expectedRequestStatus")
+        if exp is not None:
+            e["expected_status"] = exp
+        if re.search(r"ignoreGet:\s*true", block):
+            e["ignore_get"] = True
+        if "DeletionTimestamp" in block or "k8sClient.Delete(ctx, composableResource" in block:
+            e["deleted_by_user"] = True
+        m = re.search(r"setErrorMode:\s*(\w+)", block)
+        if m:
+            e["set_error_mode"] = m.group(1)
+        # which metal3 objects the entry's extraHandling creates, and with which annotations
+        # (the target Node exists in every entry except the garbage-collection ones, which delete all Nodes last)
+        objs = {"node": not e.get("expected_deleted", False),
+                "node_annotation": '"machine.openshift.io/machine":' in block,
+                "machine": "Metal3Machine{" in block, "machine_annotation": '"metal3.io/BareMetalHost":' in block,
+                "bmh": "BareMetalHost{" in block, "secret": "corev1.Secret{" in block}
+        m = re.search(r'"cluster-manager\.cdi\.io/machine":\s*' + STR, block)
+        if m:
+            objs["bmh_machine_uuid"] = unquote(m.group(1))
+        e["objects"] = objs
+        out.append(e)
+    # the fake fabric's route table (httptest handler, :663-930): path -> status + body
+    routes = {}
+    text = "\n".join(lines)
+    for m in re.finditer(r'case ' + STR + r':\n(.*?)(?=\n\t\t\tcase |\n\t\t\tdefault:)', text, re.S):
+        path, body = unquote(m.group(1)), m.group(2)
+        if not path.startswith("/") or path.startswith("/id_manager"):   # the token endpoint is auth: not restated
+            continue
+        st = re.search(r"WriteHeader\(http\.Status(\w+)\)", body)
+        r = {"status": {"OK": 200, "NotFound": 404, "Unauthorized": 401, "BadRequest": 400}[st.group(1)] if st else 200}
+        lit = re.search(r"w\.Write\(\[\]byte\(`([^`]*)`\)\)", body) or re.search(r"w\.Write\(\[\]byte\(" + STR + r"\)\)", body)
+        gen = re.search(r"w\.Write\((generate\w+)\(([^)]*)\)\)", body)
+        if lit:
+            r["body"] = lit.group(1) if "`" in lit.group(0) else unquote(lit.group(1))
+        elif gen:
+            args = [a.strip() for a in gen.group(2).split(",")]
+            val = re.search(r'val := ' + STR, body)
+            args = [(val.group(1) if (a == "&val" and val) else a) for a in args]
+            r["generator"] = gen.group(1)
+            r["args"] = [json.loads(a) if a in ("true", "false") else (None if a == "nil" else a.strip('"')) for a in args]
+        else:
+            r["body"] = ""
+        routes[path] = r
+    with open(OUT, "w") as f:
+        json.dump({"_about": "expectations of the reference's ComposableResource table tests; made by make_reference_entries.py",
+                   "source": "internal/controller/composableresource_controller_test.go", "routes": routes, "entries": out}, f, indent=1)
+        f.write("\n")
+    print(len(out), "entries ->", OUT)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -13,6 +13,8 @@
 #include "fabric.hpp"
 #include "gojson.hpp"
 #include "identity.hpp"
+#include "nodes.hpp"
+#include "provider.hpp"
 #include "reconcile.hpp"
 
 using namespace cro;
@@ -53,6 +55,11 @@ static const char* kCorpus[] = {
     "\"res_spec\":[{\"name\":\"model\",\"value\":\"NVIDIA-B200\"}],\"tenant_id\":\"t\",\"mach_id\":\"m\"}}]}]}}}}",
     "{\"a\":[1,2.5e3,-0,true,false,null,\"\\u00e9\\ud83d\\ude00\\n\"],\"b\":{\"c\":{}}}",
     "[[[[[[[[[[[[[[[[[[[[[[[[[[[[[[[[]]]]]]]]]]]]]]]]]]]]]]]]]]]]]]]]",
+    // fabric error bodies and timestamps
+    "{\"status\":404,\"detail\":{\"code\":\"E02XXXX\",\"message\":\"machine not found\"}}",
+    "{\"status\":404.5,\"detail\":{\"code\":7,\"message\":{\"k\": [1, 2]},\"data\":[]}}",
+    "<html><body>This is not JSON!</body></html>",
+    "2025-06-01T12:00:00Z", "2024-02-29T23:59:59.123456789+09:00", "0000-01-01T00:00:00-24:00", "9999-12-31T23:59:59,5Z",
 };
 
 static std::string mutate(std::string s) {
@@ -122,6 +129,36 @@ static void one(const std::string& in, const std::string& err_text) {
         sink += fabric::FMGetResources(in, "node", "m", &devs).msg.size();
         sink += fabric::CMGetResources(in, "node", "m", &devs).msg.size();
         sink += fabric::DeviceInfosToJson(devs).size();
+        // non-200 replies and the detach-side machine scan
+        sink += fabric::FMErrorFromReply("scaleup", in).msg.size() + fabric::FMErrorFromReply("scaledown", in).msg.size();
+        sink += fabric::CMErrorFromReply("get", in).msg.size() + fabric::CMErrorFromReply("scaledown", in).msg.size();
+        sink += fabric::CMCheckRemovingResources(in, "gpu", "NVIDIA-B200", "GPU-1").specUUID.size();
+    }
+    {
+        // Go's validity scanner must agree with the tree builder on what is valid JSON
+        const std::string syn = gojson::SyntaxError(in);
+        std::string e;
+        const bool parsed = (bool)gojson::parse(in, &e);
+        if (syn.empty() != parsed && e.find("nesting too deep") == std::string::npos) {
+            std::fprintf(stderr, "scanner and parser disagree: syntax='%s' parse='%s'\n", syn.c_str(), e.c_str());
+            std::abort();
+        }
+        long long t = 0, ns = 0;
+        std::string terr;
+        if (nodes::ParseRFC3339(in, &t, &ns, &terr)) {
+            const std::string back = nodes::FormatRFC3339UTC(t);      // a parsed instant formats and re-parses to itself
+            long long t2 = 0, ns2 = 0;
+            if (!nodes::ParseRFC3339(back, &t2, &ns2, &terr) || t2 != t) {
+                std::fprintf(stderr, "RFC3339 round trip failed: %s -> %s\n", in.c_str(), back.c_str());
+                std::abort();
+            }
+        }
+        nodes::DaemonSetView ds;
+        ds.DesiredNumberScheduled = ds.NumberReady = ds.CurrentNumberScheduled = 1;
+        ds.hasRestartedAt = true;
+        ds.restartedAt = in;
+        nodes::Restart what;
+        sink += nodes::RestartDaemonsetDecision("ns", "ds", ds, 1750000000, 0, &what).msg.size();
     }
 }
 

@@ -128,3 +128,67 @@ def test_deleting_drops_the_finalizer_and_the_object(cro):         # :1779
         plant_request(c, "Deleting", deleting=True)
         assert c.reconcile_request("test-composability-request") == ""
         assert c.dump()["requests"] == {}
+
+
+# ---- CRD validation: the API server's answer to a bad spec (:324-:412) --------------------------------
+INVALID = [
+    (":324", {"type": "UnknownType"}, 'spec.resource.type: Unsupported value: "UnknownType": supported values: "gpu", "cxlmemory"'),
+    (":334", {"size": -1}, "spec.resource.size: Invalid value: -1: spec.resource.size in body should be greater than or equal to 0"),
+    (":344", {"allocation_policy": "UnknownPolicy"},
+     'spec.resource.allocation_policy: Unsupported value: "UnknownPolicy": supported values: "samenode", "differentnode"'),
+    (":354", {"other_spec": {"milli_cpu": -1, "memory": 1, "ephemeral_storage": 1, "allowed_pod_number": 1}},
+     "spec.resource.other_spec.milli_cpu: Invalid value: -1: spec.resource.other_spec.milli_cpu in body should be greater than or equal to 0"),
+    (":369", {"other_spec": {"milli_cpu": 1, "memory": -1, "ephemeral_storage": 1, "allowed_pod_number": 1}},
+     "spec.resource.other_spec.memory: Invalid value: -1: spec.resource.other_spec.memory in body should be greater than or equal to 0"),
+    (":384", {"other_spec": {"milli_cpu": 1, "memory": 1, "ephemeral_storage": -1, "allowed_pod_number": 1}},
+     "spec.resource.other_spec.ephemeral_storage: Invalid value: -1: spec.resource.other_spec.ephemeral_storage in body should be greater than or equal to 0"),
+    (":399", {"other_spec": {"milli_cpu": 1, "memory": 1, "ephemeral_storage": 1, "allowed_pod_number": -1}},
+     "spec.resource.other_spec.allowed_pod_number: Invalid value: -1: spec.resource.other_spec.allowed_pod_number in body should be greater than or equal to 0"),
+]
+
+
+def test_invalid_specs_are_refused_with_the_api_servers_words(cro):
+    with cro.Cluster({"nodes": ["worker-0"]}) as c:
+        for cite, over, detail in INVALID:
+            got = c.apply("test-composability-request", dict(BASE, **over))
+            assert got == 'ComposabilityRequest.cro.hpsys.ibm.ie.com "test-composability-request" is invalid: ' + detail, cite
+        assert c.dump()["requests"] == {}
+
+
+# ---- API-server write failures (the reference's MockStatusUpdate / MockUpdate hooks, :452-:513, :694, :1784) ----
+def test_unknown_request_is_not_requeued(cro):                     # :452 "should wait when the request is invalid"
+    with cro.Cluster({"nodes": ["worker-0"]}) as c:
+        assert c.reconcile_request("unknown-request") == ""
+
+
+def test_status_update_failures_surface_from_every_state(cro):
+    for cite, state in ((":457", "NodeAllocating"), (":471", "Updating"), (":485", "Running"), (":499", "Cleaning")):
+        with cro.Cluster({"nodes": ["worker-0"]}) as c:
+            plant_request(c, state, res_states=("Online", "Online"), finalizer=True)
+            assert c.delete("test-composability-request")           # "Use Delete() to trigger r.Status().Update" (:431)
+            c.plant({"kind": "Fault", "status_update": "status update fails"})
+            assert c.reconcile_request("test-composability-request") == "status update fails", cite
+            assert status(c)["state"] == state                      # nothing was written
+            c.plant({"kind": "Fault"})                              # cleared: the same reconcile now goes through
+            assert c.reconcile_request("test-composability-request") == ""
+            assert status(c)["state"] in ("Cleaning", "Deleting")
+
+
+def test_update_failures_when_the_finalizer_changes(cro):
+    with cro.Cluster({"nodes": ["worker-0"]}) as c:                # :513 Deleting: RemoveFinalizer + Update
+        plant_request(c, "Deleting", finalizer=True)
+        c.delete("test-composability-request")
+        c.plant({"kind": "Fault", "update": "update fails"})
+        assert c.reconcile_request("test-composability-request") == "update fails"
+        assert c.dump()["requests"]["test-composability-request"]["finalizers"] == [FIN]
+    with cro.Cluster({"nodes": ["worker-0"]}) as c:                # :694 None: AddFinalizer + Update
+        assert c.apply("test-composability-request", BASE) == ""
+        c.plant({"kind": "Fault", "update": "update fails"})
+        assert c.reconcile_request("test-composability-request") == "update fails"
+        r = c.dump()["requests"]["test-composability-request"]
+        assert r["finalizers"] == [] and r["status"]["state"] == ""
+    with cro.Cluster({"nodes": ["worker-0"]}) as c:                # :1784 Deleting (its own table)
+        plant_request(c, "Deleting", finalizer=True)
+        c.delete("test-composability-request")
+        c.plant({"kind": "Fault", "update": "update fails"})
+        assert c.reconcile_request("test-composability-request") == "update fails"
