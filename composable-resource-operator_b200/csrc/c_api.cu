@@ -261,17 +261,7 @@ int cro_emit_cm_scale_down(const char* spec_uuid, int device_count, const char* 
 
 int cro_emit_sunfish_request(const char* name, long long count, const char* proc_type, const char* model,
                              char* buf, size_t cap, size_t* len) {
-    // internal/cdi/sunfish/client.go:48-61
-    gojson::Writer w;
-    w.begin_object();
-    w.field("Name", S(name));
-    w.key("Processors").begin_object().key("Members").begin_array().begin_object();
-    w.field("@Redfish.RequestCount", count);
-    w.field("ProcessorType", S(proc_type));
-    w.field("Model", S(model));
-    w.end_object().end_array().end_object();
-    w.end_object();
-    return copy_out(w.str(), buf, cap, len);
+    return copy_out(fabric::SunfishBody(S(name), count, S(proc_type), S(model)), buf, cap, len);
 }
 
 static std::map<std::string, std::string> probe_annotations(const cro_probe_result& r) {
@@ -735,6 +725,7 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
         fabric::ClientConfig cfg{env->get_string("FTI_CDI_TENANT_ID"), env->get_string("FTI_CDI_CLUSTER_ID")};
         if (kind == "fm") fti.reset(new fabric::FMClient(cfg, &transport, &store, &tokens));
         else if (kind == "cm") fti.reset(new fabric::CMClient(cfg, &transport, &store, &tokens));
+        else if (kind == "sunfish") fti.reset(new fabric::SunfishClient(&transport));
         else if (adapterErr.ok()) adapterErr = controller::Error::New("provider kind '" + kind + "' is not scripted in this harness");
     }
 
@@ -837,6 +828,7 @@ int cro_fabric_list_devices(const char* request_json, char* buf, size_t cap, siz
     fabric::ClientConfig cfg{env->get_string("FTI_CDI_TENANT_ID"), env->get_string("FTI_CDI_CLUSTER_ID")};
     if (kind == "fm") fti.reset(new fabric::FMClient(cfg, &transport, &store, &tokens));
     else if (kind == "cm") fti.reset(new fabric::CMClient(cfg, &transport, &store, &tokens));
+    else if (kind == "sunfish") fti.reset(new fabric::SunfishClient(&transport));
     else if (e.ok()) e = controller::Error::New("provider kind '" + kind + "' is not scripted in this harness");
     std::vector<fabric::DeviceInfo> devs;
     if (fti) e = fti->GetResources(&devs);

@@ -444,5 +444,40 @@ Error CMClient::GetResources(std::vector<DeviceInfo>* out) {
     return Error::Nil();
 }
 
+// ---------------------------------------------------------------------------
+// Sunfish
+// ---------------------------------------------------------------------------
+std::string SunfishBody(const std::string& name, long long count, const std::string& procType, const std::string& model) {
+    gojson::Writer w;
+    w.begin_object();
+    w.field("Name", name);
+    w.key("Processors").begin_object().key("Members").begin_array().begin_object();
+    w.field("@Redfish.RequestCount", count);
+    w.field("ProcessorType", procType);
+    w.field("Model", model);
+    w.end_object().end_array().end_object();
+    w.end_object();
+    return w.str();
+}
+
+Error SunfishClient::sendPatchRequest(const ComposableResource& instance, long long count) {
+    // only the three models of :42-46 fill the ProcessorRequest; anything else sends its zero value (:108-115)
+    const std::string& m = instance.Spec.Model;
+    const bool known = m == "Tesla-V100-PCIE-16GB" || m == "NVIDIA-A100-PCIE-40GB" || m == "NVIDIA-A100-80GB-PCIe";
+    HttpReply rep = send({"PATCH", "redfish/v1/Systems/System", "",
+                          SunfishBody(instance.Spec.TargetNode, known ? count : 0, known ? "GPU" : "", known ? m : "")});
+    if (!rep.transport_error.empty()) return Error::New(rep.transport_error);
+    if (rep.status != 200 && rep.status != 204) return Error::New("http returned code " + std::to_string(rep.status));
+    return Error::Nil();
+}
+
+Error SunfishClient::AddResource(const ComposableResource& instance, std::string* deviceID, std::string* CDIDeviceID) {
+    deviceID->clear();
+    CDIDeviceID->clear();
+    return sendPatchRequest(instance, 1);
+}
+
+Error SunfishClient::RemoveResource(ComposableResource& instance) { return sendPatchRequest(instance, 0); }
+
 }  // namespace fabric
 }  // namespace cro

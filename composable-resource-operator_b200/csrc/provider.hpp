@@ -133,5 +133,19 @@ private:
     Error getMachineInfo(const std::string& machineID, std::string* body);         // :390-430
 };
 
+// internal/cdi/sunfish/client.go:48-146 — one PATCH of a Redfish CompositionRequest; no ids come back
+// (the reference's own TODO), CheckResource / GetResources are empty.  Plain HTTP, no token, no metal3 walk.
+std::string SunfishBody(const std::string& name, long long count, const std::string& procType, const std::string& model);
+class SunfishClient : public FTIClientBase {
+public:
+    explicit SunfishClient(Transport* t) : FTIClientBase(ClientConfig(), t, nullptr, nullptr) {}
+    Error AddResource(const controller::ComposableResource& instance, std::string* deviceID, std::string* CDIDeviceID) override;
+    Error RemoveResource(controller::ComposableResource& instance) override;
+    Error GetResources(std::vector<DeviceInfo>* out) override { out->clear(); return Error::Nil(); }
+
+private:
+    Error sendPatchRequest(const controller::ComposableResource& instance, long long count);   // :78-103
+};
+
 }  // namespace fabric
 }  // namespace cro

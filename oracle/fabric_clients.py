@@ -711,3 +711,27 @@ def restart_daemonset(ns: str, name: str, ds: Dict, now: Tuple[int, int]) -> Tup
         if since <= 10 * 10 ** 9:
             return False, ""
     return True, ""
+
+
+class SunfishClient:
+    """internal/cdi/sunfish/client.go:76-146 (no reference test exercises it: parity of the body is derived)."""
+    MODELS = ("Tesla-V100-PCIE-16GB", "NVIDIA-A100-PCIE-40GB", "NVIDIA-A100-80GB-PCIe")
+
+    def __init__(self, fabric: Fabric):
+        self.f = fabric
+
+    def _patch(self, node: str, model: str, count: int) -> str:
+        known = model in self.MODELS
+        body = _o.emit_sunfish(node, count if known else 0, "GPU" if known else "", model if known else "")
+        st, _, terr = self.f.do("PATCH", "redfish/v1/Systems/System", "", body)
+        if terr:
+            return terr
+        if st not in (200, 204):
+            return "http returned code %d" % st
+        return ""
+
+    def add(self, node: str, model: str) -> Tuple[str, str, str]:
+        return "", "", self._patch(node, model, 1)
+
+    def remove(self, node: str, model: str) -> str:
+        return self._patch(node, model, 0)

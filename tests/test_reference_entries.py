@@ -480,3 +480,30 @@ def test_restart_rule_and_time_parse_fuzz_vs_oracle(cro):
                                           "enumeration": {"stdout": DEV, "stderr": ""}, "resource_slices": [], "daemonsets": {DRA_DS: ds}, "now": NOW})
         assert out["status"].get("error", "") == err, (s, out["status"], err)
         assert bool(out.get("daemonset_restarts")) == restart, (s, ds, out)
+
+
+# ---- 9. the third provider: Sunfish (internal/cdi/sunfish/client.go; the reference has no test for it) ---
+def test_sunfish_client_vs_oracle(cro, oracle):
+    import fabric_clients as fc
+    env = {"DEVICE_RESOURCE_TYPE": "DEVICE_PLUGIN", "CDI_PROVIDER_TYPE": "SUNFISH"}
+    for model in ("NVIDIA-A100-PCIE-40GB", "Tesla-V100-PCIE-16GB", MODEL, "x\"<y"):
+        for status in (200, 204, 500):
+            fabric = {"http": [{"method": "PATCH", "path": "redfish/v1/Systems/System", "status": status, "body": ""}]}
+            for state in ("Attaching", "Detaching"):
+                req = {"name": "cr", "spec": {"type": "gpu", "model": model, "target_node": "worker-0"},
+                       "status": {"state": state, "device_id": DEV if state == "Detaching" else "", "cdi_device_id": ""},
+                       "deleting": state == "Detaching", "probe": False, "env": env, "fabric": fabric,
+                       "enumeration": {"stdout": "", "stderr": ""}, "enumeration_after_remove": {"stdout": "", "stderr": ""}}
+                out = cro.reconcile_attach(None, req)
+                f = fc.Fabric(fabric)
+                c = fc.SunfishClient(f)
+                err = c.add("worker-0", model)[2] if state == "Attaching" else c.remove("worker-0", model)
+                assert out["error"] == err == ("" if status != 500 else "http returned code 500")
+                assert out["fabric_requests"] == f.requests
+                body = json.loads(out["fabric_requests"][0]["body"])
+                known = model in fc.SunfishClient.MODELS
+                assert body == {"Name": "worker-0", "Processors": {"Members": [{
+                    "@Redfish.RequestCount": 1 if (known and state == "Attaching") else 0,
+                    "ProcessorType": "GPU" if known else "", "Model": model if known else ""}]}}
+                if state == "Attaching" and not err:       # no ids come back (the reference's TODO): AddResource is asked again
+                    assert out["status"].get("device_id", "") == ""
