@@ -360,7 +360,10 @@ class ProbeContext:
         h = ctypes.c_void_p()
         rc = lib.cro_probe_init(ctypes.byref(o), ctypes.byref(h))
         if rc != OK:
-            raise ProbeError(rc, "cro_probe_init")
+            why = ctypes.create_string_buffer(1024)
+            lib.cro_last_error(None, why, 1024)       # the context died with the init: its text is per-thread
+            detail = why.value.decode("utf-8", "replace")
+            raise ProbeError(rc, "cro_probe_init" + (": " + detail if detail else ""))
         self.handle = h
 
     def close(self) -> None:

@@ -83,7 +83,7 @@ const char* cro_strerror(int code) {
 }
 
 int cro_last_error(cro_ctx* ctx, char* buf, size_t cap) {
-    if (!ctx) return CRO_ERR_INVALID_ARG;
+    if (!ctx) return copy_out(last_init_error(), buf, cap, nullptr);
     std::lock_guard<std::mutex> g(ctx->err_mu);
     return copy_out(ctx->last_error, buf, cap, nullptr);
 }

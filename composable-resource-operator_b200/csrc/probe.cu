@@ -281,6 +281,39 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
     return CRO_OK;
 }
 
+thread_local std::string g_init_error;
+const std::string& last_init_error() { return g_init_error; }
+
+}  // namespace cro
+cro_ctx::~cro_ctx() {
+    if (!last_error.empty()) cro::g_init_error = last_error;
+}
+namespace cro {
+
+Device::~Device() {
+    if (ordinal < 0) return;                      // never bound to a CUDA device: owns nothing
+    cudaSetDevice(ordinal);
+    if (stream) cudaStreamSynchronize(stream);
+    cudaFree(region);                             // cudaFree(nullptr) is a no-op
+    cudaFree(scratch.partials);
+    cudaFree(scratch.counter);
+    cudaFree(scratch.tmin);
+    cudaFree(scratch.tmax);
+    cudaFree(scratch.tile_ctr);
+    cudaFree(d_out);
+    if (h_out) cudaFreeHost(h_out);
+    cudaFree(d_result);
+    cudaFree(d_gather);
+    cudaFree(d_chase_next);
+    cudaFree(d_chase_out);
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (cudaEvent_t e : evpool) cudaEventDestroy(e);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+    cudaGetLastError();                           // a failed release must not poison the caller's next CUDA call
+}
+
 void ctx_destroy(cro_ctx* c) {
     if (!c) return;
     if (c->nccl_ready && c->nccl_lib) {
@@ -289,29 +322,7 @@ void ctx_destroy(cro_ctx* c) {
             for (void* comm : c->nccl_comms)
                 if (comm) destroy(comm);
     }
-    for (auto& dp : c->devs) {
-        Device* d = dp.get();
-        cudaSetDevice(d->ordinal);
-        cudaStreamSynchronize(d->stream);
-        cudaFree(d->region);
-        cudaFree(d->scratch.partials);
-        cudaFree(d->scratch.counter);
-        cudaFree(d->scratch.tmin);
-        cudaFree(d->scratch.tmax);
-        cudaFree(d->scratch.tile_ctr);
-        cudaFree(d->d_out);
-        cudaFreeHost(d->h_out);
-        cudaFree(d->d_result);
-        cudaFree(d->d_gather);
-        cudaFree(d->d_chase_next);
-        cudaFree(d->d_chase_out);
-        if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
-        for (cudaEvent_t e : d->evpool) cudaEventDestroy(e);
-        cudaEventDestroy(d->ev0);
-        cudaEventDestroy(d->ev1);
-        cudaStreamDestroy(d->stream);
-    }
-    delete c;
+    delete c;                                     // ~Device releases the per-device CUDA objects
 }
 
 static void drain_pending_fwd(cro_ctx* c, Device* d);

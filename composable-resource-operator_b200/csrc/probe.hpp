@@ -54,6 +54,13 @@ struct Device {
     bool have_expected = false;
     uint64_t expect_x = 0, expect_s = 0;
     unsigned sm_clock_mhz = 0, mem_clock_mhz = 0;
+
+    Device() = default;
+    Device(const Device&) = delete;
+    Device& operator=(const Device&) = delete;
+    // Releases every CUDA object this device owns (probe.cu).  Runs for half-built devices too,
+    // so a cro_probe_init that fails midway (OOM on the sweep region) leaks nothing.
+    ~Device();
 };
 
 }  // namespace cro
@@ -74,10 +81,14 @@ struct cro_ctx {
         std::lock_guard<std::mutex> g(err_mu);
         last_error = m;
     }
+    // a context that dies during cro_probe_init hands its error text to the calling thread
+    // (cro_last_error(NULL, ...)); defined in probe.cu
+    ~cro_ctx();
 };
 
 namespace cro {
 
+const std::string& last_init_error();   // calling thread's last failed ctx_create
 int ctx_create(const cro_opts* o, cro_ctx** out);
 void ctx_destroy(cro_ctx* c);
 int ctx_probe_device(cro_ctx* c, int idx, cro_probe_result* out);

@@ -435,7 +435,9 @@ int  cro_sim_dump(cro_sim *sim, char *buf, size_t cap, size_t *len);
 /* ---- diagnostics --------------------------------------------------------- */
 const char *cro_strerror(int code);
 /* Last error text recorded on this context by the calling thread's most
- * recent failing call (thread-safe copy-out). */
+ * recent failing call (thread-safe copy-out).  ctx == NULL: the text of the
+ * calling thread's last failed cro_probe_init (which returns no context), e.g.
+ * the cudaMalloc that could not be satisfied. */
 int  cro_last_error(cro_ctx *ctx, char *buf, size_t cap);
 const char *cro_version(void);
 

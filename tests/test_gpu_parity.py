@@ -231,9 +231,15 @@ def test_oom_fails_loudly_or_degrades(cro, coracle):
     """A sweep region that does not fit (2*S = 192 GiB > 180 GB): CRO_ERR_OOM by default; with
     CRO_F_DEGRADE_ON_OOM the probe halves S until it fits and says so in the result."""
     S = 96 << 30
-    with pytest.raises(cro.ProbeError) as e:
-        cro.ProbeContext(sweep_bytes=S, devices=[0])
-    assert e.value.code == cro.ERR_OOM
+    import torch
+    torch.cuda.init()
+    free_before = torch.cuda.mem_get_info(0)[0]
+    for _ in range(3):                                   # a failed init must release what it had already built
+        with pytest.raises(cro.ProbeError) as e:
+            cro.ProbeContext(sweep_bytes=S, devices=[0])
+        assert e.value.code == cro.ERR_OOM
+        assert "cudaMalloc" in str(e.value) and "asked for" in str(e.value)      # cro_last_error(NULL) carries the reason
+    assert free_before - torch.cuda.mem_get_info(0)[0] < (64 << 20)
     with cro.ProbeContext(sweep_bytes=S, devices=[0], flags=cro.F_DEGRADE_ON_OOM, read_sweeps=1, copy_sweeps=1) as c:
         r = c.probe_device(0)
         assert r.status == 0 and r.sweep_bytes == 48 << 30
