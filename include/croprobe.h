@@ -348,9 +348,23 @@ int  cro_cm_check_adding_resources(const char *machine_body, const char *existin
  *            "driver_pod_missing":bool, "daemonset_errors":{"ns/name":"error"},
  *            "load_check":{"stdout","stderr","exec_err","pod_name","driver_enabled"},
  *            "drain":{"error" | "fd_scan":{"stdout","stderr","exec_err"},"rke2":bool},
- *            "create_taint_error","delete_taint_error"}
+ *            "create_taint_error","delete_taint_error",
+ *            the DaemonSet restart rule (internal/utils/nodes.go:35-76) instead of canned errors:
+ *            "daemonsets":{"ns/name":{"desired","ready","current","unavailable","misscheduled",
+ *                                     "restarted_at":"<RFC3339>"}}, "now":"<RFC3339>",
+ *            the real FM / CM / Sunfish client (csrc/provider.hpp) instead of "provider":
+ *            "env":{"DEVICE_RESOURCE_TYPE","CDI_PROVIDER_TYPE","FTI_CDI_API_TYPE",
+ *                   "FTI_CDI_TENANT_ID","FTI_CDI_CLUSTER_ID"}   (adapter selection,
+ *                   internal/controller/composableresource_adapter.go:39-72),
+ *            "fabric":{"http":[{"method","path"|"path_contains","status","body"}..],
+ *                      "transport_error","token_error",
+ *                      "objects":{"nodes":{name:{"annotations","provider_id"}},
+ *                                 "metal3machines":{"ns/name":{"annotations"}},
+ *                                 "baremetalhosts":{"ns/name":{"annotations"}},
+ *                                 "composable_resource_device_ids":[..],"status_update_error"}}}
  * out_json: {"status":{...},"requeue_after_s":N,"delete_requested":bool,"error":"..",
- *            "status_updates":[...],"probe":{...}}
+ *            "status_updates":[...],"probe":{...},
+ *            "daemonset_restarts":["ns/name@<stamp>"..], "fabric_requests":[{method,path,query,body}..]}
  * The status object inside out_json is byte-identical to json.Marshal of the
  * reference's ComposableResourceStatus after the same step.
  */
