@@ -280,9 +280,26 @@ def run_ours(args, rank, local_rank, world):
         send = torch.as_tensor(multirank.DevBuf(ctx.result_device_ptr(0), 512), device=dev)
         gathered = torch.empty(world * 512, dtype=torch.uint8, device=dev)
 
-    request = {"name": "cr-%d" % rank, "spec": {"type": "gpu", "model": "NVIDIA-B200", "target_node": "worker-%d" % rank},
-               "status": {"state": "Attaching"}, "device_resource_type": "DEVICE_PLUGIN", "probe": True,
-               "provider": {"device_id": uuid, "cdi_device_id": "res-%d-0" % rank}}
+    # The attach reconcile with the FM provider client in the loop (csrc/provider.cpp): metal3 walk ->
+    # PATCH ScaleUpBody (emitted) -> ScaleUpResponse (parsed, op-status gate) -> probe -> status JSON.
+    # The fabric's reply is scripted: the appliance is not part of the box.
+    node, machine = "worker-%d" % rank, "machine-%d" % rank
+    fm_reply = json.dumps({"data": {"machines": [{"fabric_uuid": "", "fabric_id": 0, "mach_uuid": machine, "mach_id": 0,
+                                                  "mach_name": "", "tenant_uuid": "tenant", "resources": [{
+                                                      "res_uuid": "res-%d-0" % rank, "res_name": "", "res_type": "gpu", "res_status": 0,
+                                                      "res_op_status": "0", "res_serial_num": uuid,
+                                                      "res_spec": {"condition": [{"column": "model", "operator": "eq",
+                                                                                  "value": "NVIDIA-B200"}]}}]}]}},
+                          separators=(",", ":"))
+    request = {"name": "cr-%d" % rank, "spec": {"type": "gpu", "model": "NVIDIA-B200", "target_node": node},
+               "status": {"state": "Attaching"}, "probe": True,
+               "env": {"DEVICE_RESOURCE_TYPE": "DEVICE_PLUGIN", "CDI_PROVIDER_TYPE": "FTI_CDI", "FTI_CDI_API_TYPE": "FM",
+                       "FTI_CDI_TENANT_ID": "tenant", "FTI_CDI_CLUSTER_ID": "cluster"},
+               "fabric": {"http": [{"method": "PATCH", "path": "fabric_manager/api/v1/machines/%s/update" % machine,
+                                    "status": 200, "body": fm_reply}],
+                          "objects": {"nodes": {node: {"annotations": {"machine.openshift.io/machine": "ns/m"}}},
+                                      "metal3machines": {"ns/m": {"annotations": {"metal3.io/BareMetalHost": "ns/b"}}},
+                                      "baremetalhosts": {"ns/b": {"annotations": {"cluster-manager.cdi.io/machine": machine}}}}}}
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
     def barrier():
@@ -356,7 +373,8 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(gl)
         launches = int(gl[0])
 
-    ok = all(r.status == 0 for r in results) and last["status"]["state"] == "Online"
+    ok = (all(r.status == 0 for r in results) and last["status"]["state"] == "Online" and
+          last["status"].get("device_id") == uuid and len(last.get("fabric_requests", [])) == 1)
     if world > 1:
         # every rank must hold the same gathered array: one struct per rank, distinct devices, all ok
         everyone = multirank.results_from_bytes(bytes(gathered.cpu().numpy().tobytes()))
@@ -404,7 +422,10 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 512,
                     "d2h_bytes_per_step": 32 * (results[-1].read_sweeps + 1),
                     "host_json_in_bytes": len(json.dumps(request)), "host_json_out_bytes": len(last["_raw"]),
-                    "ms_per_step": e2e_s * 1e3 / args.steps, "call": "cro_reconcile_attach (C ABI) with host JSON buffers"},
+                    "ms_per_step": e2e_s * 1e3 / args.steps,
+                    "call": "cro_reconcile_attach (C ABI) with host JSON buffers: FM client (walk, ScaleUpBody emit, response "
+                            "parse) + probe + status emit",
+                    "fabric_request_bytes": len(last["fabric_requests"][0]["body"]) if last.get("fabric_requests") else 0},
             "specs_per_s": world * specs / e2e_s,
             "probe_gbs_best_read": S / best_read, "probe_frac_of_8000": S / best_read / 8000.0,
             "roofline": dominant, "roofline_kernels": kernels,
