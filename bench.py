@@ -134,6 +134,10 @@ def reference_step_factory():
     else:
         dev = CANNED_UUID
 
+    fm_reply = json.dumps({"data": {"machines": [{"resources": [{"res_uuid": "res-0-0", "res_type": "gpu", "res_op_status": "0",
+                                                                  "res_serial_num": dev, "res_spec": {"condition": [
+                                                                      {"column": "model", "operator": "eq", "value": "NVIDIA-B200"}]}}]}]}})
+
     def step():
         if smi:
             p = subprocess.run([smi, "--query-gpu=gpu_uuid", "--format=csv,noheader,nounits"], capture_output=True, text=True)
@@ -145,7 +149,8 @@ def reference_step_factory():
         st, rq, err, _n = co.attach_step(inp, oracle.Status("Attaching"))
         js = co.emit_status(st.state, st.error, st.device_id, st.cdi_device_id)
         body = co.emit_fm_scale_up("tenant", "machine", "gpu", "NVIDIA-B200")
-        return st.state, len(js) + len(body)
+        ids = oracle.fm_scale_up_response_to_ids(fm_reply, "cr", "gpu", "NVIDIA-B200")   # the provider's half of the step
+        return st.state, len(js) + len(body) + len(ids[0])
 
     how = ("exec nvidia-smi --query-gpu=gpu_uuid per step + oracle parse/decide/emit" if smi else
            "nvidia-smi absent: canned enumeration text + oracle parse/decide/emit (process spawn NOT included)")
