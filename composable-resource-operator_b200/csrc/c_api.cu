@@ -272,6 +272,7 @@ static std::map<std::string, std::string> probe_annotations(const cro_probe_resu
     m["cohdi.io/probe-device-minor"] = std::to_string(r.device_minor);
     m["cohdi.io/probe-sweep-bytes"] = std::to_string(r.sweep_bytes);
     m["cohdi.io/probe-checksum"] = hex16(r.checksum_xor) + ":" + hex16(r.checksum_sum);
+    m["cohdi.io/probe-ecc-uncorrected"] = std::to_string(r.ecc_errors);
     m["cohdi.io/probe-hbm-fill-gbs"] = gbs_x10(r.sweep_bytes, r.fill_ns);
     m["cohdi.io/probe-hbm-read-gbs"] = gbs_x10(r.sweep_bytes, r.read_best_ns);
     if (r.copy_sweeps) m["cohdi.io/probe-hbm-copy-gbs"] = gbs_x10(2 * r.sweep_bytes, r.copy_best_ns);

@@ -1,6 +1,8 @@
 // identity.cpp — see identity.hpp.
 #include "identity.hpp"
 
+#include <mutex>
+
 #include <dirent.h>
 #include <dlfcn.h>
 #include <sys/stat.h>
@@ -389,6 +391,31 @@ bool ScanNvml(std::vector<NvmlGpu>* out, std::string* err) {
     // the handle stays open: NVML dislikes being unloaded and re-loaded
     if (!ok && err) *err = "nvmlDeviceGetCount_v2 failed";
     return ok;
+}
+
+// One NVML session for the life of the process (init is reference-counted, so the
+// init/shutdown pairs of ScanNvml still balance): the per-probe ECC read must not pay
+// nvmlInit every time.
+bool NvmlEccUncorrected(const std::string& gpu_uuid, unsigned long long* out) {
+    struct Session {
+        int (*byUuid)(const char*, nvmlDevice_t*) = nullptr;
+        int (*ecc)(nvmlDevice_t, int, int, unsigned long long*) = nullptr;
+        bool ok = false;
+    };
+    static Session s;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return;
+        auto init = (int (*)())dlsym(h, "nvmlInit_v2");
+        s.byUuid = (int (*)(const char*, nvmlDevice_t*))dlsym(h, "nvmlDeviceGetHandleByUUID");
+        s.ecc = (int (*)(nvmlDevice_t, int, int, unsigned long long*))dlsym(h, "nvmlDeviceGetTotalEccErrors");
+        s.ok = init && s.byUuid && s.ecc && init() == 0;
+    });
+    if (!s.ok) return false;
+    nvmlDevice_t dev = nullptr;
+    if (s.byUuid(gpu_uuid.c_str(), &dev) != 0) return false;
+    return s.ecc(dev, /*NVML_MEMORY_ERROR_TYPE_UNCORRECTED*/ 1, /*NVML_VOLATILE_ECC*/ 0, out) == 0;
 }
 
 }  // namespace identity

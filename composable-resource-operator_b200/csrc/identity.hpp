@@ -76,6 +76,9 @@ struct NvmlGpu {
 };
 // dlopen("libnvidia-ml.so.1"); false if the library or any call is missing.
 bool ScanNvml(std::vector<NvmlGpu>* out, std::string* err);
+// Uncorrected volatile ECC errors of the device since the driver was loaded
+// (nvmlDeviceGetTotalEccErrors); false when NVML or ECC reporting is unavailable.
+bool NvmlEccUncorrected(const std::string& gpu_uuid, unsigned long long* out);
 
 }  // namespace identity
 }  // namespace cro

@@ -642,6 +642,13 @@ static int probe_finish(cro_ctx* c, Device* d, cro_probe_result* r) {
                          " does not reproduce the pattern checksum");
         }
     }
+    // what the memory itself reported while it was being swept: uncorrected volatile ECC errors
+    // (nvmlDeviceGetTotalEccErrors); 0 when NVML is not the identity source or ECC is off
+    if (!(o.flags & CRO_F_NO_NVML) && d->info.identity_source == 1) {
+        unsigned long long ecc = 0;
+        if (identity::NvmlEccUncorrected(std::string(d->info.gpu_uuid, strnlen(d->info.gpu_uuid, sizeof d->info.gpu_uuid)), &ecc))
+            r->ecc_errors = (uint32_t)std::min<unsigned long long>(ecc, 0xFFFFFFFFull);
+    }
     r->status = status;
     return status;
 }
