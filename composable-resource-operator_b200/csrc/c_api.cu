@@ -14,6 +14,7 @@
 #include "fabric.hpp"
 #include "provider.hpp"
 #include "nodes.hpp"
+#include "gpus.hpp"
 #include <memory>
 
 using namespace cro;
@@ -503,6 +504,112 @@ private:
     const gojson::Value* f_;
 };
 
+// ---- scripted cluster: the reference's envtest pods + gomonkey'd SPDY executor, as data -----------
+// "cluster": {"cluster_policy": {"driver_enabled": true} | {} (spec.driver.enabled unset) | null (NotFound),
+//             "pods": [{"namespace","name","node","labels":{..},"containers":[..]}],
+//             "exec": [{"needle": {"escape": "<text, matched after net/url.QueryEscape>"} | {"literal": "<raw query text>"} | null,
+//                       "stdout","stderr","exec_err"}, ...]}      first matching rule answers (`strings.Contains(url.RawQuery, needle)`)
+// ResourceSlices come from the request's "resource_slices".
+class JsonKube : public gpus::Kube {
+public:
+    JsonKube(const gojson::Value* cluster, const gojson::Value* in) : c_(cluster), in_(in) {}
+    controller::Error GetClusterPolicy(bool* found, bool* set, bool* enabled) override {
+        const gojson::Value* cp = c_->get("cluster_policy");
+        *found = cp && cp->kind == gojson::Value::Object;
+        const gojson::Value* en = *found ? cp->get("driver_enabled") : nullptr;
+        *set = en && en->kind == gojson::Value::Bool;
+        *enabled = *set && en->b;
+        const std::string err = c_->get_string("cluster_policy_error");
+        return err.empty() ? controller::Error::Nil() : controller::Error::New(err);
+    }
+    controller::Error ListPods(std::vector<gpus::Pod>* out) override {
+        const gojson::Value* pods = c_->get("pods");
+        if (pods && pods->kind == gojson::Value::Array)
+            for (const auto& p : pods->arr) {
+                if (p->kind != gojson::Value::Object) continue;
+                gpus::Pod pod;
+                pod.ns = p->get_string("namespace");
+                pod.name = p->get_string("name");
+                pod.node = p->get_string("node");
+                if (const gojson::Value* l = p->get("labels"))
+                    if (l->kind == gojson::Value::Object)
+                        for (const auto& kv : l->obj)
+                            if (kv.second->kind == gojson::Value::String) pod.labels[kv.first] = kv.second->str;
+                if (const gojson::Value* cs = p->get("containers"))
+                    if (cs->kind == gojson::Value::Array)
+                        for (const auto& cn : cs->arr)
+                            if (cn->kind == gojson::Value::String) pod.containers.push_back(cn->str);
+                out->push_back(pod);
+            }
+        return controller::Error::Nil();
+    }
+    controller::Error ListResourceSliceUUIDs(std::vector<std::string>* out) override {
+        const gojson::Value* slices = in_->get("resource_slices");
+        if (slices && slices->kind == gojson::Value::Array)
+            for (const auto& s : slices->arr) {
+                const gojson::Value* devs = s->get("devices");
+                if (!devs || devs->kind != gojson::Value::Array) continue;
+                for (const auto& d : devs->arr) {
+                    const gojson::Value* attrs = d->get("attributes");
+                    if (attrs && attrs->kind == gojson::Value::Object) {
+                        const std::string u = attrs->get_string("uuid");
+                        if (attrs->get("uuid")) out->push_back(u);
+                    }
+                }
+            }
+        return controller::Error::Nil();
+    }
+
+private:
+    const gojson::Value* c_;
+    const gojson::Value* in_;
+};
+
+class ScriptedExec : public gpus::Exec {
+public:
+    explicit ScriptedExec(const gojson::Value* cluster) : c_(cluster) {}
+    struct Entry { std::string pod, container, query; std::vector<std::string> argv; int kind; bool detached; };
+    std::vector<Entry> log;
+    int slept = 0;
+    void Sleep(int s) override { slept += s; }
+    gpus::ExecResult Run(const gpus::Pod& pod, const std::string& container, const gpus::ExecRequest& req) override {
+        const std::vector<std::string> argv = req.kind == gpus::ExecRequest::Command ? req.argv : gpus::ScanAsCommand(req);
+        const std::string query = gpus::ExecRawQuery(argv, container);
+        log.push_back({pod.ns + "/" + pod.name, container, query, argv, (int)req.kind, req.detached});
+        gpus::ExecResult r;
+        const gojson::Value* rules = c_->get("exec");
+        if (rules && rules->kind == gojson::Value::Array)
+            for (const auto& rule : rules->arr) {
+                if (rule->kind != gojson::Value::Object) continue;
+                const gojson::Value* n = rule->get("needle");
+                if (n && n->kind == gojson::Value::Object) {
+                    const gojson::Value* esc = n->get("escape");
+                    const gojson::Value* lit = n->get("literal");
+                    std::string needle;
+                    if (esc && esc->kind == gojson::Value::String) {
+                        // net/url.QueryEscape of the text, the same way ExecRawQuery escapes each argument
+                        needle = gpus::ExecRawQuery({esc->str}, "").substr(8);       // strip "command="
+                        needle = needle.substr(0, needle.find("&container="));
+                    } else if (lit && lit->kind == gojson::Value::String) {
+                        needle = lit->str;
+                    }
+                    if (query.find(needle) == std::string::npos) continue;
+                }
+                r.std_out = rule->get_string("stdout");
+                r.std_err = rule->get_string("stderr");
+                const gojson::Value* ee = rule->get("exec_err");
+                if (ee && ee->kind == gojson::Value::String) { r.failed = true; r.exec_err = ee->str; }
+                return r;
+            }
+        r.failed = true;
+        r.exec_err = "no exec rule matches " + query;
+        return r;
+    }
+
+private:
+    const gojson::Value* c_;
+};
+
 // NewComposableResourceAdapter (composableresource_adapter.go:39-72) over an env map: which
 // provider flavour, or the error the reconcile surfaces.  "" kind + nil error never happens.
 controller::Error SelectAdapter(const gojson::Value* env, std::string* kind) {
@@ -733,7 +840,21 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
     JsonProvider canned(in->get("provider"));
     controller::CdiProvider* provider = fti ? static_cast<controller::CdiProvider*>(fti.get()) : &canned;
     ProbeNodeOps node(ctx, in.get());
-    controller::ComposableResourceReconciler rec(provider, &node);
+    // With a "cluster" object the node side is csrc/gpus.cpp (internal/utils/gpus.go restated) over the
+    // scripted pods / pod-exec; DaemonSet restarts and taints stay with the canned NodeOps above.
+    const gojson::Value* cluster = in->get("cluster");
+    const bool scripted = cluster && cluster->kind == gojson::Value::Object;
+    JsonKube kube(scripted ? cluster : in.get(), in.get());
+    ScriptedExec pod_exec(scripted ? cluster : in.get());
+    struct ClusterNodeOps : gpus::GpuNodeOps {
+        ClusterNodeOps(gpus::Kube* k, gpus::Exec* e, ProbeNodeOps* canned) : gpus::GpuNodeOps(k, e), canned_(canned) {}
+        controller::Error RestartDaemonset(const std::string& ns, const std::string& name) override { return canned_->RestartDaemonset(ns, name); }
+        controller::Error CreateDeviceTaint(const controller::ComposableResource& r) override { return canned_->CreateDeviceTaint(r); }
+        controller::Error DeleteDeviceTaint(const controller::ComposableResource& r) override { return canned_->DeleteDeviceTaint(r); }
+        ProbeNodeOps* canned_;
+    } cluster_ops(&kube, &pod_exec, &node);
+    controller::NodeOps* node_ops = scripted ? static_cast<controller::NodeOps*>(&cluster_ops) : &node;
+    controller::ComposableResourceReconciler rec(provider, node_ops);
     store.updates = &rec.statusUpdates;
     controller::Result result;
     controller::Error err;
@@ -763,6 +884,21 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
     for (const auto& s : rec.statusUpdates) w.raw(s.MarshalJSON());
     w.end_array();
     if (node.probed) w.key("probe").string_map(probe_annotations(node.probe_result));
+    if (scripted) {     // every pod-exec the step issued, in order: pod, container, the URL query the mocks match on, argv
+        w.key("exec_log").begin_array();
+        for (const auto& x : pod_exec.log) {
+            w.begin_object();
+            w.field("pod", x.pod).field("container", x.container).field("query", x.query);
+            w.key("argv").begin_array();
+            for (const auto& a : x.argv) w.value(a);
+            w.end_array();
+            w.field("kind", x.kind == 0 ? std::string("command") : x.kind == 1 ? std::string("fd_scan") : x.kind == 2 ? std::string("proc_scan") : std::string("cmdline_scan"));
+            w.field("detached", x.detached);
+            w.end_object();
+        }
+        w.end_array();
+        w.field("slept_s", pod_exec.slept);
+    }
     if (!node.restarted.empty()) {
         w.key("daemonset_restarts").begin_array();
         for (const auto& r : node.restarted) w.value(r);

@@ -89,11 +89,45 @@ def main():
         objs = {"node": not e.get("expected_deleted", False),
                 "node_annotation": '"machine.openshift.io/machine":' in block,
                 "machine": "Metal3Machine{" in block, "machine_annotation": '"metal3.io/BareMetalHost":' in block,
-                "bmh": "BareMetalHost{" in block, "secret": "corev1.Secret{" in block}
+                "bmh": "BareMetalHost{" in block, "secret": "corev1.Secret{" in block,
+                # gpu-operator ClusterPolicy with spec.driver.enabled = true (absent: the RKE2 branches run)
+                "cluster_policy": "gpuv1.ClusterPolicy{" in block}
         m = re.search(r'"cluster-manager\.cdi\.io/machine":\s*' + STR, block)
         if m:
             objs["bmh_machine_uuid"] = unquote(m.group(1))
         e["objects"] = objs
+        # the entry's mock pod-exec (gomonkey patch of remotecommand.NewSPDYExecutor): an ordered chain of
+        # `strings.Contains(url.RawQuery, needle)` -> newMockExecutor(stdout, stderr); a chain without `if` is one rule
+        patches = [m.start() for m in re.finditer(r"remotecommand\.NewSPDYExecutor,", block)]
+        if patches:
+            seg = block[patches[-1]:]
+            seg = seg[:seg.find("\n\t\t\t\t\t\t)") if "\n\t\t\t\t\t\t)" in seg else len(seg)]
+            rules = []
+            pos = 0
+            for m in re.finditer(r"newMockExecutor\(" + STR + r",\s*" + STR + r"\)", seg):
+                cond = seg[pos:m.start()]
+                c = re.findall(r"strings\.Contains\(url\.RawQuery,\s*(?:neturl\.QueryEscape\(" + STR + r"\)|" + STR + r")\)", cond)
+                needle = None
+                if c:
+                    esc, lit = c[-1]
+                    needle = {"escape": unquote(esc)} if esc else {"literal": unquote(lit)}
+                rules.append({"needle": needle, "stdout": unquote(m.group(1)), "stderr": unquote(m.group(2))})
+                pos = m.end()
+            e["exec_rules"] = rules
+        # pods the entry creates (name, namespace, labels are literal in the block)
+        pods = []
+        for m in re.finditer(r"&corev1\.Pod\{\s*ObjectMeta: metav1\.ObjectMeta\{(.*?)\n\t+\},\s*Spec: corev1\.PodSpec\{(.*?)\n\t+\},", block, re.S):
+            meta, spec = m.group(1), m.group(2)
+            name = re.search(r"Name:\s*" + STR, meta)
+            ns = re.search(r"Namespace:\s*" + STR, meta)
+            labels = dict((unquote(a), unquote(b)) for a, b in re.findall(STR + r":\s*" + STR, meta[meta.find("Labels"):] if "Labels" in meta else ""))
+            node = re.search(r"NodeName:\s*(?:" + STR + r"|(\w+))", spec)
+            cont = re.findall(r"\{Name:\s*" + STR, spec)
+            pods.append({"name": unquote(name.group(1)) if name else "", "namespace": unquote(ns.group(1)) if ns else "",
+                         "labels": labels, "node": (unquote(node.group(1)) if node and node.group(1) else "worker-0") if node else "",
+                         "containers": [unquote(x) for x in cont]})
+        if pods:
+            e["pods"] = pods
         out.append(e)
     # the fake fabric's route table (httptest handler, :663-930): path -> status + body
     routes = {}

@@ -12,6 +12,7 @@
 #include "detach.hpp"
 #include "fabric.hpp"
 #include "gojson.hpp"
+#include "gpus.hpp"
 #include "identity.hpp"
 #include "nodes.hpp"
 #include "provider.hpp"
@@ -82,6 +83,36 @@ static std::string mutate(std::string s) {
 }
 
 static size_t sink = 0;   // keeps results alive
+
+// Node-side flows (csrc/gpus.cpp) with a pod-exec that answers every request with the fuzz input:
+// whatever nvidia-smi / lsmod / the scans print, the decision code must stay in bounds.
+struct FuzzKube : gpus::Kube {
+    int policy = 0;   // 0 NotFound, 1 unset, 2 disabled, 3 enabled
+    controller::Error GetClusterPolicy(bool* found, bool* set, bool* enabled) override {
+        *found = policy > 0; *set = policy > 1; *enabled = policy == 3;
+        return controller::Error::Nil();
+    }
+    controller::Error ListPods(std::vector<gpus::Pod>* out) override {
+        out->push_back({"ns", "nvidia-driver-daemonset-x", "worker-0", {{"app.kubernetes.io/component", "nvidia-driver"}}, {"ctr"}});
+        out->push_back({"ns", "nvidia-dra-driver-gpu-kubelet-plugin-x", "worker-0", {{"app.kubernetes.io/name", "nvidia-dra-driver-gpu"}}, {}});
+        out->push_back({"ns", "cro-node-agent-x", "worker-0", {{"app", "cro-node-agent"}}, {"agent"}});
+        return controller::Error::Nil();
+    }
+    controller::Error ListResourceSliceUUIDs(std::vector<std::string>* out) override { out->push_back("GPU-1"); return controller::Error::Nil(); }
+};
+struct FuzzExec : gpus::Exec {
+    const std::string* text = nullptr;
+    unsigned n = 0;
+    gpus::ExecResult Run(const gpus::Pod&, const std::string& container, const gpus::ExecRequest& req) override {
+        gpus::ExecResult r;
+        ++n;
+        sink += gpus::ExecRawQuery(req.kind == gpus::ExecRequest::Command ? req.argv : gpus::ScanAsCommand(req), container).size();
+        if (n % 3 != 0) r.std_out = *text;          // sometimes the answer is on stdout, sometimes stderr, sometimes empty
+        else if (n % 2 == 0) r.std_err = *text;
+        if (n % 11 == 0) { r.failed = true; r.exec_err = "command terminated with exit code 1"; }
+        return r;
+    }
+};
 
 static void one(const std::string& in, const std::string& err_text) {
     const char* exec_err = (rnd() & 7) == 0 ? "command terminated with exit code 1" : nullptr;
@@ -159,6 +190,23 @@ static void one(const std::string& in, const std::string& err_text) {
         ds.restartedAt = in;
         nodes::Restart what;
         sink += nodes::RestartDaemonsetDecision("ns", "ds", ds, 1750000000, 0, &what).msg.size();
+    }
+    {
+        FuzzKube kube;
+        FuzzExec exec;
+        exec.text = &in;
+        gpus::GpuNodeOps ops(&kube, &exec);
+        controller::ComposableResource res;
+        res.Spec.TargetNode = "worker-0";
+        res.Status.DeviceID = "GPU-1";
+        const std::string uuid = "GPU-1";
+        for (kube.policy = 0; kube.policy < 4; ++kube.policy)
+            for (const char* type : {"DRA", "DEVICE_PLUGIN"}) {
+                bool visible = false;
+                sink += ops.RunNvidiaSmi("worker-0").msg.size() + ops.CheckGPUVisible(type, res, &visible).msg.size();
+                sink += ops.CheckNoGPULoadsFor("worker-0", &uuid).msg.size() + ops.CheckNoGPULoadsFor("worker-0", nullptr).msg.size();
+                sink += ops.DrainGPU("worker-0", uuid, type).msg.size();
+            }
     }
 }
 
