@@ -145,6 +145,14 @@ uint32_t resolve_copy_variant(uint32_t v) {
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
+// Caches the device's uncorrected volatile ECC count (0 when NVML is not the identity source or ECC is off).
+static void refresh_ecc(cro_ctx* c, Device* d) {
+    if ((c->opts.flags & CRO_F_NO_NVML) || d->info.identity_source != 1) return;
+    unsigned long long ecc = 0;
+    if (identity::NvmlEccUncorrected(std::string(d->info.gpu_uuid, strnlen(d->info.gpu_uuid, sizeof d->info.gpu_uuid)), &ecc))
+        d->ecc_uncorrected = (uint32_t)std::min<unsigned long long>(ecc, 0xFFFFFFFFull);
+}
+
 int ctx_create(const cro_opts* o, cro_ctx** out) {
     if (!out) return CRO_ERR_INVALID_ARG;
     *out = nullptr;
@@ -275,6 +283,7 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
             int rc = ensure_region(c.get(), d);
             if (rc) return rc;
         }
+        refresh_ecc(c.get(), d);
         c->devs.push_back(std::move(keyed[i].d));
     }
     *out = c.release();
@@ -642,13 +651,12 @@ static int probe_finish(cro_ctx* c, Device* d, cro_probe_result* r) {
                          " does not reproduce the pattern checksum");
         }
     }
-    // what the memory itself reported while it was being swept: uncorrected volatile ECC errors
-    // (nvmlDeviceGetTotalEccErrors); 0 when NVML is not the identity source or ECC is off
-    if (!(o.flags & CRO_F_NO_NVML) && d->info.identity_source == 1) {
-        unsigned long long ecc = 0;
-        if (identity::NvmlEccUncorrected(std::string(d->info.gpu_uuid, strnlen(d->info.gpu_uuid, sizeof d->info.gpu_uuid)), &ecc))
-            r->ecc_errors = (uint32_t)std::min<unsigned long long>(ecc, 0xFFFFFFFFull);
-    }
+    // What the memory itself reported: uncorrected volatile ECC errors (nvmlDeviceGetTotalEccErrors).
+    // NVML calls serialise across processes (measured: ~2 ms each with 4 ranks probing, enough to skew the
+    // ranks' all-gather), so the warm probe reuses the count read at init / at the last full-box probe and
+    // only a FAILED probe pays for a fresh read.
+    if (status != CRO_OK) refresh_ecc(c, d);
+    r->ecc_errors = d->ecc_uncorrected;
     r->status = status;
     return status;
 }
@@ -1034,6 +1042,8 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
     for (int i = 0; i < n; ++i) {
         Device* d = c->devs[(size_t)i].get();
         std::lock_guard<std::mutex> g(d->mu);
+        refresh_ecc(c, d);                        // the full-box probe is rare enough to afford a fresh read
+        res[(size_t)i].ecc_errors = d->ecc_uncorrected;
         int rc = publish_result(c, d, &res[(size_t)i]);
         if (rc) return rc;
     }

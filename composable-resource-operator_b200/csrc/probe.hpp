@@ -54,6 +54,7 @@ struct Device {
     bool have_expected = false;
     uint64_t expect_x = 0, expect_s = 0;
     unsigned sm_clock_mhz = 0, mem_clock_mhz = 0;
+    uint32_t ecc_uncorrected = 0;      // NVML count cached at init / full-box probe / failed probe
 
     Device() = default;
     Device(const Device&) = delete;

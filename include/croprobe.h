@@ -131,7 +131,8 @@ typedef struct cro_probe_result {
     uint32_t sm_count;             /* 168 */
     uint32_t sm_clock_mhz;         /* 172 */
     uint32_t mem_clock_mhz;        /* 176 */
-    uint32_t ecc_errors;           /* 180  uncorrected volatile ECC errors NVML reports after the sweeps */
+    uint32_t ecc_errors;           /* 180  uncorrected volatile ECC errors (NVML), read at init, at
+                                           cro_probe_all and after any failed probe */
     uint64_t p2p_read_ns[8];       /* 184  best time to read p2p_bytes from peer j   */
     uint64_t p2p_checksum_xor[8];  /* 248 */
     uint32_t p2p_latency_ns_x16[8];/* 312  mean hop latency x16 (fixed point)        */
