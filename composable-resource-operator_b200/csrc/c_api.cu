@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 
 #include "../../include/croprobe.h"
@@ -560,7 +561,56 @@ public:
         return controller::Error::Nil();
     }
 
+    // DeviceTaintRules: "taints": ["<name>", ..] exist already; "taint_get_error" / "taint_create_error" /
+    // "taint_delete_error" make the corresponding API call fail; every create / delete is logged.
+    controller::Error ListResourceSliceDevices(std::vector<SliceDevice>* out) override {
+        const gojson::Value* slices = in_->get("resource_slices");
+        if (slices && slices->kind == gojson::Value::Array)
+            for (const auto& s : slices->arr) {
+                const gojson::Value* pool = s->get("pool");
+                const gojson::Value* devs = s->get("devices");
+                if (!devs || devs->kind != gojson::Value::Array) continue;
+                for (const auto& d : devs->arr) {
+                    const gojson::Value* attrs = d->get("attributes");
+                    if (!attrs || attrs->kind != gojson::Value::Object || !attrs->get("uuid")) continue;
+                    out->push_back({s->get_string("driver"), pool ? pool->get_string("name") : std::string(), d->get_string("name"),
+                                    attrs->get_string("uuid")});
+                }
+            }
+        return controller::Error::Nil();
+    }
+    controller::Error GetDeviceTaintRule(const std::string& name, bool* found) override {
+        *found = created_.count(name) > 0;
+        const gojson::Value* t = c_->get("taints");
+        if (t && t->kind == gojson::Value::Array)
+            for (const auto& e : t->arr)
+                if (e->kind == gojson::Value::String && e->str == name && !deleted_.count(name)) *found = true;
+        return fail("taint_get_error");
+    }
+    controller::Error CreateDeviceTaintRule(const TaintRule& r) override {
+        controller::Error e = fail("taint_create_error");
+        if (!e.ok()) return e;
+        created_.insert(r.name);
+        taint_ops.push_back("create " + r.name + " driver=" + r.driver + " pool=" + r.pool + " device=" + r.device + " " + r.key + "=" +
+                            r.value + ":" + r.effect);
+        return e;
+    }
+    controller::Error DeleteDeviceTaintRule(const std::string& name) override {
+        controller::Error e = fail("taint_delete_error");
+        if (!e.ok()) return e;
+        created_.erase(name);
+        deleted_.insert(name);
+        taint_ops.push_back("delete " + name);
+        return e;
+    }
+    std::vector<std::string> taint_ops;
+
 private:
+    controller::Error fail(const char* key) {
+        const std::string e = c_->get_string(key);
+        return e.empty() ? controller::Error::Nil() : controller::Error::New(e);
+    }
+    std::set<std::string> created_, deleted_;
     const gojson::Value* c_;
     const gojson::Value* in_;
 };
@@ -849,8 +899,6 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
     struct ClusterNodeOps : gpus::GpuNodeOps {
         ClusterNodeOps(gpus::Kube* k, gpus::Exec* e, ProbeNodeOps* canned) : gpus::GpuNodeOps(k, e), canned_(canned) {}
         controller::Error RestartDaemonset(const std::string& ns, const std::string& name) override { return canned_->RestartDaemonset(ns, name); }
-        controller::Error CreateDeviceTaint(const controller::ComposableResource& r) override { return canned_->CreateDeviceTaint(r); }
-        controller::Error DeleteDeviceTaint(const controller::ComposableResource& r) override { return canned_->DeleteDeviceTaint(r); }
         ProbeNodeOps* canned_;
     } cluster_ops(&kube, &pod_exec, &node);
     controller::NodeOps* node_ops = scripted ? static_cast<controller::NodeOps*>(&cluster_ops) : &node;
@@ -898,6 +946,9 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
         }
         w.end_array();
         w.field("slept_s", pod_exec.slept);
+        w.key("taint_ops").begin_array();
+        for (const auto& op : kube.taint_ops) w.value(op);
+        w.end_array();
     }
     if (!node.restarted.empty()) {
         w.key("daemonset_restarts").begin_array();

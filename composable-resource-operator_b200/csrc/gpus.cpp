@@ -395,5 +395,38 @@ Error GpuNodeOps::DrainGPU(const std::string& node, const std::string& targetGPU
     return Error::Nil();
 }
 
+// ---------------------------------------------------------------------------
+// device taints (DRA): keep the scheduler away from a device that is being detached
+// ---------------------------------------------------------------------------
+Error GpuNodeOps::CreateDeviceTaint(const controller::ComposableResource& resource) {
+    const std::string taintName = resource.Name + "-taint";
+    bool exists = false;
+    Error e = kube_->GetDeviceTaintRule(taintName, &exists);
+    if (!e.ok()) return e;                       // any error but NotFound is returned as is (:697-699)
+    if (exists) return Error::Nil();
+    std::vector<Kube::SliceDevice> devices;
+    e = kube_->ListResourceSliceDevices(&devices);
+    if (!e.ok()) return e;
+    const Kube::SliceDevice* hit = nullptr;
+    for (const auto& d : devices)
+        if (d.uuid == resource.Status.DeviceID) { hit = &d; break; }
+    if (!hit || hit->device.empty()) return Error::Nil();   // the slice no longer lists it: nothing to taint
+    Kube::TaintRule rule{taintName, hit->driver, hit->pool, hit->device, "k8s.io/device-uuid", resource.Status.DeviceID, "NoSchedule"};
+    e = kube_->CreateDeviceTaintRule(rule);
+    if (!e.ok()) return Error::New("failed to create DeviceTaintRule " + taintName + ": " + e.msg);
+    return Error::Nil();
+}
+
+Error GpuNodeOps::DeleteDeviceTaint(const controller::ComposableResource& resource) {
+    const std::string taintName = resource.Name + "-taint";
+    bool exists = false;
+    Error e = kube_->GetDeviceTaintRule(taintName, &exists);
+    if (!e.ok()) return Error::New("failed to get DeviceTaintRule " + taintName + ": " + e.msg);
+    if (!exists) return Error::Nil();
+    e = kube_->DeleteDeviceTaintRule(taintName);
+    if (!e.ok()) return Error::New("failed to delete DeviceTaintRule " + taintName + ": " + e.msg);
+    return Error::Nil();
+}
+
 }  // namespace gpus
 }  // namespace cro

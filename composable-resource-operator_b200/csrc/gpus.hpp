@@ -42,6 +42,13 @@ public:
     virtual Error GetClusterPolicy(bool* found, bool* set, bool* enabled) = 0;
     virtual Error ListPods(std::vector<Pod>* out) = 0;                      // every namespace, API order
     virtual Error ListResourceSliceUUIDs(std::vector<std::string>* out) = 0; // attribute "uuid" of every device (DRA)
+    // DeviceTaintRule bookkeeping of the DRA detach (gpus.go:691-786); the defaults make taints a no-op
+    struct SliceDevice { std::string driver, pool, device, uuid; };
+    struct TaintRule { std::string name, driver, pool, device, key, value, effect; };
+    virtual Error ListResourceSliceDevices(std::vector<SliceDevice>* /*out*/) { return Error::Nil(); }
+    virtual Error GetDeviceTaintRule(const std::string& /*name*/, bool* found) { *found = false; return Error::Nil(); }
+    virtual Error CreateDeviceTaintRule(const TaintRule& /*rule*/) { return Error::Nil(); }
+    virtual Error DeleteDeviceTaintRule(const std::string& /*name*/) { return Error::Nil(); }
 };
 
 struct ExecRequest {
@@ -80,6 +87,8 @@ public:
                           bool* visible) override;                                                  // :54-86
     Error DrainGPU(const std::string& node, const std::string& targetGPUUUID,
                    const std::string& deviceResourceType) override;                                 // :188-664
+    Error CreateDeviceTaint(const controller::ComposableResource& resource) override;               // :691-748
+    Error DeleteDeviceTaint(const controller::ComposableResource& resource) override;               // :750-766
     // cluster bookkeeping stays with the host
     Error RestartDaemonset(const std::string&, const std::string&) override { return Error::Nil(); }
 
