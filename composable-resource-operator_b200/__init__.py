@@ -116,6 +116,7 @@ EXPORTS = [
     "cro_check_no_gpu_loads", "cro_check_gpu_drain_status", "cro_check_device_file_scan",
     "cro_scan_device_file_holders", "cro_sim_reconcile_resource", "cro_sim_sync_upstream",
     "cro_fabric_check_resource", "cro_fabric_get_resources", "cro_fabric_list_devices",
+    "cro_local_node_op", "cro_scan_cmdline_for",
 ]
 
 
@@ -179,6 +180,8 @@ def _load() -> ctypes.CDLL:
         "cro_fabric_check_resource": (i32, [c, c, c, c, c, c, sz]),
         "cro_fabric_get_resources": (i32, [c, c, c, c] + out),
         "cro_fabric_list_devices": (i32, [c] + out),
+        "cro_local_node_op": (i32, [vp, c] + out),
+        "cro_scan_cmdline_for": (i32, [c, c, ctypes.POINTER(i32)]),
         "cro_sim_reconcile_resource": (i32, [vp, c, c, sz]),
         "cro_sim_sync_upstream": (i32, [vp, c, ctypes.c_longlong, c, sz]),
         "cro_check_no_gpu_loads": (i32, [c, c, c, c, c, c, i32, c, sz]),
@@ -478,6 +481,20 @@ def fabric_list_devices(request: Dict) -> Dict:
     """CdiProvider.GetResources of the FM / CM client over a scripted fabric (what the UpstreamSyncer
     tick reads: upstreamsyncer_controller.go:77-84).  request = {"env": {...}, "fabric": {...}}."""
     return json.loads(_text(lib.cro_fabric_list_devices, _b(json.dumps(request))))
+
+
+def local_node_op(ctx: Optional["ProbeContext"], request: Dict) -> Dict:
+    """One node-side operation of internal/utils/gpus.go run locally (scans native, read-only commands spawned,
+    mutating ones only with allow_mutation).  See cro_local_node_op in include/croprobe.h."""
+    return json.loads(_text(lib.cro_local_node_op, ctx.handle if ctx is not None else None, _b(json.dumps(request))))
+
+
+def scan_cmdline_for(proc_root: str, needle: str) -> bool:
+    found = ctypes.c_int(0)
+    rc = lib.cro_scan_cmdline_for(_b(proc_root), _b(needle), ctypes.byref(found))
+    if rc != OK:
+        raise ProbeError(rc, "cro_scan_cmdline_for")
+    return bool(found.value)
 
 
 def CheckNoGPULoadsFromOutput(std_out: str, std_err: str, exec_err: Optional[str], pod_name: str, node_name: str,

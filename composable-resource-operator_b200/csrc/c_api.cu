@@ -1036,6 +1036,66 @@ int cro_fabric_list_devices(const char* request_json, char* buf, size_t cap, siz
     return copy_out(w.str(), buf, cap, len);
 }
 
+// ---- node-side operations on the node itself ----------------------------------------
+
+int cro_scan_cmdline_for(const char* proc_root, const char* needle, int* found) {
+    if (!needle || !found) return CRO_ERR_INVALID_ARG;
+    *found = detach::ScanCmdlineFor(S(proc_root), needle).empty() ? 0 : 1;
+    return CRO_OK;
+}
+
+int cro_local_node_op(cro_ctx* ctx, const char* request_json, char* buf, size_t cap, size_t* len) {
+    if (!request_json) return CRO_ERR_INVALID_ARG;
+    std::string perr;
+    gojson::ValuePtr in = gojson::parse(request_json, &perr);
+    if (!in || in->kind != gojson::Value::Object) {
+        copy_out("bad request: " + perr, buf, cap, len);
+        return CRO_ERR_PARSE;
+    }
+    std::vector<cro_dev_info> devs;
+    if (ctx)
+        for (auto& d : ctx->devs) devs.push_back(d->info);
+    gpus::LocalExec::Options o;
+    o.proc_root = in->get_string("proc_root");
+    o.allow_mutation = in->get_bool("allow_mutation");
+    if (ctx) { o.devs = devs.data(); o.n_devs = (int)devs.size(); }
+    gpus::LocalExec exec(o);
+    const std::string node = in->get_string("node", "local");
+    gpus::LocalKube kube(node, in->get_bool("driver_container", true));
+    gpus::GpuNodeOps ops(&kube, &exec);
+    const std::string op = in->get_string("op");
+    const std::string uuid = in->get_string("device_id");
+    const std::string type = in->get_string("device_resource_type", "DEVICE_PLUGIN");
+    controller::Error e;
+    bool visible = false;
+    if (op == "check_no_gpu_loads") e = ops.CheckNoGPULoadsFor(node, uuid.empty() ? nullptr : &uuid);
+    else if (op == "run_nvidia_smi") e = ops.RunNvidiaSmi(node);
+    else if (op == "check_gpu_visible") {
+        controller::ComposableResource r;
+        r.Spec.TargetNode = node;
+        r.Status.DeviceID = uuid;
+        e = ops.CheckGPUVisible(type, r, &visible);
+    } else if (op == "drain") e = ops.DrainGPU(node, uuid, type);
+    else return CRO_ERR_INVALID_ARG;
+    gojson::Writer w;
+    w.begin_object();
+    w.field("error", e.ok() ? std::string() : e.msg);
+    w.field("visible", visible);
+    w.key("exec_log").begin_array();
+    for (const auto& x : exec.log) {
+        w.begin_object();
+        w.field("kind", x.kind == 0 ? std::string("command") : x.kind == 1 ? std::string("fd_scan") : x.kind == 2 ? std::string("proc_scan") : std::string("cmdline_scan"));
+        w.key("argv").begin_array();
+        for (const auto& a : x.argv) w.value(a);
+        w.end_array();
+        w.field("how", x.how).field("failed", x.failed);
+        w.end_object();
+    }
+    w.end_array();
+    w.end_object();
+    return copy_out(w.str(), buf, cap, len);
+}
+
 // ---- detach-side pre-flight -------------------------------------------------------
 
 static int finish_err(const controller::Error& e, char* err_buf, size_t err_cap) {

@@ -1,6 +1,8 @@
 // detach.cpp — see detach.hpp.
 #include "detach.hpp"
 
+#include <iterator>
+
 #include <dirent.h>
 #include <limits.h>
 #include <sys/stat.h>
@@ -154,6 +156,27 @@ std::string ScanDeviceFileHolders(const std::string& proc_root, const std::strin
         }
     }
     return out;
+}
+
+std::string ScanCmdlineFor(const std::string& proc_root, const std::string& target) {
+    const std::string root = proc_root.empty() ? "/proc" : proc_root;
+    const std::string self = std::to_string((long long)getpid()), parent = std::to_string((long long)getppid());
+    std::vector<std::string> pids;
+    if (DIR* d = opendir(root.c_str())) {
+        while (dirent* e = readdir(d))
+            if (e->d_name[0] >= '0' && e->d_name[0] <= '9') pids.push_back(e->d_name);
+        closedir(d);
+    }
+    for (const std::string& pid : pids) {
+        if (proc_root.empty() && (pid == self || pid == parent)) continue;   // the scanner never reports itself
+        std::ifstream f(root + "/" + pid + "/cmdline", std::ios::binary);
+        if (!f) continue;
+        std::string cmd((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        for (char& c : cmd)
+            if (c == '\0') c = ' ';                                          // tr '\0' ' '
+        if (!cmd.empty() && cmd.find(target) != std::string::npos) return "true\n";
+    }
+    return "";
 }
 
 }  // namespace detach

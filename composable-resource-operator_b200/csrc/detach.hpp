@@ -38,5 +38,10 @@ Error CheckDeviceFileScanResult(const std::string& stdOut, const std::string& st
 // "PID comm, PID comm".  proc_root lets tests point at a fake /proc.
 std::string ScanDeviceFileHolders(const std::string& proc_root, const std::string& target, bool rke2);
 
+// Native replacement of the cmdline scan of checkResetGPUCommandStillRunning (gpus.go:1182-1226): is some
+// OTHER process's command line mentioning `target` (the sysfs "remove" file a detached `tee` writes to)?
+// Prints what the script prints: "true\n" or nothing.
+std::string ScanCmdlineFor(const std::string& proc_root, const std::string& target);
+
 }  // namespace detach
 }  // namespace cro

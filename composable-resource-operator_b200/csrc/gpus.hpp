@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/croprobe.h"
 #include "reconcile.hpp"
 
 namespace cro {
@@ -110,6 +111,42 @@ protected:
 
     Kube* kube_;
     Exec* exec_;
+};
+
+// ---- the seams answered on the node itself (gpus_local.cpp) --------------------------------------------
+// Scans are native /proc walks, `nvidia-smi --query-gpu=...` is answered from already-enumerated devices
+// when they are handed in, other commands are spawned with the chroot prefix dropped.  Commands that change
+// the node (persistence mode, drain -m / -r, rm, modprobe, the sysfs remove) are only run with
+// allow_mutation; otherwise they are logged as skipped and succeed, which makes DrainGPU a dry run that
+// still performs every read-only check for real.
+class LocalExec : public Exec {
+public:
+    struct Options {
+        std::string proc_root;                 // "" = /proc
+        bool allow_mutation = false;
+        const cro_dev_info* devs = nullptr;    // devices a probe context enumerated (optional)
+        int n_devs = -1;
+    };
+    struct LogEntry { int kind = 0; std::vector<std::string> argv; std::string how; bool failed = false; };
+    explicit LocalExec(const Options& o);
+    ExecResult Run(const Pod& pod, const std::string& container, const ExecRequest& req) override;
+    void Sleep(int seconds) override;
+    std::vector<LogEntry> log;
+
+private:
+    Options o_;
+};
+
+class LocalKube : public Kube {
+public:
+    LocalKube(const std::string& node, bool driver_container) : node_(node), driver_container_(driver_container) {}
+    Error GetClusterPolicy(bool* found, bool* set, bool* enabled) override;
+    Error ListPods(std::vector<Pod>* out) override;
+    Error ListResourceSliceUUIDs(std::vector<std::string>*) override { return Error::Nil(); }
+
+private:
+    std::string node_;
+    bool driver_container_;
 };
 
 }  // namespace gpus

@@ -1,0 +1,152 @@
+// gpus_local.cpp — the Kube / Exec seams of gpus.hpp answered ON the node: what a node agent that links
+// libcroprobe does instead of the operator's SPDY execs into other pods (internal/utils/gpus.go:788-815).
+#include <poll.h>
+#include <spawn.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <cstring>
+
+#include "detach.hpp"
+#include "gpus.hpp"
+#include "identity.hpp"
+
+extern char** environ;
+
+namespace cro {
+namespace gpus {
+
+namespace {
+
+bool mutating(const std::vector<std::string>& argv) {
+    for (size_t i = 0; i < argv.size(); ++i) {
+        const std::string& a = argv[i];
+        if (a == "-pm" || a == "-r" || a == "-m") return true;                       // persistence mode, drain -m / -r
+        if (a.size() >= 3 && a.compare(a.size() - 3, 3, "/rm") == 0) return true;
+        if (a.find("modprobe") != std::string::npos || a.find("/tee ") != std::string::npos) return true;
+    }
+    return false;
+}
+
+// posix_spawn + pipes; the error text is kubectl-exec's ("command terminated with exit code N").
+ExecResult spawn(const std::vector<std::string>& argv) {
+    ExecResult r;
+    if (argv.empty()) { r.failed = true; r.exec_err = "empty command"; return r; }
+    int out[2], err[2];
+    if (pipe(out) != 0) { r.failed = true; r.exec_err = "pipe failed"; return r; }
+    if (pipe(err) != 0) { close(out[0]); close(out[1]); r.failed = true; r.exec_err = "pipe failed"; return r; }
+    posix_spawn_file_actions_t fa;
+    posix_spawn_file_actions_init(&fa);
+    posix_spawn_file_actions_adddup2(&fa, out[1], 1);
+    posix_spawn_file_actions_adddup2(&fa, err[1], 2);
+    posix_spawn_file_actions_addclose(&fa, out[0]);
+    posix_spawn_file_actions_addclose(&fa, err[0]);
+    std::vector<char*> av;
+    for (const auto& a : argv) av.push_back(const_cast<char*>(a.c_str()));
+    av.push_back(nullptr);
+    pid_t pid = 0;
+    const int rc = posix_spawn(&pid, argv[0].c_str(), &fa, nullptr, av.data(), environ);
+    posix_spawn_file_actions_destroy(&fa);
+    close(out[1]);
+    close(err[1]);
+    if (rc != 0) {
+        close(out[0]);
+        close(err[0]);
+        r.failed = true;
+        r.exec_err = std::string("exec: \"") + argv[0] + "\": " + strerror(rc);
+        return r;
+    }
+    pollfd fds[2] = {{out[0], POLLIN, 0}, {err[0], POLLIN, 0}};
+    int open_fds = 2;
+    char buf[4096];
+    while (open_fds > 0) {
+        if (poll(fds, 2, -1) < 0) break;
+        for (int i = 0; i < 2; ++i) {
+            if (fds[i].fd < 0 || !(fds[i].revents & (POLLIN | POLLHUP | POLLERR))) continue;
+            const ssize_t n = read(fds[i].fd, buf, sizeof buf);
+            if (n > 0) (i == 0 ? r.std_out : r.std_err).append(buf, (size_t)n);
+            else { close(fds[i].fd); fds[i].fd = -1; --open_fds; }
+        }
+    }
+    int status = 0;
+    waitpid(pid, &status, 0);
+    if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) {
+        r.failed = true;
+        r.exec_err = "command terminated with exit code " + std::to_string(WIFEXITED(status) ? WEXITSTATUS(status) : 128 + WTERMSIG(status));
+    }
+    return r;
+}
+
+}  // namespace
+
+LocalExec::LocalExec(const Options& o) : o_(o) {}
+
+void LocalExec::Sleep(int s) {
+    if (o_.allow_mutation) sleep((unsigned)s);
+}
+
+ExecResult LocalExec::Run(const Pod&, const std::string&, const ExecRequest& req) {
+    LogEntry le;
+    le.kind = (int)req.kind;
+    le.argv = req.kind == ExecRequest::Command ? req.argv : ScanAsCommand(req);
+    ExecResult r;
+    switch (req.kind) {
+        case ExecRequest::FdScan:
+            le.how = "native";
+            r.std_out = detach::ScanDeviceFileHolders(o_.proc_root, req.target, req.rke2_format);
+            break;
+        case ExecRequest::CmdlineScan:
+            le.how = "native";
+            r.std_out = detach::ScanCmdlineFor(o_.proc_root, req.target);
+            break;
+        case ExecRequest::ProcScan: {
+            le.how = "native";
+            for (const identity::ProcGpu& g : identity::ScanProc(o_.proc_root.empty() ? std::string("/proc") : o_.proc_root))
+                r.std_out += g.minor + "," + g.uuid + "," + g.bus + "\n";
+            break;
+        }
+        case ExecRequest::Command: {
+            std::vector<std::string> argv = req.argv;
+            if (argv.size() > 2 && argv[0] == "/bin/chroot" && argv[1] == "/host-root") argv.erase(argv.begin(), argv.begin() + 2);
+            // `nvidia-smi --query-gpu=<fields> --format=csv,noheader,nounits` from the devices the probe context already
+            // enumerated (NVML + /proc): no process spawn — and it knows device_minor, which driver 580's nvidia-smi
+            // refuses to print ("not a valid field to query"), so the reference's own DrainGPU cannot even start there
+            if (o_.devs && o_.n_devs >= 0 && argv.size() == 3 && argv[1].compare(0, 12, "--query-gpu=") == 0) {
+                std::string out, err;
+                if (identity::EmitCsv(o_.devs, o_.n_devs, argv[1].substr(12), &out, &err) == 0) {
+                    le.how = "native";
+                    r.std_out = out;
+                    break;
+                }
+            }
+            if (mutating(argv) && !o_.allow_mutation) {
+                le.how = "skipped (dry run)";
+                break;
+            }
+            le.how = "spawned";
+            r = spawn(argv);
+            break;
+        }
+    }
+    le.failed = r.failed;
+    log.push_back(le);
+    return r;
+}
+
+Error LocalKube::GetClusterPolicy(bool* found, bool* set, bool* enabled) {
+    *found = driver_container_;       // a containerised driver (gpu-operator) or the host's own (RKE2 flavour)
+    *set = driver_container_;
+    *enabled = driver_container_;
+    return Error::Nil();
+}
+
+Error LocalKube::ListPods(std::vector<Pod>* out) {
+    // one stand-in per role: on the node every "pod" is this process
+    out->push_back({"local", "nvidia-driver-daemonset-local", node_, {{"app.kubernetes.io/component", "nvidia-driver"}}, {"local"}});
+    out->push_back({"local", "nvidia-dra-driver-gpu-kubelet-plugin-local", node_, {{"app.kubernetes.io/name", "nvidia-dra-driver-gpu"}}, {"local"}});
+    out->push_back({"local", "cro-node-agent-local", node_, {{"app", "cro-node-agent"}}, {"local"}});
+    return Error::Nil();
+}
+
+}  // namespace gpus
+}  // namespace cro

@@ -447,6 +447,27 @@ int  cro_sim_reconcile_resource(cro_sim *sim, const char *name, char *err_buf, s
 int  cro_sim_sync_upstream(cro_sim *sim, const char *devices_json, long long now_s, char *err_buf, size_t err_cap);
 int  cro_sim_dump(cro_sim *sim, char *buf, size_t cap, size_t *len);
 
+/* ---- node-side operations run ON the node ---------------------------------- */
+
+/*
+ * One of the node-side operations of internal/utils/gpus.go, executed locally instead of through pod
+ * execs: scans are native /proc walks, `nvidia-smi --query-gpu=...` is answered from ctx's enumeration
+ * (ctx may be NULL: then nvidia-smi is spawned), every other command is spawned.
+ * request_json: {"op": "check_no_gpu_loads" (gpus.go:88-186) | "run_nvidia_smi" (:666-689) |
+ *                      "check_gpu_visible" (:54-86) | "drain" (:188-664),
+ *                "node": "...", "device_id": "GPU-...", "device_resource_type": "DEVICE_PLUGIN"|"DRA",
+ *                "driver_container": bool   (true: the gpu-operator flavour; false: the RKE2 / host-driver flavour),
+ *                "allow_mutation": bool     (false = dry run: persistence-mode / drain / rm / modprobe / sysfs
+ *                                            writes are logged as skipped and succeed),
+ *                "proc_root": "/proc"}
+ * Reply: {"error": "<the reference's error text or empty>", "visible": bool,
+ *         "exec_log": [{"kind","argv","how": "native"|"spawned"|"skipped (dry run)","failed"}..]}
+ */
+int  cro_local_node_op(cro_ctx *ctx, const char *request_json, char *buf, size_t cap, size_t *len);
+/* The cmdline scan of checkResetGPUCommandStillRunning (gpus.go:1182-1226), natively:
+ * *found = 1 if another process's command line mentions `needle`. */
+int  cro_scan_cmdline_for(const char *proc_root, const char *needle, int *found);
+
 /* ---- diagnostics --------------------------------------------------------- */
 const char *cro_strerror(int code);
 /* Last error text recorded on this context by the calling thread's most
