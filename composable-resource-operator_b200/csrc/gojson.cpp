@@ -146,10 +146,34 @@ Writer& Writer::raw(const std::string& json) { comma(); out_ += json; return *th
 // ---------------------------------------------------------------------------
 // reader
 // ---------------------------------------------------------------------------
+namespace {
+// encoding/json matches an input key to a struct field exactly or under Unicode simple case folding
+// (bytes.EqualFold).  Every field name we look up is ASCII, and the only non-ASCII runes that fold onto
+// ASCII letters are U+017F (long s) and U+212A (Kelvin sign).
+std::string foldKey(const std::string& s) {
+    std::string o;
+    for (size_t i = 0; i < s.size(); ++i) {
+        const unsigned char c = (unsigned char)s[i];
+        if (c >= 'A' && c <= 'Z') o.push_back((char)(c + 32));
+        else if (c == 0xC5 && i + 1 < s.size() && (unsigned char)s[i + 1] == 0xBF) { o.push_back('s'); ++i; }
+        else if (c == 0xE2 && i + 2 < s.size() && (unsigned char)s[i + 1] == 0x84 && (unsigned char)s[i + 2] == 0xAA) { o.push_back('k'); i += 2; }
+        else o.push_back((char)c);
+    }
+    return o;
+}
+}  // namespace
+
+// The member a Go struct field tagged `k` would receive: keys are taken in input order, each one that names
+// the field (exactly or case-folded) overwrites the previous, so the LAST such key wins.
 const Value* Value::get(const std::string& k) const {
     const Value* found = nullptr;
-    for (const auto& kv : obj)
-        if (kv.first == k) found = kv.second.get();
+    std::string folded;
+    for (const auto& kv : obj) {
+        if (kv.first == k) { found = kv.second.get(); continue; }
+        if (kv.first.size() < k.size()) continue;             // folding never lengthens: long s / Kelvin shrink
+        if (folded.empty()) folded = foldKey(k);
+        if (foldKey(kv.first) == folded) found = kv.second.get();
+    }
     return found;
 }
 std::string Value::get_string(const std::string& k, const std::string& dflt) const {

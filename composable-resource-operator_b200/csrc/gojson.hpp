@@ -72,7 +72,7 @@ struct Value {
     std::vector<std::pair<std::string, ValuePtr>> obj;  // insertion order
     size_t raw_begin = 0, raw_end = 0;                   // [begin, end) of this value in the parsed text (json.RawMessage)
 
-    const Value* get(const std::string& k) const;  // last duplicate wins (Go)
+    const Value* get(const std::string& k) const;  // Go's struct-field match: exact or case-folded key, last one wins
     std::string get_string(const std::string& k, const std::string& dflt = "") const;
     bool get_bool(const std::string& k, bool dflt = false) const;
     long long get_int(const std::string& k, long long dflt = 0) const;

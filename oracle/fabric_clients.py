@@ -214,7 +214,7 @@ def unmarshal(data: str, go_type: str):
     err = go_json_syntax_error(data.encode("utf-8", "surrogatepass"))
     if err:
         return None, err
-    v = json.loads(data)
+    v = _o.go_loads(data)
     if v is None:
         return {}, ""
     if not isinstance(v, dict):
@@ -427,7 +427,7 @@ class FMClient(_Client):
         _, err = unmarshal(body, "api.ScaleUpResponse")
         if err:
             return "", "", "failed to unmarshal FM scaleup response body into scaleUpResponse. Original error: " + err
-        return _o.fm_scale_up_response_to_ids(body if json.loads(body) is not None else "{}", name, typ, model)
+        return _o.fm_scale_up_response_to_ids(body if _o.go_loads(body) is not None else "{}", name, typ, model)
 
     def remove(self, typ, node, cdi_device_id) -> str:
         mid, err = self.machine_id(node)
@@ -436,7 +436,7 @@ class FMClient(_Client):
         body, err = self.machine_info(mid)
         if err:
             return err
-        machines = ((json.loads(body) or {}).get("data") or {}).get("machines") or []
+        machines = ((_o.go_loads(body) or {}).get("data") or {}).get("machines") or []
         if not machines:
             return "runtime error: index out of range [0] with length 0"
         if not any(r.get("res_type", "") == typ and r.get("res_uuid", "") == cdi_device_id for r in machines[0].get("resources") or []):
@@ -458,7 +458,7 @@ class FMClient(_Client):
         body, err = self.machine_info(mid)
         if err:
             return err
-        return _o.fabric_check_resource("fm", body if json.loads(body) is not None else "{}", typ, model, device_id)
+        return _o.fabric_check_resource("fm", body if _o.go_loads(body) is not None else "{}", typ, model, device_id)
 
     def resources(self) -> Tuple[List[Dict[str, str]], str]:
         out: List[Dict[str, str]] = []
@@ -469,7 +469,7 @@ class FMClient(_Client):
             body, err = self.machine_info(mid)
             if err:
                 continue
-            out += _o.fabric_get_resources("fm", body if json.loads(body) is not None else "{}", n, mid)
+            out += _o.fabric_get_resources("fm", body if _o.go_loads(body) is not None else "{}", n, mid)
         return out, ""
 
 
@@ -488,7 +488,7 @@ class CMClient(_Client):
         _, err = unmarshal(body, "api.MachineData")
         if err:
             return "", "failed to unmarshal CM get machine response body into machineData: " + err
-        return body if json.loads(body) is not None else "{}", ""
+        return body if _o.go_loads(body) is not None else "{}", ""
 
     def add(self, name, typ, model, node) -> Tuple[str, str, str]:
         mid, err = machine_id_from_annotations(self.f, node)
@@ -518,7 +518,7 @@ class CMClient(_Client):
         if err:
             return err, None
         spec_uuid, count, reason = "", 0, None
-        for s in ((((json.loads(body).get("data") or {}).get("cluster") or {}).get("machine") or {}).get("resspecs")) or []:
+        for s in ((((_o.go_loads(body).get("data") or {}).get("cluster") or {}).get("machine") or {}).get("resspecs")) or []:
             if s.get("type", "") != typ:
                 continue
             conds = (((s.get("selector") or {}).get("expression") or {}).get("conditions")) or []

@@ -295,11 +295,55 @@ def emit_sunfish(name: str, count: int, proc_type: str, model: str) -> str:
 
 
 # --------------------------------------------------------------------------
+# Go's struct decoding of JSON objects
+# --------------------------------------------------------------------------
+def _fold(s: str) -> str:
+    """bytes.EqualFold's normal form for keys compared with ASCII field names (U+017F -> s, U+212A -> k)."""
+    return "".join("s" if ch == "\u017f" else "k" if ch == "\u212a" else (ch.lower() if "A" <= ch <= "Z" else ch) for ch in s)
+
+
+class GoObj(dict):
+    """A JSON object as encoding/json sees it when it fills a struct: keys come in input order and each key that
+    names a field — exactly or case-folded — overwrites what an earlier one stored, so the LAST such key wins."""
+
+    @classmethod
+    def from_pairs(cls, pairs):
+        o = cls(pairs)
+        o.pairs = list(pairs)
+        return o
+
+    def _field(self, key):
+        hit, found = None, False
+        f = _fold(key)
+        for k, v in getattr(self, "pairs", list(self.items())):
+            if k == key or _fold(k) == f:
+                hit, found = v, True
+        return hit, found
+
+    def get(self, key, default=None):
+        v, found = self._field(key)
+        return v if found else default
+
+    def __getitem__(self, key):
+        v, found = self._field(key)
+        if not found:
+            raise KeyError(key)
+        return v
+
+    def __contains__(self, key):
+        return self._field(key)[1]
+
+
+def go_loads(text: str):
+    return json.loads(text, object_pairs_hook=GoObj.from_pairs)
+
+
+# --------------------------------------------------------------------------
 # FM gate + attach step
 # --------------------------------------------------------------------------
 def fm_scale_up_response_to_ids(body: str, name: str, spec_type: str, spec_model: str) -> Tuple[str, str, str]:
     """internal/cdi/fti/fm/client.go:184-213.  Returns (deviceID, CDIDeviceID, err)."""
-    data = json.loads(body)
+    data = go_loads(body)
     machines = (data.get("data") or {}).get("machines") or []
     if machines and (machines[0].get("resources") or []) and machines[0]["resources"][0].get("res_type", "") == spec_type:
         res = machines[0]["resources"][0]
@@ -330,7 +374,7 @@ def _op_status(op: str, device_id: str, where: str) -> str:
 
 def fabric_check_resource(kind: str, body: str, spec_type: str, spec_model: str, device_id: str) -> str:
     """FM: internal/cdi/fti/fm/client.go:314-359.  CM: internal/cdi/fti/cm/client.go:262-304."""
-    data = json.loads(body)
+    data = go_loads(body)
     if kind == "fm":
         machines = (data.get("data") or {}).get("machines") or []
         if not machines:
@@ -359,7 +403,7 @@ def fabric_check_resource(kind: str, body: str, spec_type: str, spec_model: str,
 
 def fabric_get_resources(kind: str, body: str, node: str, machine_uuid: str) -> List[Dict[str, str]]:
     """FM: internal/cdi/fti/fm/client.go:385-410.  CM: internal/cdi/fti/cm/client.go:335-343."""
-    data = json.loads(body)
+    data = go_loads(body)
     out = []
     if kind == "fm":
         machines = (data.get("data") or {}).get("machines") or []
@@ -461,7 +505,7 @@ def check_device_file_scan(std_out: str, std_err: str, exec_err: Optional[str], 
 def cm_check_adding_resources(machine_body: str, existing_device_ids: List[str], spec_type: str, spec_model: str):
     """internal/cdi/fti/cm/client.go:432-459 (checkAddingResources), :485-499 (isSpecMatch),
     :501-509 (findAvailableDevice).  Returns (specUUID, deviceCount, deviceID, CDIDeviceID, err)."""
-    data = json.loads(machine_body)
+    data = go_loads(machine_body)
     specs = ((((data.get("data") or {}).get("cluster") or {}).get("machine") or {}).get("resspecs")) or []
     for spec in specs:
         if spec.get("type", "") != spec_type:
