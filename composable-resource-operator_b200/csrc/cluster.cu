@@ -320,9 +320,30 @@ Error Cluster::Apply(const gojson::Value& v) {
             return Error::New("ComposabilityRequest.cro.hpsys.ibm.ie.com \"" + name + "\" is invalid: " + all);
         }
     }
-    // admission webhook (internal/webhook/v1alpha1/composabilityrequest_webhook.go:107-110)
-    if (d.AllocationPolicy == "differentnode" && !d.TargetNode.empty())
-        return Error::New("TargetNode cannot be specified when AllocationPolicy is set to 'differentnode'");
+    // validating admission webhook, create and update alike (internal/webhook/v1alpha1/composabilityrequest_webhook.go:
+    // validateRequest :100-147); the API server wraps the webhook's message in its own sentence
+    {
+        const std::string denied = "admission webhook \"vcomposabilityrequest.kb.io\" denied the request: ";
+        if (d.AllocationPolicy == "differentnode" && !d.TargetNode.empty())
+            return Error::New(denied + "TargetNode cannot be specified when AllocationPolicy is set to 'differentnode'");
+        // one request per (type, model) cluster-wide for "differentnode"; one per (node, type, model) for "samenode", where
+        // a request without target_node counts for the node its first child landed on ("" while it has none)
+        for (const auto& kv : requests_) {        // List() order: by name
+            const ComposabilityRequest& o = kv.second;
+            if (o.Name == name) continue;
+            bool clash = false;
+            if (d.AllocationPolicy == "differentnode") {
+                clash = o.Spec.AllocationPolicy == "differentnode" && o.Spec.Type == d.Type && o.Spec.Model == d.Model;
+            } else if (d.AllocationPolicy == "samenode") {
+                std::string targetNode = o.Spec.TargetNode;
+                if (targetNode.empty() && !o.Status.Resources.empty()) targetNode = o.Status.Resources.begin()->second.NodeName;
+                clash = targetNode == d.TargetNode && o.Spec.Type == d.Type && o.Spec.Model == d.Model;
+            }
+            if (clash)
+                return Error::New(denied + "composabilityRequest resource " + o.Name + " with type " + d.Type + " and model " + d.Model +
+                                  " already exists");
+        }
+    }
     auto it = requests_.find(name);
     if (it == requests_.end()) {
         ComposabilityRequest r;

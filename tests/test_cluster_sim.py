@@ -139,6 +139,7 @@ def test_spec_change_kats(cro, cite, policy, over, dropped, expect):
 def test_admission_rules(cro):
     with cro.Cluster({"nodes": NODES}) as c:
         assert c.apply("a", dict(BASE, allocation_policy="differentnode", target_node="worker-0")) == \
+            'admission webhook "vcomposabilityrequest.kb.io" denied the request: ' \
             "TargetNode cannot be specified when AllocationPolicy is set to 'differentnode'"
         assert "Unsupported value" in c.apply("b", dict(BASE, type="fpga"))
         assert c.apply("c", BASE) == ""
