@@ -919,7 +919,9 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
             std::vector<std::pair<int, int>> directed;
             for (const auto& p : round) {
                 directed.push_back({p.first, p.second});
-                directed.push_back({p.second, p.first});
+                // CRO_P2P_UNIDIR=1 (measurement only, tools/p2p_variants.py): one direction per pair, to see what the
+                // link gives when its other half is idle; the reverse direction's result slots stay zero
+                if (!env_u32("CRO_P2P_UNIDIR", 0)) directed.push_back({p.second, p.first});
             }
             for (int rep = 0; rep < 2; ++rep) {   // rep 0 warms the mappings, rep 1 is timed
                 for (const auto& pr : directed) {
