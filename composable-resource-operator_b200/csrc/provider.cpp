@@ -263,6 +263,20 @@ Error FTIClientBase::machineIDFromAnnotations(const std::string& nodeName, bool 
 // ---------------------------------------------------------------------------
 // FM
 // ---------------------------------------------------------------------------
+namespace {
+// url.Values{"tenant_uuid": {id}}.Encode() (fm/client.go:153-155 and twins)
+std::string tenantQuery(const std::string& tenant) {
+    static const char hex[] = "0123456789ABCDEF";
+    std::string o = "tenant_uuid=";
+    for (unsigned char c : tenant) {
+        if ((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '-' || c == '_' || c == '.' || c == '~') o.push_back((char)c);
+        else if (c == ' ') o.push_back('+');
+        else { o.push_back('%'); o.push_back(hex[c >> 4]); o.push_back(hex[c & 15]); }
+    }
+    return o;
+}
+}  // namespace
+
 Error FMClient::getNodeMachineID(const std::string& nodeName, std::string* machineID) {
     if (!cfg_.clusterID.empty()) return machineIDFromAnnotations(nodeName, true, machineID);
     K8sObject node;                                                          // :451-463
@@ -278,7 +292,7 @@ Error FMClient::getNodeMachineID(const std::string& nodeName, std::string* machi
 Error FMClient::getMachineInfo(const std::string& machineID, std::string* body) {
     Error e = token_->GetToken();
     if (!e.ok()) return e;
-    HttpReply rep = send({"GET", "fabric_manager/api/v1/machines/" + machineID, "tenant_uuid=" + cfg_.tenantID, ""});
+    HttpReply rep = send({"GET", "fabric_manager/api/v1/machines/" + machineID, tenantQuery(cfg_.tenantID), ""});
     if (!rep.transport_error.empty()) return Error::New(rep.transport_error);
     if (rep.status != 200) return FMErrorFromReply("get", rep.body);
     std::string perr;
@@ -295,7 +309,7 @@ Error FMClient::AddResource(const ComposableResource& instance, std::string* dev
     if (!e.ok()) return e;
     e = token_->GetToken();
     if (!e.ok()) return e;
-    HttpReply rep = send({"PATCH", "fabric_manager/api/v1/machines/" + machineID + "/update", "tenant_uuid=" + cfg_.tenantID,
+    HttpReply rep = send({"PATCH", "fabric_manager/api/v1/machines/" + machineID + "/update", tenantQuery(cfg_.tenantID),
                           FMScaleUpBody(cfg_.tenantID, machineID, instance.Spec.Type, instance.Spec.Model)});
     if (!rep.transport_error.empty()) return Error::New(rep.transport_error);
     if (rep.status != 200) return FMErrorFromReply("scaleup", rep.body);
@@ -323,7 +337,7 @@ Error FMClient::RemoveResource(ComposableResource& instance) {
     if (!exists) return Error::Nil();          // already gone: nothing to send (:238-241)
     e = token_->GetToken();
     if (!e.ok()) return e;
-    HttpReply rep = send({"DELETE", "fabric_manager/api/v1/machines/" + machineID + "/update", "tenant_uuid=" + cfg_.tenantID,
+    HttpReply rep = send({"DELETE", "fabric_manager/api/v1/machines/" + machineID + "/update", tenantQuery(cfg_.tenantID),
                           FMScaleDownBody(cfg_.tenantID, machineID, instance.Spec.Type, instance.Status.CDIDeviceID)});
     if (!rep.transport_error.empty()) return Error::New(rep.transport_error);
     if (rep.status != 200 && rep.status != 204) return FMErrorFromReply("scaledown", rep.body);

@@ -382,6 +382,11 @@ def cm_error(what: str, body: str) -> str:
     return "failed to process CM %s request. http returned status: '%d', cm return code: '%s', error message: '%s'" % (what, status, code, message)
 
 
+def _query_escape(s: str) -> str:      # net/url.QueryEscape
+    from urllib.parse import quote_plus
+    return quote_plus(s, safe="-_.~")
+
+
 class _Client:
     def __init__(self, fabric: Fabric, tenant: str, cluster: str):
         self.f, self.tenant, self.cluster = fabric, tenant, cluster
@@ -402,7 +407,7 @@ class FMClient(_Client):
     def machine_info(self, mid: str) -> Tuple[str, str]:
         if self.f.token():
             return "", self.f.token()
-        st, body, terr = self.f.do("GET", "fabric_manager/api/v1/machines/" + mid, "tenant_uuid=" + self.tenant, "")
+        st, body, terr = self.f.do("GET", "fabric_manager/api/v1/machines/" + mid, "tenant_uuid=" + _query_escape(self.tenant), "")
         if terr:
             return "", terr
         if st != 200:
@@ -418,7 +423,7 @@ class FMClient(_Client):
             return "", "", err
         if self.f.token():
             return "", "", self.f.token()
-        st, body, terr = self.f.do("PATCH", "fabric_manager/api/v1/machines/%s/update" % mid, "tenant_uuid=" + self.tenant,
+        st, body, terr = self.f.do("PATCH", "fabric_manager/api/v1/machines/%s/update" % mid, "tenant_uuid=" + _query_escape(self.tenant),
                                    _o.emit_fm_scale_up(self.tenant, mid, typ, model))
         if terr:
             return "", "", terr
@@ -443,7 +448,7 @@ class FMClient(_Client):
             return ""
         if self.f.token():
             return self.f.token()
-        st, rbody, terr = self.f.do("DELETE", "fabric_manager/api/v1/machines/%s/update" % mid, "tenant_uuid=" + self.tenant,
+        st, rbody, terr = self.f.do("DELETE", "fabric_manager/api/v1/machines/%s/update" % mid, "tenant_uuid=" + _query_escape(self.tenant),
                                     _o.emit_fm_scale_down(self.tenant, mid, typ, cdi_device_id))
         if terr:
             return terr

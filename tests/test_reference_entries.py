@@ -384,7 +384,8 @@ def test_clients_fuzz_vs_oracle(cro, oracle):
     tally = collections.Counter()
     for it in range(600):
         kind = rng.choice(["cm", "fm"])
-        tenant, cluster = "tenant-%d" % rng.randrange(3), rng.choice(["", "cluster-a"]) if kind == "fm" else "cluster-a"
+        tenant = rng.choice(["tenant-0", "tenant-1", "tenant 2/ü&x=y"])       # the last one exercises url.Values.Encode
+        cluster = rng.choice(["", "cluster-a"]) if kind == "fm" else "cluster-a"
         def mostly(good, *bad):      # the metal3 walk usually succeeds so the HTTP legs get exercised
             return good if rng.random() < 0.93 else rng.choice(bad)
         objs = {"nodes": {"worker-0": {"annotations": {"machine.openshift.io/machine": mostly("ns/m0", "m0", "a/b/c", "")},
