@@ -1,0 +1,23 @@
+"""One tiny full probe (S = 4 MiB, every read variant, verify-copy) for runs under compute-sanitizer."""
+import importlib
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import __graft_entry__ as g
+
+g.build()
+import oracle
+
+cro = importlib.import_module("composable-resource-operator_b200")
+S = 4 << 20
+with cro.ProbeContext(sweep_bytes=S, devices=[0], flags=cro.F_VERIFY_COPY, read_sweeps=2, copy_sweeps=2) as ctx:
+    r = ctx.probe_device(0)
+    want = oracle.COracle().checksum(r.seed, 0, S // 8)
+    assert (r.checksum_xor, r.checksum_sum) == want == (r.copy_checksum_xor, r.copy_checksum_sum), (r.status, want)
+    for v in (cro.READ_LDG, cro.READ_TMA, cro.READ_LDG256):
+        s = ctx.hbm_read_checksum(0, v)
+        assert (s.checksum_xor, s.checksum_sum) == want
+    print("tiny probe ok", hex(r.checksum_xor))
