@@ -41,6 +41,7 @@ type ProbeResult struct {
 	P2PReadNs    [8]uint64
 	P2PWriteNs   [8]uint64
 	P2PLatencyNs [8]uint32
+	EccErrors    uint32 // uncorrected volatile ECC errors (NVML), read at init / full-box probe / failed probe
 	Annotations  string // Go-marshalled map[string]string of cohdi.io/probe-* keys
 }
 
@@ -130,6 +131,7 @@ func convert(r *C.cro_probe_result) ProbeResult {
 		GPUUUID: C.GoString(&r.gpu_uuid[0]), PCIBusID: C.GoString(&r.pci_bus_id[0]),
 		SweepBytes: uint64(r.sweep_bytes), ChecksumXor: uint64(r.checksum_xor), ChecksumSum: uint64(r.checksum_sum),
 		FillNs: uint64(r.fill_ns), ReadBestNs: uint64(r.read_best_ns), CopyBestNs: uint64(r.copy_best_ns),
+		EccErrors: uint32(r.ecc_errors),
 	}
 	for j := 0; j < 8; j++ {
 		out.P2PReadNs[j] = uint64(r.p2p_read_ns[j])
