@@ -67,3 +67,21 @@ def test_owned_device_is_not_drift_and_vanished_device_is_forgotten(cro):
 def test_bad_upstream_payload(cro):
     with cro.Cluster({"nodes": ["worker-0"]}) as c:
         assert c.sync_upstream({"not": "a list"}, T0).startswith("failed to fetch data from upstream server")
+
+
+def test_syncer_fed_by_the_real_cm_client(cro):
+    """The whole tick the way the reference's entries run it (upstreamsyncer_controller_test.go:329-515): the CM client
+    lists the fabric's devices (cluster ...0001 holds DEV), the syncer tracks the orphan and, past the grace period,
+    creates the detach CR.  Note the CM flavour reports no model (cm/client.go:335-341), so the CR's Spec.Model is ""."""
+    from test_reference_entries import ENTRIES, HTTP, objects_for
+    env = {"DEVICE_RESOURCE_TYPE": "DRA", "CDI_PROVIDER_TYPE": "FTI_CDI", "FTI_CDI_API_TYPE": "CM",
+           "FTI_CDI_TENANT_ID": "tenant00-uuid-temp-0000-000000000000", "FTI_CDI_CLUSTER_ID": "cluster0-uuid-temp-0000-000000000001"}
+    listed = cro.fabric_list_devices({"env": env, "fabric": {"http": HTTP, "objects": objects_for(ENTRIES[1739])}})
+    assert listed["error"] == "" and [d["device_id"] for d in listed["devices"]] == [DEV]
+    with cro.Cluster({"nodes": ["worker-0"], "uuids": [DEV]}) as c:
+        assert c.sync_upstream(listed["devices"], T0 - 20 * 60) == ""
+        assert c.dump()["missing_devices"] == {DEV: T0 - 20 * 60}
+        assert c.sync_upstream(listed["devices"], T0) == ""
+        (name, cr), = _detach_crs(c.dump()).items()
+        assert cr["spec"] == {"type": "gpu", "model": "", "target_node": "worker-0"}
+        assert cr["labels"]["cohdi.io/ready-to-detach-cdi-device-id"] == RES
