@@ -189,6 +189,20 @@ def test_launch_count_is_kernels(cro):
         assert c.launch_count() - first == 1 + 4 + 3   # the closed form is cached per device
 
 
+def test_probe_all_on_a_single_device(cro, coracle):
+    """A one-GPU node: no NVLink rounds, no NCCL (nothing to gather from), same result as the per-device probe."""
+    S = 64 << 20
+    with cro.ProbeContext(sweep_bytes=S, devices=[0], read_sweeps=2, copy_sweeps=1) as c:
+        res = c.probe_all()
+        assert len(res) == 1
+        r = res[0]
+        assert r.status == 0 and r.rank == 0 and r.world == 1
+        assert (r.checksum_xor, r.checksum_sum) == coracle.checksum(r.seed, 0, S // 8)
+        assert all(x == 0 for x in r.p2p_read_ns) and all(x == 0 for x in r.p2p_write_ns)
+        one = c.probe_device(0)
+        assert (one.checksum_xor, one.checksum_sum, one.gpu_uuid) == (r.checksum_xor, r.checksum_sum, r.gpu_uuid)
+
+
 def test_multi_device_probe_all(cro, coracle):
     import ctypes
     with cro.ProbeContext(sweep_bytes=256 << 20, p2p_bytes=64 << 20, read_sweeps=2, copy_sweeps=1, latency_hops=2048) as c:
