@@ -68,6 +68,8 @@ ExecResult spawn(const std::vector<std::string>& argv) {
             else { close(fds[i].fd); fds[i].fd = -1; --open_fds; }
         }
     }
+    for (pollfd& f : fds)
+        if (f.fd >= 0) close(f.fd);               // poll() failed mid-way: do not leak the read ends
     int status = 0;
     waitpid(pid, &status, 0);
     if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) {
