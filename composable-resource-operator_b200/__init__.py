@@ -116,7 +116,7 @@ EXPORTS = [
     "cro_check_no_gpu_loads", "cro_check_gpu_drain_status", "cro_check_device_file_scan",
     "cro_scan_device_file_holders", "cro_sim_reconcile_resource", "cro_sim_sync_upstream",
     "cro_fabric_check_resource", "cro_fabric_get_resources", "cro_fabric_list_devices",
-    "cro_local_node_op", "cro_scan_cmdline_for",
+    "cro_local_node_op", "cro_scan_cmdline_for", "cro_token_from_reply",
 ]
 
 
@@ -180,6 +180,7 @@ def _load() -> ctypes.CDLL:
         "cro_fabric_check_resource": (i32, [c, c, c, c, c, c, sz]),
         "cro_fabric_get_resources": (i32, [c, c, c, c] + out),
         "cro_fabric_list_devices": (i32, [c] + out),
+        "cro_token_from_reply": (i32, [c] + out),
         "cro_local_node_op": (i32, [vp, c] + out),
         "cro_scan_cmdline_for": (i32, [c, c, ctypes.POINTER(i32)]),
         "cro_sim_reconcile_resource": (i32, [vp, c, c, sz]),
@@ -481,6 +482,12 @@ def fabric_list_devices(request: Dict) -> Dict:
     """CdiProvider.GetResources of the FM / CM client over a scripted fabric (what the UpstreamSyncer
     tick reads: upstreamsyncer_controller.go:77-84).  request = {"env": {...}, "fabric": {...}}."""
     return json.loads(_text(lib.cro_fabric_list_devices, _b(json.dumps(request))))
+
+
+def token_from_reply(reply: Dict) -> Dict:
+    """What fti.CachedToken.Token makes of the id_manager's answer (fti/token.go:96-175):
+    reply = {"secret_error","transport_error","status","body"} -> {"error", "expiry"}."""
+    return json.loads(_text(lib.cro_token_from_reply, _b(json.dumps(reply))))
 
 
 def local_node_op(ctx: Optional["ProbeContext"], request: Dict) -> Dict:

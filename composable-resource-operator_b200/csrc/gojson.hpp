@@ -95,5 +95,17 @@ ValuePtr parse(const std::string& text, std::string* err);
 // value is not an object.  JSON null decodes into the zero struct (true).
 bool rootOk(const ValuePtr& root, std::string* perr, const char* goType);
 
+// json.Unmarshal of an object into a struct whose fields are all `string` or `int64` (fti/token.go:40-54).
+// Members are taken in input order; each is matched to a field by its tag (exactly, else case-folded), null
+// leaves the field alone, a value of the wrong JSON type is skipped and the FIRST such mismatch is returned as
+// go1.24's UnmarshalTypeError text ("json: cannot unmarshal number 1.5 into Go struct field token.expires_in of
+// type int64") — decoding goes on, so later members still land.  (Mismatch wording: unpinned by the reference.)
+struct FlatField {
+    const char* tag;
+    char type;                      // 's' string, 'i' int64
+};
+std::string DecodeFlat(const Value& root, const std::string& text, const char* structName, const FlatField* fields,
+                       size_t n, std::map<std::string, std::string>* strs, std::map<std::string, long long>* ints);
+
 }  // namespace gojson
 }  // namespace cro

@@ -179,16 +179,34 @@ private:
     const gojson::Value* o_;
 };
 
+// "token_error": "<text GetToken returns>" (canned), or "token": {"secret_error","transport_error","status","body"}
+// = what the id_manager answered, decoded by fabric::TokenFromReply (fti/token.go:96-175); "now" as elsewhere.
 class JsonTokenSource : public fabric::TokenSource {
 public:
-    explicit JsonTokenSource(const gojson::Value* f) : f_(f) {}
+    JsonTokenSource(const gojson::Value* f, const gojson::Value* in) : f_(f) {
+        const gojson::Value* t = f ? f->get("token") : nullptr;
+        if (t && t->kind == gojson::Value::Object) {
+            fabric::TokenReply r;
+            r.secret_error = t->get_string("secret_error");
+            r.transport_error = t->get_string("transport_error");
+            r.status = (int)t->get_int("status", 200);
+            r.body = t->get_string("body");
+            long long now = 0, ns = 0;
+            std::string perr;
+            nodes::ParseRFC3339(in ? in->get_string("now", "2025-01-01T00:00:00Z") : std::string("2025-01-01T00:00:00Z"), &now, &ns, &perr);
+            real_.reset(new fabric::ReplyTokenSource(r, now));
+        }
+    }
     controller::Error GetToken() override {
+        if (real_) return real_->GetToken();
         const std::string e = f_ ? f_->get_string("token_error") : std::string();
         return e.empty() ? controller::Error::Nil() : controller::Error::New(e);
     }
+    int fetches() const { return real_ ? real_->fetches : 0; }
 
 private:
     const gojson::Value* f_;
+    std::unique_ptr<fabric::ReplyTokenSource> real_;
 };
 
 // ---- scripted cluster: the reference's envtest pods + gomonkey'd SPDY executor, as data -----------
@@ -559,7 +577,7 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
     const gojson::Value* fab = in->get("fabric");
     ScriptedTransport transport(fab);
     JsonObjectStore store(fab);
-    JsonTokenSource tokens(fab);
+    JsonTokenSource tokens(fab, in.get());
     std::unique_ptr<fabric::FTIClientBase> fti;
     controller::Error adapterErr;
     if (env && env->kind == gojson::Value::Object) {
@@ -642,6 +660,7 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
         w.end_array();
     }
     if (fti) {
+        w.field("token_fetches", tokens.fetches());
         w.key("fabric_requests").begin_array();
         for (const auto& r : fti->requests) {
             w.begin_object();
@@ -667,7 +686,7 @@ int cro_fabric_list_devices(const char* request_json, char* buf, size_t cap, siz
     if (!env || env->kind != gojson::Value::Object) return CRO_ERR_INVALID_ARG;
     ScriptedTransport transport(fab);
     JsonObjectStore store(fab);
-    JsonTokenSource tokens(fab);
+    JsonTokenSource tokens(fab, in.get());
     std::string kind;
     controller::Error e = SelectAdapter(env, &kind);
     std::unique_ptr<fabric::FTIClientBase> fti;
@@ -682,6 +701,7 @@ int cro_fabric_list_devices(const char* request_json, char* buf, size_t cap, siz
     w.begin_object();
     w.key("devices").raw(fabric::DeviceInfosToJson(devs));
     w.field("error", e.ok() ? std::string() : e.msg);
+    w.field("token_fetches", tokens.fetches());
     w.key("fabric_requests").begin_array();
     if (fti)
         for (const auto& r : fti->requests) {
@@ -690,6 +710,29 @@ int cro_fabric_list_devices(const char* request_json, char* buf, size_t cap, siz
             w.end_object();
         }
     w.end_array();
+    w.end_object();
+    return copy_out(w.str(), buf, cap, len);
+}
+
+int cro_token_from_reply(const char* reply_json, char* buf, size_t cap, size_t* len) {
+    if (!reply_json) return CRO_ERR_INVALID_ARG;
+    std::string perr;
+    gojson::ValuePtr in = gojson::parse(reply_json, &perr);
+    if (!in || in->kind != gojson::Value::Object) {
+        copy_out("bad request: " + perr, buf, cap, len);
+        return CRO_ERR_PARSE;
+    }
+    fabric::TokenReply r;
+    r.secret_error = in->get_string("secret_error");
+    r.transport_error = in->get_string("transport_error");
+    r.status = (int)in->get_int("status", 200);
+    r.body = in->get_string("body");
+    long long exp = 0;
+    controller::Error e = fabric::TokenFromReply(r, &exp);
+    gojson::Writer w;
+    w.begin_object();
+    w.field("error", e.ok() ? std::string() : e.msg);
+    w.field("expiry", e.ok() ? exp : 0LL);
     w.end_object();
     return copy_out(w.str(), buf, cap, len);
 }

@@ -181,6 +181,91 @@ Error CMErrorFromReply(const std::string& what, const std::string& body) {
 }
 
 // ---------------------------------------------------------------------------
+// token reply
+// ---------------------------------------------------------------------------
+bool DecodeBase64RawURL(const std::string& in, std::string* out, std::string* err) {
+    // encoding/base64 decodeQuantum for an unpadded URL alphabet: CR / LF are skipped, any other byte outside the
+    // alphabet is corrupt at its own offset, and a dangling single character is corrupt at ITS offset (si - j)
+    auto val = [](unsigned char c) -> int {
+        if (c >= 'A' && c <= 'Z') return c - 'A';
+        if (c >= 'a' && c <= 'z') return c - 'a' + 26;
+        if (c >= '0' && c <= '9') return c - '0' + 52;
+        if (c == '-') return 62;
+        if (c == '_') return 63;
+        return -1;
+    };
+    out->clear();
+    unsigned acc[4];
+    int j = 0;
+    size_t si = 0;
+    for (; si < in.size(); ++si) {
+        const unsigned char c = (unsigned char)in[si];
+        if (c == '\n' || c == '\r') continue;
+        const int v = val(c);
+        if (v < 0) {
+            *err = "illegal base64 data at input byte " + std::to_string(si);
+            return false;
+        }
+        acc[j++] = (unsigned)v;
+        if (j == 4) {
+            out->push_back((char)((acc[0] << 2) | (acc[1] >> 4)));
+            out->push_back((char)(((acc[1] & 15) << 4) | (acc[2] >> 2)));
+            out->push_back((char)(((acc[2] & 3) << 6) | acc[3]));
+            j = 0;
+        }
+    }
+    if (j == 1) {
+        *err = "illegal base64 data at input byte " + std::to_string(si - 1);
+        return false;
+    }
+    if (j >= 2) out->push_back((char)((acc[0] << 2) | (acc[1] >> 4)));
+    if (j == 3) out->push_back((char)(((acc[1] & 15) << 4) | (acc[2] >> 2)));
+    return true;
+}
+
+Error TokenFromReply(const TokenReply& r, long long* expiryUnix) {
+    if (!r.secret_error.empty()) return Error::New(r.secret_error);
+    if (!r.transport_error.empty()) return Error::New(r.transport_error);
+    if (r.status != 200) return Error::New("http returned code: " + std::to_string(r.status) + ", response body: " + r.body);
+    std::string perr;
+    gojson::ValuePtr root = gojson::parse(r.body, &perr);
+    if (!gojson::rootOk(root, &perr, "fti.token"))
+        return Error::New("failed to read id_manager response body into Token: " + perr);
+    static const gojson::FlatField kToken[] = {{"access_token", 's'}, {"expires_in", 'i'}, {"refresh_expires_in", 'i'},
+                                               {"refresh_token", 's'}, {"token_type", 's'}, {"id_token", 's'},
+                                               {"not-before-policy", 'i'}, {"session_state", 's'}, {"scope", 's'}};
+    static const gojson::FlatField kClaims[] = {{"exp", 'i'}};
+    std::map<std::string, std::string> strs;
+    std::map<std::string, long long> ints;
+    perr = gojson::DecodeFlat(*root, r.body, "token", kToken, sizeof kToken / sizeof kToken[0], &strs, &ints);
+    if (!perr.empty()) return Error::New("failed to read id_manager response body into Token: " + perr);
+    const std::string access = strs["access_token"];
+    const std::vector<std::string> parts = identity::Split(access, ".");
+    if (parts.size() != 3) return Error::New("invalid access token: " + access);
+    std::string payload, derr;
+    if (!DecodeBase64RawURL(parts[1], &payload, &derr)) return Error::New("failed to decode id_manager payload: " + derr);
+    gojson::ValuePtr claims = gojson::parse(payload, &perr);
+    if (!gojson::rootOk(claims, &perr, "fti.accessToken")) return Error::New("failed to unmarshal id_manager json: " + perr);
+    strs.clear();
+    ints.clear();
+    perr = gojson::DecodeFlat(*claims, payload, "accessToken", kClaims, 1, &strs, &ints);
+    if (!perr.empty()) return Error::New("failed to unmarshal id_manager json: " + perr);
+    *expiryUnix = ints["exp"];
+    return Error::Nil();
+}
+
+Error ReplyTokenSource::GetToken() {
+    if (have_ && expiry_ - 30 > now_) return Error::Nil();            // leeway 30 s (token.go:68,78)
+    ++fetches;
+    long long exp = 0;
+    Error e = TokenFromReply(reply_, &exp);
+    if (!e.ok()) return Error::New("unable to rotate token: " + e.msg);
+    have_ = true;
+    expiry_ = exp;
+    return Error::Nil();
+}
+
+// ---------------------------------------------------------------------------
 // CM checkRemovingResources
 // ---------------------------------------------------------------------------
 namespace {

@@ -6,8 +6,8 @@
 // path, query, JSON body), how each reply — 200, error status, non-JSON — turns
 // into (deviceID, CDIDeviceID, error), and the Node -> Metal3Machine ->
 // BareMetalHost annotation walk that names the machine.  The sockets, TLS and
-// the OAuth2 token cache (fti/token.go) stay with the host: `Transport`,
-// `ObjectStore` and `TokenSource` are the seams, so the same code runs against
+// the credential POST of fti/token.go stay with the host (what its reply means is
+// restated below: TokenFromReply): `Transport`, `ObjectStore` and `TokenSource` are the seams, so the same code runs against
 // the Go operator's clients and against the scripted fabric
 // of the parity tests (the reference's httptest server,
 // composableresource_controller_test.go:663-930, restated as data).
@@ -62,6 +62,33 @@ class TokenSource {   // fti.CachedToken.GetToken; the error text is surfaced ve
 public:
     virtual ~TokenSource() {}
     virtual Error GetToken() = 0;
+};
+
+// What the id_manager answered, turned into what CachedToken.GetToken returns (fti/token.go:72-175).  The POST
+// itself — credentials from the Secret, TLS — stays with the host; the cache rule (a token is reused while
+// expiry - 30 s is still ahead) and every error text are restated.
+struct TokenReply {
+    std::string secret_error;     // Secrets(...).Get failed: its text, e.g. `secrets "credentials" not found`
+    std::string transport_error;  // client.PostForm failed
+    int status = 200;
+    std::string body;
+};
+// nil + *expiryUnix, or the error Token() returns (no "unable to rotate token: " prefix yet).
+Error TokenFromReply(const TokenReply& r, long long* expiryUnix);
+// base64.RawURLEncoding.DecodeString: false + Go's CorruptInputError text on bad input.
+bool DecodeBase64RawURL(const std::string& in, std::string* out, std::string* err);
+
+class ReplyTokenSource : public TokenSource {
+public:
+    ReplyTokenSource(const TokenReply& reply, long long nowUnix) : reply_(reply), now_(nowUnix) {}
+    Error GetToken() override;
+    int fetches = 0;              // how often the id_manager had to be asked
+
+private:
+    TokenReply reply_;
+    long long now_;
+    bool have_ = false;
+    long long expiry_ = 0;
 };
 
 struct ClientConfig {

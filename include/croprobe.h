@@ -387,10 +387,17 @@ int  cro_fabric_get_resources(const char *kind, const char *machine_body, const 
 /* CdiProvider.GetResources of the whole FM / CM client (internal/cdi/fti/fm/client.go:361-413,
  * internal/cdi/fti/cm/client.go:306-346) over a scripted fabric: request_json =
  * {"env": {"CDI_PROVIDER_TYPE","FTI_CDI_API_TYPE","DEVICE_RESOURCE_TYPE","FTI_CDI_TENANT_ID","FTI_CDI_CLUSTER_ID"},
- *  "fabric": {"http": [...], "objects": {...}, "token_error": ""}} (the same "fabric" object
+ *  "fabric": {"http": [...], "objects": {...}, "token_error": "" | "token": {...}}} (the same "fabric" object
  * cro_reconcile_attach takes).  Reply: {"devices": [DeviceInfo...], "error": "", "fabric_requests": [...]};
  * the FM flavour skips nodes that fail, the CM flavour aborts with the first error. */
 int  cro_fabric_list_devices(const char *request_json, char *buf, size_t cap, size_t *len);
+/* What CachedToken.Token makes of the id_manager's answer (internal/cdi/fti/token.go:96-175): reply_json =
+ * {"secret_error": "", "transport_error": "", "status": 200, "body": "<reply body>"}; writes
+ * {"error": "<text, without the 'unable to rotate token: ' prefix GetToken adds>", "expiry": <exp claim, unix s>}.
+ * The same object under "fabric"."token" makes cro_reconcile_attach / cro_fabric_list_devices run the
+ * token cache (reuse while expiry - 30 s > "now") in front of every fabric request; they then also report
+ * "token_fetches". */
+int  cro_token_from_reply(const char *reply_json, char *buf, size_t cap, size_t *len);
 
 /* ---- detach-side pre-flight (the step on the other side of the path) ------ */
 

@@ -209,18 +209,121 @@ def go_json_syntax_error(data: bytes) -> str:
         return str(e)
 
 
-def unmarshal(data: str, go_type: str):
+def unmarshal(data, go_type: str):
     """(value, err): json.Unmarshal into a struct of type go_type (objects and null only)."""
-    err = go_json_syntax_error(data.encode("utf-8", "surrogatepass"))
+    raw = data if isinstance(data, bytes) else data.encode("utf-8", "surrogatepass")
+    err = go_json_syntax_error(raw)
     if err:
         return None, err
-    v = _o.go_loads(data)
+    v = _o.go_loads(raw.decode("utf-8", "replace") if isinstance(data, bytes) else data)   # invalid UTF-8 -> U+FFFD, as Go
     if v is None:
         return {}, ""
     if not isinstance(v, dict):
         kind = "array" if isinstance(v, list) else "string" if isinstance(v, str) else "bool" if isinstance(v, bool) else "number"
         return None, "json: cannot unmarshal %s into Go value of type %s" % (kind, go_type)
     return v, ""
+
+
+# --------------------------------------------------------------------------
+# the id_manager's answer -> token expiry or error (fti/token.go:96-175)
+# --------------------------------------------------------------------------
+_B64URL = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789-_"
+
+
+def decode_base64_raw_url(s: str) -> Tuple[Optional[bytes], str]:
+    """base64.RawURLEncoding.DecodeString: CR/LF skipped, no padding, non-strict trailing bits."""
+    raw = s.encode("utf-8", "surrogatepass")
+    acc: List[int] = []
+    out = bytearray()
+    for i, c in enumerate(raw):
+        if c in (10, 13):
+            continue
+        v = _B64URL.find(chr(c)) if c < 128 else -1
+        if v < 0:
+            return None, "illegal base64 data at input byte %d" % i
+        acc.append(v)
+        if len(acc) == 4:
+            out += bytes([(acc[0] << 2 | acc[1] >> 4) & 255, (acc[1] << 4 | acc[2] >> 2) & 255, (acc[2] << 6 | acc[3]) & 255])
+            acc = []
+    if len(acc) == 1:
+        return None, "illegal base64 data at input byte %d" % (len(raw) - 1)
+    if len(acc) >= 2:
+        out.append((acc[0] << 2 | acc[1] >> 4) & 255)
+    if len(acc) == 3:
+        out.append((acc[1] << 4 | acc[2] >> 2) & 255)
+    return bytes(out), ""
+
+
+class _Lit(str):
+    """a JSON number kept as its literal"""
+
+
+class _Pairs(list):
+    """a JSON object kept as its members in input order"""
+
+
+_TOKEN_FIELDS = {"access_token": "string", "expires_in": "int64", "refresh_expires_in": "int64", "refresh_token": "string",
+                 "token_type": "string", "id_token": "string", "not-before-policy": "int64", "session_state": "string",
+                 "scope": "string"}                                    # fti/token.go:40-50
+
+
+def decode_flat(data, struct: str, fields: Dict[str, str]) -> Tuple[Dict, str]:
+    """json.Unmarshal of syntactically valid `data` (object or null) into a struct of string / int64 fields:
+    (values, first UnmarshalTypeError text).  Members in input order; a mismatch is skipped, decoding goes on."""
+    raw = data if isinstance(data, bytes) else data.encode("utf-8", "surrogatepass")
+    top = json.loads(raw.decode("utf-8", "replace"), object_pairs_hook=_Pairs, parse_int=_Lit, parse_float=_Lit)
+    vals: Dict = {}
+    first = ""
+    if not isinstance(top, _Pairs):
+        return vals, first
+    folded = {_o._fold(k): k for k in fields}
+    for k, v in top:
+        tag = k if k in fields else folded.get(_o._fold(k))
+        if tag is None or v is None:
+            continue
+        typ = fields[tag]
+        if typ == "string" and isinstance(v, str) and not isinstance(v, _Lit):
+            vals[tag] = v
+            continue
+        if typ == "int64" and isinstance(v, _Lit) and re.fullmatch(r"-?[0-9]+", v) and -2**63 <= int(v) < 2**63:
+            vals[tag] = int(v)
+            continue
+        if first:
+            continue
+        what = ("object" if isinstance(v, _Pairs) else "array" if isinstance(v, list) else "bool" if isinstance(v, bool) else
+                ("number " + v if typ == "int64" else "number") if isinstance(v, _Lit) else "string")
+        first = "json: cannot unmarshal %s into Go struct field %s.%s of type %s" % (what, struct, tag, typ)
+    return vals, first
+
+
+def token_from_reply(t: Dict) -> Tuple[int, str]:
+    """(expiry unix, "") or (0, the error CachedToken.Token returns)."""
+    if t.get("secret_error"):
+        return 0, t["secret_error"]                                   # token.go:98-101
+    if t.get("transport_error"):
+        return 0, t["transport_error"]                                # token.go:127-130
+    status, body = int(t.get("status", 200)), t.get("body", "")
+    if status != 200:
+        return 0, "http returned code: %d, response body: %s" % (status, body)          # :138-140
+    tok, err = unmarshal(body, "fti.token")
+    if err:
+        return 0, "failed to read id_manager response body into Token: " + err           # :143-145
+    vals, err = decode_flat(body, "token", _TOKEN_FIELDS)
+    if err:
+        return 0, "failed to read id_manager response body into Token: " + err
+    access = vals.get("access_token", "")
+    parts = access.split(".")
+    if len(parts) != 3:
+        return 0, "invalid access token: " + access                                      # :156-159
+    payload, err = decode_base64_raw_url(parts[1])
+    if err:
+        return 0, "failed to decode id_manager payload: " + err                          # :161-164
+    claims, err = unmarshal(payload, "fti.accessToken")
+    if not err:
+        claims, err = decode_flat(payload, "accessToken", {"exp": "int64"})
+    if err:
+        return 0, "failed to unmarshal id_manager json: " + err                          # :166-169
+    return claims.get("exp", 0), ""
 
 
 # --------------------------------------------------------------------------
@@ -231,6 +334,9 @@ class Fabric:
         self.spec = spec or {}
         self.requests: List[Dict[str, str]] = []
         self.status_updates: List[str] = []
+        self.now = 1735689600                      # 2025-01-01T00:00:00Z unless the caller sets it
+        self.token_fetches = 0
+        self._expiry: Optional[int] = None
 
     def do(self, method: str, path: str, query: str, body: str) -> Tuple[int, str, str]:
         self.requests.append({"method": method, "path": path, "query": query, "body": body})
@@ -248,7 +354,18 @@ class Fabric:
         return 0, "", '%s "https://fabric/%s": no route in the scripted fabric' % (method, path)
 
     def token(self) -> str:
-        return self.spec.get("token_error", "")
+        """CachedToken.GetToken (fti/token.go:72-94): "" or the error text."""
+        t = self.spec.get("token")
+        if not isinstance(t, dict):
+            return self.spec.get("token_error", "")
+        if self._expiry is not None and self._expiry - 30 > self.now:      # leeway, token.go:68,78
+            return ""
+        self.token_fetches += 1
+        exp, err = token_from_reply(t)
+        if err:
+            return "unable to rotate token: " + err
+        self._expiry = exp
+        return ""
 
     def _get(self, coll: str, resource: str, key: str, name: str):
         v = ((self.spec.get("objects") or {}).get(coll) or {}).get(key)

@@ -151,9 +151,39 @@ def main():
         else:
             r["body"] = ""
         routes[path] = r
+    # the fake id_manager (:665-716): username of the Secret -> what the token endpoint answers.  An Encode()d map is kept
+    # as its fields; the access token's middle part is symbolic ("payload": claims made at run time | raw text to encode)
+    id_manager = {}
+    idm = re.search(r'case "/id_manager[^"]*":\n(.*?)\n\t\t\tcase "/', text, re.S).group(1)
+    for m in re.finditer(r'\n\t\t\t\tcase ' + STR + r':\n(.*?)(?=\n\t\t\t\tcase |\n\t\t\t\tdefault:)', idm, re.S):
+        user, body = unquote(m.group(1)), m.group(2)
+        st = re.search(r"WriteHeader\(http\.Status(\w+)\)", body)
+        r = {"status": {"OK": 200, "Unauthorized": 401, "BadRequest": 400}[st.group(1)]}
+        lit = re.search(r"w\.Write\(\[\]byte\(`([^`]*)`\)\)", body) or re.search(r"w\.Write\(\[\]byte\(" + STR + r"\)\)", body)
+        if lit:
+            r["body"] = lit.group(1) if "`" in lit.group(0) else unquote(lit.group(1))
+        else:
+            fields = {}
+            enc = re.search(r"Encode\(map\[string\]interface\{\}\{(.*?)\n\t\t\t\t\t\}\)", body, re.S).group(1) + "\n"
+            for k, v in re.findall(r"\n\s*" + STR + r":\s*(.*?),(?=\n)", enc):
+                v = v.strip()
+                if v.startswith('"') and "+" not in v:
+                    fields[unquote(k)] = unquote(v[1:-1])
+                elif "+" in v:
+                    parts = [x.strip() for x in v.split("+")]
+                    var = parts[1]
+                    raw = re.search(var + r" := base64\.RawURLEncoding\.EncodeToString\(\[\]byte\(" + STR + r"\)\)", body)
+                    hours = re.search(r"time\.Now\(\)\.Add\((\d+) \* time\.Hour\)", body)
+                    fields[unquote(k)] = {"prefix": unquote(parts[0][1:-1]), "suffix": unquote(parts[2][1:-1]),
+                                          "payload": {"raw": unquote(raw.group(1))} if raw else {"claims_exp_in_hours": int(hours.group(1))}}
+                else:
+                    fields[unquote(k)] = int(v)
+            r["encode"] = fields
+        id_manager[user] = r
     with open(OUT, "w") as f:
         json.dump({"_about": "expectations of the reference's ComposableResource table tests; made by make_reference_entries.py",
-                   "source": "internal/controller/composableresource_controller_test.go", "routes": routes, "entries": out}, f, indent=1)
+                   "source": "internal/controller/composableresource_controller_test.go", "routes": routes,
+                   "id_manager": id_manager, "entries": out}, f, indent=1)
         f.write("\n")
     print(len(out), "entries ->", OUT)
 

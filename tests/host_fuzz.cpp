@@ -166,6 +166,36 @@ static void one(const std::string& in, const std::string& err_text) {
         sink += fabric::CMCheckRemovingResources(in, "gpu", "NVIDIA-B200", "GPU-1").specUUID.size();
     }
     {
+        // the id_manager's answer: as the reply body, and as the access token's middle part
+        long long exp = 0;
+        fabric::TokenReply tr;
+        tr.body = in;
+        sink += fabric::TokenFromReply(tr, &exp).msg.size();
+        std::string dec, derr;
+        sink += (size_t)fabric::DecodeBase64RawURL(in, &dec, &derr) + dec.size() + derr.size();
+        std::string quoted;
+        gojson::append_string(quoted, in);
+        tr.body = "{\"access_token\":" + quoted + "}";
+        sink += fabric::TokenFromReply(tr, &exp).msg.size();
+        static const char kAlpha[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789-_";
+        std::string mid;                       // RawURL-encode `in` so the claims decoder sees the mutated text too
+        for (size_t i = 0; i < in.size(); i += 3) {
+            const unsigned a = (unsigned char)in[i], b = i + 1 < in.size() ? (unsigned char)in[i + 1] : 0,
+                           c = i + 2 < in.size() ? (unsigned char)in[i + 2] : 0;
+            mid.push_back(kAlpha[a >> 2]);
+            mid.push_back(kAlpha[((a & 3) << 4) | (b >> 4)]);
+            if (i + 1 < in.size()) mid.push_back(kAlpha[((b & 15) << 2) | (c >> 6)]);
+            if (i + 2 < in.size()) mid.push_back(kAlpha[c & 63]);
+        }
+        if (!fabric::DecodeBase64RawURL(mid, &dec, &derr) || dec != in) {
+            std::fprintf(stderr, "base64 round trip failed\n");
+            std::abort();
+        }
+        tr.body = "{\"access_token\":\"h." + mid + ".s\"}";
+        fabric::ReplyTokenSource src(tr, 1748779200);
+        sink += src.GetToken().msg.size() + src.GetToken().msg.size() + (size_t)src.fetches;
+    }
+    {
         // Go's validity scanner must agree with the tree builder on what is valid JSON
         const std::string syn = gojson::SyntaxError(in);
         std::string e;

@@ -67,6 +67,38 @@ def fabric_http():
 
 
 HTTP = fabric_http()
+NOW_UNIX = 1748779200       # NOW ("2025-06-01T12:00:00Z") below
+
+
+def _go_encode_map(fields):
+    """json.NewEncoder(w).Encode(map[string]interface{}): keys sorted, HTML-safe escapes, trailing newline."""
+    import json as _j
+    s = _j.dumps(fields, sort_keys=True, separators=(",", ":"), ensure_ascii=False)
+    return s.replace("<", "\\u003c").replace(">", "\\u003e").replace("&", "\\u0026") + "\n"
+
+
+def _b64url(raw):
+    import base64
+    return base64.urlsafe_b64encode(raw).rstrip(b"=").decode()
+
+
+def id_manager_reply(user, now=NOW_UNIX):
+    import json as _j
+    r = GOLD["id_manager"].get(user) or {"status": 400, "body": '{"error":"unsupported_test_user"}'}
+    if "body" in r:
+        return {"status": r["status"], "body": r["body"]}
+    fields = {}
+    for k, v in r["encode"].items():
+        if isinstance(v, dict):
+            p = v["payload"]
+            if "raw" in p:
+                mid = _b64url(p["raw"].encode())
+            else:            # createTokenPayload (:617-627)
+                mid = _b64url(_j.dumps({"admin": True, "exp": now + 3600 * p["claims_exp_in_hours"], "iat": now,
+                                        "name": "John Doe", "sub": "1234567890"}, separators=(",", ":")).encode())
+            v = v["prefix"] + mid + v["suffix"]
+        fields[k] = v
+    return {"status": r["status"], "body": _go_encode_map(fields)}
 
 
 def objects_for(e, bmh_uuid=None):
@@ -104,17 +136,16 @@ def state_of(e):
 
 def request_for(e, **extra):
     init = e.get("initial_status") or {}
-    token_error = ""
-    if e["objects"]["bmh"] and e["objects"].get("bmh_machine_uuid") and not e["objects"]["secret"]:
-        token_error = 'unable to rotate token: secrets "credentials" not found'       # fti/token.go:94 (auth: passed through)
-    if e.get("username", "good_user") != "good_user":
-        token_error = e["expected_error"]                                             # id_manager replies: auth, not restated
+    # what the fake id_manager answers this entry's Secret (:665-716); a missing Secret is the clientset's NotFound
+    token = id_manager_reply(e.get("username", "good_user"))
+    if not e["objects"]["secret"]:
+        token = {"secret_error": 'secrets "credentials" not found'}
     r = {"name": e.get("resourceName", "test-composable-resource"),
          "spec": {"type": "gpu", "model": MODEL, "target_node": "worker-0"},
          "status": {"state": state_of(e), "error": init.get("Error", ""), "device_id": init.get("DeviceID", ""),
                     "cdi_device_id": init.get("CDIDeviceID", "")},
          "deleting": False, "probe": False, "env": env_for(e), "now": NOW,
-         "fabric": {"http": HTTP, "objects": objects_for(e), "token_error": token_error},
+         "fabric": {"http": HTTP, "objects": objects_for(e), "token": token},
          "enumeration": {"stdout": "", "stderr": ""}, "resource_slices": []}
     r.update(extra)
     return r
