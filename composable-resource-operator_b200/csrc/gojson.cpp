@@ -176,35 +176,43 @@ const Value* Value::get(const std::string& k) const {
     }
     return found;
 }
+int MatchField(const std::string& key, const char* const* tags, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (key == tags[i]) return (int)i;
+    const std::string folded = foldKey(key);
+    for (size_t i = 0; i < n; ++i)
+        if (foldKey(tags[i]) == folded) return (int)i;
+    return -1;
+}
+
+std::string MismatchKind(const Value& v, const std::string& text, bool intTarget) {
+    switch (v.kind) {
+        case Value::Object: return "object";
+        case Value::Array: return "array";
+        case Value::String: return "string";
+        case Value::Bool: return "bool";
+        case Value::Number: return intTarget ? "number " + text.substr(v.raw_begin, v.raw_end - v.raw_begin) : "number";
+        default: return "null";
+    }
+}
+
 std::string DecodeFlat(const Value& root, const std::string& text, const char* structName, const FlatField* fields,
                        size_t n, std::map<std::string, std::string>* strs, std::map<std::string, long long>* ints) {
     std::string first;
     if (root.kind != Value::Object) return first;
+    std::vector<const char*> tags;
+    for (size_t i = 0; i < n; ++i) tags.push_back(fields[i].tag);
     for (const auto& kv : root.obj) {
-        const FlatField* f = nullptr;
-        for (size_t i = 0; i < n && !f; ++i)
-            if (kv.first == fields[i].tag) f = &fields[i];
-        if (!f) {
-            const std::string folded = foldKey(kv.first);
-            for (size_t i = 0; i < n && !f; ++i)
-                if (foldKey(fields[i].tag) == folded) f = &fields[i];
-        }
-        if (!f) continue;
+        const int fi = MatchField(kv.first, tags.data(), n);
+        if (fi < 0) continue;
+        const FlatField* f = &fields[fi];
         const Value& v = *kv.second;
         if (v.kind == Value::Null) continue;
         if (f->type == 's' && v.kind == Value::String) { (*strs)[f->tag] = v.str; continue; }
         if (f->type == 'i' && v.kind == Value::Number && v.is_int) { (*ints)[f->tag] = v.inum; continue; }
         if (!first.empty()) continue;
-        std::string what;
-        switch (v.kind) {
-            case Value::Object: what = "object"; break;
-            case Value::Array: what = "array"; break;
-            case Value::String: what = "string"; break;
-            case Value::Bool: what = "bool"; break;
-            default: what = f->type == 'i' ? "number " + text.substr(v.raw_begin, v.raw_end - v.raw_begin) : "number"; break;
-        }
-        first = "json: cannot unmarshal " + what + " into Go struct field " + structName + "." + f->tag + " of type " +
-                (f->type == 's' ? "string" : "int64");
+        first = "json: cannot unmarshal " + MismatchKind(v, text, f->type == 'i') + " into Go struct field " + structName + "." +
+                f->tag + " of type " + (f->type == 's' ? "string" : "int64");
     }
     return first;
 }

@@ -100,6 +100,13 @@ bool rootOk(const ValuePtr& root, std::string* perr, const char* goType);
 // leaves the field alone, a value of the wrong JSON type is skipped and the FIRST such mismatch is returned as
 // go1.24's UnmarshalTypeError text ("json: cannot unmarshal number 1.5 into Go struct field token.expires_in of
 // type int64") — decoding goes on, so later members still land.  (Mismatch wording: unpinned by the reference.)
+// encoding/json's field lookup for one input key: index of the tag that equals it, else of the one equal under
+// case folding, else -1.
+int MatchField(const std::string& key, const char* const* tags, size_t n);
+// The "%s" of UnmarshalTypeError for value v: "object" | "array" | "string" | "bool" | "number" — and, only where an
+// integer field refused a number, "number <literal>".
+std::string MismatchKind(const Value& v, const std::string& text, bool intTarget);
+
 struct FlatField {
     const char* tag;
     char type;                      // 's' string, 'i' int64

@@ -108,35 +108,39 @@ std::string decodeErrorBody(const std::string& body, bool fm, ErrorBody* out) {
     if (root.kind == Value::Null) return "";
     if (root.kind != Value::Object)
         return std::string("json: cannot unmarshal ") + goKind(root) + " into Go value of type api.ErrorBody";
+    // members in input order, as the decoder walks them: the FIRST mismatch is the one Unmarshal returns, and a
+    // later well-typed duplicate still overwrites the field
     std::string first;
-    auto mismatch = [&](const Value& v, const char* strct, const char* field, const char* type) {
-        if (!first.empty()) return;
-        std::string what = goKind(v);
-        if (v.kind == Value::Number) what += " " + body.substr(v.raw_begin, v.raw_end - v.raw_begin);
-        first = "json: cannot unmarshal " + what + " into Go struct field " + strct + "." + field + " of type " + type;
+    auto mismatch = [&](const Value& v, const char* where, const char* type, bool intTarget) {
+        if (first.empty())
+            first = "json: cannot unmarshal " + gojson::MismatchKind(v, body, intTarget) + " into Go struct field " + where + " of type " + type;
     };
-    if (const Value* s = root.get("status")) {
-        if (s->kind == Value::Number && s->is_int) out->status = s->inum;
-        else if (s->kind != Value::Null) mismatch(*s, "ErrorBody", "status", "int");
-    }
-    if (const Value* d = root.get("detail")) {
-        if (d->kind == Value::Object) {
-            out->detail = d;
-            if (const Value* c = d->get("code")) {
-                if (c->kind == Value::String) out->code = c->str;
-                else if (c->kind != Value::Null) mismatch(*c, "ErrorDetail", "detail.code", "string");
+    static const char* const kBody[] = {"status", "detail"};
+    static const char* const kDetail[] = {"code", "message", "data"};
+    for (const auto& kv : root.obj) {
+        const int f = gojson::MatchField(kv.first, kBody, 2);
+        const Value& v = *kv.second;
+        if (f < 0 || v.kind == Value::Null) continue;
+        if (f == 0) {
+            if (v.kind == Value::Number && v.is_int) out->status = v.inum;
+            else mismatch(v, "ErrorBody.status", "int", true);
+            continue;
+        }
+        if (v.kind != Value::Object) { mismatch(v, "ErrorBody.detail", "api.ErrorDetail", false); continue; }
+        out->detail = &v;
+        for (const auto& dk : v.obj) {
+            const int g = gojson::MatchField(dk.first, kDetail, fm ? 3 : 2);
+            const Value& m = *dk.second;
+            if (g < 0) continue;
+            if (g == 1 && fm) { out->rawMessage = &m; continue; }         // json.RawMessage takes any value, null included
+            if (m.kind == Value::Null) continue;
+            if (g == 2) {
+                if (m.kind != Value::Object) mismatch(m, "ErrorDetail.detail.data", "map[string]interface {}", false);
+            } else if (m.kind == Value::String) {
+                (g == 0 ? out->code : out->message) = m.str;
+            } else {
+                mismatch(m, g == 0 ? "ErrorDetail.detail.code" : "ErrorDetail.detail.message", "string", false);
             }
-            if (const Value* m = d->get("message")) {
-                if (fm) out->rawMessage = m;
-                else if (m->kind == Value::String) out->message = m->str;
-                else if (m->kind != Value::Null) mismatch(*m, "ErrorDetail", "detail.message", "string");
-            }
-            if (fm)
-                if (const Value* data = d->get("data"))
-                    if (data->kind != Value::Object && data->kind != Value::Null)
-                        mismatch(*data, "ErrorDetail", "detail.data", "map[string]interface {}");
-        } else if (d->kind != Value::Null) {
-            mismatch(*d, "ErrorBody", "detail", "api.ErrorDetail");
         }
     }
     return first;
@@ -144,15 +148,12 @@ std::string decodeErrorBody(const std::string& body, bool fm, ErrorBody* out) {
 
 }  // namespace
 
-std::string formatFMErrorDetail(const Value* detail, const std::string& text) {
-    std::string code, message;
-    if (detail && detail->kind == Value::Object) {
-        code = detail->get_string("code");
-        if (const Value* m = detail->get("message")) {
-            if (m->kind == Value::String) message = m->str;                 // it unmarshals into a Go string
-            else if (m->kind == Value::Null) message = "";                  // Unmarshal("null", &s) leaves s == ""
-            else message = identity::TrimSpace(text.substr(m->raw_begin, m->raw_end - m->raw_begin));
-        }
+std::string formatFMErrorDetail(const std::string& code, const Value* m, const std::string& text) {
+    std::string message;
+    if (m) {
+        if (m->kind == Value::String) message = m->str;                 // it unmarshals into a Go string
+        else if (m->kind == Value::Null) message = "";                  // Unmarshal("null", &s) leaves s == ""
+        else message = identity::TrimSpace(text.substr(m->raw_begin, m->raw_end - m->raw_begin));
     }
     return "code: '" + code + "', error message: '" + message + "'";
 }
@@ -165,7 +166,7 @@ Error FMErrorFromReply(const std::string& what, const std::string& body) {
         const std::string subject = what == "scaledown" ? "scaledown" : "FM " + what;
         return Error::New("failed to unmarshal " + subject + " error response body into errBody. Original error: " + uerr);
     }
-    return Error::New("failed to process FM " + what + " request. FM returned " + formatFMErrorDetail(eb.detail, body));
+    return Error::New("failed to process FM " + what + " request. FM returned " + formatFMErrorDetail(eb.code, eb.rawMessage, body));
 }
 
 Error CMErrorFromReply(const std::string& what, const std::string& body) {

@@ -107,7 +107,7 @@ std::string CMScaleDownBody(const std::string& specUUID, long long deviceCount, 
 // message ("scaleup", "scaledown", "get").
 Error FMErrorFromReply(const std::string& what, const std::string& body);   // fm/client.go:172-181, 299-308, 495-503
 Error CMErrorFromReply(const std::string& what, const std::string& body);   // cm/client.go:169-178, 249-257, 414-421
-std::string formatFMErrorDetail(const gojson::Value* detail, const std::string& text);   // fm/client.go:60-72
+std::string formatFMErrorDetail(const std::string& code, const gojson::Value* rawMessage, const std::string& text);   // fm/client.go:60-72
 
 // checkRemovingResources (cm/client.go:461-483) over the machine JSON.
 struct CMRemovingResult {

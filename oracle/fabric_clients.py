@@ -254,12 +254,85 @@ def decode_base64_raw_url(s: str) -> Tuple[Optional[bytes], str]:
     return bytes(out), ""
 
 
-class _Lit(str):
-    """a JSON number kept as its literal"""
+class _Node:
+    """One JSON value of a syntactically valid text: kind in {"null","bool","number","string","array","object"}, its
+    [begin, end) span, and v = python value | raw literal (number) | [nodes] | [(key, node)] in input order."""
+    __slots__ = ("kind", "v", "b", "e")
+
+    def __init__(self, kind, v, b, e):
+        self.kind, self.v, self.b, self.e = kind, v, b, e
 
 
-class _Pairs(list):
-    """a JSON object kept as its members in input order"""
+_WS = " \t\r\n"
+_STR_RE = re.compile(r'"(?:[^"\\]|\\.)*"', re.S)
+_NUM_RE = re.compile(r"-?(?:0|[1-9][0-9]*)(?:\.[0-9]+)?(?:[eE][+-]?[0-9]+)?")
+
+
+def _parse_spans(s: str, i: int = 0) -> Tuple[_Node, int]:
+    while s[i] in _WS:
+        i += 1
+    c = s[i]
+    if c == "{":
+        b, members = i, []
+        i += 1
+        while True:
+            while s[i] in _WS:
+                i += 1
+            if s[i] == "}":
+                return _Node("object", members, b, i + 1), i + 1
+            if s[i] == ",":
+                i += 1
+                continue
+            m = _STR_RE.match(s, i)
+            key = json.loads(m.group(0), strict=False)
+            i = m.end()
+            while s[i] in _WS:
+                i += 1
+            val, i = _parse_spans(s, i + 1)            # s[i] == ":"
+            members.append((key, val))
+    if c == "[":
+        b, items = i, []
+        i += 1
+        while True:
+            while s[i] in _WS:
+                i += 1
+            if s[i] == "]":
+                return _Node("array", items, b, i + 1), i + 1
+            if s[i] == ",":
+                i += 1
+                continue
+            val, i = _parse_spans(s, i)
+            items.append(val)
+    if c == '"':
+        m = _STR_RE.match(s, i)
+        return _Node("string", json.loads(m.group(0), strict=False), i, m.end()), m.end()
+    for lit, val in (("true", True), ("false", False), ("null", None)):
+        if s.startswith(lit, i):
+            return _Node("null" if val is None else "bool", val, i, i + len(lit)), i + len(lit)
+    m = _NUM_RE.match(s, i)
+    return _Node("number", m.group(0), i, m.end()), m.end()
+
+
+def _spans(data) -> Tuple[_Node, str]:
+    s = data.decode("utf-8", "replace") if isinstance(data, bytes) else data
+    return _parse_spans(s)[0], s
+
+
+def _match_field(key: str, tags) -> Optional[str]:
+    """encoding/json's field lookup: the exact tag, else the one equal under case folding."""
+    if key in tags:
+        return key
+    f = _o._fold(key)
+    for t in tags:
+        if _o._fold(t) == f:
+            return t
+    return None
+
+
+def _as_int(n: _Node) -> Optional[int]:
+    if n.kind == "number" and re.fullmatch(r"-?[0-9]+", n.v) and -2**63 <= int(n.v) < 2**63:
+        return int(n.v)
+    return None
 
 
 _TOKEN_FIELDS = {"access_token": "string", "expires_in": "int64", "refresh_expires_in": "int64", "refresh_token": "string",
@@ -270,28 +343,25 @@ _TOKEN_FIELDS = {"access_token": "string", "expires_in": "int64", "refresh_expir
 def decode_flat(data, struct: str, fields: Dict[str, str]) -> Tuple[Dict, str]:
     """json.Unmarshal of syntactically valid `data` (object or null) into a struct of string / int64 fields:
     (values, first UnmarshalTypeError text).  Members in input order; a mismatch is skipped, decoding goes on."""
-    raw = data if isinstance(data, bytes) else data.encode("utf-8", "surrogatepass")
-    top = json.loads(raw.decode("utf-8", "replace"), object_pairs_hook=_Pairs, parse_int=_Lit, parse_float=_Lit)
+    top, _ = _spans(data)
     vals: Dict = {}
     first = ""
-    if not isinstance(top, _Pairs):
+    if top.kind != "object":
         return vals, first
-    folded = {_o._fold(k): k for k in fields}
-    for k, v in top:
-        tag = k if k in fields else folded.get(_o._fold(k))
-        if tag is None or v is None:
+    for k, n in top.v:
+        tag = _match_field(k, fields)
+        if tag is None or n.kind == "null":
             continue
         typ = fields[tag]
-        if typ == "string" and isinstance(v, str) and not isinstance(v, _Lit):
-            vals[tag] = v
+        if typ == "string" and n.kind == "string":
+            vals[tag] = n.v
             continue
-        if typ == "int64" and isinstance(v, _Lit) and re.fullmatch(r"-?[0-9]+", v) and -2**63 <= int(v) < 2**63:
-            vals[tag] = int(v)
+        if typ == "int64" and _as_int(n) is not None:
+            vals[tag] = _as_int(n)
             continue
         if first:
             continue
-        what = ("object" if isinstance(v, _Pairs) else "array" if isinstance(v, list) else "bool" if isinstance(v, bool) else
-                ("number " + v if typ == "int64" else "number") if isinstance(v, _Lit) else "string")
+        what = ("number " + n.v) if (n.kind == "number" and typ == "int64") else n.kind
         first = "json: cannot unmarshal %s into Go struct field %s.%s of type %s" % (what, struct, tag, typ)
     return vals, first
 
@@ -425,61 +495,46 @@ def _error_body(data: str, fm: bool):
     v, err = unmarshal(data, "api.ErrorBody")
     if err:
         return 0, "", "", err
-    first = ""
+    top, text = _spans(data)
+    state = {"first": "", "status": 0, "code": "", "message": ""}
 
-    def kind(x):
-        return ("null" if x is None else "bool" if isinstance(x, bool) else "number" if isinstance(x, (int, float)) else
-                "string" if isinstance(x, str) else "array" if isinstance(x, list) else "object")
+    def mismatch(n: _Node, where: str, typ: str, literal: bool):
+        if not state["first"]:
+            what = ("number " + n.v) if (n.kind == "number" and literal) else n.kind
+            state["first"] = "json: cannot unmarshal %s into Go struct field %s of type %s" % (what, where, typ)
 
-    status, code, message = 0, "", ""
-    s = v.get("status")
-    if isinstance(s, int) and not isinstance(s, bool):
-        status = s
-    elif s is not None:
-        first = first or "json: cannot unmarshal %s into Go struct field ErrorBody.status of type int" % _kind_with_literal(data, "status", s)
-    d = v.get("detail")
-    if isinstance(d, dict):
-        c = d.get("code")
-        if isinstance(c, str):
-            code = c
-        elif c is not None:
-            first = first or "json: cannot unmarshal %s into Go struct field ErrorDetail.detail.code of type string" % _kind_with_literal(data, "code", c)
-        m = d.get("message")
-        if fm:
-            if isinstance(m, str):
-                message = m
-            elif m is not None:
-                message = _raw_member(data, "message").strip(" \t\r\n")
-        elif isinstance(m, str):
-            message = m
-        elif m is not None:
-            first = first or "json: cannot unmarshal %s into Go struct field ErrorDetail.detail.message of type string" % _kind_with_literal(data, "message", m)
-        if fm and d.get("data") is not None and not isinstance(d.get("data"), dict):
-            first = first or "json: cannot unmarshal %s into Go struct field ErrorDetail.detail.data of type map[string]interface {}" % _kind_with_literal(data, "data", d["data"])
-    elif d is not None:
-        first = first or "json: cannot unmarshal %s into Go struct field ErrorBody.detail of type api.ErrorDetail" % _kind_with_literal(data, "detail", d)
-    return status, code, message, first
+    def detail(d: _Node):
+        for k, n in d.v:
+            tag = _match_field(k, ("code", "message", "data") if fm else ("code", "message"))
+            if tag is None:
+                continue
+            if tag == "message" and fm:                      # json.RawMessage: the member's own text, null included
+                state["message"] = "" if n.kind == "null" else n.v if n.kind == "string" else text[n.b:n.e].strip(_WS)
+            elif n.kind == "null":
+                continue
+            elif tag == "data":
+                if n.kind != "object":
+                    mismatch(n, "ErrorDetail.detail.data", "map[string]interface {}", False)
+            elif n.kind == "string":
+                state[tag] = n.v
+            else:
+                mismatch(n, "ErrorDetail.detail." + tag, "string", False)
 
-
-def _raw_member(data: str, key: str) -> str:
-    """Raw text of the LAST member called `key` (good enough for the fixtures: keys are unique)."""
-    dec = json.JSONDecoder()
-    best = ""
-    for m in re.finditer(r'"%s"\s*:\s*' % re.escape(key), data):
-        try:
-            _, end = dec.raw_decode(data, m.end())
-            best = data[m.end():end]
-        except ValueError:
-            pass
-    return best
-
-
-def _kind_with_literal(data: str, key: str, v) -> str:
-    if isinstance(v, bool):
-        return "bool"
-    if isinstance(v, (int, float)):
-        return "number " + _raw_member(data, key)
-    return "string" if isinstance(v, str) else "array" if isinstance(v, list) else "object"
+    if top.kind == "object":
+        for k, n in top.v:                                   # members in input order; the first mismatch is the one reported
+            tag = _match_field(k, ("status", "detail"))
+            if tag is None or n.kind == "null":
+                continue
+            if tag == "status":
+                if _as_int(n) is not None:
+                    state["status"] = _as_int(n)
+                else:
+                    mismatch(n, "ErrorBody.status", "int", True)
+            elif n.kind == "object":
+                detail(n)
+            else:
+                mismatch(n, "ErrorBody.detail", "api.ErrorDetail", False)
+    return state["status"], state["code"], state["message"], state["first"]
 
 
 def fm_error(what: str, body: str) -> str:
