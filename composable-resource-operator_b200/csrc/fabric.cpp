@@ -1,5 +1,6 @@
 // fabric.cpp — see fabric.hpp.
 #include "fabric.hpp"
+#include "gotypes.hpp"
 
 #include "gojson.hpp"
 
@@ -32,7 +33,7 @@ Error FMCheckResource(const std::string& body, const std::string& specType, cons
                       const std::string& deviceID) {
     std::string perr;
     gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!gojson::rootOk(root, &perr, "api.GetMachineResponse"))
+    if (!gojson::decodesInto(root, body, gotypes::FMGetMachineResponse(), &perr))
         return Error::New("failed to unmarshal FM get machine response body into machineData: " + perr);
     const Value* machines = arr(root->get("data"), "machines");
     if (!machines || machines->arr.empty())   // fm/client.go:331 indexes Machines[0] unguarded
@@ -58,7 +59,7 @@ Error FMGetResources(const std::string& body, const std::string& nodeName, const
                      std::vector<DeviceInfo>* out) {
     std::string perr;
     gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!gojson::rootOk(root, &perr, "api.GetMachineResponse"))
+    if (!gojson::decodesInto(root, body, gotypes::FMGetMachineResponse(), &perr))
         return Error::New("failed to unmarshal FM get machine response body into machineData: " + perr);
     const Value* machines = arr(root->get("data"), "machines");
     if (!machines || machines->arr.empty()) return Error::Nil();   // fm/client.go:385-387
@@ -83,7 +84,7 @@ Error CMCheckResource(const std::string& body, const std::string& specType, cons
                       const std::string& deviceID) {
     std::string perr;
     gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!gojson::rootOk(root, &perr, "api.MachineData"))
+    if (!gojson::decodesInto(root, body, gotypes::CMMachineData(), &perr))
         return Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
     const Value* data = root->get("data");
     const Value* cluster = data ? data->get("cluster") : nullptr;
@@ -113,7 +114,7 @@ Error CMGetResources(const std::string& body, const std::string& nodeName, const
                      std::vector<DeviceInfo>* out) {
     std::string perr;
     gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!gojson::rootOk(root, &perr, "api.MachineData"))
+    if (!gojson::decodesInto(root, body, gotypes::CMMachineData(), &perr))
         return Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
     const Value* data = root->get("data");
     const Value* cluster = data ? data->get("cluster") : nullptr;

@@ -626,5 +626,72 @@ bool rootOk(const ValuePtr& root, std::string* perr, const char* goType) {
     return false;
 }
 
+namespace {
+struct TypeWalk {
+    const std::string& text;
+    std::string first;
+    std::vector<std::string> stack;                 // errorContext.FieldStack
+    const GoType* strct = nullptr;                  // errorContext.Struct
+
+    void save(const Value& v, const GoType& t) {
+        if (!first.empty()) return;
+        const std::string what = MismatchKind(v, text, t.kind == GoType::Int);
+        if (!strct && stack.empty()) {
+            first = "json: cannot unmarshal " + what + " into Go value of type " + t.name;
+            return;
+        }
+        std::string path;
+        for (size_t i = 0; i < stack.size(); ++i) path += (i ? "." : "") + stack[i];
+        first = "json: cannot unmarshal " + what + " into Go struct field " + (strct ? strct->structName : std::string()) + "." + path +
+                " of type " + t.name;
+    }
+
+    void walk(const Value& v, const GoType& t) {
+        if (v.kind == Value::Null || t.kind == GoType::RawMessage) return;
+        switch (t.kind) {
+            case GoType::String: if (v.kind != Value::String) save(v, t); return;
+            case GoType::Bool: if (v.kind != Value::Bool) save(v, t); return;
+            case GoType::Int: if (v.kind != Value::Number || !v.is_int) save(v, t); return;
+            case GoType::MapOfAny: if (v.kind != Value::Object) save(v, t); return;
+            case GoType::Slice:
+                if (v.kind != Value::Array) { save(v, t); return; }
+                for (const auto& e : v.arr) walk(*e, *t.elem);
+                return;
+            case GoType::Struct: {
+                if (v.kind != Value::Object) { save(v, t); return; }
+                std::vector<const char*> tags;
+                for (const auto& f : t.fields) tags.push_back(f.first.c_str());
+                for (const auto& kv : v.obj) {
+                    const int fi = MatchField(kv.first, tags.data(), tags.size());
+                    if (fi < 0) continue;
+                    const GoType* outer = strct;
+                    stack.push_back(t.fields[fi].first);
+                    strct = &t;
+                    walk(*kv.second, *t.fields[fi].second);
+                    stack.pop_back();
+                    strct = outer;
+                }
+                return;
+            }
+            default: return;
+        }
+    }
+};
+}  // namespace
+
+std::string TypeMismatch(const Value& root, const std::string& text, const GoType& t) {
+    TypeWalk w{text};
+    w.walk(root, t);
+    return w.first;
+}
+
+bool decodesInto(const ValuePtr& root, const std::string& text, const GoType& t, std::string* perr) {
+    if (!root) return false;                        // *perr already holds the syntax error
+    const std::string e = TypeMismatch(*root, text, t);
+    if (e.empty()) return true;
+    *perr = e;
+    return false;
+}
+
 }  // namespace gojson
 }  // namespace cro

@@ -100,6 +100,23 @@ bool rootOk(const ValuePtr& root, std::string* perr, const char* goType);
 // leaves the field alone, a value of the wrong JSON type is skipped and the FIRST such mismatch is returned as
 // go1.24's UnmarshalTypeError text ("json: cannot unmarshal number 1.5 into Go struct field token.expires_in of
 // type int64") — decoding goes on, so later members still land.  (Mismatch wording: unpinned by the reference.)
+// A Go type as json.Unmarshal sees it, for the typed walk below.  Only what the reference's wire structs use.
+struct GoType {
+    enum Kind { String, Int, Bool, Struct, Slice, RawMessage, MapOfAny } kind;
+    std::string name;                                               // reflect.Type.String(): "int", "api.Condition", "[]api.ConditionItem"
+    std::string structName;                                         // Struct: reflect.Type.Name(), "Condition"
+    std::vector<std::pair<std::string, const GoType*>> fields;      // Struct: json tag -> type
+    const GoType* elem = nullptr;                                   // Slice
+};
+// The error json.Unmarshal(text, &T{}) returns for a syntactically valid `root`: "" or go1.24's UnmarshalTypeError
+// text of the FIRST value (input order) whose JSON type does not fit the Go field it lands in — "json: cannot
+// unmarshal string into Go struct field GetMachineItem.data.machines.fabric_id of type int", or "... into Go value
+// of type api.X" at the top.  null fits everything; unknown keys are skipped; keys fold as in Value::get.
+// (The wording is go1.24's and has no reference vector; THAT a mismatch is an error is what matters to callers.)
+std::string TypeMismatch(const Value& root, const std::string& text, const GoType& t);
+// rootOk + TypeMismatch: can `root` (a parse() result) be decoded into T?  False with *perr = Unmarshal's message.
+bool decodesInto(const ValuePtr& root, const std::string& text, const GoType& t, std::string* perr);
+
 // encoding/json's field lookup for one input key: index of the tag that equals it, else of the one equal under
 // case folding, else -1.
 int MatchField(const std::string& key, const char* const* tags, size_t n);

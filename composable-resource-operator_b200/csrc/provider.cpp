@@ -1,5 +1,6 @@
 // provider.cpp — see provider.hpp.
 #include "provider.hpp"
+#include "gotypes.hpp"
 
 #include "identity.hpp"
 
@@ -295,7 +296,7 @@ CMRemovingResult CMCheckRemovingResources(const std::string& machineBody, const 
     CMRemovingResult r;
     std::string perr;
     gojson::ValuePtr root = gojson::parse(machineBody, &perr);
-    if (!root) {
+    if (!gojson::decodesInto(root, machineBody, gotypes::CMMachineData(), &perr)) {
         r.err = Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
         return r;
     }
@@ -383,7 +384,7 @@ Error FMClient::getMachineInfo(const std::string& machineID, std::string* body) 
     if (rep.status != 200) return FMErrorFromReply("get", rep.body);
     std::string perr;
     gojson::ValuePtr root = gojson::parse(rep.body, &perr);
-    if (!gojson::rootOk(root, &perr, "api.GetMachineResponse"))
+    if (!gojson::decodesInto(root, rep.body, gotypes::FMGetMachineResponse(), &perr))
         return Error::New("failed to unmarshal FM get machine response body into machineData: " + perr);
     *body = rep.body;
     return Error::Nil();
@@ -465,7 +466,7 @@ Error CMClient::getMachineInfo(const std::string& machineID, std::string* body) 
     if (rep.status != 200) return CMErrorFromReply("get", rep.body);
     std::string perr;
     gojson::ValuePtr root = gojson::parse(rep.body, &perr);
-    if (!gojson::rootOk(root, &perr, "api.MachineData"))
+    if (!gojson::decodesInto(root, rep.body, gotypes::CMMachineData(), &perr))
         return Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
     *body = rep.body;
     return Error::Nil();

@@ -1,5 +1,6 @@
 // reconcile.cpp — see reconcile.hpp.
 #include "reconcile.hpp"
+#include "gotypes.hpp"
 
 namespace cro {
 namespace controller {
@@ -27,7 +28,7 @@ Error FMScaleUpResponseToIDs(const std::string& body, const std::string& instanc
     CDIDeviceID->clear();
     std::string perr;
     gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!gojson::rootOk(root, &perr, "api.ScaleUpResponse"))
+    if (!gojson::decodesInto(root, body, gotypes::FMScaleUpResponse(), &perr))
         return Error::New(
             "failed to unmarshal FM scaleup response body into scaleUpResponse. Original error: " + perr);
     const gojson::Value* data = root->get("data");
@@ -73,7 +74,7 @@ CMAddingResult CMCheckAddingResources(const std::string& machineBody,
     CMAddingResult out;
     std::string perr;
     gojson::ValuePtr root = gojson::parse(machineBody, &perr);
-    if (!gojson::rootOk(root, &perr, "api.MachineData")) {
+    if (!gojson::decodesInto(root, machineBody, gotypes::CMMachineData(), &perr)) {
         out.err = Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
         return out;
     }

@@ -215,6 +215,10 @@ def unmarshal(data, go_type: str):
     err = go_json_syntax_error(raw)
     if err:
         return None, err
+    if go_type in TYPES:
+        err = type_mismatch(data, TYPES[go_type])
+        if err:
+            return None, err
     v = _o.go_loads(raw.decode("utf-8", "replace") if isinstance(data, bytes) else data)   # invalid UTF-8 -> U+FFFD, as Go
     if v is None:
         return {}, ""
@@ -327,6 +331,87 @@ def _match_field(key: str, tags) -> Optional[str]:
         if _o._fold(t) == f:
             return t
     return None
+
+
+# ---- the wire structs as type descriptions (fm/api/*.go, cm/api/machine.go) ----
+def _struct(_go_name: str, **fields):
+    return ("struct", _go_name, dict(fields))
+
+
+def _slice(elem):
+    return ("slice", elem)
+
+
+def _type_name(t) -> str:
+    return t if isinstance(t, str) else "api." + t[1] if t[0] == "struct" else "[]" + _type_name(t[1])
+
+
+_S, _I, _B = "string", "int", "bool"
+_FM_COND = _struct("Condition", condition=_slice(_struct("ConditionItem", column=_S, operator=_S, value=_S)))
+_FM_RES = dict(res_uuid=_S, res_name=_S, res_type=_S, res_status=_I, res_op_status=_S, res_serial_num=_S, res_spec=_FM_COND)
+_FM_MACH = dict(fabric_uuid=_S, fabric_id=_I, mach_uuid=_S, mach_id=_I, mach_name=_S, tenant_uuid=_S)
+TYPES = {
+    "api.ScaleUpResponse": _struct("ScaleUpResponse", data=_struct("ScaleUpResponseData", machines=_slice(
+        _struct("ScaleUpResponseMachineItem", resources=_slice(_struct("ScaleUpResponseResourceItem", **_FM_RES)), **_FM_MACH)))),
+    "api.GetMachineResponse": _struct("GetMachineResponse", data=_struct("GetMachineData", machines=_slice(
+        _struct("GetMachineItem", mach_status=_I, mach_status_detail=_S, resources=_slice(_struct("GetMachineResource", **_FM_RES)), **_FM_MACH)))),
+    "api.MachineData": None,
+}
+_CM_DEVSPEC = _struct("DeviceResourceSpec", resspec_uuid=_S, productname=_S, model=_S, vendor=_S, removable=_B)
+_CM_DETAIL = _struct("DeviceDetail", fabric_uuid=_S, fabric_id=_I, res_uuid=_S, fabr_gid=_S, res_type=_S, res_name=_S, res_status=_S,
+                     res_op_status=_S, tenant_uuid=_S, mach_uuid=_S, resspecs=_slice(_CM_DEVSPEC))
+_CM_DEVICE = _struct("Device", device_id=_S, status=_S, status_reason=_S, detail=_CM_DETAIL)
+_CM_SELECTOR = _struct("Selector", version=_S, expression=_struct("Expression", conditions=_slice(
+    _struct("Condition", column=_S, operator=_S, value=_S))))
+_CM_SPEC = _struct("ResourceSpec", spec_uuid=_S, type=_S, min_resspec_count=_I, max_resspec_count=_I, device_count=_I,
+                   selector=_CM_SELECTOR, devices=_slice(_CM_DEVICE))
+_CM_MACHINE = _struct("Machine", uuid=_S, name=_S, status=_S, status_reason=_S, resspecs=_slice(_CM_SPEC))
+TYPES["api.MachineData"] = _struct("MachineData", data=_struct("Data", tenant_uuid=_S, cluster=_struct(
+    "Cluster", cluster_uuid=_S, machine=_CM_MACHINE)))
+
+
+def type_mismatch(data, typ) -> str:
+    """"" or the UnmarshalTypeError json.Unmarshal(data, &T{}) returns for syntactically valid data: the first value, in
+    input order, whose JSON type does not fit the Go field it lands in (go1.24 wording: Struct = innermost struct's name,
+    Field = dotted path of tags from the root; slices add nothing to the path)."""
+    top, _ = _spans(data)
+    first: List[str] = []
+
+    def save(n: _Node, t, stack, strct):
+        if first:
+            return
+        what = ("number " + n.v) if (n.kind == "number" and t == "int") else n.kind
+        if strct is None and not stack:
+            first.append("json: cannot unmarshal %s into Go value of type %s" % (what, _type_name(t)))
+        else:
+            first.append("json: cannot unmarshal %s into Go struct field %s.%s of type %s" % (what, strct or "", ".".join(stack), _type_name(t)))
+
+    def walk(n: _Node, t, stack, strct):
+        if n.kind == "null":
+            return
+        if t == "string":
+            ok = n.kind == "string"
+        elif t == "bool":
+            ok = n.kind == "bool"
+        elif t == "int":
+            ok = _as_int(n) is not None
+        elif t[0] == "slice":
+            ok = n.kind == "array"
+            if ok:
+                for e in n.v:
+                    walk(e, t[1], stack, strct)
+        else:
+            ok = n.kind == "object"
+            if ok:
+                for k, m in n.v:
+                    tag = _match_field(k, t[2])
+                    if tag is not None:
+                        walk(m, t[2][tag], stack + [tag], t[1])
+        if not ok:
+            save(n, t, stack, strct)
+
+    walk(top, typ, [], None)
+    return first[0] if first else ""
 
 
 def _as_int(n: _Node) -> Optional[int]:
@@ -613,7 +698,7 @@ class FMClient(_Client):
         body, err = self.machine_info(mid)
         if err:
             return err
-        machines = ((_o.go_loads(body) or {}).get("data") or {}).get("machines") or []
+        machines = ((_o.go_struct_loads(body) or {}).get("data") or {}).get("machines") or []
         if not machines:
             return "runtime error: index out of range [0] with length 0"
         if not any(r.get("res_type", "") == typ and r.get("res_uuid", "") == cdi_device_id for r in machines[0].get("resources") or []):
@@ -695,7 +780,7 @@ class CMClient(_Client):
         if err:
             return err, None
         spec_uuid, count, reason = "", 0, None
-        for s in ((((_o.go_loads(body).get("data") or {}).get("cluster") or {}).get("machine") or {}).get("resspecs")) or []:
+        for s in ((((_o.go_struct_loads(body).get("data") or {}).get("cluster") or {}).get("machine") or {}).get("resspecs")) or []:
             if s.get("type", "") != typ:
                 continue
             conds = (((s.get("selector") or {}).get("expression") or {}).get("conditions")) or []
