@@ -721,7 +721,9 @@ int ctx_probe_poll(cro_ctx* c, int idx) {
     std::lock_guard<std::mutex> g(d->mu);
     if (!d->pending) return 1;
     cudaSetDevice(d->ordinal);
-    return cudaStreamQuery(d->stream) == cudaSuccess ? 1 : 0;
+    // anything but "still running" counts as finished: a failed stream must not keep a poller spinning —
+    // cro_probe_end then reports the CUDA error
+    return cudaStreamQuery(d->stream) == cudaErrorNotReady ? 0 : 1;
 }
 
 // Blocks until the probe in flight on this device (if any) has finished; does not collect it.
