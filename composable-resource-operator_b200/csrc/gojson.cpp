@@ -278,7 +278,17 @@ struct Parser {
             const unsigned char c = (unsigned char)t[i];
             if (c == '"') { ++i; return true; }
             if (c < 0x20) return fail("control character in string");
-            if (c != '\\') { o->push_back((char)c); ++i; continue; }
+            if (c < 0x80) {
+                if (c != '\\') { o->push_back((char)c); ++i; continue; }
+            } else {
+                // unquote() runs utf8.DecodeRune: a well-formed sequence is kept, anything else — stray continuation
+                // byte, overlong form, encoded surrogate, > U+10FFFF, truncated tail — costs ONE byte and becomes U+FFFD
+                unsigned rune = 0;
+                const size_t n = utf8_len(t, i, &rune);
+                if (n) { o->append(t, i, n); i += n; }
+                else { put_utf8(*o, 0xFFFD); ++i; }
+                continue;
+            }
             if (++i >= t.size()) break;
             const char e = t[i++];
             switch (e) {
