@@ -117,6 +117,7 @@ EXPORTS = [
     "cro_scan_device_file_holders", "cro_sim_reconcile_resource", "cro_sim_sync_upstream",
     "cro_fabric_check_resource", "cro_fabric_get_resources", "cro_fabric_list_devices",
     "cro_local_node_op", "cro_scan_cmdline_for", "cro_token_from_reply",
+    "cro_selftest_exception_barrier",
 ]
 
 
@@ -181,6 +182,7 @@ def _load() -> ctypes.CDLL:
         "cro_fabric_get_resources": (i32, [c, c, c, c] + out),
         "cro_fabric_list_devices": (i32, [c] + out),
         "cro_token_from_reply": (i32, [c] + out),
+        "cro_selftest_exception_barrier": (i32, [i32]),
         "cro_local_node_op": (i32, [vp, c] + out),
         "cro_scan_cmdline_for": (i32, [c, c, ctypes.POINTER(i32)]),
         "cro_sim_reconcile_resource": (i32, [vp, c, c, sz]),

@@ -18,6 +18,8 @@
 #include "nodes.hpp"
 #include "gpus.hpp"
 #include <memory>
+#include <new>
+#include <stdexcept>
 
 using namespace cro;
 
@@ -32,6 +34,25 @@ static_assert(offsetof(cro_probe_result, p2p_write_ns) == 440, "layout");
 
 using namespace cro::capi;
 
+
+namespace cro {
+namespace capi {
+int on_exception() noexcept {
+    try {
+        throw;
+    } catch (const std::bad_alloc&) {
+        set_thread_error("out of host memory");
+        return CRO_ERR_OOM;
+    } catch (const std::exception& e) {
+        set_thread_error(std::string("internal error: ") + e.what());
+        return CRO_ERR_INTERNAL;
+    } catch (...) {
+        set_thread_error("internal error: unknown exception");
+        return CRO_ERR_INTERNAL;
+    }
+}
+}  // namespace capi
+}  // namespace cro
 
 extern "C" {
 
@@ -58,31 +79,38 @@ const char* cro_strerror(int code) {
     }
 }
 
-int cro_last_error(cro_ctx* ctx, char* buf, size_t cap) {
+int cro_last_error(cro_ctx* ctx, char* buf, size_t cap) try {
     if (!ctx) return copy_out(last_init_error(), buf, cap, nullptr);
     std::lock_guard<std::mutex> g(ctx->err_mu);
     return copy_out(ctx->last_error, buf, cap, nullptr);
-}
+} CRO_API_CATCH
 
-int cro_probe_init(const cro_opts* opts, cro_ctx** out) { return ctx_create(opts, out); }
+int cro_selftest_exception_barrier(int kind) try {
+    if (kind == 0) throw std::runtime_error("exception barrier self-test");
+    if (kind == 1) throw std::bad_alloc();
+    if (kind == 2) throw 42;
+    return CRO_OK;
+} CRO_API_CATCH
+
+int cro_probe_init(const cro_opts* opts, cro_ctx** out) try { return ctx_create(opts, out); } CRO_API_CATCH
 void cro_probe_destroy(cro_ctx* ctx) { ctx_destroy(ctx); }
 
-int cro_device_count(cro_ctx* ctx, int* n) {
+int cro_device_count(cro_ctx* ctx, int* n) try {
     if (!ctx || !n) return CRO_ERR_INVALID_ARG;
     *n = (int)ctx->devs.size();
     return CRO_OK;
-}
+} CRO_API_CATCH
 
-int cro_enumerate(cro_ctx* ctx, cro_dev_info* out, int cap, int* n) {
+int cro_enumerate(cro_ctx* ctx, cro_dev_info* out, int cap, int* n) try {
     if (!ctx || !n) return CRO_ERR_INVALID_ARG;
     *n = (int)ctx->devs.size();
     if (*n == 0) return CRO_OK;
     if (!out || cap < *n) return CRO_ERR_BUFFER_SMALL;
     for (int i = 0; i < *n; ++i) out[i] = ctx->devs[(size_t)i]->info;
     return CRO_OK;
-}
+} CRO_API_CATCH
 
-int cro_emit_csv(const cro_dev_info* devs, int n, const char* query, char* buf, size_t cap, size_t* len) {
+int cro_emit_csv(const cro_dev_info* devs, int n, const char* query, char* buf, size_t cap, size_t* len) try {
     if (!query || (n > 0 && !devs)) return CRO_ERR_INVALID_ARG;
     std::string out, err;
     int rc = identity::EmitCsv(devs, n, query, &out, &err);
@@ -91,7 +119,7 @@ int cro_emit_csv(const cro_dev_info* devs, int n, const char* query, char* buf, 
         return rc;
     }
     return copy_out(out, buf, cap, len);
-}
+} CRO_API_CATCH
 
 static int finish_parse(const identity::GpuInfoResult& r, char* buf, size_t cap, size_t* len) {
     if (r.code != CRO_OK) {
@@ -102,108 +130,108 @@ static int finish_parse(const identity::GpuInfoResult& r, char* buf, size_t cap,
 }
 
 int cro_parse_gpu_csv(const char* std_out, const char* std_err, const char* exec_err, const char* query,
-                      char* buf, size_t cap, size_t* len) {
+                      char* buf, size_t cap, size_t* len) try {
     if (!query) return CRO_ERR_INVALID_ARG;
     return finish_parse(identity::getGPUInfoFromNvidiaSmiOutput(S(std_out), S(std_err), exec_err, query),
                         buf, cap, len);
-}
+} CRO_API_CATCH
 
 int cro_parse_proc_csv(const char* std_out, const char* std_err, const char* exec_err, const char* query,
-                       char* buf, size_t cap, size_t* len) {
+                       char* buf, size_t cap, size_t* len) try {
     if (!query) return CRO_ERR_INVALID_ARG;
     return finish_parse(identity::getGPUInfoFromProcOutput(S(std_out), S(std_err), exec_err, query), buf,
                         cap, len);
-}
+} CRO_API_CATCH
 
-int cro_proc_information_to_line(const char* text, char* buf, size_t cap, size_t* len) {
+int cro_proc_information_to_line(const char* text, char* buf, size_t cap, size_t* len) try {
     if (!text) return CRO_ERR_INVALID_ARG;
     return copy_out(identity::ProcInformationToLine(text), buf, cap, len);
-}
+} CRO_API_CATCH
 
-int cro_check_gpu_visible(const cro_dev_info* devs, int n, const char* device_id, int* visible) {
+int cro_check_gpu_visible(const cro_dev_info* devs, int n, const char* device_id, int* visible) try {
     if (!visible || !device_id || (n > 0 && !devs)) return CRO_ERR_INVALID_ARG;
     *visible = identity::CheckGPUVisible(devs, n, device_id) ? 1 : 0;
     return CRO_OK;
-}
+} CRO_API_CATCH
 
-int cro_normalize(int kind, const char* in, char* buf, size_t cap, size_t* len) {
+int cro_normalize(int kind, const char* in, char* buf, size_t cap, size_t* len) try {
     if (!in) return CRO_ERR_INVALID_ARG;
     std::string out;
     int rc = identity::Normalize(kind, in, &out);
     if (rc) return rc;
     return copy_out(out, buf, cap, len);
-}
+} CRO_API_CATCH
 
-int cro_probe_device(cro_ctx* ctx, int dev_index, cro_probe_result* out) {
+int cro_probe_device(cro_ctx* ctx, int dev_index, cro_probe_result* out) try {
     if (!ctx) return CRO_ERR_INVALID_ARG;
     return ctx_probe_device(ctx, dev_index, out);
-}
+} CRO_API_CATCH
 
-int cro_probe_begin(cro_ctx* ctx, int dev_index) { return ctx ? ctx_probe_begin(ctx, dev_index) : CRO_ERR_INVALID_ARG; }
-int cro_probe_end(cro_ctx* ctx, int dev_index, cro_probe_result* out) {
+int cro_probe_begin(cro_ctx* ctx, int dev_index) try { return ctx ? ctx_probe_begin(ctx, dev_index) : CRO_ERR_INVALID_ARG; } CRO_API_CATCH
+int cro_probe_end(cro_ctx* ctx, int dev_index, cro_probe_result* out) try {
     return ctx ? ctx_probe_end(ctx, dev_index, out) : CRO_ERR_INVALID_ARG;
-}
+} CRO_API_CATCH
 
-int cro_probe_all(cro_ctx* ctx, cro_probe_result* out, int cap, int* n) {
+int cro_probe_all(cro_ctx* ctx, cro_probe_result* out, int cap, int* n) try {
     return ctx_probe_all(ctx, out, cap, n);
-}
+} CRO_API_CATCH
 
-int cro_result_device_ptr(cro_ctx* ctx, int dev_index, uint64_t* dptr) {
+int cro_result_device_ptr(cro_ctx* ctx, int dev_index, uint64_t* dptr) try {
     if (!ctx || !dptr || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return CRO_ERR_INVALID_ARG;
     *dptr = (uint64_t)(uintptr_t)ctx->devs[(size_t)dev_index]->d_result;
     return CRO_OK;
-}
+} CRO_API_CATCH
 
-int cro_hbm_fill(cro_ctx* ctx, int i, cro_sweep_result* out) { return ctx ? ctx_fill(ctx, i, 1, out) : CRO_ERR_INVALID_ARG; }
-int cro_hbm_fill_loop(cro_ctx* ctx, int i, uint32_t iters, cro_sweep_result* out) {
+int cro_hbm_fill(cro_ctx* ctx, int i, cro_sweep_result* out) try { return ctx ? ctx_fill(ctx, i, 1, out) : CRO_ERR_INVALID_ARG; } CRO_API_CATCH
+int cro_hbm_fill_loop(cro_ctx* ctx, int i, uint32_t iters, cro_sweep_result* out) try {
     return ctx ? ctx_fill(ctx, i, iters, out) : CRO_ERR_INVALID_ARG;
-}
-int cro_hbm_read_checksum(cro_ctx* ctx, int i, uint32_t variant, cro_sweep_result* out) {
+} CRO_API_CATCH
+int cro_hbm_read_checksum(cro_ctx* ctx, int i, uint32_t variant, cro_sweep_result* out) try {
     return ctx ? ctx_read(ctx, i, variant, 1, false, out) : CRO_ERR_INVALID_ARG;
-}
-int cro_hbm_read_checksum_dst(cro_ctx* ctx, int i, uint32_t variant, cro_sweep_result* out) {
+} CRO_API_CATCH
+int cro_hbm_read_checksum_dst(cro_ctx* ctx, int i, uint32_t variant, cro_sweep_result* out) try {
     return ctx ? ctx_read(ctx, i, variant, 1, true, out) : CRO_ERR_INVALID_ARG;
-}
-int cro_hbm_read_loop(cro_ctx* ctx, int i, uint32_t variant, uint32_t iters, cro_sweep_result* out) {
+} CRO_API_CATCH
+int cro_hbm_read_loop(cro_ctx* ctx, int i, uint32_t variant, uint32_t iters, cro_sweep_result* out) try {
     return ctx ? ctx_read(ctx, i, variant, iters, false, out) : CRO_ERR_INVALID_ARG;
-}
-int cro_hbm_copy(cro_ctx* ctx, int i, uint32_t variant, cro_sweep_result* out) {
+} CRO_API_CATCH
+int cro_hbm_copy(cro_ctx* ctx, int i, uint32_t variant, cro_sweep_result* out) try {
     return ctx ? ctx_copy(ctx, i, variant, 1, out) : CRO_ERR_INVALID_ARG;
-}
-int cro_hbm_copy_loop(cro_ctx* ctx, int i, uint32_t variant, uint32_t iters, cro_sweep_result* out) {
+} CRO_API_CATCH
+int cro_hbm_copy_loop(cro_ctx* ctx, int i, uint32_t variant, uint32_t iters, cro_sweep_result* out) try {
     return ctx ? ctx_copy(ctx, i, variant, iters, out) : CRO_ERR_INVALID_ARG;
-}
-int cro_hbm_expected_checksum(cro_ctx* ctx, int i, cro_sweep_result* out) {
+} CRO_API_CATCH
+int cro_hbm_expected_checksum(cro_ctx* ctx, int i, cro_sweep_result* out) try {
     return ctx ? ctx_expected(ctx, i, out) : CRO_ERR_INVALID_ARG;
-}
-int cro_inject_fault(cro_ctx* ctx, int i, uint64_t word, uint64_t mask) {
+} CRO_API_CATCH
+int cro_inject_fault(cro_ctx* ctx, int i, uint64_t word, uint64_t mask) try {
     return ctx ? ctx_inject(ctx, i, word, mask) : CRO_ERR_INVALID_ARG;
-}
-int cro_read_words(cro_ctx* ctx, int i, uint64_t first, uint64_t n, uint64_t* out) {
+} CRO_API_CATCH
+int cro_read_words(cro_ctx* ctx, int i, uint64_t first, uint64_t n, uint64_t* out) try {
     return ctx ? ctx_read_words(ctx, i, first, n, out) : CRO_ERR_INVALID_ARG;
-}
-int cro_device_seed(cro_ctx* ctx, int i, uint64_t* seed) {
+} CRO_API_CATCH
+int cro_device_seed(cro_ctx* ctx, int i, uint64_t* seed) try {
     if (!ctx || !seed || i < 0 || i >= (int)ctx->devs.size()) return CRO_ERR_INVALID_ARG;
     *seed = ctx->devs[(size_t)i]->seed;
     return CRO_OK;
-}
+} CRO_API_CATCH
 uint64_t cro_launch_count(cro_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 // ---- emitters --------------------------------------------------------------
 
 int cro_emit_status_json(const char* state, const char* error, const char* device_id,
-                         const char* cdi_device_id, char* buf, size_t cap, size_t* len) {
+                         const char* cdi_device_id, char* buf, size_t cap, size_t* len) try {
     controller::ComposableResourceStatus st;
     st.State = S(state);
     st.Error = S(error);
     st.DeviceID = S(device_id);
     st.CDIDeviceID = S(cdi_device_id);
     return copy_out(st.MarshalJSON(), buf, cap, len);
-}
+} CRO_API_CATCH
 
 int cro_emit_scalar_status_json(const char* state, const char* device_id, const char* cdi_device_id,
                                 const char* node_name, const char* error, char* buf, size_t cap,
-                                size_t* len) {
+                                size_t* len) try {
     // api/v1alpha1/composabilityrequest_types.go:74-80 (declaration order)
     gojson::Writer w;
     w.begin_object();
@@ -214,31 +242,31 @@ int cro_emit_scalar_status_json(const char* state, const char* device_id, const 
     w.field_omitempty("error", S(error));
     w.end_object();
     return copy_out(w.str(), buf, cap, len);
-}
+} CRO_API_CATCH
 
 int cro_emit_fm_scale_up(const char* tenant_uuid, const char* mach_uuid, const char* res_type,
-                         const char* model, char* buf, size_t cap, size_t* len) {
+                         const char* model, char* buf, size_t cap, size_t* len) try {
     return copy_out(fabric::FMScaleUpBody(S(tenant_uuid), S(mach_uuid), S(res_type), S(model)), buf, cap, len);
-}
+} CRO_API_CATCH
 
 int cro_emit_fm_scale_down(const char* tenant_uuid, const char* mach_uuid, const char* res_type,
-                           const char* res_uuid, char* buf, size_t cap, size_t* len) {
+                           const char* res_uuid, char* buf, size_t cap, size_t* len) try {
     return copy_out(fabric::FMScaleDownBody(S(tenant_uuid), S(mach_uuid), S(res_type), S(res_uuid)), buf, cap, len);
-}
+} CRO_API_CATCH
 
-int cro_emit_cm_scale_up(const char* spec_uuid, int device_count, char* buf, size_t cap, size_t* len) {
+int cro_emit_cm_scale_up(const char* spec_uuid, int device_count, char* buf, size_t cap, size_t* len) try {
     return copy_out(fabric::CMScaleUpBody(S(spec_uuid), device_count), buf, cap, len);
-}
+} CRO_API_CATCH
 
 int cro_emit_cm_scale_down(const char* spec_uuid, int device_count, const char* device_id, char* buf,
-                           size_t cap, size_t* len) {
+                           size_t cap, size_t* len) try {
     return copy_out(fabric::CMScaleDownBody(S(spec_uuid), device_count, S(device_id)), buf, cap, len);
-}
+} CRO_API_CATCH
 
 int cro_emit_sunfish_request(const char* name, long long count, const char* proc_type, const char* model,
-                             char* buf, size_t cap, size_t* len) {
+                             char* buf, size_t cap, size_t* len) try {
     return copy_out(fabric::SunfishBody(S(name), count, S(proc_type), S(model)), buf, cap, len);
-}
+} CRO_API_CATCH
 
 }  // extern "C" (reopened below)
 std::map<std::string, std::string> cro::capi::probe_annotations(const cro_probe_result& r) {
@@ -276,16 +304,16 @@ std::map<std::string, std::string> cro::capi::probe_annotations(const cro_probe_
 
 extern "C" {
 
-int cro_emit_probe_annotations_json(const cro_probe_result* r, char* buf, size_t cap, size_t* len) {
+int cro_emit_probe_annotations_json(const cro_probe_result* r, char* buf, size_t cap, size_t* len) try {
     if (!r) return CRO_ERR_INVALID_ARG;
     gojson::Writer w;
     w.string_map(probe_annotations(*r));
     return copy_out(w.str(), buf, cap, len);
-}
+} CRO_API_CATCH
 
 int cro_fm_parse_scale_up_response(const char* body, const char* resource_name, const char* res_type,
                                    const char* model, char* device_id, size_t device_id_cap,
-                                   char* cdi_device_id, size_t cdi_cap, char* err_buf, size_t err_cap) {
+                                   char* cdi_device_id, size_t cdi_cap, char* err_buf, size_t err_cap) try {
     if (!body) return CRO_ERR_INVALID_ARG;
     std::string dev, cdi;
     controller::Error e = controller::FMScaleUpResponseToIDs(body, S(resource_name), S(res_type), S(model), &dev, &cdi);
@@ -296,12 +324,12 @@ int cro_fm_parse_scale_up_response(const char* body, const char* resource_name, 
     int rc = copy_out(dev, device_id, device_id_cap, nullptr);
     if (rc) return rc;
     return copy_out(cdi, cdi_device_id, cdi_cap, nullptr);
-}
+} CRO_API_CATCH
 
 int cro_cm_check_adding_resources(const char* machine_body, const char* existing_device_ids,
                                   const char* res_type, const char* model, char* spec_uuid, size_t spec_cap,
                                   int* device_count, char* device_id, size_t device_id_cap,
-                                  char* cdi_device_id, size_t cdi_cap, char* err_buf, size_t err_cap) {
+                                  char* cdi_device_id, size_t cdi_cap, char* err_buf, size_t err_cap) try {
     if (!machine_body) return CRO_ERR_INVALID_ARG;
     std::vector<std::string> existing;
     if (existing_device_ids) existing = identity::Split(existing_device_ids, "\n");
@@ -313,12 +341,12 @@ int cro_cm_check_adding_resources(const char* machine_body, const char* existing
     if ((rc = copy_out(r.CDIDeviceID, cdi_device_id, cdi_cap, nullptr))) return rc;
     copy_out(r.err.ok() ? std::string() : r.err.msg, err_buf, err_cap, nullptr);
     return r.err.ok() ? CRO_OK : CRO_ERR_PARSE;
-}
+} CRO_API_CATCH
 
 // ---- fabric wire codec ---------------------------------------------------------------
 
 int cro_fabric_check_resource(const char* kind, const char* machine_body, const char* res_type, const char* model,
-                              const char* device_id, char* err_buf, size_t err_cap) {
+                              const char* device_id, char* err_buf, size_t err_cap) try {
     if (!kind || !machine_body) return CRO_ERR_INVALID_ARG;
     controller::Error e;
     if (S(kind) == "fm") e = fabric::FMCheckResource(machine_body, S(res_type), S(model), S(device_id));
@@ -326,10 +354,10 @@ int cro_fabric_check_resource(const char* kind, const char* machine_body, const 
     else return CRO_ERR_INVALID_ARG;
     copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
     return e.ok() ? CRO_OK : CRO_ERR_EXEC;
-}
+} CRO_API_CATCH
 
 int cro_fabric_get_resources(const char* kind, const char* machine_body, const char* node_name, const char* machine_uuid,
-                             char* buf, size_t cap, size_t* len) {
+                             char* buf, size_t cap, size_t* len) try {
     if (!kind || !machine_body) return CRO_ERR_INVALID_ARG;
     std::vector<fabric::DeviceInfo> v;
     controller::Error e;
@@ -341,7 +369,7 @@ int cro_fabric_get_resources(const char* kind, const char* machine_body, const c
         return CRO_ERR_PARSE;
     }
     return copy_out(fabric::DeviceInfosToJson(v), buf, cap, len);
-}
+} CRO_API_CATCH
 
 // ---- detach-side pre-flight -------------------------------------------------------
 
@@ -352,30 +380,30 @@ static int finish_err(const controller::Error& e, char* err_buf, size_t err_cap)
 
 int cro_check_no_gpu_loads(const char* std_out, const char* std_err, const char* exec_err, const char* pod_name,
                            const char* node_name, const char* target_uuid, int driver_enabled, char* err_buf,
-                           size_t err_cap) {
+                           size_t err_cap) try {
     std::string uuid = S(target_uuid);
     return finish_err(detach::CheckNoGPULoadsFromOutput(S(std_out), S(std_err), exec_err, S(pod_name), S(node_name),
                                                         target_uuid ? &uuid : nullptr, driver_enabled != 0),
                       err_buf, err_cap);
-}
+} CRO_API_CATCH
 
 int cro_check_gpu_drain_status(const char* std_out, const char* std_err, const char* exec_err, const char* node_name,
-                               const char* bus_id, int* draining, char* err_buf, size_t err_cap) {
+                               const char* bus_id, int* draining, char* err_buf, size_t err_cap) try {
     bool d = false;
     controller::Error e = detach::checkGPUDrainStatusFromOutput(S(std_out), S(std_err), exec_err, S(node_name), S(bus_id), &d);
     if (draining) *draining = d ? 1 : 0;
     return finish_err(e, err_buf, err_cap);
-}
+} CRO_API_CATCH
 
 int cro_check_device_file_scan(const char* std_out, const char* std_err, const char* exec_err, int rke2, char* err_buf,
-                               size_t err_cap) {
+                               size_t err_cap) try {
     return finish_err(detach::CheckDeviceFileScanResult(S(std_out), S(std_err), exec_err, rke2 != 0), err_buf, err_cap);
-}
+} CRO_API_CATCH
 
-int cro_scan_device_file_holders(const char* proc_root, const char* target, int rke2, char* buf, size_t cap, size_t* len) {
+int cro_scan_device_file_holders(const char* proc_root, const char* target, int rke2, char* buf, size_t cap, size_t* len) try {
     if (!target) return CRO_ERR_INVALID_ARG;
     return copy_out(detach::ScanDeviceFileHolders(S(proc_root), target, rke2 != 0), buf, cap, len);
-}
+} CRO_API_CATCH
 
 // ---- in-memory cluster -----------------------------------------------------------
 
@@ -384,7 +412,7 @@ struct cro_sim {
     std::mutex mu;
 };
 
-int cro_sim_create(cro_ctx* ctx, const char* config_json, cro_sim** out) {
+int cro_sim_create(cro_ctx* ctx, const char* config_json, cro_sim** out) try {
     if (!out) return CRO_ERR_INVALID_ARG;
     std::string perr;
     gojson::ValuePtr cfg = gojson::parse(config_json ? config_json : "{}", &perr);
@@ -393,7 +421,7 @@ int cro_sim_create(cro_ctx* ctx, const char* config_json, cro_sim** out) {
     s->cluster.reset(new sim::Cluster(ctx, *cfg));
     *out = s;
     return CRO_OK;
-}
+} CRO_API_CATCH
 void cro_sim_destroy(cro_sim* s) { delete s; }
 
 static int sim_json_call(cro_sim* s, const char* json, char* err_buf, size_t err_cap,
@@ -410,38 +438,38 @@ static int sim_json_call(cro_sim* s, const char* json, char* err_buf, size_t err
     copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
     return e.ok() ? CRO_OK : CRO_ERR_INVALID_ARG;
 }
-int cro_sim_apply(cro_sim* s, const char* json, char* err_buf, size_t err_cap) {
+int cro_sim_apply(cro_sim* s, const char* json, char* err_buf, size_t err_cap) try {
     return sim_json_call(s, json, err_buf, err_cap, &sim::Cluster::Apply);
-}
-int cro_sim_plant(cro_sim* s, const char* json, char* err_buf, size_t err_cap) {
+} CRO_API_CATCH
+int cro_sim_plant(cro_sim* s, const char* json, char* err_buf, size_t err_cap) try {
     return sim_json_call(s, json, err_buf, err_cap, &sim::Cluster::Plant);
-}
-int cro_sim_delete(cro_sim* s, const char* name) {
+} CRO_API_CATCH
+int cro_sim_delete(cro_sim* s, const char* name) try {
     if (!s || !name) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(s->mu);
     return s->cluster->Delete(name).ok() ? CRO_OK : CRO_ERR_INVALID_ARG;
-}
-int cro_sim_run(cro_sim* s, long long max_reconciles, char* buf, size_t cap, size_t* len) {
+} CRO_API_CATCH
+int cro_sim_run(cro_sim* s, long long max_reconciles, char* buf, size_t cap, size_t* len) try {
     if (!s) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(s->mu);
     s->cluster->Run(max_reconciles > 0 ? max_reconciles : (1ll << 40));
     return copy_out(s->cluster->StatsJSON(), buf, cap, len);
-}
-int cro_sim_reconcile_request(cro_sim* s, const char* name, char* err_buf, size_t err_cap) {
+} CRO_API_CATCH
+int cro_sim_reconcile_request(cro_sim* s, const char* name, char* err_buf, size_t err_cap) try {
     if (!s || !name) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(s->mu);
     controller::Error e = s->cluster->ReconcileRequestOnce(name);
     copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
     return e.ok() ? CRO_OK : CRO_ERR_EXEC;
-}
-int cro_sim_reconcile_resource(cro_sim* s, const char* name, char* err_buf, size_t err_cap) {
+} CRO_API_CATCH
+int cro_sim_reconcile_resource(cro_sim* s, const char* name, char* err_buf, size_t err_cap) try {
     if (!s || !name) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(s->mu);
     controller::Error e = s->cluster->ReconcileResourceOnce(name);
     copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
     return e.ok() ? CRO_OK : CRO_ERR_EXEC;
-}
-int cro_sim_sync_upstream(cro_sim* s, const char* devices_json, long long now_s, char* err_buf, size_t err_cap) {
+} CRO_API_CATCH
+int cro_sim_sync_upstream(cro_sim* s, const char* devices_json, long long now_s, char* err_buf, size_t err_cap) try {
     if (!s || !devices_json) return CRO_ERR_INVALID_ARG;
     std::string perr;
     gojson::ValuePtr v = gojson::parse(devices_json, &perr);
@@ -453,11 +481,11 @@ int cro_sim_sync_upstream(cro_sim* s, const char* devices_json, long long now_s,
     controller::Error e = s->cluster->SyncUpstream(*v, now_s);
     copy_out(e.ok() ? std::string() : e.msg, err_buf, err_cap, nullptr);
     return e.ok() ? CRO_OK : CRO_ERR_EXEC;
-}
-int cro_sim_dump(cro_sim* s, char* buf, size_t cap, size_t* len) {
+} CRO_API_CATCH
+int cro_sim_dump(cro_sim* s, char* buf, size_t cap, size_t* len) try {
     if (!s) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(s->mu);
     return copy_out(s->cluster->DumpJSON(), buf, cap, len);
-}
+} CRO_API_CATCH
 
 }  // extern "C"

@@ -38,6 +38,13 @@ inline std::string hex16(uint64_t v) {
     return b;
 }
 
+// No C++ exception may cross the C ABI (the caller is cgo / ctypes: unwinding into it is undefined).  Every
+// `int cro_*` entry point is a function-try-block ending in CRO_API_CATCH; on_exception() rethrows to classify:
+// std::bad_alloc -> CRO_ERR_OOM, anything else -> CRO_ERR_INTERNAL, the what() text kept for the calling thread
+// (cro_last_error(NULL, ...)).  Defined in c_api.cu.
+int on_exception() noexcept;
+#define CRO_API_CATCH catch (...) { return ::cro::capi::on_exception(); }
+
 // cohdi.io/probe-* annotations of one result (defined in c_api.cu)
 std::map<std::string, std::string> probe_annotations(const cro_probe_result& r);
 

@@ -542,7 +542,7 @@ private:
 
 }  // namespace
 
-int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t cap, size_t* len) {
+int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t cap, size_t* len) try {
     if (!in_json) return CRO_ERR_INVALID_ARG;
     std::string perr;
     gojson::ValuePtr in = gojson::parse(in_json, &perr);
@@ -671,9 +671,9 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
     }
     w.end_object();
     return copy_out(w.str(), buf, cap, len);
-}
+} CRO_API_CATCH
 
-int cro_fabric_list_devices(const char* request_json, char* buf, size_t cap, size_t* len) {
+int cro_fabric_list_devices(const char* request_json, char* buf, size_t cap, size_t* len) try {
     if (!request_json) return CRO_ERR_INVALID_ARG;
     std::string perr;
     gojson::ValuePtr in = gojson::parse(request_json, &perr);
@@ -712,9 +712,9 @@ int cro_fabric_list_devices(const char* request_json, char* buf, size_t cap, siz
     w.end_array();
     w.end_object();
     return copy_out(w.str(), buf, cap, len);
-}
+} CRO_API_CATCH
 
-int cro_token_from_reply(const char* reply_json, char* buf, size_t cap, size_t* len) {
+int cro_token_from_reply(const char* reply_json, char* buf, size_t cap, size_t* len) try {
     if (!reply_json) return CRO_ERR_INVALID_ARG;
     std::string perr;
     gojson::ValuePtr in = gojson::parse(reply_json, &perr);
@@ -735,17 +735,17 @@ int cro_token_from_reply(const char* reply_json, char* buf, size_t cap, size_t* 
     w.field("expiry", e.ok() ? exp : 0LL);
     w.end_object();
     return copy_out(w.str(), buf, cap, len);
-}
+} CRO_API_CATCH
 
 // ---- node-side operations on the node itself ----------------------------------------
 
-int cro_scan_cmdline_for(const char* proc_root, const char* needle, int* found) {
+int cro_scan_cmdline_for(const char* proc_root, const char* needle, int* found) try {
     if (!needle || !found) return CRO_ERR_INVALID_ARG;
     *found = detach::ScanCmdlineFor(S(proc_root), needle).empty() ? 0 : 1;
     return CRO_OK;
-}
+} CRO_API_CATCH
 
-int cro_local_node_op(cro_ctx* ctx, const char* request_json, char* buf, size_t cap, size_t* len) {
+int cro_local_node_op(cro_ctx* ctx, const char* request_json, char* buf, size_t cap, size_t* len) try {
     if (!request_json) return CRO_ERR_INVALID_ARG;
     std::string perr;
     gojson::ValuePtr in = gojson::parse(request_json, &perr);
@@ -795,6 +795,6 @@ int cro_local_node_op(cro_ctx* ctx, const char* request_json, char* buf, size_t 
     w.end_array();
     w.end_object();
     return copy_out(w.str(), buf, cap, len);
-}
+} CRO_API_CATCH
 
 }  // extern "C"

@@ -292,6 +292,9 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
 
 thread_local std::string g_init_error;
 const std::string& last_init_error() { return g_init_error; }
+void set_thread_error(const std::string& m) noexcept {
+    try { g_init_error = m; } catch (...) {}
+}
 
 }  // namespace cro
 cro_ctx::~cro_ctx() {
@@ -877,11 +880,15 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
         std::vector<std::thread> th;
         for (int i = 0; i < n; ++i)
             th.emplace_back([&, i] {
-                Device* d = c->devs[(size_t)i].get();
-                std::lock_guard<std::mutex> g(d->mu);
-                drain_pending(c, d);
-                d->have_pending_result = false;
-                rcs[(size_t)i] = probe_locked(c, d, &res[(size_t)i]);
+                try {
+                    Device* d = c->devs[(size_t)i].get();
+                    std::lock_guard<std::mutex> g(d->mu);
+                    drain_pending(c, d);
+                    d->have_pending_result = false;
+                    rcs[(size_t)i] = probe_locked(c, d, &res[(size_t)i]);
+                } catch (...) {                   // an exception leaving a thread would terminate the host process
+                    rcs[(size_t)i] = CRO_ERR_INTERNAL;
+                }
             });
         for (auto& t : th) t.join();
     }

@@ -89,7 +89,8 @@ struct cro_ctx {
 
 namespace cro {
 
-const std::string& last_init_error();   // calling thread's last failed ctx_create
+const std::string& last_init_error();   // calling thread's last failed ctx_create (or exception stopped at the C ABI)
+void set_thread_error(const std::string& m) noexcept;
 int ctx_create(const cro_opts* o, cro_ctx** out);
 void ctx_destroy(cro_ctx* c);
 int ctx_probe_device(cro_ctx* c, int idx, cro_probe_result* out);

@@ -482,6 +482,11 @@ const char *cro_strerror(int code);
  * calling thread's last failed cro_probe_init (which returns no context), e.g.
  * the cudaMalloc that could not be satisfied. */
 int  cro_last_error(cro_ctx *ctx, char *buf, size_t cap);
+/* No C++ exception crosses this ABI: every entry point catches, returns CRO_ERR_OOM (std::bad_alloc) or
+ * CRO_ERR_INTERNAL (anything else) and keeps the text for cro_last_error(NULL, ...).  This self-test throws on purpose
+ * behind the same barrier — kind 0: std::runtime_error, 1: std::bad_alloc, 2: a non-std exception — and returns what the
+ * barrier made of it; any other kind returns CRO_OK without throwing. */
+int  cro_selftest_exception_barrier(int kind);
 const char *cro_version(void);
 
 #ifdef __cplusplus

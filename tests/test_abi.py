@@ -103,3 +103,38 @@ def test_product_never_touches_the_oracle():
     so = os.path.join(pkg, "libcroprobe.so")
     out = subprocess.run(["nm", "-D", so], capture_output=True, text=True).stdout
     assert "oracle_" not in out
+
+
+def test_no_exception_crosses_the_abi(cro):
+    """Every entry point is a function-try-block (c_api_util.hpp: CRO_API_CATCH): an exception thrown behind the ABI comes
+    back as a code, with its text kept for the calling thread."""
+    import ctypes
+    buf = ctypes.create_string_buffer(256)
+    assert cro.lib.cro_selftest_exception_barrier(0) == cro.ERR_INTERNAL
+    cro.lib.cro_last_error(None, buf, len(buf))
+    assert buf.value == b"internal error: exception barrier self-test"
+    assert cro.lib.cro_selftest_exception_barrier(1) == cro.ERR_OOM
+    cro.lib.cro_last_error(None, buf, len(buf))
+    assert buf.value == b"out of host memory"
+    assert cro.lib.cro_selftest_exception_barrier(2) == cro.ERR_INTERNAL
+    assert cro.lib.cro_selftest_exception_barrier(7) == cro.OK
+
+
+def test_only_the_c_abi_is_exported():
+    """csrc/croprobe.map: the C++ internals and the static CUDA runtime stay local to the library."""
+    import subprocess
+    out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "composable-resource-operator_b200", "libcroprobe.so")], text=True)
+    names = [ln.split()[-1] for ln in out.splitlines() if ln.strip()]
+    assert names and all(n.startswith("cro_") for n in names), [n for n in names if not n.startswith("cro_")][:5]
+
+
+def test_every_int_entry_point_has_the_barrier():
+    """Source check: each `int cro_*(...)` definition in the extern "C" units opens with `try {` and ends in CRO_API_CATCH."""
+    import re
+    for unit in ("c_api.cu", "harness.cu"):
+        text = open(os.path.join(ROOT, "composable-resource-operator_b200", "csrc", unit)).read()
+        defs = re.findall(r"^int\s+(cro_\w+)\([^;{]*\)\s*(try\s*)?\{", text, re.M)
+        assert defs, unit
+        missing = [name for name, t in defs if not t]
+        assert not missing, (unit, missing)
+        assert text.count("CRO_API_CATCH") == len(defs), (unit, text.count("CRO_API_CATCH"), len(defs))
