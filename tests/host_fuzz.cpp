@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "detach.hpp"
@@ -20,7 +21,7 @@
 
 using namespace cro;
 
-static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+static thread_local uint64_t rng_state = 0x9E3779B97F4A7C15ull;
 static uint64_t rnd() {
     rng_state ^= rng_state << 13;
     rng_state ^= rng_state >> 7;
@@ -82,7 +83,7 @@ static std::string mutate(std::string s) {
     return s;
 }
 
-static size_t sink = 0;   // keeps results alive
+static thread_local size_t sink = 0;   // keeps results alive
 
 // Node-side flows (csrc/gpus.cpp) with a pod-exec that answers every request with the fuzz input:
 // whatever nvidia-smi / lsmod / the scans print, the decision code must stay in bounds.
@@ -248,10 +249,23 @@ int main(int argc, char** argv) {
     one("{\"a\":" + std::string(1 << 18, '{'), "");
     one(std::string(1 << 20, ','), "");                      // a million empty CSV fields
     one(std::string(1 << 16, '\n'), "");
-    for (long i = 0; i < iters; ++i) {
-        std::string s = mutate(kCorpus[rnd() % n]);
-        if ((rnd() & 3) == 0) s = mutate(s);
-        one(s, (rnd() & 7) == 0 ? mutate("NVIDIA-SMI has failed") : "");
+    auto run = [&](long count, uint64_t seed) {
+        rng_state = seed;
+        for (long i = 0; i < count; ++i) {
+            std::string s = mutate(kCorpus[rnd() % n]);
+            if ((rnd() & 3) == 0) s = mutate(s);
+            one(s, (rnd() & 7) == 0 ? mutate("NVIDIA-SMI has failed") : "");
+        }
+    };
+    // argv[2] = N: the same stream of inputs split over N threads calling the entry points at once (ThreadSanitizer
+    // build: the host functions keep no shared mutable state — lazily built tables must be built race-free)
+    const int threads = argc > 2 ? std::atoi(argv[2]) : 1;
+    if (threads > 1) {
+        std::vector<std::thread> th;
+        for (int k = 0; k < threads; ++k) th.emplace_back(run, iters / threads, 0x9E3779B97F4A7C15ull + (uint64_t)k * 0x1234567ull);
+        for (auto& x : th) x.join();
+    } else {
+        run(iters, rng_state);
     }
     std::printf("host fuzz ok: %ld inputs, sink %zu\n", iters, sink);
     return 0;

@@ -27,3 +27,21 @@ def test_parsers_survive_mutation_fuzz_under_asan_ubsan(tmp_path):
     assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
     assert "host fuzz ok: 20000 inputs" in run.stdout
     assert "runtime error" not in run.stderr and "AddressSanitizer" not in run.stderr
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="g++ unavailable")
+def test_concurrent_callers_under_tsan(tmp_path):
+    """Eight threads drive the same host functions at once under ThreadSanitizer: the parsers, clients and node-side flows
+    keep no shared mutable state (the Go host calls them from whatever OS thread a goroutine happens to be on)."""
+    exe = str(tmp_path / "host_fuzz_tsan")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-fno-omit-frame-pointer", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
+           os.path.join(ROOT, "tests", "host_fuzz.cpp")] + [os.path.join(CSRC, s) for s in HOST_SOURCES] + ["-o", exe, "-ldl", "-lpthread"]
+    build = subprocess.run(cmd, capture_output=True, text=True)
+    if build.returncode != 0 and "tsan" in build.stderr.lower():
+        pytest.skip("libtsan not installed: " + build.stderr[-200:])
+    assert build.returncode == 0, build.stderr[-2000:]
+    run = subprocess.run([exe, "4000", "8"], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0:report_signal_unsafe=0"))
+    assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
+    assert "host fuzz ok: 4000 inputs" in run.stdout
+    assert "ThreadSanitizer" not in run.stderr, run.stderr[-3000:]
