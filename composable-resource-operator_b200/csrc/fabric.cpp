@@ -32,8 +32,8 @@ Error notFound(const std::string& deviceID) {
 Error FMCheckResource(const std::string& body, const std::string& specType, const std::string& specModel,
                       const std::string& deviceID) {
     std::string perr;
-    gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!gojson::decodesInto(root, body, gotypes::FMGetMachineResponse(), &perr))
+    gojson::ValuePtr root = gojson::DecodeAs(gojson::parse(body, &perr), body, gotypes::FMGetMachineResponse(), &perr);
+    if (!root)
         return Error::New("failed to unmarshal FM get machine response body into machineData: " + perr);
     const Value* machines = arr(root->get("data"), "machines");
     if (!machines || machines->arr.empty())   // fm/client.go:331 indexes Machines[0] unguarded
@@ -58,8 +58,8 @@ Error FMCheckResource(const std::string& body, const std::string& specType, cons
 Error FMGetResources(const std::string& body, const std::string& nodeName, const std::string& machineID,
                      std::vector<DeviceInfo>* out) {
     std::string perr;
-    gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!gojson::decodesInto(root, body, gotypes::FMGetMachineResponse(), &perr))
+    gojson::ValuePtr root = gojson::DecodeAs(gojson::parse(body, &perr), body, gotypes::FMGetMachineResponse(), &perr);
+    if (!root)
         return Error::New("failed to unmarshal FM get machine response body into machineData: " + perr);
     const Value* machines = arr(root->get("data"), "machines");
     if (!machines || machines->arr.empty()) return Error::Nil();   // fm/client.go:385-387
@@ -83,8 +83,8 @@ Error FMGetResources(const std::string& body, const std::string& nodeName, const
 Error CMCheckResource(const std::string& body, const std::string& specType, const std::string& specModel,
                       const std::string& deviceID) {
     std::string perr;
-    gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!gojson::decodesInto(root, body, gotypes::CMMachineData(), &perr))
+    gojson::ValuePtr root = gojson::DecodeAs(gojson::parse(body, &perr), body, gotypes::CMMachineData(), &perr);
+    if (!root)
         return Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
     const Value* data = root->get("data");
     const Value* cluster = data ? data->get("cluster") : nullptr;
@@ -113,8 +113,8 @@ Error CMCheckResource(const std::string& body, const std::string& specType, cons
 Error CMGetResources(const std::string& body, const std::string& nodeName, const std::string& machineID,
                      std::vector<DeviceInfo>* out) {
     std::string perr;
-    gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!gojson::decodesInto(root, body, gotypes::CMMachineData(), &perr))
+    gojson::ValuePtr root = gojson::DecodeAs(gojson::parse(body, &perr), body, gotypes::CMMachineData(), &perr);
+    if (!root)
         return Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
     const Value* data = root->get("data");
     const Value* cluster = data ? data->get("cluster") : nullptr;

@@ -695,6 +695,92 @@ std::string TypeMismatch(const Value& root, const std::string& text, const GoTyp
     return w.first;
 }
 
+namespace {
+ValuePtr zeroOf(const GoType& t) {
+    ValuePtr v = std::make_shared<Value>();
+    switch (t.kind) {
+        case GoType::String: v->kind = Value::String; break;
+        case GoType::Int: v->kind = Value::Number; v->is_int = true; break;
+        case GoType::Bool: v->kind = Value::Bool; break;
+        case GoType::Struct: v->kind = Value::Object; break;
+        default: v->kind = Value::Null; break;          // nil slice / map / RawMessage
+    }
+    return v;
+}
+
+// dst: what the Go variable holds so far (nullptr = zero value).  Nodes reachable from dst are either leaves shared
+// with the parse tree (never written) or containers made here.
+void mergeInto(ValuePtr& dst, const ValuePtr& src, const GoType& t) {
+    if (src->kind == Value::Null) return;
+    switch (t.kind) {
+        case GoType::String: if (src->kind == Value::String) dst = src; return;
+        case GoType::Bool: if (src->kind == Value::Bool) dst = src; return;
+        case GoType::Int: if (src->kind == Value::Number && src->is_int) dst = src; return;
+        case GoType::RawMessage: dst = src; return;
+        case GoType::MapOfAny: {
+            if (src->kind != Value::Object) return;
+            ValuePtr m = std::make_shared<Value>();
+            m->kind = Value::Object;
+            if (dst && dst->kind == Value::Object) m->obj = dst->obj;           // an existing map is kept and written into
+            for (const auto& kv : src->obj) {
+                bool hit = false;
+                for (auto& e : m->obj)
+                    if (e.first == kv.first) { e.second = kv.second; hit = true; }
+                if (!hit) m->obj.push_back(kv);
+            }
+            dst = m;
+            return;
+        }
+        case GoType::Slice: {
+            if (src->kind != Value::Array) return;
+            ValuePtr a = std::make_shared<Value>();
+            a->kind = Value::Array;
+            for (size_t k = 0; k < src->arr.size(); ++k) {
+                ValuePtr e = (dst && dst->kind == Value::Array && k < dst->arr.size()) ? dst->arr[k] : nullptr;
+                if (e && e->kind == Value::Object) {            // a container made by an earlier pass: copy before writing
+                    ValuePtr c = std::make_shared<Value>(*e);
+                    e = c;
+                }
+                mergeInto(e, src->arr[k], *t.elem);
+                a->arr.push_back(e ? e : zeroOf(*t.elem));
+            }
+            dst = a;
+            return;
+        }
+        case GoType::Struct: {
+            if (src->kind != Value::Object) return;
+            ValuePtr o = std::make_shared<Value>();
+            o->kind = Value::Object;
+            if (dst && dst->kind == Value::Object) o->obj = dst->obj;
+            std::vector<const char*> tags;
+            for (const auto& f : t.fields) tags.push_back(f.first.c_str());
+            for (const auto& kv : src->obj) {
+                const int fi = MatchField(kv.first, tags.data(), tags.size());
+                if (fi < 0) continue;
+                const std::string& tag = t.fields[fi].first;
+                ValuePtr* slot = nullptr;
+                for (auto& e : o->obj)
+                    if (e.first == tag) slot = &e.second;
+                ValuePtr cur = slot ? *slot : nullptr;
+                mergeInto(cur, kv.second, *t.fields[fi].second);
+                if (!cur) continue;                              // nothing landed (null, or a skipped mismatch)
+                if (slot) *slot = cur;
+                else o->obj.emplace_back(tag, cur);
+            }
+            dst = o;
+            return;
+        }
+    }
+}
+}  // namespace
+
+ValuePtr DecodeAs(const ValuePtr& root, const std::string& text, const GoType& t, std::string* perr) {
+    if (!decodesInto(root, text, t, perr)) return nullptr;
+    ValuePtr out;
+    mergeInto(out, root, t);
+    return out ? out : zeroOf(t);
+}
+
 bool decodesInto(const ValuePtr& root, const std::string& text, const GoType& t, std::string* perr) {
     if (!root) return false;                        // *perr already holds the syntax error
     const std::string e = TypeMismatch(*root, text, t);

@@ -116,6 +116,12 @@ struct GoType {
 std::string TypeMismatch(const Value& root, const std::string& text, const GoType& t);
 // rootOk + TypeMismatch: can `root` (a parse() result) be decoded into T?  False with *perr = Unmarshal's message.
 bool decodesInto(const ValuePtr& root, const std::string& text, const GoType& t, std::string* perr);
+// What a zero T holds after json.Unmarshal(text, &v), as a canonical tree: a struct is an Object whose keys are
+// exactly the tags of the members that were set; null left a field alone; a repeated struct member merged into
+// what an earlier one stored; a repeated slice member was decoded over the earlier elements and truncated to the
+// new length (decode.go object() / array()); a null slice element is the zero struct.  nullptr with *perr =
+// Unmarshal's message when `root` is null (syntax error already in *perr) or some value does not fit T.
+ValuePtr DecodeAs(const ValuePtr& root, const std::string& text, const GoType& t, std::string* perr);
 
 // encoding/json's field lookup for one input key: index of the tag that equals it, else of the one equal under
 // case folding, else -1.

@@ -295,8 +295,8 @@ CMRemovingResult CMCheckRemovingResources(const std::string& machineBody, const 
                                           const std::string& specModel, const std::string& deviceID) {
     CMRemovingResult r;
     std::string perr;
-    gojson::ValuePtr root = gojson::parse(machineBody, &perr);
-    if (!gojson::decodesInto(root, machineBody, gotypes::CMMachineData(), &perr)) {
+    gojson::ValuePtr root = gojson::DecodeAs(gojson::parse(machineBody, &perr), machineBody, gotypes::CMMachineData(), &perr);
+    if (!root) {
         r.err = Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
         return r;
     }
@@ -410,7 +410,7 @@ Error FMClient::RemoveResource(ComposableResource& instance) {
     e = getMachineInfo(machineID, &machineBody);
     if (!e.ok()) return e;
     std::string perr;
-    gojson::ValuePtr root = gojson::parse(machineBody, &perr);
+    gojson::ValuePtr root = gojson::DecodeAs(gojson::parse(machineBody, &perr), machineBody, gotypes::FMGetMachineResponse(), &perr);
     const Value* machines = arrOf(root ? root->get("data") : nullptr, "machines");
     if (!machines || machines->arr.empty())   // :231 indexes Machines[0] unguarded
         return Error::New("runtime error: index out of range [0] with length 0");

@@ -27,8 +27,8 @@ Error FMScaleUpResponseToIDs(const std::string& body, const std::string& instanc
     deviceID->clear();
     CDIDeviceID->clear();
     std::string perr;
-    gojson::ValuePtr root = gojson::parse(body, &perr);
-    if (!gojson::decodesInto(root, body, gotypes::FMScaleUpResponse(), &perr))
+    gojson::ValuePtr root = gojson::DecodeAs(gojson::parse(body, &perr), body, gotypes::FMScaleUpResponse(), &perr);
+    if (!root)
         return Error::New(
             "failed to unmarshal FM scaleup response body into scaleUpResponse. Original error: " + perr);
     const gojson::Value* data = root->get("data");
@@ -73,8 +73,8 @@ CMAddingResult CMCheckAddingResources(const std::string& machineBody,
                                       const std::string& specType, const std::string& specModel) {
     CMAddingResult out;
     std::string perr;
-    gojson::ValuePtr root = gojson::parse(machineBody, &perr);
-    if (!gojson::decodesInto(root, machineBody, gotypes::CMMachineData(), &perr)) {
+    gojson::ValuePtr root = gojson::DecodeAs(gojson::parse(machineBody, &perr), machineBody, gotypes::CMMachineData(), &perr);
+    if (!root) {
         out.err = Error::New("failed to unmarshal CM get machine response body into machineData: " + perr);
         return out;
     }

@@ -21,8 +21,12 @@ import ctypes
 import json
 import os
 import subprocess
+import sys
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import go_decode  # noqa: E402  (same directory; how encoding/json fills the wire structs)
 
 import numpy as np
 
@@ -338,16 +342,10 @@ def go_loads(text: str):
     return json.loads(text, object_pairs_hook=GoObj.from_pairs)
 
 
-def go_struct_loads(text: str):
-    """go_loads, then what a Go struct would hold: a null member leaves the field as it was (dropped here, so an
-    earlier duplicate or the zero value shows through) and a null slice element is the zero struct."""
-    def norm(v):
-        if isinstance(v, GoObj):
-            return GoObj.from_pairs([(k, norm(x)) for k, x in getattr(v, "pairs", list(v.items())) if x is not None])
-        if isinstance(v, list):
-            return [GoObj.from_pairs([]) if x is None else norm(x) for x in v]
-        return v
-    return norm(go_loads(text))
+def go_struct_loads(text: str, go_type: str):
+    """What a zero `go_type` holds after json.Unmarshal(text, &v): go_decode.decode_as over the wire-struct
+    descriptions (null leaves a field alone, repeated members merge, repeated slices decode over earlier elements)."""
+    return go_decode.decode_as(text, go_decode.TYPES[go_type])
 
 
 # --------------------------------------------------------------------------
@@ -355,7 +353,7 @@ def go_struct_loads(text: str):
 # --------------------------------------------------------------------------
 def fm_scale_up_response_to_ids(body: str, name: str, spec_type: str, spec_model: str) -> Tuple[str, str, str]:
     """internal/cdi/fti/fm/client.go:184-213.  Returns (deviceID, CDIDeviceID, err)."""
-    data = go_struct_loads(body)
+    data = go_struct_loads(body, "api.ScaleUpResponse")
     machines = (data.get("data") or {}).get("machines") or []
     if machines and (machines[0].get("resources") or []) and machines[0]["resources"][0].get("res_type", "") == spec_type:
         res = machines[0]["resources"][0]
@@ -386,7 +384,7 @@ def _op_status(op: str, device_id: str, where: str) -> str:
 
 def fabric_check_resource(kind: str, body: str, spec_type: str, spec_model: str, device_id: str) -> str:
     """FM: internal/cdi/fti/fm/client.go:314-359.  CM: internal/cdi/fti/cm/client.go:262-304."""
-    data = go_struct_loads(body)
+    data = go_struct_loads(body, "api.GetMachineResponse" if kind == "fm" else "api.MachineData")
     if kind == "fm":
         machines = (data.get("data") or {}).get("machines") or []
         if not machines:
@@ -415,7 +413,7 @@ def fabric_check_resource(kind: str, body: str, spec_type: str, spec_model: str,
 
 def fabric_get_resources(kind: str, body: str, node: str, machine_uuid: str) -> List[Dict[str, str]]:
     """FM: internal/cdi/fti/fm/client.go:385-410.  CM: internal/cdi/fti/cm/client.go:335-343."""
-    data = go_struct_loads(body)
+    data = go_struct_loads(body, "api.GetMachineResponse" if kind == "fm" else "api.MachineData")
     out = []
     if kind == "fm":
         machines = (data.get("data") or {}).get("machines") or []
@@ -517,7 +515,7 @@ def check_device_file_scan(std_out: str, std_err: str, exec_err: Optional[str], 
 def cm_check_adding_resources(machine_body: str, existing_device_ids: List[str], spec_type: str, spec_model: str):
     """internal/cdi/fti/cm/client.go:432-459 (checkAddingResources), :485-499 (isSpecMatch),
     :501-509 (findAvailableDevice).  Returns (specUUID, deviceCount, deviceID, CDIDeviceID, err)."""
-    data = go_struct_loads(machine_body)
+    data = go_struct_loads(machine_body, "api.MachineData")
     specs = ((((data.get("data") or {}).get("cluster") or {}).get("machine") or {}).get("resspecs")) or []
     for spec in specs:
         if spec.get("type", "") != spec_type:

@@ -128,3 +128,73 @@ def test_type_swaps(cro):
         assert got == oracle, (it, kind, state, body, got, oracle)
         tally["mismatch" if "cannot unmarshal" in oracle else "clean"] += 1
     assert tally["mismatch"] > 500 and tally["clean"] > 300, tally
+
+
+# ---- repeated members: encoding/json merges, it does not "take the last one" -----------------------------------
+def test_repeated_members_merge_like_go(cro):
+    # two "data" objects: the second one's machines array is decoded OVER the first one's elements, so element 0 keeps the
+    # resources it got first; the device is found although the last "data" alone does not hold it
+    first = json.loads(fm_machine_data([(RES, "gpu", "0", DEV, MODEL)]))["data"]
+    body = '{"data":%s,"DATA":{"machines":[{"mach_name":"renamed"}]}}' % json.dumps(first)
+    got, oracle = run(cro, "FM", "Online", body)
+    assert got == oracle == ""
+    # ... and a shorter second array truncates: the machine is gone
+    body = '{"data":%s,"data":{"machines":[]}}' % json.dumps(first)
+    got, oracle = run(cro, "FM", "Online", body)
+    assert got == oracle == "runtime error: index out of range [0] with length 0"
+    # null leaves what was there
+    body = '{"data":%s,"data":null}' % json.dumps(first)
+    got, oracle = run(cro, "FM", "Online", body)
+    assert got == oracle == ""
+    # CM: the op status arrives in a second copy of the device list, merged into the first device
+    cm = json.loads(cm_machine_data([(DEV, "ADD_COMPLETE", "", RES, "0")]))
+    specs = cm["data"]["cluster"]["machine"]["resspecs"]
+    at = [i for i, s in enumerate(specs) if s["devices"]][0]                 # the matching spec is not the first one:
+    patch_specs = [None] * at + [{"devices": [{"detail": {"res_op_status": "2"}}]}] + [None] * (len(specs) - at - 1)
+    patch = {"data": {"cluster": {"machine": {"resspecs": patch_specs}}}}     # null elements leave their slots alone
+    body = json.dumps(cm)[:-1] + "," + json.dumps(patch)[1:]
+    assert specs[at]["devices"][0]["detail"]["res_op_status"] == "0"
+    got, oracle = run(cro, "CM", "Online", body)
+    assert got == oracle == "the target gpu '%s' is showing a Critical status in CM" % DEV
+
+
+def test_duplicated_member_fuzz(cro):
+    """Valid replies where random subtrees are repeated under the same (or a case-variant) key, sometimes edited."""
+    rng = random.Random(4242)
+    seeds = {("CM", "Online"): cm_machine_data([(DEV, "ADD_COMPLETE", "", RES, "0")]),
+             ("CM", "Attaching"): cm_machine_data([(DEV, "ADD_COMPLETE", "", RES, "0")]),
+             ("FM", "Online"): fm_machine_data([(RES, "gpu", "0", DEV, MODEL)]),
+             ("FM", "Attaching"): [v for k, v in KATS["fixtures"]["fm_update_body"].items() if k != "_cite"][-1]}
+
+    def emit(v):
+        """json.dumps that repeats some object members"""
+        if isinstance(v, dict):
+            parts = []
+            for k, x in v.items():
+                parts.append('"%s":%s' % (k, emit(x)))
+                if rng.random() < 0.25:
+                    y = copy.deepcopy(x)
+                    r = rng.random()
+                    if r < 0.3:
+                        y = None
+                    elif r < 0.6 and isinstance(y, list):
+                        y = y[:rng.randrange(len(y) + 1)] + ([{}] if rng.random() < 0.3 else [])
+                    elif r < 0.8 and isinstance(y, dict) and y:
+                        y.pop(rng.choice(sorted(y)))
+                    elif isinstance(y, str):
+                        y = rng.choice([y, "", "2", "gpu", MODEL])
+                    parts.append('"%s":%s' % (k.upper() if rng.random() < 0.3 else k, emit(y)))
+            return "{" + ",".join(parts) + "}"
+        if isinstance(v, list):
+            return "[" + ",".join(emit(x) for x in v) + "]"
+        return json.dumps(v)
+
+    outcomes = set()
+    for it in range(800):
+        (kind, state), body = rng.choice(sorted(seeds.items()))
+        text = emit(json.loads(body))
+        json.loads(text)
+        got, oracle = run(cro, kind, state, text)
+        assert got == oracle, (it, kind, state, text, got, oracle)
+        outcomes.add(oracle[:40])
+    assert len(outcomes) >= 4, outcomes
