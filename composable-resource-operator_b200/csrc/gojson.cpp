@@ -231,6 +231,7 @@ long long Value::get_int(const std::string& k, long long dflt) const {
 }
 
 namespace {
+constexpr int kMaxTreeDepth = 512;       // recursion bound of the tree builder (and of ~Value)
 struct Parser {
     const std::string& t;
     size_t i = 0;
@@ -321,13 +322,39 @@ struct Parser {
         }
         return fail("unterminated string");
     }
+    // Steps over one container of already validated text without recursing (strings may hold brackets).
+    void skip_container() {
+        size_t open = 0;
+        for (; i < t.size(); ++i) {
+            const char c = t[i];
+            if (c == '"') {
+                for (++i; i < t.size() && t[i] != '"'; ++i)
+                    if (t[i] == '\\') ++i;
+            } else if (c == '{' || c == '[') {
+                ++open;
+            } else if (c == '}' || c == ']') {
+                if (--open == 0) { ++i; return; }
+            }
+        }
+    }
     ValuePtr value() {
-        if (++depth > 512) { fail("nesting too deep"); return nullptr; }
+        ++depth;
         ws();
         ValuePtr v = std::make_shared<Value>();
         v->raw_begin = i;
         if (i >= t.size()) { fail("unexpected end"); return nullptr; }
         const char c = t[i];
+        if (depth > kMaxTreeDepth && (c == '{' || c == '[')) {
+            // Deeper than any wire struct reaches (they end near depth 12): whatever sits here can only land in an
+            // unknown field, a json.RawMessage or a map[string]any — none of which looks inside.  Kept as an empty
+            // container that remembers its text span; parse() has already run Go's scanner over the whole input, so
+            // the text is valid and Go's own limit (10000, "exceeded max depth") has been enforced there.
+            v->kind = c == '{' ? Value::Object : Value::Array;
+            skip_container();
+            --depth;
+            v->raw_end = i;
+            return v;
+        }
         if (c == '{') {
             v->kind = Value::Object;
             ++i; ws();

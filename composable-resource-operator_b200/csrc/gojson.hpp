@@ -85,8 +85,9 @@ struct Value {
 // (composableresource_controller_test.go:1479,1674,1804,...).
 std::string SyntaxError(const std::string& text);
 
-// Returns nullptr and fills *err on malformed input; *err is SyntaxError(text).
-// Deviation: trees deeper than 512 are refused (Go allows 10000).
+// Returns nullptr and fills *err on malformed input; *err is SyntaxError(text) — which also enforces Go's
+// nesting limit of 10000.  Containers nested deeper than 512 are kept as childless nodes that remember their
+// text span: no wire struct reaches that deep, so only unknown fields / RawMessage / map[string]any see them.
 ValuePtr parse(const std::string& text, std::string* err);
 
 // Can a parse() result be decoded into a Go struct of type `goType`?  False with

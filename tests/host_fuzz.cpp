@@ -201,7 +201,7 @@ static void one(const std::string& in, const std::string& err_text) {
         const std::string syn = gojson::SyntaxError(in);
         std::string e;
         const bool parsed = (bool)gojson::parse(in, &e);
-        if (syn.empty() != parsed && e.find("nesting too deep") == std::string::npos) {
+        if (syn.empty() != parsed) {
             std::fprintf(stderr, "scanner and parser disagree: syntax='%s' parse='%s'\n", syn.c_str(), e.c_str());
             std::abort();
         }
@@ -246,6 +246,19 @@ int main(int argc, char** argv) {
     const size_t n = sizeof kCorpus / sizeof *kCorpus;
     for (size_t i = 0; i < n; ++i) one(kCorpus[i], "");
     one(std::string(1 << 20, '['), "");                      // nesting bomb: must fail cleanly, not overflow the stack
+    {
+        // valid documents nested deeper than the tree builder recurses (but within Go's 10000): they must parse, as an
+        // unknown field, as a RawMessage and as map[string]any content alike
+        const std::string deep = std::string(9000, '[') + "{\"k\":\"]}\\\"[\"}" + std::string(9000, ']');
+        one(deep, "");
+        one("{\"status\":500,\"detail\":{\"code\":\"E\",\"message\":" + deep + ",\"data\":{\"x\":" + deep + "}},\"junk\":" + deep + "}", "");
+        one("{\"data\":{\"machines\":[{\"unknown\":" + deep + ",\"resources\":[]}]}}", "");
+        std::string e;
+        if (!gojson::parse(deep, &e)) {
+            std::fprintf(stderr, "deep but valid JSON was refused: %s\n", e.c_str());
+            std::abort();
+        }
+    }
     one("{\"a\":" + std::string(1 << 18, '{'), "");
     one(std::string(1 << 20, ','), "");                      // a million empty CSV fields
     one(std::string(1 << 16, '\n'), "");
