@@ -7,7 +7,11 @@ the struct-field lookup (exact tag, else case-folded); the wire structs of inter
 internal/cdi/fti/cm/api/machine.go as type descriptions (TYPES); json.Unmarshal's UnmarshalTypeError for the first
 value whose JSON type does not fit (type_mismatch); and the VALUE a zero struct holds afterwards (decode_as): null
 leaves a field alone, a repeated struct member merges into what an earlier one stored, a repeated slice member is
-decoded over the earlier elements and truncated to the new length (decode.go: object(), array())."""
+decoded over the earlier elements and truncated to the new length (decode.go: object(), array()).
+
+Parity status: pinned only indirectly — every golden reply of tests/golden/reference_entries.json decodes to what the
+reference's entries expect.  The UnmarshalTypeError WORDING and the merge rules have no reference vector (the reference's
+tests never send a mistyped or repeated member): parity unpinned for those; this file and csrc/gojson.cpp check each other."""
 from __future__ import annotations
 
 import json
