@@ -30,7 +30,7 @@ from typing import Dict, List, Optional, Tuple
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcroprobe.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_DEVICES = 16
 
 OK = 0
@@ -40,7 +40,8 @@ ERR_PARSE, ERR_EXEC, ERR_P2P, ERR_INTERNAL = -11, -12, -13, -14
 
 F_SKIP_COPY, F_SKIP_P2P, F_SKIP_NCCL, F_NO_NVML, F_VERIFY_COPY, F_LAZY_ALLOC, F_DEGRADE_ON_OOM, F_SKIP_P2P_WRITE = 1, 2, 4, 8, 16, 32, 64, 128
 READ_AUTO, READ_LDG, READ_TMA, READ_LDG256 = 0, 1, 2, 3
-COPY_AUTO, COPY_LDG, COPY_TMA = 0, 1, 2
+COPY_AUTO, COPY_LDG, COPY_TMA, COPY_TMA_FUSED = 0, 1, 2, 3
+FAIL_NONE, FAIL_EXPECT, FAIL_COPY_SRC, FAIL_READ, FAIL_P2P_READ, FAIL_P2P_PUSH, FAIL_P2P_CHASE, FAIL_STALE = range(8)
 
 
 class ProbeError(RuntimeError):
@@ -71,6 +72,7 @@ class DevInfo(ctypes.Structure):
 
 
 class ProbeResult(ctypes.Structure):
+    """cro_probe_result (ABI 2): written on the device by the finalize kernel, 512 bytes."""
     _fields_ = [
         ("abi_version", ctypes.c_uint32), ("status", ctypes.c_int32),
         ("cuda_ordinal", ctypes.c_int32), ("device_minor", ctypes.c_int32),
@@ -84,18 +86,57 @@ class ProbeResult(ctypes.Structure):
         ("p2p_read_ns", ctypes.c_uint64 * 8), ("p2p_checksum_xor", ctypes.c_uint64 * 8),
         ("p2p_latency_ns_x16", ctypes.c_uint32 * 8), ("p2p_access", ctypes.c_uint8 * 8),
         ("p2p_bytes", ctypes.c_uint64), ("expect_xor", ctypes.c_uint64), ("expect_sum", ctypes.c_uint64),
-        ("read_variant", ctypes.c_uint32), ("copy_variant", ctypes.c_uint32),
-        ("read_sweeps", ctypes.c_uint32), ("copy_sweeps", ctypes.c_uint32),
-        ("copy_checksum_xor", ctypes.c_uint64), ("copy_checksum_sum", ctypes.c_uint64),
-        ("rank", ctypes.c_uint32), ("world", ctypes.c_uint32),
-        ("total_ns", ctypes.c_uint64), ("read_total_ns", ctypes.c_uint64), ("copy_total_ns", ctypes.c_uint64),
-        ("p2p_write_ns", ctypes.c_uint64 * 8), ("reserved", ctypes.c_uint8 * 8),
+        ("expect_wsum", ctypes.c_uint64), ("checksum_wsum", ctypes.c_uint64),
+        ("copy_checksum_xor", ctypes.c_uint64), ("copy_checksum_sum", ctypes.c_uint64), ("copy_checksum_wsum", ctypes.c_uint64),
+        ("total_ns", ctypes.c_uint64), ("p2p_write_ns", ctypes.c_uint64 * 8),
+        ("nonce", ctypes.c_uint32), ("rank", ctypes.c_uint8), ("world", ctypes.c_uint8),
+        ("read_variant", ctypes.c_uint8), ("copy_variant", ctypes.c_uint8),
+        ("read_sweeps", ctypes.c_uint8), ("copy_sweeps", ctypes.c_uint8), ("copy_verified", ctypes.c_uint8),
+        ("fail_code", ctypes.c_uint8), ("fail_index", ctypes.c_uint8), ("p2p_ok", ctypes.c_uint8),
+        ("reserved8", ctypes.c_uint8 * 2), ("t_start_ns", ctypes.c_uint64),
     ]
+
+    @property
+    def checksum(self) -> Tuple[int, int, int]:
+        return (self.checksum_xor, self.checksum_sum, self.checksum_wsum)
+
+    @property
+    def expect(self) -> Tuple[int, int, int]:
+        return (self.expect_xor, self.expect_sum, self.expect_wsum)
+
+    @property
+    def copy_checksum(self) -> Tuple[int, int, int]:
+        return (self.copy_checksum_xor, self.copy_checksum_sum, self.copy_checksum_wsum)
 
 
 class SweepResult(ctypes.Structure):
     _fields_ = [("bytes", ctypes.c_uint64), ("ns", ctypes.c_uint64), ("checksum_xor", ctypes.c_uint64),
-                ("checksum_sum", ctypes.c_uint64), ("variant", ctypes.c_uint32), ("launches", ctypes.c_uint32)]
+                ("checksum_sum", ctypes.c_uint64), ("variant", ctypes.c_uint32), ("launches", ctypes.c_uint32),
+                ("checksum_wsum", ctypes.c_uint64), ("timer_ns", ctypes.c_uint64)]
+
+    @property
+    def checksum(self) -> Tuple[int, int, int]:
+        return (self.checksum_xor, self.checksum_sum, self.checksum_wsum)
+
+
+class SweepTime(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_uint32), ("index", ctypes.c_uint32), ("bytes", ctypes.c_uint64),
+                ("event_ns", ctypes.c_uint64), ("timer_ns", ctypes.c_uint64)]
+
+
+class P2PDetail(ctypes.Structure):
+    _fields_ = [("read_ns", ctypes.c_uint64), ("push_ns", ctypes.c_uint64), ("reread_ns", ctypes.c_uint64),
+                ("read_xor", ctypes.c_uint64), ("read_sum", ctypes.c_uint64), ("read_wsum", ctypes.c_uint64),
+                ("landed_xor", ctypes.c_uint64), ("landed_sum", ctypes.c_uint64), ("landed_wsum", ctypes.c_uint64),
+                ("expect_xor", ctypes.c_uint64), ("expect_sum", ctypes.c_uint64), ("expect_wsum", ctypes.c_uint64),
+                ("chase_ns", ctypes.c_uint64),
+                ("chase_end", ctypes.c_uint32), ("chase_expect", ctypes.c_uint32), ("hops", ctypes.c_uint32), ("access", ctypes.c_uint32)]
+
+
+class FullBoxTime(ctypes.Structure):
+    _fields_ = [("enqueue_ns", ctypes.c_uint64), ("wall_ns", ctypes.c_uint64), ("hbm_ns", ctypes.c_uint64),
+                ("p2p_ns", ctypes.c_uint64), ("chase_ns", ctypes.c_uint64), ("gather_ns", ctypes.c_uint64),
+                ("rounds", ctypes.c_uint32), ("host_syncs", ctypes.c_uint32)]
 
 
 assert ctypes.sizeof(ProbeResult) == 512, ctypes.sizeof(ProbeResult)
@@ -117,7 +158,8 @@ EXPORTS = [
     "cro_scan_device_file_holders", "cro_sim_reconcile_resource", "cro_sim_sync_upstream",
     "cro_fabric_check_resource", "cro_fabric_get_resources", "cro_fabric_list_devices",
     "cro_local_node_op", "cro_scan_cmdline_for", "cro_token_from_reply",
-    "cro_selftest_exception_barrier",
+    "cro_selftest_exception_barrier", "cro_probe_sweep_times", "cro_p2p_detail_get", "cro_fullbox_times",
+    "cro_chase_end", "cro_validate_env",
 ]
 
 
@@ -158,6 +200,11 @@ def _load() -> ctypes.CDLL:
         "cro_inject_fault": (i32, [vp, i32, u64, u64]),
         "cro_read_words": (i32, [vp, i32, u64, u64, ctypes.POINTER(u64)]),
         "cro_device_seed": (i32, [vp, i32, ctypes.POINTER(u64)]),
+        "cro_probe_sweep_times": (i32, [vp, i32, ctypes.POINTER(SweepTime), i32, ctypes.POINTER(i32)]),
+        "cro_p2p_detail_get": (i32, [vp, i32, i32, ctypes.POINTER(P2PDetail)]),
+        "cro_fullbox_times": (i32, [vp, ctypes.POINTER(FullBoxTime)]),
+        "cro_chase_end": (i32, [i32, i32, u32, ctypes.POINTER(u32)]),
+        "cro_validate_env": (i32, [c, c, c, sz]),
         "cro_launch_count": (u64, [vp]),
         "cro_emit_status_json": (i32, [c, c, c, c] + out),
         "cro_emit_scalar_status_json": (i32, [c, c, c, c, c] + out),
@@ -466,6 +513,40 @@ class ProbeContext:
 
     def launch_count(self) -> int:
         return int(lib.cro_launch_count(self.handle))
+
+    def sweep_times(self, dev: int = 0) -> List[SweepTime]:
+        """Per-sweep CUDA-event and %globaltimer times of the device's last probe (fill, copies, reads)."""
+        arr = (SweepTime * 64)()
+        n = ctypes.c_int()
+        self._check(lib.cro_probe_sweep_times(self.handle, dev, arr, 64, ctypes.byref(n)))
+        return [arr[i] for i in range(n.value)]
+
+    def p2p_detail(self, dev: int, peer: int) -> P2PDetail:
+        d = P2PDetail()
+        self._check(lib.cro_p2p_detail_get(self.handle, dev, peer, ctypes.byref(d)))
+        return d
+
+    def fullbox_times(self) -> FullBoxTime:
+        t = FullBoxTime()
+        self._check(lib.cro_fullbox_times(self.handle, ctypes.byref(t)))
+        return t
+
+
+def chase_end(minor_src: int, minor_dst: int, hops: int) -> int:
+    """Slot reached after `hops` steps of the latency permutation of the directed pair (host arithmetic)."""
+    e = ctypes.c_uint32()
+    rc = lib.cro_chase_end(minor_src, minor_dst, hops, ctypes.byref(e))
+    if rc != OK:
+        raise ProbeError(rc, "cro_chase_end")
+    return e.value
+
+
+def validate_env(name: Optional[str] = None, value: Optional[str] = None) -> str:
+    """"" when the CRO_* knob (or, with no name, the process environment) is legal, else the reference-style
+    sentence "the env variable X has an invalid value: 'v'" (composableresource_adapter.go:44)."""
+    err = ctypes.create_string_buffer(512)
+    rc = lib.cro_validate_env(_b(name), _b(value), err, 512)
+    return "" if rc == OK else err.value.decode("utf-8", "replace")
 
 
 def fabric_check_resource(kind: str, machine_body: str, res_type: str, model: str, device_id: str) -> str:

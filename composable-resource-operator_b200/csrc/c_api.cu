@@ -17,6 +17,7 @@
 #include "provider.hpp"
 #include "nodes.hpp"
 #include "gpus.hpp"
+#include "env.hpp"
 #include <memory>
 #include <new>
 #include <stdexcept>
@@ -29,8 +30,11 @@ static_assert(offsetof(cro_probe_result, pci_bus_id) == 64, "layout");
 static_assert(offsetof(cro_probe_result, checksum_xor) == 112, "layout");
 static_assert(offsetof(cro_probe_result, p2p_read_ns) == 184, "layout");
 static_assert(offsetof(cro_probe_result, p2p_access) == 344, "layout");
-static_assert(offsetof(cro_probe_result, rank) == 408, "layout");
-static_assert(offsetof(cro_probe_result, p2p_write_ns) == 440, "layout");
+static_assert(offsetof(cro_probe_result, p2p_bytes) == 352, "layout");
+static_assert(offsetof(cro_probe_result, p2p_write_ns) == 424, "layout");
+static_assert(offsetof(cro_probe_result, nonce) == 488, "layout");
+static_assert(offsetof(cro_probe_result, t_start_ns) == 504, "layout");
+static_assert(sizeof(cro_sweep_result) == 56, "layout");
 
 using namespace cro::capi;
 
@@ -56,7 +60,7 @@ int on_exception() noexcept {
 
 extern "C" {
 
-const char* cro_version(void) { return "croprobe 0.1.0 (sm_100a)"; }
+const char* cro_version(void) { return "croprobe 0.2.0 (sm_100a, abi 2)"; }
 
 const char* cro_strerror(int code) {
     switch (code) {
@@ -212,8 +216,62 @@ int cro_read_words(cro_ctx* ctx, int i, uint64_t first, uint64_t n, uint64_t* ou
 } CRO_API_CATCH
 int cro_device_seed(cro_ctx* ctx, int i, uint64_t* seed) try {
     if (!ctx || !seed || i < 0 || i >= (int)ctx->devs.size()) return CRO_ERR_INVALID_ARG;
-    *seed = ctx->devs[(size_t)i]->seed;
+    std::lock_guard<std::mutex> g(ctx->devs[(size_t)i]->mu);
+    *seed = ctx->devs[(size_t)i]->seed_cur;
     return CRO_OK;
+} CRO_API_CATCH
+
+int cro_probe_sweep_times(cro_ctx* ctx, int i, cro_sweep_time* out, int cap, int* n) try {
+    return ctx ? ctx_sweep_times(ctx, i, out, cap, n) : CRO_ERR_INVALID_ARG;
+} CRO_API_CATCH
+
+int cro_p2p_detail_get(cro_ctx* ctx, int i, int peer, cro_p2p_detail* out) try {
+    return ctx ? ctx_p2p_detail(ctx, i, peer, out) : CRO_ERR_INVALID_ARG;
+} CRO_API_CATCH
+
+int cro_fullbox_times(cro_ctx* ctx, cro_fullbox_time* out) try {
+    if (!ctx || !out) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(ctx->all_mu);
+    const FullBoxTimes& f = ctx->fullbox;
+    out->enqueue_ns = f.enqueue_ns;
+    out->wall_ns = f.wall_ns;
+    out->hbm_ns = f.hbm_ns;
+    out->p2p_ns = f.p2p_ns;
+    out->chase_ns = f.chase_ns;
+    out->gather_ns = f.gather_ns;
+    out->rounds = f.rounds;
+    out->host_syncs = f.host_syncs;
+    return CRO_OK;
+} CRO_API_CATCH
+
+int cro_chase_end(int minor_src, int minor_dst, uint32_t hops, uint32_t* end) try {
+    if (!end) return CRO_ERR_INVALID_ARG;
+    std::vector<uint32_t> perm;
+    chase_permutation(minor_src, minor_dst, &perm);
+    uint32_t at = 0;
+    for (uint32_t h = 0; h < hops; ++h) at = perm[at];
+    *end = at;
+    return CRO_OK;
+} CRO_API_CATCH
+
+int cro_validate_env(const char* name, const char* value, char* err_buf, size_t err_cap) try {
+    int n = 0;
+    const env::Knob* t = env::table(&n);
+    std::string why;
+    if (name) {
+        for (int i = 0; i < n; ++i) {
+            if (S(name) != t[i].name) continue;
+            unsigned v = 0;
+            if (env::parse(t[i], value, &v, &why)) return CRO_OK;
+            copy_out(why, err_buf, err_cap, nullptr);
+            return CRO_ERR_INVALID_ARG;
+        }
+        copy_out("unknown knob " + S(name), err_buf, err_cap, nullptr);
+        return CRO_ERR_UNSUPPORTED;
+    }
+    if (env::reload(&why)) return CRO_OK;
+    copy_out(why, err_buf, err_cap, nullptr);
+    return CRO_ERR_INVALID_ARG;
 } CRO_API_CATCH
 uint64_t cro_launch_count(cro_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
@@ -276,7 +334,9 @@ std::map<std::string, std::string> cro::capi::probe_annotations(const cro_probe_
     m["cohdi.io/probe-pci-bus-id"] = fixed_str(r.pci_bus_id, sizeof r.pci_bus_id);
     m["cohdi.io/probe-device-minor"] = std::to_string(r.device_minor);
     m["cohdi.io/probe-sweep-bytes"] = std::to_string(r.sweep_bytes);
-    m["cohdi.io/probe-checksum"] = hex16(r.checksum_xor) + ":" + hex16(r.checksum_sum);
+    m["cohdi.io/probe-checksum"] = hex16(r.checksum_xor) + ":" + hex16(r.checksum_sum) + ":" + hex16(r.checksum_wsum);
+    m["cohdi.io/probe-nonce"] = std::to_string(r.nonce);
+    if (r.copy_sweeps) m["cohdi.io/probe-copies-verified"] = std::to_string((unsigned)r.copy_verified) + "/" + std::to_string((unsigned)r.copy_sweeps);
     m["cohdi.io/probe-ecc-uncorrected"] = std::to_string(r.ecc_errors);
     m["cohdi.io/probe-hbm-fill-gbs"] = gbs_x10(r.sweep_bytes, r.fill_ns);
     m["cohdi.io/probe-hbm-read-gbs"] = gbs_x10(r.sweep_bytes, r.read_best_ns);

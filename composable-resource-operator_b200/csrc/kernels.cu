@@ -5,16 +5,20 @@
 // slot.  They are HBM-bound integer sweeps:
 //
 //   hbm_fill          S bytes written   w[i] = splitmix64-step(seed + i)
-//   hbm_read_*        S bytes read      (XOR-fold, wrapping sum) of all words
-//   hbm_copy_*        2S bytes moved
+//   hbm_read_*        S bytes read      (XOR, wrapping sum, position-weighted sum) of all words
+//   hbm_copy_fused    2S bytes moved    + the same checksum of the source stream, folded out of shared memory
+//   hbm_copy_*        2S bytes moved    (plain variants, kept for comparison)
 //   hbm_expected      0 bytes           the same checksum from the closed form
-//   chase             pointer chase over a peer-resident permutation (latency)
+//   chase             pointer chase over peer-resident permutations (latency)
+//   probe_finalize / p2p_finalize       the verdict: the 512-byte result struct is written on the device
 //
 // Two data paths per sweep: 128-bit ld.global.nc / st.global vector accesses
 // (also used on peer-mapped pointers for the NVLink probe), and 1-D TMA bulk
 // copies (cp.async.bulk + mbarrier) through a shared-memory ring.
 // No tensor cores: there is no contraction anywhere on this path.
 #include "kernels.cuh"
+
+#include "env.hpp"
 
 #include <algorithm>
 #include <cstdio>
@@ -170,34 +174,62 @@ __device__ __forceinline__ void tma_wait_all() {
 }
 
 // ---------------------------------------------------------------------------
-// CTA reduction + "last CTA publishes" epilogue shared by read / expected.
-// XOR and wrapping add are associative and commutative, so the result is
-// independent of grid shape and scheduling: bit-exact by construction.
+// Checksum accumulator.  A sweep over words w[0..n) yields (XOR, wrapping sum,
+// wrapping sum of w[i] * (2i + 1)).  Threads fold 16-byte vectors (a, b) =
+// (w[2v], w[2v+1]); with m = 2*(2v)+1 = 4v+1 the weighted part of the pair is
+//   a*m + b*(m+2) = (a+b)*m + 2b,
+// so one 64-bit multiply per VECTOR plus a running sum of the odd words.
+// All three components are associative and commutative over words, so the
+// result does not depend on grid shape or scheduling: bit-exact by construction.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void publish(unsigned long long x, unsigned long long s,
+struct Acc {
+    unsigned long long x0 = 0, x1 = 0, s = 0, w = 0, d = 0;
+};
+__device__ __forceinline__ void fold2(Acc& A, unsigned long long a, unsigned long long b,
+                                      unsigned long long m /* 4*vector_index + 1 */) {
+    const unsigned long long c = a + b;
+    A.x0 ^= a;
+    A.x1 ^= b;
+    A.s += c;
+    A.w += c * m;
+    A.d += b;
+}
+__device__ __forceinline__ unsigned long long acc_x(const Acc& A) { return A.x0 ^ A.x1; }
+__device__ __forceinline__ unsigned long long acc_w(const Acc& A) { return A.w + 2ull * A.d; }
+
+// ---------------------------------------------------------------------------
+// CTA reduction + "last CTA publishes" epilogue shared by read / fused copy /
+// expected.  The last CTA also re-arms the scratch (ticket, timers, dynamic
+// tile counter), so no memset node sits between two sweeps.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void publish(unsigned long long x, unsigned long long s, unsigned long long w,
                                         unsigned long long t_start, const SweepScratch sc,
-                                        SweepOut* out) {
-    __shared__ unsigned long long sx[32], ss[32];
+                                        SweepOut* out, const ProbeParams& imm, const ProbeParams* pp,
+                                        unsigned long long n_words) {
+    __shared__ unsigned long long sx[32], ss[32], sw[32];
     __shared__ bool is_last;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         x ^= __shfl_xor_sync(0xffffffffu, x, o);
         s += __shfl_xor_sync(0xffffffffu, s, o);
+        w += __shfl_xor_sync(0xffffffffu, w, o);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = (blockDim.x + 31) >> 5;
-    if (lane == 0) { sx[warp] = x; ss[warp] = s; }
+    if (lane == 0) { sx[warp] = x; ss[warp] = s; sw[warp] = w; }
     __syncthreads();
     if (warp == 0) {
         x = lane < nwarps ? sx[lane] : 0ull;
         s = lane < nwarps ? ss[lane] : 0ull;
+        w = lane < nwarps ? sw[lane] : 0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             x ^= __shfl_xor_sync(0xffffffffu, x, o);
             s += __shfl_xor_sync(0xffffffffu, s, o);
+            w += __shfl_xor_sync(0xffffffffu, w, o);
         }
         if (lane == 0) {
-            sc.partials[blockIdx.x] = make_ulonglong2(x, s);
+            sc.partials[blockIdx.x] = make_ulonglong4(x, s, w, 0ull);
             atomicMin(sc.tmin, t_start);
             atomicMax(sc.tmax, globaltimer_ns());
             __threadfence();
@@ -208,29 +240,35 @@ __device__ __forceinline__ void publish(unsigned long long x, unsigned long long
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    x = 0; s = 0;
+    x = 0; s = 0; w = 0;
     for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-        ulonglong2 p = __ldcg(&sc.partials[i]);
-        x ^= p.x; s += p.y;
+        const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&sc.partials[i]);
+        const ulonglong2 p0 = __ldcg(q), p1 = __ldcg(q + 1);
+        x ^= p0.x; s += p0.y; w += p1.x;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         x ^= __shfl_xor_sync(0xffffffffu, x, o);
         s += __shfl_xor_sync(0xffffffffu, s, o);
+        w += __shfl_xor_sync(0xffffffffu, w, o);
     }
     __syncthreads();
-    if (lane == 0) { sx[warp] = x; ss[warp] = s; }
+    if (lane == 0) { sx[warp] = x; ss[warp] = s; sw[warp] = w; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        x = 0; s = 0;
-        for (int w = 0; w < nwarps; ++w) { x ^= sx[w]; s += ss[w]; }
+        x = 0; s = 0; w = 0;
+        for (int k = 0; k < nwarps; ++k) { x ^= sx[k]; s += ss[k]; w += sw[k]; }
         out->x = x;
         out->s = s;
+        out->w = w;
         out->t0 = *((volatile unsigned long long*)sc.tmin);
         out->t1 = *((volatile unsigned long long*)sc.tmax);
+        out->stamp = pp ? pp->nonce : imm.nonce;
+        out->n_words = n_words;
         *sc.counter = 0u;
         *sc.tmin = ~0ull;
         *sc.tmax = 0ull;
+        if (sc.tile_ctr) *sc.tile_ctr = 0ull;
         __threadfence();
     }
 }
@@ -238,10 +276,16 @@ __device__ __forceinline__ void publish(unsigned long long x, unsigned long long
 // ---------------------------------------------------------------------------
 // hbm_fill: S bytes written.  Thread t of a tile stores vectors t, t+T, ...
 // so each warp-level store instruction covers 512 contiguous bytes.
+// The CTAs also keep the sweep's %globaltimer window (first start, last store
+// issued) so the device-written result needs no host-side event arithmetic.
 // ---------------------------------------------------------------------------
 template <int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS)
-hbm_fill_kernel(uint4* __restrict__ base, unsigned long long n_vec, unsigned long long seed) {
+hbm_fill_kernel(uint4* __restrict__ base, unsigned long long n_vec, const ProbeParams imm,
+                const ProbeParams* __restrict__ pp, SweepScratch sc, SweepOut* out) {
+    const unsigned long long seed = pp ? pp->seed : imm.seed;
+    unsigned long long t_start = 0;
+    if (threadIdx.x == 0) t_start = globaltimer_ns();
     const unsigned long long tile_vecs = (unsigned long long)THREADS * UNROLL;
     const unsigned long long n_tiles = n_vec / tile_vecs;
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -264,39 +308,62 @@ hbm_fill_kernel(uint4* __restrict__ base, unsigned long long n_vec, unsigned lon
         stg_stream(base + v,
                    make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32)));
     }
+    if (!out) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicMin(sc.tmin, t_start);
+        atomicMax(sc.tmax, globaltimer_ns());
+        __threadfence();
+        const unsigned ticket = atomicAdd(sc.counter, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            out->x = 0; out->s = 0; out->w = 0;
+            out->t0 = *((volatile unsigned long long*)sc.tmin);
+            out->t1 = *((volatile unsigned long long*)sc.tmax);
+            out->stamp = pp ? pp->nonce : imm.nonce;
+            out->n_words = 2 * n_vec;
+            *sc.counter = 0u;
+            *sc.tmin = ~0ull;
+            *sc.tmax = 0ull;
+            __threadfence();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
 // hbm_read (LDG path): UNROLL independent 128-bit ld.global.nc per thread in
-// flight, read-only path, no L1 allocation.  Also the NVLink P2P read kernel
-// (base may be a peer-mapped pointer).
+// flight, read-only path, no L1 allocation.  Also usable on a peer-mapped
+// pointer (NVLink read).
 // ---------------------------------------------------------------------------
 template <int THREADS, bool WIDE>
 __global__ void __launch_bounds__(THREADS)
-hbm_read_ldg_kernel(const uint4* __restrict__ base, unsigned long long n_vec, SweepScratch sc,
-                    SweepOut* out) {
+hbm_read_ldg_kernel(const uint4* __restrict__ base, unsigned long long n_vec, const ProbeParams imm,
+                    const ProbeParams* __restrict__ pp, SweepScratch sc, SweepOut* out) {
     const unsigned long long t_start = globaltimer_ns();
-    unsigned long long x0 = 0, x1 = 0, s0 = 0, s1 = 0;
+    Acc A, B;
     constexpr unsigned long long tile_vecs = (unsigned long long)THREADS * 8;  // 128 B / thread
     const unsigned long long n_tiles = n_vec / tile_vecs;
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (WIDE) {
-            // thread t owns 32-byte vectors t, t+T, t+2T, t+3T of the tile
-            const unsigned char* p = reinterpret_cast<const unsigned char*>(base + tile * tile_vecs) +
-                                     (size_t)threadIdx.x * 32;
+            // thread t owns 32-byte vectors t, t+T, t+2T, t+3T of the tile (two 16-byte vectors each)
+            const unsigned long long v0 = tile * tile_vecs + 2ull * threadIdx.x;
+            const unsigned char* p = reinterpret_cast<const unsigned char*>(base + v0);
             unsigned long long w[16];
             ldg256_x4<THREADS * 32>(p, w);
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                x0 ^= w[j]; x1 ^= w[j + 1]; s0 += w[j]; s1 += w[j + 1];
+            for (int j = 0; j < 4; ++j) {
+                const unsigned long long v = v0 + 2ull * j * THREADS;
+                fold2(A, w[4 * j], w[4 * j + 1], 4 * v + 1);
+                fold2(B, w[4 * j + 2], w[4 * j + 3], 4 * (v + 1) + 1);
             }
         } else {
-            const uint4* p = base + tile * tile_vecs + threadIdx.x;
+            const unsigned long long v0 = tile * tile_vecs + threadIdx.x;
             unsigned long long a[8], b[8];
-            ldg128_x8<THREADS * 16>(p, a, b);
+            ldg128_x8<THREADS * 16>(base + v0, a, b);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                x0 ^= a[j]; x1 ^= b[j]; s0 += a[j]; s1 += b[j];
+            for (int j = 0; j < 8; j += 2) {
+                fold2(A, a[j], b[j], 4 * (v0 + (unsigned long long)j * THREADS) + 1);
+                fold2(B, a[j + 1], b[j + 1], 4 * (v0 + (unsigned long long)(j + 1) * THREADS) + 1);
             }
         }
     }
@@ -304,22 +371,43 @@ hbm_read_ldg_kernel(const uint4* __restrict__ base, unsigned long long n_vec, Sw
                                 threadIdx.x;
          i < n_vec; i += (unsigned long long)gridDim.x * THREADS) {
         const uint4 v = ldg_stream(base + i);
-        const unsigned long long a = lo64(v), b = hi64(v);
-        x0 ^= a; x1 ^= b; s0 += a; s1 += b;
+        fold2(A, lo64(v), hi64(v), 4 * i + 1);
     }
-    publish(x0 ^ x1, s0 + s1, t_start, sc, out);
+    publish(acc_x(A) ^ acc_x(B), A.s + B.s, acc_w(A) + acc_w(B), t_start, sc, out, imm, pp, 2 * n_vec);
+}
+
+// Consumer side shared by the TMA read kernel and the checksumming copy: folds
+// one landed tile out of shared memory with conflict-free LDS.128.
+// v_tile = index (in 16-byte vectors, relative to the sweep's base) of the tile's first vector.
+__device__ __forceinline__ void fold_tile(Acc& A, Acc& B, const uint4* sp, unsigned nvec, unsigned ctid,
+                                          unsigned n_cons, unsigned long long v_tile) {
+    unsigned i = ctid;
+    // 4 independent LDS.128 per trip
+    for (; i + 3 * n_cons < nvec; i += 4 * n_cons) {
+        const uint4 a = sp[i], b = sp[i + n_cons], c = sp[i + 2 * n_cons], d = sp[i + 3 * n_cons];
+        const unsigned long long m = 4 * (v_tile + i) + 1, step = 4ull * n_cons;
+        fold2(A, lo64(a), hi64(a), m);
+        fold2(B, lo64(b), hi64(b), m + step);
+        fold2(A, lo64(c), hi64(c), m + 2 * step);
+        fold2(B, lo64(d), hi64(d), m + 3 * step);
+    }
+    for (; i < nvec; i += n_cons) {
+        const uint4 a = sp[i];
+        fold2(A, lo64(a), hi64(a), 4 * (v_tile + i) + 1);
+    }
 }
 
 // ---------------------------------------------------------------------------
 // hbm_read (TMA path): warp 0 / lane 0 is the producer, issuing 1-D bulk
 // copies of `tile_bytes` into a `stages`-deep shared-memory ring; the consumer
-// warps fold each landed tile with conflict-free LDS.128 and hand the slot
-// back through an "empty" mbarrier.  Bytes in flight per SM = stages*tile.
+// warps fold each landed tile and hand the slot back through an "empty"
+// mbarrier.  Bytes in flight per SM = stages*tile.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 hbm_read_tma_kernel(const unsigned char* __restrict__ base, unsigned long long bytes,
                     unsigned tile_bytes, unsigned stages, unsigned chunk,
-                    unsigned long long* tile_ctr, SweepScratch sc, SweepOut* out) {
+                    unsigned long long* tile_ctr, const ProbeParams imm, const ProbeParams* __restrict__ pp,
+                    SweepScratch sc, SweepOut* out) {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) uint64_t full_bar[16];
     __shared__ __align__(8) uint64_t empty_bar[16];
@@ -340,7 +428,7 @@ hbm_read_tma_kernel(const unsigned char* __restrict__ base, unsigned long long b
     }
     __syncthreads();
 
-    unsigned long long x0 = 0, x1 = 0, s0 = 0, s1 = 0;
+    Acc A, B;
     constexpr unsigned long long kEnd = ~0ull;
     if (warp == 0) {
         if (lane == 0) {
@@ -387,27 +475,13 @@ hbm_read_tma_kernel(const unsigned char* __restrict__ base, unsigned long long b
             const unsigned long long off = tile * tile_bytes;
             const unsigned long long left = bytes - off;
             const unsigned nvec = (left < tile_bytes ? (unsigned)left : tile_bytes) >> 4;
-            const uint4* sp = reinterpret_cast<const uint4*>(ring + (size_t)stage * tile_bytes);
-            unsigned i = ctid;
-            // 4 independent LDS.128 per trip
-            for (; i + 3 * n_cons < nvec; i += 4 * n_cons) {
-                const uint4 a = sp[i], b = sp[i + n_cons], c = sp[i + 2 * n_cons],
-                            d = sp[i + 3 * n_cons];
-                x0 ^= lo64(a) ^ lo64(c); x1 ^= hi64(a) ^ hi64(c);
-                s0 += lo64(a) + lo64(c); s1 += hi64(a) + hi64(c);
-                x0 ^= lo64(b) ^ lo64(d); x1 ^= hi64(b) ^ hi64(d);
-                s0 += lo64(b) + lo64(d); s1 += hi64(b) + hi64(d);
-            }
-            for (; i < nvec; i += n_cons) {
-                const uint4 a = sp[i];
-                x0 ^= lo64(a); x1 ^= hi64(a); s0 += lo64(a); s1 += hi64(a);
-            }
+            fold_tile(A, B, reinterpret_cast<const uint4*>(ring + (size_t)stage * tile_bytes), nvec, ctid, n_cons, off >> 4);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
     }
-    publish(x0 ^ x1, s0 + s1, t_start, sc, out);
+    publish(acc_x(A) ^ acc_x(B), A.s + B.s, acc_w(A) + acc_w(B), t_start, sc, out, imm, pp, bytes >> 3);
 }
 
 // ---------------------------------------------------------------------------
@@ -439,7 +513,7 @@ hbm_copy_ldg_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
 // ---------------------------------------------------------------------------
 // hbm_copy (TMA path): one thread per CTA drives everything.  Tiles go
 // global -> smem (bulk load, mbarrier) -> global (bulk store, bulk group);
-// data never touches the register file.
+// data never touches the register file.  Moves bytes, checks nothing.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(32, 1)
 hbm_copy_tma_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src,
@@ -514,20 +588,143 @@ hbm_copy_tma_kernel(unsigned char* __restrict__ dst, const unsigned char* __rest
 }
 
 // ---------------------------------------------------------------------------
+// hbm_copy, checksumming (the probe's default copy): the tile that the bulk
+// load lands in shared memory is (1) handed to the bulk store and (2) folded
+// by the consumer warps, both straight out of the same shared-memory slot.
+// The sweep therefore yields the checksum of its SOURCE as actually read at
+// no extra HBM traffic.  The probe runs its copy sweeps ping-pong (A->B, B->A,
+// ...), so the fold of sweep k+1 is the verification of what sweep k WROTE.
+//   warp 0 lane 0: producer — claims tiles, issues bulk loads, issues the bulk
+//                  store of a tile as soon as it has landed, refills a slot
+//                  once both its store has read it (bulk-group wait) and the
+//                  consumers have released it (empty mbarrier)
+//   warps 1..n   : consumers — LDS.128 fold of each landed tile
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+hbm_copy_fused_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src,
+                      unsigned long long bytes, unsigned tile_bytes, unsigned stages, unsigned chunk,
+                      unsigned long long* tile_ctr, const ProbeParams imm, const ProbeParams* __restrict__ pp,
+                      SweepScratch sc, SweepOut* out) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) uint64_t full_bar[16];
+    __shared__ __align__(8) uint64_t empty_bar[16];
+    __shared__ unsigned long long tile_of[16];
+    const unsigned long long t_start = globaltimer_ns();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned n_cons_warps = (blockDim.x >> 5) - 1;
+    const unsigned long long n_tiles = (bytes + tile_bytes - 1) / tile_bytes;
+    chunk &= 0xFFFFu;
+
+    if (threadIdx.x == 0) {
+        for (unsigned s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], n_cons_warps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    Acc A, B;
+    constexpr unsigned long long kEnd = ~0ull;
+    if (warp == 0) {
+        if (lane == 0) {
+            unsigned long long fetched = 0;
+            bool dry = false;
+            unsigned long long cur = 0, end = 0;
+            auto fetch = [&]() -> unsigned long long {
+                unsigned long long t;
+                if (tile_ctr) {
+                    if (cur == end) { cur = atomicAdd(tile_ctr, (unsigned long long)chunk); end = cur + chunk; }
+                    t = cur++;
+                } else {
+                    t = blockIdx.x + fetched * (unsigned long long)gridDim.x;
+                }
+                ++fetched;
+                if (t >= n_tiles) dry = true;
+                return t;
+            };
+            auto tile_len = [&](unsigned long long off) {
+                const unsigned long long left = bytes - off;
+                return left < tile_bytes ? (unsigned)left : tile_bytes;
+            };
+            // use number u of slot st (u-th tile through it): consumers must have released use u-1
+            auto issue_load = [&](unsigned st, unsigned long long use, unsigned long long tile) {
+                if (use > 0) mbar_wait(&empty_bar[st], (unsigned)((use - 1) & 1ull));
+                const unsigned long long off = tile * tile_bytes;
+                const unsigned nb = tile_len(off);
+                tile_of[st] = tile;
+                mbar_expect_tx(&full_bar[st], nb);   // release: publishes tile_of[st]
+                tma_load_1d(ring + (size_t)st * tile_bytes, src + off, nb, &full_bar[st]);
+            };
+            unsigned long long loaded = 0;
+            for (unsigned s = 0; s < stages && !dry; ++s) {
+                const unsigned long long t = fetch();
+                if (!dry) { issue_load(s, 0, t); ++loaded; }
+            }
+            for (unsigned long long k = 0; k < loaded; ++k) {
+                const unsigned st = (unsigned)(k % stages);
+                mbar_wait(&full_bar[st], (unsigned)((k / stages) & 1ull));
+                const unsigned long long off = tile_of[st] * tile_bytes;
+                tma_store_1d(dst + off, ring + (size_t)st * tile_bytes, tile_len(off));
+                tma_commit();
+                if (k >= 1 && !dry) {
+                    const unsigned long long t = fetch();
+                    if (!dry) {
+                        tma_wait_read<1>();   // the store of trip k-1 has finished reading its slot
+                        issue_load((unsigned)((k - 1) % stages), (k - 1) / stages + 1, t);
+                        ++loaded;
+                    }
+                }
+            }
+            // tell the consumers there is nothing more: the slot after the last tile carries the end mark
+            {
+                const unsigned st = (unsigned)(loaded % stages);
+                const unsigned long long use = loaded / stages;
+                if (use > 0) {
+                    // that slot's previous store must have drained before the mark reuses its barrier phase
+                    mbar_wait(&empty_bar[st], (unsigned)((use - 1) & 1ull));
+                }
+                tile_of[st] = kEnd;
+                mbar_arrive(&full_bar[st]);
+            }
+            tma_wait_all();
+        }
+    } else {
+        const unsigned ctid = threadIdx.x - 32;
+        const unsigned n_cons = n_cons_warps * 32;
+        unsigned stage = 0, phase = 0;
+        for (;;) {
+            mbar_wait(&full_bar[stage], phase);
+            const unsigned long long tile = *reinterpret_cast<volatile unsigned long long*>(&tile_of[stage]);
+            if (tile == kEnd) break;
+            const unsigned long long off = tile * tile_bytes;
+            const unsigned long long left = bytes - off;
+            const unsigned nvec = (left < tile_bytes ? (unsigned)left : tile_bytes) >> 4;
+            fold_tile(A, B, reinterpret_cast<const uint4*>(ring + (size_t)stage * tile_bytes), nvec, ctid, n_cons, off >> 4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+    }
+    publish(acc_x(A) ^ acc_x(B), A.s + B.s, acc_w(A) + acc_w(B), t_start, sc, out, imm, pp, bytes >> 3);
+}
+
+// ---------------------------------------------------------------------------
 // hbm_expected: the checksum of the pattern from its closed form, no HBM.
 // An independent generator: a fill or read bug cannot cancel out.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-hbm_expected_kernel(unsigned long long n_words, unsigned long long seed, SweepScratch sc,
-                    SweepOut* out) {
+hbm_expected_kernel(unsigned long long n_words, const ProbeParams imm,
+                    const ProbeParams* __restrict__ pp, SweepScratch sc, SweepOut* out) {
+    const unsigned long long seed = pp ? pp->seed : imm.seed;
     const unsigned long long t_start = globaltimer_ns();
-    unsigned long long x = 0, s = 0;
+    unsigned long long x = 0, s = 0, w = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
          i < n_words; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long w = pattern_word(seed, i);
-        x ^= w; s += w;
+        const unsigned long long v = pattern_word(seed, i);
+        x ^= v; s += v; w += v * (2 * i + 1);
     }
-    publish(x, s, t_start, sc, out);
+    publish(x, s, w, t_start, sc, out, imm, pp, n_words);
 }
 
 __global__ void xor_word_kernel(unsigned long long* base, unsigned long long idx,
@@ -535,25 +732,165 @@ __global__ void xor_word_kernel(unsigned long long* base, unsigned long long idx
     base[idx] ^= mask;
 }
 
-// Latency: dependent loads, system scope, one slot per 128-byte line.
-__global__ void chase_kernel(const unsigned long long* __restrict__ next, unsigned start,
-                             unsigned hops, unsigned long long* out) {
-    unsigned long long idx = start;
+// Latency: dependent loads, system scope, one slot per 128-byte line.  Warp j
+// (its lane 0) walks table j; the warps run concurrently, one outstanding load
+// each, so n-1 peers are measured in the time of one chase.
+__global__ void __launch_bounds__(32 * CRO_MAX_DEVICES)
+chase_kernel(const ChaseArgs a, unsigned long long* __restrict__ out) {
+    const unsigned j = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) != 0 || j >= a.n) return;
+    const unsigned long long* next = a.table[j];
+    if (!next) return;
+    unsigned long long idx = a.start[j];
     // warm the TLB / first line
     {
         unsigned long long v;
         asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(next + idx * 16));
-        if (v == ~0ull) out[2] = v;   // keep the warm-up load alive
+        if (v == ~0ull) out[2 * j] = v;   // keep the warm-up load alive
     }
     const unsigned long long t0 = globaltimer_ns();
-    for (unsigned h = 0; h < hops; ++h) {
+    for (unsigned h = 0; h < a.hops; ++h) {
         unsigned long long v;
         asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(next + idx * 16));
         idx = v;
     }
     const unsigned long long t1 = globaltimer_ns();
-    out[0] = idx;
-    out[1] = t1 - t0;
+    out[2 * j] = idx;
+    out[2 * j + 1] = t1 - t0;
+}
+
+// ---------------------------------------------------------------------------
+// finalize: the verdict, on the device.  One CTA; thread 0 does the (tiny)
+// arithmetic after the CTA has copied the identity template.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool same_fold(const SweepOut& a, const SweepOut& b) {
+    return a.x == b.x && a.s == b.s && a.w == b.w;
+}
+__device__ void best_and_median(const unsigned long long* t, unsigned n, unsigned long long* best,
+                                unsigned long long* median) {
+    unsigned long long v[kMaxSweepsEach];
+    for (unsigned i = 0; i < n; ++i) {      // insertion sort, n <= 30
+        unsigned long long x = t[i];
+        unsigned k = i;
+        while (k > 0 && v[k - 1] > x) { v[k] = v[k - 1]; --k; }
+        v[k] = x;
+    }
+    *best = n ? v[0] : 0ull;
+    *median = n ? v[n / 2] : 0ull;
+}
+
+__global__ void __launch_bounds__(128)
+probe_finalize_kernel(const FinalizeArgs a) {
+    // identity, options and whatever the host staged: 512 bytes, one uint4 per thread
+    if (threadIdx.x < sizeof(cro_probe_result) / 16)
+        reinterpret_cast<uint4*>(a.out)[threadIdx.x] = reinterpret_cast<const uint4*>(a.tmpl)[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    cro_probe_result* r = a.out;
+    const SweepOut* sl = a.slots;
+    const unsigned long long nonce = a.pp->nonce;
+    const unsigned long long n_words = a.sweep_bytes >> 3;
+    const unsigned C = a.copy_sweeps, R = a.read_sweeps;
+    const SweepOut& E = sl[kSlotExpect];
+    int status = CRO_OK;
+    unsigned fail_code = CRO_FAIL_NONE, fail_index = 0;
+    auto fail = [&](unsigned code, unsigned index) {
+        if (status == CRO_OK) { status = CRO_ERR_CHECKSUM; fail_code = code; fail_index = index; }
+    };
+    r->seed = a.pp->seed;
+    r->nonce = (uint32_t)nonce;
+    r->sweep_bytes = a.sweep_bytes;
+    r->read_sweeps = (uint8_t)R;
+    r->copy_sweeps = (uint8_t)C;
+    r->read_variant = (uint8_t)a.read_variant;
+    r->copy_variant = (uint8_t)a.copy_variant;
+    r->expect_xor = E.x; r->expect_sum = E.s; r->expect_wsum = E.w;
+    if (E.stamp != nonce || E.n_words != n_words) fail(CRO_FAIL_EXPECT, 0);
+    if (sl[kSlotFill].stamp != nonce || sl[kSlotFill].n_words != n_words) fail(CRO_FAIL_STALE, 0);
+
+    unsigned long long tc[kMaxSweepsEach], tr[kMaxSweepsEach];
+    unsigned verified = 0;
+    // copy sweep i reads what sweep i-1 wrote (sweep 0 reads the fill): its fold IS the check of that data
+    for (unsigned i = 0; i < C; ++i) {
+        const SweepOut& s = sl[kSlotSweep0 + i];
+        tc[i] = s.t1 - s.t0;
+        if (!a.fused) continue;
+        if (s.stamp != nonce || s.n_words != n_words) fail(CRO_FAIL_STALE, 1 + i);
+        else if (!same_fold(s, E)) fail(CRO_FAIL_COPY_SRC, i);
+        else if (i > 0) ++verified;            // sweep i-1's destination reproduced the pattern
+    }
+    // read sweep 0 reads the last copy's destination
+    const SweepOut* shown = &sl[kSlotSweep0 + C];
+    for (unsigned i = 0; i < R; ++i) {
+        const SweepOut& s = sl[kSlotSweep0 + C + i];
+        tr[i] = s.t1 - s.t0;
+        bool ok = true;
+        if (s.stamp != nonce || s.n_words != n_words) { if (status == CRO_OK) shown = &s; fail(CRO_FAIL_STALE, 1 + C + i); ok = false; }
+        else if (!same_fold(s, E)) { if (status == CRO_OK) shown = &s; fail(CRO_FAIL_READ, i); ok = false; }
+        if (i == 0 && ok && C > 0) ++verified;
+    }
+    r->checksum_xor = shown->x; r->checksum_sum = shown->s; r->checksum_wsum = shown->w;
+    if (C > 0 && R > 0) {
+        const SweepOut& d = sl[kSlotSweep0 + C];
+        r->copy_checksum_xor = d.x; r->copy_checksum_sum = d.s; r->copy_checksum_wsum = d.w;
+    }
+    r->copy_verified = (uint8_t)verified;
+    r->fill_ns = sl[kSlotFill].t1 - sl[kSlotFill].t0;
+    unsigned long long best, med;
+    best_and_median(tr, R, &best, &med);
+    r->read_best_ns = best; r->read_median_ns = med;
+    best_and_median(tc, C, &best, &med);
+    r->copy_best_ns = best; r->copy_median_ns = med;
+    unsigned long long t_end = sl[kSlotFill].t1;
+    for (unsigned i = 0; i < C + R; ++i) t_end = sl[kSlotSweep0 + i].t1 > t_end ? sl[kSlotSweep0 + i].t1 : t_end;
+    r->t_start_ns = sl[kSlotFill].t0;
+    r->total_ns = t_end - sl[kSlotFill].t0;
+    r->fail_code = (uint8_t)fail_code;
+    r->fail_index = (uint8_t)fail_index;
+    r->status = status;
+}
+
+__global__ void __launch_bounds__(32)
+p2p_finalize_kernel(const P2PFinalizeArgs a) {
+    if (threadIdx.x != 0) return;
+    cro_probe_result* r = a.out;
+    int status = r->status;
+    unsigned fail_code = r->fail_code, fail_index = r->fail_index;
+    auto fail = [&](unsigned code, unsigned index) {
+        if (status == CRO_OK) { status = CRO_ERR_CHECKSUM; fail_code = code; fail_index = index; }
+    };
+    unsigned ok_mask = 0;
+    r->p2p_bytes = a.p2p_bytes;
+    for (unsigned j = 0; j < a.n && j < 8; ++j) {
+        if (j == a.self || !r->p2p_access[j] || !a.peer_slots[j]) continue;
+        bool ok = true;
+        const SweepOut& rd = a.slots[kSlotP2P0 + 3 * j];
+        // what the owner itself says its first p2p_bytes must fold to (its closed-form slot, read over NVLink)
+        const SweepOut want = a.peer_slots[j][kSlotPrefix];
+        r->p2p_read_ns[j] = rd.t1 - rd.t0;
+        r->p2p_checksum_xor[j] = rd.x;
+        if (want.stamp != a.peer_stamp[j] || want.n_words != (a.p2p_bytes >> 3)) { fail(CRO_FAIL_EXPECT, j); ok = false; }
+        if (rd.stamp != a.stamp || !same_fold(rd, want)) { fail(CRO_FAIL_P2P_READ, j); ok = false; }
+        const SweepOut& ps = a.slots[kSlotP2P0 + 3 * j + 1];          // my push into j (fold of my own prefix as read)
+        if (ps.stamp == a.stamp) r->p2p_write_ns[j] = ps.t1 - ps.t0;
+        if (a.have_push) {
+            const SweepOut& rr = a.slots[kSlotP2P0 + 3 * j + 2];      // my re-read of what j pushed into me
+            const SweepOut mine = a.slots[kSlotPrefix];
+            if (ps.stamp != a.stamp || !same_fold(ps, mine)) { fail(CRO_FAIL_P2P_PUSH, j); ok = false; }
+            if (rr.stamp != a.stamp || !same_fold(rr, want)) { fail(CRO_FAIL_P2P_PUSH, j); ok = false; }
+        }
+        if (a.hops) {
+            const unsigned long long end = a.chase_out[2 * j], ns = a.chase_out[2 * j + 1];
+            const unsigned long long x16 = ns * 16ull / a.hops;
+            r->p2p_latency_ns_x16[j] = (uint32_t)(x16 > 0xFFFFFFFFull ? 0xFFFFFFFFull : x16);
+            if (end != a.chase_expect[j]) { fail(CRO_FAIL_P2P_CHASE, j); ok = false; }
+        }
+        if (ok) ok_mask |= 1u << j;
+    }
+    r->p2p_ok = (uint8_t)ok_mask;
+    r->fail_code = (uint8_t)fail_code;
+    r->fail_index = (uint8_t)fail_index;
+    r->status = status;
 }
 
 // ---------------------------------------------------------------------------
@@ -563,37 +900,6 @@ namespace {
 constexpr int kFillThreads = 512, kFillUnroll = 4;
 constexpr int kReadThreads = 512;
 constexpr int kCopyThreads = 512, kCopyUnroll = 8;
-
-int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    if (!v || !*v) return dflt;
-    return atoi(v);
-}
-
-struct TmaTune { unsigned tile, stages, threads, chunk; };
-TmaTune read_tma_tune() {
-    TmaTune t;
-    // defaults = best point of the sweeps in profiles/r01_sweeps.md
-    t.tile = (unsigned)env_int("CRO_TMA_READ_TILE", 32768);
-    t.stages = (unsigned)env_int("CRO_TMA_READ_STAGES", 4);
-    t.threads = (unsigned)env_int("CRO_TMA_READ_THREADS", 160);  // 1 producer + 4 consumer warps
-    t.chunk = (unsigned)env_int("CRO_TMA_READ_CHUNK", 1);
-    if (t.chunk < 1) t.chunk = 1;
-    t.chunk = (t.chunk & 0xFFFFu) | ((unsigned)env_int("CRO_TMA_READ_HINT", 0) << 16);
-    if (t.stages > 16) t.stages = 16;
-    return t;
-}
-TmaTune copy_tma_tune() {
-    TmaTune t;
-    t.tile = (unsigned)env_int("CRO_TMA_COPY_TILE", 32768);
-    t.stages = (unsigned)env_int("CRO_TMA_COPY_STAGES", 4);
-    t.threads = 32;
-    t.chunk = (unsigned)env_int("CRO_TMA_COPY_CHUNK", 1);
-    if (t.chunk < 1) t.chunk = 1;
-    t.chunk = (t.chunk & 0xFFFFu) | ((unsigned)env_int("CRO_TMA_COPY_HINT", 0) << 16);
-    if (t.stages > 16) t.stages = 16;
-    return t;
-}
 }  // namespace
 
 cudaError_t plan_kernels(int device, KernelPlan* plan) {
@@ -607,48 +913,71 @@ cudaError_t plan_kernels(int device, KernelPlan* plan) {
     auto fill = hbm_fill_kernel<kFillThreads, kFillUnroll>;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fill, kFillThreads, 0)) != cudaSuccess)
         return e;
-    plan->fill = {sms * (occ > 0 ? occ : 1) * env_int("CRO_FILL_WAVES", 64), kFillThreads, 0};
+    plan->fill = {sms * (occ > 0 ? occ : 1) * (int)env::get("CRO_FILL_WAVES"), kFillThreads, 0};
 
     auto rd = hbm_read_ldg_kernel<kReadThreads, false>;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rd, kReadThreads, 0)) != cudaSuccess)
         return e;
-    plan->read_ldg = {sms * (occ > 0 ? occ : 1) * env_int("CRO_READ_WAVES", 1), kReadThreads, 0};
+    plan->read_ldg = {sms * (occ > 0 ? occ : 1) * (int)env::get("CRO_READ_WAVES"), kReadThreads, 0};
     auto rdw = hbm_read_ldg_kernel<kReadThreads, true>;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rdw, kReadThreads, 0)) != cudaSuccess)
         return e;
-    plan->read_ldg256 = {sms * (occ > 0 ? occ : 1) * env_int("CRO_READ_WAVES", 1), kReadThreads, 0};
+    plan->read_ldg256 = {sms * (occ > 0 ? occ : 1) * (int)env::get("CRO_READ_WAVES"), kReadThreads, 0};
 
     auto cp = hbm_copy_ldg_kernel<kCopyThreads, kCopyUnroll>;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cp, kCopyThreads, 0)) != cudaSuccess)
         return e;
-    plan->copy_ldg = {sms * (occ > 0 ? occ : 1) * env_int("CRO_COPY_WAVES", 128), kCopyThreads, 0};
+    plan->copy_ldg = {sms * (occ > 0 ? occ : 1) * (int)env::get("CRO_COPY_WAVES"), kCopyThreads, 0};
 
     {
-        const TmaTune t = read_tma_tune();
-        const size_t smem = (size_t)t.tile * t.stages;
+        plan->read_tile = env::get("CRO_TMA_READ_TILE");
+        plan->read_stages = env::get("CRO_TMA_READ_STAGES");
+        plan->read_chunk = (env::get("CRO_TMA_READ_CHUNK") & 0xFFFFu) | (env::get("CRO_TMA_READ_HINT") << 16);
+        plan->read_dyn = env::get("CRO_TMA_READ_DYN");
+        const int threads = (int)env::get("CRO_TMA_READ_THREADS");
+        const size_t smem = (size_t)plan->read_tile * plan->read_stages;
         if ((e = cudaFuncSetAttribute(hbm_read_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem)) != cudaSuccess)
             return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hbm_read_tma_kernel,
-                                                               (int)t.threads, smem)) != cudaSuccess)
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hbm_read_tma_kernel, threads, smem)) != cudaSuccess)
             return e;
-        plan->read_tma = {sms * (occ > 0 ? occ : 1) * env_int("CRO_TMA_READ_WAVES", 1), (int)t.threads, smem};
+        plan->read_tma = {sms * (occ > 0 ? occ : 1) * (int)env::get("CRO_TMA_READ_WAVES"), threads, smem};
     }
     {
-        const TmaTune t = copy_tma_tune();
-        const size_t smem = (size_t)t.tile * t.stages;
+        plan->copy_tile = env::get("CRO_TMA_COPY_TILE");
+        plan->copy_stages = env::get("CRO_TMA_COPY_STAGES");
+        plan->copy_chunk = (env::get("CRO_TMA_COPY_CHUNK") & 0xFFFFu) | (env::get("CRO_TMA_COPY_HINT") << 16);
+        plan->copy_dyn = env::get("CRO_TMA_COPY_DYN");
+        const size_t smem = (size_t)plan->copy_tile * plan->copy_stages;
         if ((e = cudaFuncSetAttribute(hbm_copy_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem)) != cudaSuccess)
             return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hbm_copy_tma_kernel, 32, smem)) !=
             cudaSuccess)
             return e;
-        plan->copy_tma = {sms * (occ > 0 ? occ : 1) * env_int("CRO_TMA_COPY_WAVES", 1), 32, smem};
+        plan->copy_tma = {sms * (occ > 0 ? occ : 1) * (int)env::get("CRO_TMA_COPY_WAVES"), 32, smem};
+    }
+    {
+        plan->fused_tile = env::get("CRO_FUSED_TILE");
+        plan->fused_stages = env::get("CRO_FUSED_STAGES");
+        plan->fused_chunk = env::get("CRO_FUSED_CHUNK") & 0xFFFFu;
+        plan->fused_threads = env::get("CRO_FUSED_THREADS");
+        const size_t smem = (size_t)plan->fused_tile * plan->fused_stages;
+        if ((e = cudaFuncSetAttribute(hbm_copy_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem)) != cudaSuccess)
+            return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hbm_copy_fused_kernel,
+                                                               (int)plan->fused_threads, smem)) != cudaSuccess)
+            return e;
+        plan->copy_fused = {sms * (occ > 0 ? occ : 1), (int)plan->fused_threads, smem};
     }
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hbm_expected_kernel, 256, 0)) !=
         cudaSuccess)
         return e;
-    plan->expect = {sms * (occ > 0 ? occ : 1), 256, 0};
+    // The generator runs BESIDE the copy sweeps: it may not fill the SM, or the copy's CTA (160 threads, 128 KiB of
+    // shared memory) would have to wait for it to drain.  2 CTAs of 256 threads per SM keep the ALUs ~busy and leave
+    // the copy's consumer warps their issue slots.
+    plan->expect = {sms * std::min<int>(occ > 0 ? occ : 1, (int)env::get("CRO_EXPECT_CTAS")), 256, 0};
     return cudaSuccess;
 }
 
@@ -658,48 +987,50 @@ static int clamp_grid(int planned, uint64_t bytes, uint64_t tile_bytes) {
     return (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)planned, tiles));
 }
 
-cudaError_t launch_fill(const KernelPlan& p, void* base, uint64_t bytes, uint64_t seed,
-                        cudaStream_t st) {
+cudaError_t launch_fill(const KernelPlan& p, void* base, uint64_t bytes, const Params& pr,
+                        const SweepScratch& sc, SweepOut* out, cudaStream_t st) {
     hbm_fill_kernel<kFillThreads, kFillUnroll><<<clamp_grid(p.fill.grid, bytes, kFillThreads * kFillUnroll * 16), p.fill.block, 0, st>>>(
-        static_cast<uint4*>(base), bytes >> 4, seed);
+        static_cast<uint4*>(base), bytes >> 4, pr.imm, pr.pp, sc, out);
     return cudaGetLastError();
 }
 
 cudaError_t launch_read(const KernelPlan& p, unsigned variant, const void* base, uint64_t bytes,
-                        const SweepScratch& sc, SweepOut* out, cudaStream_t st) {
+                        const Params& pr, const SweepScratch& sc, SweepOut* out, cudaStream_t st) {
     if (variant == READ_TMA) {
-        const TmaTune t = read_tma_tune();
-        unsigned long long* ctr = nullptr;
-        if (env_int("CRO_TMA_READ_DYN", 1) && sc.tile_ctr) {
-            ctr = sc.tile_ctr;
-            cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st);
-            if (e != cudaSuccess) return e;
-        }
-        hbm_read_tma_kernel<<<clamp_grid(p.read_tma.grid, bytes, t.tile), p.read_tma.block, p.read_tma.smem, st>>>(
-            static_cast<const unsigned char*>(base), bytes, t.tile, t.stages, t.chunk, ctr, sc, out);
+        hbm_read_tma_kernel<<<clamp_grid(p.read_tma.grid, bytes, p.read_tile), p.read_tma.block, p.read_tma.smem, st>>>(
+            static_cast<const unsigned char*>(base), bytes, p.read_tile, p.read_stages, p.read_chunk,
+            (p.read_dyn && sc.tile_ctr) ? sc.tile_ctr : nullptr, pr.imm, pr.pp, sc, out);
     } else if (variant == READ_LDG256) {
         hbm_read_ldg_kernel<kReadThreads, true><<<clamp_grid(p.read_ldg256.grid, bytes, kReadThreads * 128), p.read_ldg256.block, 0, st>>>(
-            static_cast<const uint4*>(base), bytes >> 4, sc, out);
+            static_cast<const uint4*>(base), bytes >> 4, pr.imm, pr.pp, sc, out);
     } else {
         hbm_read_ldg_kernel<kReadThreads, false><<<clamp_grid(p.read_ldg.grid, bytes, kReadThreads * 128), p.read_ldg.block, 0, st>>>(
-            static_cast<const uint4*>(base), bytes >> 4, sc, out);
+            static_cast<const uint4*>(base), bytes >> 4, pr.imm, pr.pp, sc, out);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_copy(const KernelPlan& p, unsigned variant, void* dst, const void* src,
-                        uint64_t bytes, const SweepScratch& sc, cudaStream_t st) {
-    if (variant == COPY_TMA) {
-        const TmaTune t = copy_tma_tune();
+cudaError_t launch_copy(const KernelPlan& p, unsigned variant, void* dst, const void* src, uint64_t bytes,
+                        const Params& pr, const SweepScratch& sc, SweepOut* out, cudaStream_t st) {
+    if (variant == COPY_TMA_FUSED) {
+        if (!out) return cudaErrorInvalidValue;
+        hbm_copy_fused_kernel<<<clamp_grid(p.copy_fused.grid, bytes, p.fused_tile), p.copy_fused.block, p.copy_fused.smem, st>>>(
+            static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), bytes, p.fused_tile,
+            p.fused_stages, p.fused_chunk, sc.tile_ctr, pr.imm, pr.pp, sc, out);
+    } else if (variant == COPY_TMA) {
         unsigned long long* ctr = nullptr;
-        if (env_int("CRO_TMA_COPY_DYN", 1) && sc.tile_ctr) {
+        if (p.copy_dyn && sc.tile_ctr) {     // this kernel has no epilogue that could re-arm the counter
             ctr = sc.tile_ctr;
             cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st);
             if (e != cudaSuccess) return e;
         }
-        hbm_copy_tma_kernel<<<clamp_grid(p.copy_tma.grid, bytes, t.tile), p.copy_tma.block, p.copy_tma.smem, st>>>(
-            static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), bytes, t.tile,
-            t.stages, t.chunk, ctr);
+        hbm_copy_tma_kernel<<<clamp_grid(p.copy_tma.grid, bytes, p.copy_tile), p.copy_tma.block, p.copy_tma.smem, st>>>(
+            static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), bytes, p.copy_tile,
+            p.copy_stages, p.copy_chunk, ctr);
+        if (ctr) {
+            cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st);   // leave it armed for the self-resetting kernels
+            if (e != cudaSuccess) return e;
+        }
     } else {
         hbm_copy_ldg_kernel<kCopyThreads, kCopyUnroll><<<clamp_grid(p.copy_ldg.grid, bytes, kCopyThreads * kCopyUnroll * 16), p.copy_ldg.block, 0, st>>>(
             static_cast<uint4*>(dst), static_cast<const uint4*>(src), bytes >> 4);
@@ -707,9 +1038,9 @@ cudaError_t launch_copy(const KernelPlan& p, unsigned variant, void* dst, const 
     return cudaGetLastError();
 }
 
-cudaError_t launch_expected(const KernelPlan& p, uint64_t bytes, uint64_t seed,
+cudaError_t launch_expected(const KernelPlan& p, uint64_t bytes, const Params& pr,
                             const SweepScratch& sc, SweepOut* out, cudaStream_t st) {
-    hbm_expected_kernel<<<p.expect.grid, p.expect.block, 0, st>>>(bytes >> 3, seed, sc, out);
+    hbm_expected_kernel<<<p.expect.grid, p.expect.block, 0, st>>>(bytes >> 3, pr.imm, pr.pp, sc, out);
     return cudaGetLastError();
 }
 
@@ -718,9 +1049,19 @@ cudaError_t launch_xor_word(void* base, uint64_t word_index, uint64_t mask, cuda
     return cudaGetLastError();
 }
 
-cudaError_t launch_chase(const unsigned long long* next, uint32_t start, uint32_t hops,
-                         unsigned long long* out, cudaStream_t st) {
-    chase_kernel<<<1, 1, 0, st>>>(next, start, hops, out);
+cudaError_t launch_chase(const ChaseArgs& a, unsigned long long* out, cudaStream_t st) {
+    if (a.n == 0 || a.n > CRO_MAX_DEVICES) return cudaErrorInvalidValue;
+    chase_kernel<<<1, 32 * a.n, 0, st>>>(a, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
+    probe_finalize_kernel<<<1, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_p2p_finalize(const P2PFinalizeArgs& a, cudaStream_t st) {
+    p2p_finalize_kernel<<<1, 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -1,5 +1,6 @@
-// probe.cu — probe context: enumeration, resident sweep buffers, timed sweeps,
-// concurrent multi-device probe with NVLink rounds and the one NCCL all-gather.
+// probe.cu — probe context: enumeration, resident sweep buffers, the probe as
+// one CUDA graph with a device-written verdict, and the full-box probe
+// (concurrent HBM probes, NVLink rounds chained by events, one NCCL all-gather).
 //
 // Reference slot: utils.RunNvidiaSmi (internal/utils/gpus.go:666-689) and
 // utils.CheckGPUVisible (internal/utils/gpus.go:54-86) as called from
@@ -17,18 +18,19 @@
 #include <random>
 #include <thread>
 
+#include <nvtx3/nvToolsExt.h>
+
+#include "env.hpp"
 #include "identity.hpp"
 
 namespace cro {
 
 namespace {
 
-constexpr int kMaxSweeps = 64;
 constexpr uint64_t kDefaultSweep = 4ull << 30;
 constexpr uint64_t kDefaultP2P = 1ull << 30;
 constexpr uint64_t kDefaultSeedBase = 0x00C0FFEE00000000ull;
-constexpr uint32_t kDefaultHops = 4096;
-constexpr uint32_t kChaseSlots = 16384;      // one 8-byte slot per 128-byte line → 2 MiB
+constexpr uint32_t kDefaultHops = 16384;
 
 #define CU_TRY(ctx, expr)                                                              \
     do {                                                                               \
@@ -40,11 +42,20 @@ constexpr uint32_t kChaseSlots = 16384;      // one 8-byte slot per 128-byte lin
     } while (0)
 
 uint64_t ms_to_ns(float ms) { return (uint64_t)((double)ms * 1.0e6 + 0.5); }
-
-int env_u32(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
+uint64_t now_ns() {
+    return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+
+// NVTX ranges around the host-side phases; nsys / ncu --nvtx pick them up, nothing else pays.
+struct Range {
+    bool on;
+    Range(const cro_ctx* c, const char* name) : on(c->nvtx) { if (on) nvtxRangePushA(name); }
+    ~Range() { if (on) nvtxRangePop(); }
+};
+
+Params imm_params(const Device* d) { return Params{ProbeParams{d->seed_cur, d->nonce_cur}, nullptr}; }
+Params graph_params(const Device* d) { return Params{ProbeParams{0, 0}, d->d_params}; }
+uint64_t seed_of(const Device* d, uint64_t nonce) { return d->seed_dev + nonce * kNonceStride; }
 
 int ensure_region(cro_ctx* c, Device* d) {
     if (d->region) return CRO_OK;
@@ -59,7 +70,6 @@ int ensure_region(cro_ctx* c, Device* d) {
         if (e == cudaSuccess) {
             if (s != d->sweep_bytes) {
                 d->sweep_bytes = s;
-                d->have_expected = false;   // the closed form depends on S
                 if (d->graph_exec) { cudaGraphExecDestroy(d->graph_exec); d->graph_exec = nullptr; }
             }
             break;
@@ -80,23 +90,9 @@ int ensure_filled(cro_ctx* c, Device* d) {
     int rc = ensure_region(c, d);
     if (rc) return rc;
     if (d->filled) return CRO_OK;
-    CU_TRY(c, launch_fill(d->plan, d->region, d->sweep_bytes, d->seed, d->stream));
+    CU_TRY(c, launch_fill(d->plan, d->region, d->sweep_bytes, imm_params(d), d->scratch, nullptr, d->stream));
     c->launches++;
     d->filled = true;
-    return CRO_OK;
-}
-
-int ensure_expected(cro_ctx* c, Device* d) {
-    if (d->have_expected) return CRO_OK;
-    CU_TRY(c, launch_expected(d->plan, d->sweep_bytes, d->seed, d->scratch, &d->d_out[kMaxSweeps - 1],
-                              d->stream));
-    c->launches++;
-    CU_TRY(c, cudaMemcpyAsync(&d->h_out[kMaxSweeps - 1], &d->d_out[kMaxSweeps - 1], sizeof(SweepOut),
-                              cudaMemcpyDeviceToHost, d->stream));
-    CU_TRY(c, cudaStreamSynchronize(d->stream));
-    d->expect_x = d->h_out[kMaxSweeps - 1].x;
-    d->expect_s = d->h_out[kMaxSweeps - 1].s;
-    d->have_expected = true;
     return CRO_OK;
 }
 
@@ -129,17 +125,53 @@ void copy_cstr(char* dst, size_t cap, const std::string& s) {
     memcpy(dst, s.data(), std::min(cap - 1, s.size()));
 }
 
+int alloc_scratch(cro_ctx* c, SweepScratch* sc, int max_grid) {
+    CU_TRY(c, cudaMalloc(&sc->partials, sizeof(ulonglong4) * (size_t)max_grid));
+    CU_TRY(c, cudaMalloc(&sc->counter, sizeof(unsigned)));
+    CU_TRY(c, cudaMalloc(&sc->tmin, sizeof(unsigned long long)));
+    CU_TRY(c, cudaMalloc(&sc->tmax, sizeof(unsigned long long)));
+    CU_TRY(c, cudaMalloc(&sc->tile_ctr, sizeof(unsigned long long)));
+    CU_TRY(c, cudaMemset(sc->tile_ctr, 0, sizeof(unsigned long long)));
+    CU_TRY(c, cudaMemset(sc->counter, 0, sizeof(unsigned)));
+    CU_TRY(c, cudaMemset(sc->tmin, 0xFF, sizeof(unsigned long long)));
+    CU_TRY(c, cudaMemset(sc->tmax, 0, sizeof(unsigned long long)));
+    return CRO_OK;
+}
+void free_scratch(SweepScratch* sc) {
+    cudaFree(sc->partials);
+    cudaFree(sc->counter);
+    cudaFree(sc->tmin);
+    cudaFree(sc->tmax);
+    cudaFree(sc->tile_ctr);
+}
+
 }  // namespace
 
 uint32_t resolve_read_variant(uint32_t v, uint64_t bytes) {
     // AUTO: the TMA ring wins from ~1 GiB up (7.46 vs 7.31 TB/s at 4 GiB); for small sweeps its fixed
     // cost (one CTA per SM, atomic tile claims) loses to plain LDG (profiles/r01_size_sweep.jsonl).
-    if (v == CRO_READ_AUTO) v = (uint32_t)env_u32("CRO_READ_VARIANT", bytes <= (128ull << 20) ? CRO_READ_LDG : CRO_READ_TMA);
+    if (v == CRO_READ_AUTO) {
+        v = env::get("CRO_READ_VARIANT");
+        if (v == CRO_READ_AUTO) v = bytes <= (128ull << 20) ? CRO_READ_LDG : CRO_READ_TMA;
+    }
     return (v == READ_LDG || v == READ_TMA || v == READ_LDG256) ? v : (uint32_t)READ_TMA;
 }
 uint32_t resolve_copy_variant(uint32_t v) {
-    if (v == CRO_COPY_AUTO) v = (uint32_t)env_u32("CRO_COPY_VARIANT", CRO_COPY_TMA);
-    return (v == COPY_LDG || v == COPY_TMA) ? v : (uint32_t)COPY_TMA;
+    if (v == CRO_COPY_AUTO) {
+        v = env::get("CRO_COPY_VARIANT");
+        if (v == CRO_COPY_AUTO) v = CRO_COPY_TMA_FUSED;
+    }
+    return (v == COPY_LDG || v == COPY_TMA || v == COPY_TMA_FUSED) ? v : (uint32_t)COPY_TMA_FUSED;
+}
+
+void chase_permutation(int minor_src, int minor_dst, std::vector<uint32_t>* perm) {
+    perm->resize(kChaseSlots);
+    for (uint32_t i = 0; i < kChaseSlots; ++i) (*perm)[i] = i;
+    std::mt19937_64 rng((uint64_t)((long long)minor_src * 8 + (long long)minor_dst));
+    for (uint32_t i = kChaseSlots - 1; i > 0; --i) {        // Sattolo: one cycle through every slot
+        const uint32_t j = (uint32_t)(rng() % i);
+        std::swap((*perm)[i], (*perm)[j]);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -151,6 +183,37 @@ static void refresh_ecc(cro_ctx* c, Device* d) {
     unsigned long long ecc = 0;
     if (identity::NvmlEccUncorrected(std::string(d->info.gpu_uuid, strnlen(d->info.gpu_uuid, sizeof d->info.gpu_uuid)), &ecc))
         d->ecc_uncorrected = (uint32_t)std::min<unsigned long long>(ecc, 0xFFFFFFFFull);
+}
+
+// Stages the fields of the result that the device cannot know (identity strings, NVML readings, options)
+// into the template the finalize kernel starts from.  Caller has the device current.
+static int stage_template(cro_ctx* c, Device* d) {
+    cro_probe_result& t = d->tmpl;
+    memset(&t, 0, sizeof t);
+    t.abi_version = CRO_ABI_VERSION;
+    t.cuda_ordinal = d->ordinal;
+    t.device_minor = d->info.device_minor;
+    memcpy(t.gpu_uuid, d->info.gpu_uuid, sizeof t.gpu_uuid);
+    memcpy(t.pci_bus_id, d->info.pci_bus_id, sizeof t.pci_bus_id);
+    t.hbm_bytes_total = d->info.hbm_bytes_total;
+    t.sweep_bytes = d->sweep_bytes;
+    t.sm_count = d->info.sm_count;
+    t.sm_clock_mhz = d->sm_clock_mhz;
+    t.mem_clock_mhz = d->mem_clock_mhz;
+    t.ecc_errors = d->ecc_uncorrected;
+    t.rank = (uint8_t)(c->opts.rank_base + (uint32_t)d->index);
+    t.world = (uint8_t)(c->opts.world_override ? c->opts.world_override : (uint32_t)c->devs.size());
+    t.p2p_bytes = c->opts.p2p_bytes;
+    if (c->peers_enabled)
+        for (size_t j = 0; j < c->devs.size() && j < 8; ++j) {
+            if ((int)j == d->index) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, d->ordinal, c->devs[j]->ordinal);
+            t.p2p_access[j] = (uint8_t)can;
+        }
+    CU_TRY(c, cudaMemcpyAsync(d->d_tmpl, &t, sizeof t, cudaMemcpyHostToDevice, d->stream));
+    CU_TRY(c, cudaStreamSynchronize(d->stream));    // `t` lives in pageable memory
+    return CRO_OK;
 }
 
 int ctx_create(const cro_opts* o, cro_ctx** out) {
@@ -168,12 +231,24 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
     if (opts.seed_base == 0) opts.seed_base = kDefaultSeedBase;
     if (opts.read_sweeps == 0) opts.read_sweeps = 5;
     if (opts.copy_sweeps == 0) opts.copy_sweeps = 5;
-    if (opts.read_sweeps > kMaxSweeps - 2 || opts.copy_sweeps > kMaxSweeps - 2) return CRO_ERR_INVALID_ARG;
+    if (opts.read_sweeps > kMaxSweepsEach || opts.copy_sweeps > kMaxSweepsEach) return CRO_ERR_INVALID_ARG;
     if (opts.latency_hops == 0) opts.latency_hops = kDefaultHops;
     if (opts.n_devices < 0 || opts.n_devices > CRO_MAX_DEVICES) return CRO_ERR_INVALID_ARG;
 
     std::unique_ptr<cro_ctx> c(new cro_ctx);
     c->opts = opts;
+    {
+        // the CRO_* knobs, validated the way the reference validates its own environment
+        // (internal/controller/composableresource_adapter.go:42-45)
+        std::string why;
+        if (!env::reload(&why)) {
+            c->set_error(why);
+            return CRO_ERR_INVALID_ARG;
+        }
+        c->nvtx = env::get("CRO_NVTX") != 0;
+        if (const char* pr = getenv("CRO_PROC_ROOT"))
+            if (*pr) c->proc_root = pr;
+    }
 
     int n_cuda = 0;
     cudaError_t e = cudaGetDeviceCount(&n_cuda);
@@ -197,10 +272,12 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
         for (int i = 0; i < n_cuda && i < CRO_MAX_DEVICES; ++i) ordinals.push_back(i);
     }
 
+    // Identity: /proc first (a directory walk, ~0.06 ms), NVML only when asked to (its first call costs
+    // tens of ms and serialises across processes) — CRO_F_NO_NVML keeps it off the hot-plug path entirely.
+    const std::vector<identity::ProcGpu> proc = identity::ScanProc(c->proc_root);
     std::vector<identity::NvmlGpu> nvml;
     bool have_nvml = false;
     if (!(opts.flags & CRO_F_NO_NVML)) have_nvml = identity::ScanNvml(&nvml, nullptr);
-    const std::vector<identity::ProcGpu> proc = identity::ScanProc("/proc");
 
     struct Keyed { std::unique_ptr<Device> d; long long key; };
     std::vector<Keyed> keyed;
@@ -256,35 +333,45 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
         Device* d = keyed[i].d.get();
         d->index = (int)i;
         d->sweep_bytes = opts.sweep_bytes;
-        d->seed = opts.seed_base | (uint64_t)(d->info.device_minor >= 0 ? d->info.device_minor : d->ordinal);
+        d->seed_dev = opts.seed_base | (uint64_t)(d->info.device_minor >= 0 ? d->info.device_minor : d->ordinal);
+        d->seed_cur = d->seed_dev;
         CU_TRY(c.get(), cudaSetDevice(d->ordinal));
         CU_TRY(c.get(), cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        CU_TRY(c.get(), cudaStreamCreateWithFlags(&d->aux, cudaStreamNonBlocking));
         CU_TRY(c.get(), cudaEventCreate(&d->ev0));
         CU_TRY(c.get(), cudaEventCreate(&d->ev1));
+        for (cudaEvent_t* ev : {&d->ev_fork, &d->ev_join, &d->ev_hbm_done, &d->ev_aux_done, &d->ev_chase_ready})
+            CU_TRY(c.get(), cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         CU_TRY(c.get(), plan_kernels(d->ordinal, &d->plan));
-        int max_grid = std::max({d->plan.fill.grid, d->plan.read_ldg.grid, d->plan.read_ldg256.grid,
-                                 d->plan.read_tma.grid, d->plan.expect.grid, 1});
-        CU_TRY(c.get(), cudaMalloc(&d->scratch.partials, sizeof(ulonglong2) * (size_t)max_grid));
-        CU_TRY(c.get(), cudaMalloc(&d->scratch.counter, sizeof(unsigned)));
-        CU_TRY(c.get(), cudaMalloc(&d->scratch.tmin, sizeof(unsigned long long)));
-        CU_TRY(c.get(), cudaMalloc(&d->scratch.tmax, sizeof(unsigned long long)));
-        CU_TRY(c.get(), cudaMalloc(&d->scratch.tile_ctr, sizeof(unsigned long long)));
-        CU_TRY(c.get(), cudaMemset(d->scratch.tile_ctr, 0, sizeof(unsigned long long)));
-        CU_TRY(c.get(), cudaMemset(d->scratch.counter, 0, sizeof(unsigned)));
-        CU_TRY(c.get(), cudaMemset(d->scratch.tmin, 0xFF, sizeof(unsigned long long)));
-        CU_TRY(c.get(), cudaMemset(d->scratch.tmax, 0, sizeof(unsigned long long)));
-        CU_TRY(c.get(), cudaMalloc(&d->d_out, sizeof(SweepOut) * kMaxSweeps));
-        CU_TRY(c.get(), cudaMallocHost(&d->h_out, sizeof(SweepOut) * kMaxSweeps));
+        const int max_grid = std::max({d->plan.fill.grid, d->plan.read_ldg.grid, d->plan.read_ldg256.grid,
+                                       d->plan.read_tma.grid, d->plan.copy_fused.grid, d->plan.expect.grid, 1});
+        int rc = alloc_scratch(c.get(), &d->scratch, max_grid);
+        if (rc) return rc;
+        if ((rc = alloc_scratch(c.get(), &d->scratch_aux, max_grid))) return rc;
+        if ((rc = alloc_scratch(c.get(), &d->scratch_pfx, max_grid))) return rc;
+        CU_TRY(c.get(), cudaMalloc(&d->d_out, sizeof(SweepOut) * kSlotCount));
+        CU_TRY(c.get(), cudaMemset(d->d_out, 0xFF, sizeof(SweepOut) * kSlotCount));   // no slot starts with a plausible stamp
+        CU_TRY(c.get(), cudaMallocHost(&d->h_out, sizeof(SweepOut) * kSlotCount));
+        CU_TRY(c.get(), cudaMalloc(&d->d_params, sizeof(ProbeParams)));
+        CU_TRY(c.get(), cudaMallocHost(&d->h_params, sizeof(ProbeParams)));
+        CU_TRY(c.get(), cudaMalloc(&d->d_tmpl, sizeof(cro_probe_result)));
         CU_TRY(c.get(), cudaMalloc(&d->d_result, sizeof(cro_probe_result)));
         CU_TRY(c.get(), cudaMalloc(&d->d_gather, sizeof(cro_probe_result) * CRO_MAX_DEVICES));
+        CU_TRY(c.get(), cudaMallocHost(&d->h_result, sizeof(cro_probe_result)));
+        CU_TRY(c.get(), cudaMallocHost(&d->h_gather, sizeof(cro_probe_result) * CRO_MAX_DEVICES));
         CU_TRY(c.get(), cudaMemset(d->d_result, 0, sizeof(cro_probe_result)));
-        CU_TRY(c.get(), cudaMalloc(&d->d_chase_out, 4 * sizeof(unsigned long long)));
+        CU_TRY(c.get(), cudaMalloc(&d->d_chase_out, 2 * CRO_MAX_DEVICES * sizeof(unsigned long long)));
+        CU_TRY(c.get(), cudaMallocHost(&d->h_chase_out, 2 * CRO_MAX_DEVICES * sizeof(unsigned long long)));
         if (!(opts.flags & CRO_F_LAZY_ALLOC)) {
-            int rc = ensure_region(c.get(), d);
-            if (rc) return rc;
+            if ((rc = ensure_region(c.get(), d))) return rc;
         }
         refresh_ecc(c.get(), d);
         c->devs.push_back(std::move(keyed[i].d));
+    }
+    for (auto& d : c->devs) {
+        CU_TRY(c.get(), cudaSetDevice(d->ordinal));
+        int rc = stage_template(c.get(), d.get());
+        if (rc) return rc;
     }
     *out = c.release();
     return CRO_OK;
@@ -306,22 +393,30 @@ Device::~Device() {
     if (ordinal < 0) return;                      // never bound to a CUDA device: owns nothing
     cudaSetDevice(ordinal);
     if (stream) cudaStreamSynchronize(stream);
+    if (aux) cudaStreamSynchronize(aux);
     cudaFree(region);                             // cudaFree(nullptr) is a no-op
-    cudaFree(scratch.partials);
-    cudaFree(scratch.counter);
-    cudaFree(scratch.tmin);
-    cudaFree(scratch.tmax);
-    cudaFree(scratch.tile_ctr);
+    free_scratch(&scratch);
+    free_scratch(&scratch_aux);
+    free_scratch(&scratch_pfx);
     cudaFree(d_out);
     if (h_out) cudaFreeHost(h_out);
+    cudaFree(d_params);
+    if (h_params) cudaFreeHost(h_params);
+    cudaFree(d_tmpl);
     cudaFree(d_result);
     cudaFree(d_gather);
-    cudaFree(d_chase_next);
+    if (h_result) cudaFreeHost(h_result);
+    if (h_gather) cudaFreeHost(h_gather);
+    for (unsigned long long* t : d_chase_tables) cudaFree(t);
     cudaFree(d_chase_out);
+    if (h_chase_out) cudaFreeHost(h_chase_out);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     for (cudaEvent_t e : evpool) cudaEventDestroy(e);
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
+    for (cudaEvent_t e : ev_push_done) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_reread_done) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ev0, ev1, ev_fork, ev_join, ev_hbm_done, ev_aux_done, ev_chase_ready})
+        if (e) cudaEventDestroy(e);
+    if (aux) cudaStreamDestroy(aux);
     if (stream) cudaStreamDestroy(stream);
     cudaGetLastError();                           // a failed release must not poison the caller's next CUDA call
 }
@@ -337,7 +432,7 @@ void ctx_destroy(cro_ctx* c) {
     delete c;                                     // ~Device releases the per-device CUDA objects
 }
 
-static void drain_pending_fwd(cro_ctx* c, Device* d);
+static void drain_pending(cro_ctx* c, Device* d);
 
 static Device* dev_at(cro_ctx* c, int idx) {
     if (!c || idx < 0 || idx >= (int)c->devs.size()) return nullptr;
@@ -345,28 +440,37 @@ static Device* dev_at(cro_ctx* c, int idx) {
 }
 
 // ---------------------------------------------------------------------------
-// single sweeps
+// single sweeps (tests, tuning, bench context): immediate seed, scratch slots
 // ---------------------------------------------------------------------------
+static void slot_to_result(const SweepOut& s, cro_sweep_result* out) {
+    out->checksum_xor = s.x;
+    out->checksum_sum = s.s;
+    out->checksum_wsum = s.w;
+    out->timer_ns = s.t1 - s.t0;
+}
+
 int ctx_fill(cro_ctx* c, int idx, uint32_t iters, cro_sweep_result* out) {
     Device* d = dev_at(c, idx);
     if (!d || !out || iters == 0) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
-    drain_pending_fwd(c, d);
+    drain_pending(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
     int rc = ensure_region(c, d);
     if (rc) return rc;
     CU_TRY(c, cudaEventRecord(d->ev0, d->stream));
     for (uint32_t i = 0; i < iters; ++i)
-        CU_TRY(c, launch_fill(d->plan, d->region, d->sweep_bytes, d->seed, d->stream));
+        CU_TRY(c, launch_fill(d->plan, d->region, d->sweep_bytes, imm_params(d), d->scratch, &d->d_out[kSlotScratch], d->stream));
     CU_TRY(c, cudaEventRecord(d->ev1, d->stream));
     c->launches += iters;
     d->filled = true;
+    CU_TRY(c, cudaMemcpyAsync(&d->h_out[kSlotScratch], &d->d_out[kSlotScratch], sizeof(SweepOut), cudaMemcpyDeviceToHost, d->stream));
     if ((rc = wait_stream(c, d))) return rc;
     float ms = 0;
     CU_TRY(c, cudaEventElapsedTime(&ms, d->ev0, d->ev1));
     memset(out, 0, sizeof *out);
     out->bytes = d->sweep_bytes * iters;
     out->ns = ms_to_ns(ms);
+    out->timer_ns = d->h_out[kSlotScratch].t1 - d->h_out[kSlotScratch].t0;
     out->launches = iters;
     return CRO_OK;
 }
@@ -377,17 +481,17 @@ int ctx_read(cro_ctx* c, int idx, uint32_t variant, uint32_t iters, bool dst_hal
     if (!d || !out || iters == 0) return CRO_ERR_INVALID_ARG;
     variant = resolve_read_variant(variant, d->sweep_bytes);
     std::lock_guard<std::mutex> g(d->mu);
-    drain_pending_fwd(c, d);
+    drain_pending(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
     int rc = ensure_filled(c, d);
     if (rc) return rc;
     const unsigned char* base = d->region + (dst_half ? d->sweep_bytes : 0);
     CU_TRY(c, cudaEventRecord(d->ev0, d->stream));
     for (uint32_t i = 0; i < iters; ++i)
-        CU_TRY(c, launch_read(d->plan, variant, base, d->sweep_bytes, d->scratch, &d->d_out[0], d->stream));
+        CU_TRY(c, launch_read(d->plan, variant, base, d->sweep_bytes, imm_params(d), d->scratch, &d->d_out[kSlotScratch], d->stream));
     CU_TRY(c, cudaEventRecord(d->ev1, d->stream));
     c->launches += iters;
-    CU_TRY(c, cudaMemcpyAsync(&d->h_out[0], &d->d_out[0], sizeof(SweepOut), cudaMemcpyDeviceToHost,
+    CU_TRY(c, cudaMemcpyAsync(&d->h_out[kSlotScratch], &d->d_out[kSlotScratch], sizeof(SweepOut), cudaMemcpyDeviceToHost,
                               d->stream));
     if ((rc = wait_stream(c, d))) return rc;
     float ms = 0;
@@ -395,8 +499,7 @@ int ctx_read(cro_ctx* c, int idx, uint32_t variant, uint32_t iters, bool dst_hal
     memset(out, 0, sizeof *out);
     out->bytes = d->sweep_bytes * iters;
     out->ns = ms_to_ns(ms);
-    out->checksum_xor = d->h_out[0].x;
-    out->checksum_sum = d->h_out[0].s;
+    slot_to_result(d->h_out[kSlotScratch], out);
     out->variant = variant;
     out->launches = iters;
     return CRO_OK;
@@ -407,22 +510,26 @@ int ctx_copy(cro_ctx* c, int idx, uint32_t variant, uint32_t iters, cro_sweep_re
     if (!d || !out || iters == 0) return CRO_ERR_INVALID_ARG;
     variant = resolve_copy_variant(variant);
     std::lock_guard<std::mutex> g(d->mu);
-    drain_pending_fwd(c, d);
+    drain_pending(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
     int rc = ensure_filled(c, d);
     if (rc) return rc;
+    CU_TRY(c, cudaMemsetAsync(&d->d_out[kSlotScratch], 0, sizeof(SweepOut), d->stream));
     CU_TRY(c, cudaEventRecord(d->ev0, d->stream));
     for (uint32_t i = 0; i < iters; ++i)
-        CU_TRY(c, launch_copy(d->plan, variant, d->region + d->sweep_bytes, d->region, d->sweep_bytes,
-                              d->scratch, d->stream));
+        CU_TRY(c, launch_copy(d->plan, variant, d->region + d->sweep_bytes, d->region, d->sweep_bytes, imm_params(d),
+                              d->scratch, &d->d_out[kSlotScratch], d->stream));
     CU_TRY(c, cudaEventRecord(d->ev1, d->stream));
     c->launches += iters;
+    CU_TRY(c, cudaMemcpyAsync(&d->h_out[kSlotScratch], &d->d_out[kSlotScratch], sizeof(SweepOut), cudaMemcpyDeviceToHost,
+                              d->stream));
     if ((rc = wait_stream(c, d))) return rc;
     float ms = 0;
     CU_TRY(c, cudaEventElapsedTime(&ms, d->ev0, d->ev1));
     memset(out, 0, sizeof *out);
     out->bytes = 2 * d->sweep_bytes * iters;
     out->ns = ms_to_ns(ms);
+    if (variant == COPY_TMA_FUSED) slot_to_result(d->h_out[kSlotScratch], out);   // checksum of the source as read
     out->variant = variant;
     out->launches = iters;
     return CRO_OK;
@@ -432,21 +539,21 @@ int ctx_expected(cro_ctx* c, int idx, cro_sweep_result* out) {
     Device* d = dev_at(c, idx);
     if (!d || !out) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
-    drain_pending_fwd(c, d);
+    drain_pending(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
-    d->have_expected = false;
     CU_TRY(c, cudaEventRecord(d->ev0, d->stream));
-    int rc = ensure_expected(c, d);
-    if (rc) return rc;
+    CU_TRY(c, launch_expected(d->plan, d->sweep_bytes, imm_params(d), d->scratch, &d->d_out[kSlotScratch], d->stream));
+    c->launches++;
     CU_TRY(c, cudaEventRecord(d->ev1, d->stream));
+    CU_TRY(c, cudaMemcpyAsync(&d->h_out[kSlotScratch], &d->d_out[kSlotScratch], sizeof(SweepOut), cudaMemcpyDeviceToHost,
+                              d->stream));
     CU_TRY(c, cudaStreamSynchronize(d->stream));
     float ms = 0;
     CU_TRY(c, cudaEventElapsedTime(&ms, d->ev0, d->ev1));
     memset(out, 0, sizeof *out);
     out->bytes = 0;
     out->ns = ms_to_ns(ms);
-    out->checksum_xor = d->expect_x;
-    out->checksum_sum = d->expect_s;
+    slot_to_result(d->h_out[kSlotScratch], out);
     out->launches = 1;
     return CRO_OK;
 }
@@ -454,9 +561,9 @@ int ctx_expected(cro_ctx* c, int idx, cro_sweep_result* out) {
 int ctx_inject(cro_ctx* c, int idx, uint64_t word, uint64_t mask) {
     Device* d = dev_at(c, idx);
     if (!d) return CRO_ERR_INVALID_ARG;
-    if (word >= d->sweep_bytes / 8) return CRO_ERR_INVALID_ARG;
+    if (word >= 2 * (d->sweep_bytes / 8)) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
-    drain_pending_fwd(c, d);
+    drain_pending(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
     int rc = ensure_filled(c, d);
     if (rc) return rc;
@@ -469,9 +576,11 @@ int ctx_inject(cro_ctx* c, int idx, uint64_t word, uint64_t mask) {
 int ctx_read_words(cro_ctx* c, int idx, uint64_t first, uint64_t n, uint64_t* out) {
     Device* d = dev_at(c, idx);
     if (!d || !out) return CRO_ERR_INVALID_ARG;
-    if (first + n > 2 * d->sweep_bytes / 8) return CRO_ERR_INVALID_ARG;
+    const uint64_t limit = 2 * (d->sweep_bytes / 8);
+    if (n > limit || first > limit - n) return CRO_ERR_INVALID_ARG;    // no wrap: first + n may not overflow
+    if (n == 0) return CRO_OK;
     std::lock_guard<std::mutex> g(d->mu);
-    drain_pending_fwd(c, d);
+    drain_pending(c, d);
     CU_TRY(c, cudaSetDevice(d->ordinal));
     int rc = ensure_filled(c, d);
     if (rc) return rc;
@@ -483,89 +592,110 @@ int ctx_read_words(cro_ctx* c, int idx, uint64_t first, uint64_t n, uint64_t* ou
 // ---------------------------------------------------------------------------
 // full per-device probe
 // ---------------------------------------------------------------------------
-static uint64_t median_of(std::vector<uint64_t> v) {
-    std::sort(v.begin(), v.end());
-    return v.empty() ? 0 : v[v.size() / 2];
+// Which half (0 = A, 1 = B) a sweep touches.  Copies run ping-pong — A->B, B->A, ... — so the checksum
+// copy k+1 folds out of its source is the verification of what copy k wrote; the first read sweep reads the
+// last copy's destination and the reads alternate from there.
+static int copy_src_half(uint32_t k) { return (int)(k & 1u); }
+static int read_half(uint32_t copies, uint32_t k) {
+    if (copies == 0) return 0;
+    const int last_dst = (int)(copies & 1u);           // C odd: B, C even: A
+    return (k & 1u) ? 1 - last_dst : last_dst;
 }
 
-// Caller holds d->mu.  Enqueues one whole probe (fill, reads, copies, result
-// copy-back) on the device's stream and returns without waiting.
-static int probe_enqueue(cro_ctx* c, Device* d, cro_probe_result* r) {
+// Caller holds d->mu and has the device current.  Enqueues one whole probe on the device's stream and returns
+// without waiting: params refresh, fill, copy sweeps, read sweeps, the closed-form generator on the side
+// stream, the finalize kernel that writes the result struct, and the copy-back of that struct.
+static int probe_enqueue(cro_ctx* c, Device* d) {
     const cro_opts& o = c->opts;
-    memset(r, 0, sizeof *r);
-    r->abi_version = CRO_ABI_VERSION;
-    r->cuda_ordinal = d->ordinal;
-    r->device_minor = d->info.device_minor;
-    memcpy(r->gpu_uuid, d->info.gpu_uuid, sizeof r->gpu_uuid);
-    memcpy(r->pci_bus_id, d->info.pci_bus_id, sizeof r->pci_bus_id);
-    r->hbm_bytes_total = d->info.hbm_bytes_total;
-    r->sweep_bytes = d->sweep_bytes;
-    r->seed = d->seed;
-    r->sm_count = d->info.sm_count;
-    r->sm_clock_mhz = d->sm_clock_mhz;
-    r->mem_clock_mhz = d->mem_clock_mhz;
-    r->rank = c->opts.rank_base + (uint32_t)d->index;
-    r->world = c->opts.world_override ? c->opts.world_override : (uint32_t)c->devs.size();
-    r->p2p_bytes = o.p2p_bytes;
-    const uint32_t rv = resolve_read_variant(o.read_variant, d->sweep_bytes);
-    const uint32_t cv = resolve_copy_variant(o.copy_variant);
-    r->read_variant = rv;
-    r->copy_variant = cv;
-    r->read_sweeps = o.read_sweeps;
-    r->copy_sweeps = (o.flags & CRO_F_SKIP_COPY) ? 0 : o.copy_sweeps;
-
+    Range nv(c, "cro.probe.enqueue");
     CU_TRY(c, cudaSetDevice(d->ordinal));
     int rc = ensure_region(c, d);
-    if (rc) { r->status = rc; return rc; }
-    if ((rc = ensure_expected(c, d))) { r->status = rc; return rc; }
-    r->sweep_bytes = d->sweep_bytes;   // ensure_region may have degraded it (CRO_F_DEGRADE_ON_OOM)
-    r->expect_xor = d->expect_x;
-    r->expect_sum = d->expect_s;
+    if (rc) return rc;
+    const uint32_t rv = resolve_read_variant(o.read_variant, d->sweep_bytes);
+    const uint32_t cv = resolve_copy_variant(o.copy_variant);
+    const uint32_t R = o.read_sweeps;
+    const uint32_t C = (o.flags & CRO_F_SKIP_COPY) ? 0 : o.copy_sweeps;
+    if (d->tmpl.sweep_bytes != d->sweep_bytes) {      // ensure_region degraded S
+        if ((rc = stage_template(c, d))) return rc;
+    }
 
-    // events: fill | R reads | C copies   (pool lives with the device)
-    const size_t need = 2 + o.read_sweeps + r->copy_sweeps + 2;
+    // events: one before the fill, one after every sweep (pool lives with the device)
+    const size_t need = 2 + R + C;
     while (d->evpool.size() < need) {
         cudaEvent_t e;
         CU_TRY(c, cudaEventCreate(&e));
         d->evpool.push_back(e);
     }
     std::vector<cudaEvent_t>& ev = d->evpool;
+    const bool overlap = env::get("CRO_EXPECT_OVERLAP") != 0;
+    unsigned char* half[2] = {d->region, d->region + d->sweep_bytes};
+    const Params gp = graph_params(d);
 
-    const bool verify = (o.flags & CRO_F_VERIFY_COPY) && r->copy_sweeps > 0;
     size_t k = 0;
     // The whole probe as one sequence; `external` records the timing events as external event-record
     // nodes so that the same sequence can be stream-captured into a CUDA graph once and replayed.
     auto issue = [&](bool external) -> int {
         const unsigned flag = external ? cudaEventRecordExternal : cudaEventRecordDefault;
         k = 0;
+        CU_TRY(c, cudaMemcpyAsync(d->d_params, d->h_params, sizeof(ProbeParams), cudaMemcpyHostToDevice, d->stream));
         CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
-        CU_TRY(c, launch_fill(d->plan, d->region, d->sweep_bytes, d->seed, d->stream));
+        CU_TRY(c, launch_fill(d->plan, half[0], d->sweep_bytes, gp, d->scratch, &d->d_out[kSlotFill], d->stream));
         CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
-        for (uint32_t i = 0; i < o.read_sweeps; ++i) {
-            CU_TRY(c, launch_read(d->plan, rv, d->region, d->sweep_bytes, d->scratch, &d->d_out[i], d->stream));
+        // the closed form: ALU only, so it runs beside the copy sweeps (which leave the ALUs idle)
+        cudaStream_t es = overlap ? d->aux : d->stream;
+        if (overlap) {
+            CU_TRY(c, cudaEventRecord(d->ev_fork, d->stream));
+            CU_TRY(c, cudaStreamWaitEvent(d->aux, d->ev_fork, 0));
+        }
+        CU_TRY(c, launch_expected(d->plan, d->sweep_bytes, gp, d->scratch_aux, &d->d_out[kSlotExpect], es));
+        if (overlap) CU_TRY(c, cudaEventRecord(d->ev_join, d->aux));
+        for (uint32_t i = 0; i < C; ++i) {
+            const int s = copy_src_half(i);
+            CU_TRY(c, launch_copy(d->plan, cv, half[1 - s], half[s], d->sweep_bytes, gp, d->scratch,
+                                  &d->d_out[kSlotSweep0 + i], d->stream));
             CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
         }
-        for (uint32_t i = 0; i < r->copy_sweeps; ++i) {
-            CU_TRY(c, launch_copy(d->plan, cv, d->region + d->sweep_bytes, d->region, d->sweep_bytes, d->scratch, d->stream));
+        for (uint32_t i = 0; i < R; ++i) {
+            CU_TRY(c, launch_read(d->plan, rv, half[read_half(C, i)], d->sweep_bytes, gp, d->scratch,
+                                  &d->d_out[kSlotSweep0 + C + i], d->stream));
             CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
         }
-        if (verify)
-            CU_TRY(c, launch_read(d->plan, rv, d->region + d->sweep_bytes, d->sweep_bytes, d->scratch,
-                                  &d->d_out[o.read_sweeps], d->stream));
-        CU_TRY(c, cudaMemcpyAsync(d->h_out, d->d_out, sizeof(SweepOut) * (o.read_sweeps + 1),
-                                  cudaMemcpyDeviceToHost, d->stream));
+        if (overlap) CU_TRY(c, cudaStreamWaitEvent(d->stream, d->ev_join, 0));
+        FinalizeArgs fa{};
+        fa.tmpl = d->d_tmpl;
+        fa.out = d->d_result;
+        fa.slots = d->d_out;
+        fa.pp = d->d_params;
+        fa.sweep_bytes = d->sweep_bytes;
+        fa.read_sweeps = R;
+        fa.copy_sweeps = C;
+        fa.read_variant = rv;
+        fa.copy_variant = C ? cv : 0;
+        fa.fused = (cv == COPY_TMA_FUSED) ? 1u : 0u;
+        CU_TRY(c, launch_finalize(fa, d->stream));
+        CU_TRY(c, cudaMemcpyAsync(d->h_result, d->d_result, sizeof(cro_probe_result), cudaMemcpyDeviceToHost, d->stream));
+        CU_TRY(c, cudaMemcpyAsync(d->h_out, d->d_out, sizeof(SweepOut) * 64, cudaMemcpyDeviceToHost, d->stream));
         return CRO_OK;
     };
-    // One graph launch instead of ~35 runtime calls per probe (matters when one host thread feeds 8 GPUs).
+
+    // this probe's seed: the host refreshes the 16 bytes the graph's first node copies to the device
+    const uint64_t nonce = d->nonce_next++;
+    d->h_params->seed = seed_of(d, nonce);
+    d->h_params->nonce = nonce;
+    d->seed_cur = d->h_params->seed;
+    d->nonce_cur = nonce;
+
+    // One graph launch instead of ~40 runtime calls per probe (matters when one host thread feeds 8 GPUs).
     // The graph is tied to the options it was captured with; any capture problem falls back to direct launches.
-    const uint64_t graph_key = ((uint64_t)rv << 48) ^ ((uint64_t)cv << 40) ^ ((uint64_t)o.read_sweeps << 24) ^
-                               ((uint64_t)r->copy_sweeps << 8) ^ (verify ? 1u : 0u);
-    if (env_u32("CRO_USE_GRAPH", 1) && !d->graph_failed) {
+    const uint64_t graph_key = ((uint64_t)rv << 48) ^ ((uint64_t)cv << 40) ^ ((uint64_t)R << 24) ^ ((uint64_t)C << 8) ^
+                               (overlap ? 1u : 0u) ^ (d->sweep_bytes << 1);
+    if (env::get("CRO_USE_GRAPH") && !d->graph_failed) {
         if (d->graph_exec && d->graph_key != graph_key) {
             cudaGraphExecDestroy(d->graph_exec);
             d->graph_exec = nullptr;
         }
         if (!d->graph_exec) {
+            Range nvc(c, "cro.probe.capture");
             cudaGraph_t graph = nullptr;
             bool ok = cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             if (ok) {
@@ -593,81 +723,60 @@ static int probe_enqueue(cro_ctx* c, Device* d, cro_probe_result* r) {
         if (irc) return irc;
     }
     d->filled = true;
-    c->launches += 1 + o.read_sweeps + r->copy_sweeps + (verify ? 1 : 0);
+    c->launches += 3 + R + C;       // fill + closed form + sweeps + finalize
     d->pending_events = k;
+    d->last_reads = R;
+    d->last_copies = C;
+    d->last_timed = true;
     return CRO_OK;
 }
 
-// Caller holds d->mu.  Waits for the probe enqueued by probe_enqueue and
-// evaluates it into *r (which probe_enqueue started filling).
-static int probe_finish(cro_ctx* c, Device* d, cro_probe_result* r) {
-    const cro_opts& o = c->opts;
-    std::vector<cudaEvent_t>& ev = d->evpool;
-    const size_t k = d->pending_events;
-    const bool verify = (o.flags & CRO_F_VERIFY_COPY) && r->copy_sweeps > 0;
-    CU_TRY(c, cudaSetDevice(d->ordinal));
-    int rc;
-    if ((rc = wait_stream(c, d))) { r->status = rc; return rc; }
-
-    float ms = 0;
-    CU_TRY(c, cudaEventElapsedTime(&ms, ev[0], ev[1]));
-    r->fill_ns = ms_to_ns(ms);
-    std::vector<uint64_t> rt, ct;
-    for (uint32_t i = 0; i < o.read_sweeps; ++i) {
-        CU_TRY(c, cudaEventElapsedTime(&ms, ev[1 + i], ev[2 + i]));
-        rt.push_back(ms_to_ns(ms));
+static std::string describe_failure(const Device* d, const cro_probe_result& r) {
+    const std::string who = std::string(d->info.gpu_uuid, strnlen(d->info.gpu_uuid, sizeof d->info.gpu_uuid));
+    const std::string idx = std::to_string((unsigned)r.fail_index);
+    switch (r.fail_code) {
+        case CRO_FAIL_EXPECT: return "closed-form checksum slot on " + who + " is stale: the generator kernel did not run";
+        case CRO_FAIL_COPY_SRC:
+            return "HBM copy sweep " + idx + " on " + who + " read something else than the pattern" +
+                   (r.fail_index ? " (the destination of sweep " + std::to_string((unsigned)r.fail_index - 1) + " is corrupt)" : " (the fill is corrupt)");
+        case CRO_FAIL_READ: return "HBM read sweep " + idx + " on " + who + " does not reproduce the pattern checksum";
+        case CRO_FAIL_P2P_READ: return "NVLink read of peer " + idx + " from " + who + " does not reproduce the pattern checksum";
+        case CRO_FAIL_P2P_PUSH: return "NVLink push between " + who + " and peer " + idx + " did not land the pattern checksum";
+        case CRO_FAIL_P2P_CHASE: return "NVLink pointer chase from " + who + " through peer " + idx + " ended on the wrong slot";
+        case CRO_FAIL_STALE: return "sweep slot " + idx + " on " + who + " carries another probe's stamp: a kernel of the probe did not run";
+        default: return "probe of " + who + " failed";
     }
-    for (uint32_t i = 0; i < r->copy_sweeps; ++i) {
-        CU_TRY(c, cudaEventElapsedTime(&ms, ev[1 + o.read_sweeps + i], ev[2 + o.read_sweeps + i]));
-        ct.push_back(ms_to_ns(ms));
-    }
-    CU_TRY(c, cudaEventElapsedTime(&ms, ev[0], ev[k - 1]));
-    r->total_ns = ms_to_ns(ms);
-    for (uint64_t t : rt) r->read_total_ns += t;
-    for (uint64_t t : ct) r->copy_total_ns += t;
-    r->read_best_ns = *std::min_element(rt.begin(), rt.end());
-    r->read_median_ns = median_of(rt);
-    if (!ct.empty()) {
-        r->copy_best_ns = *std::min_element(ct.begin(), ct.end());
-        r->copy_median_ns = median_of(ct);
-    }
-    // every sweep must reproduce the closed form, not just the last one
-    r->checksum_xor = d->h_out[0].x;
-    r->checksum_sum = d->h_out[0].s;
-    int status = CRO_OK;
-    for (uint32_t i = 0; i < o.read_sweeps; ++i) {
-        if (d->h_out[i].x != d->expect_x || d->h_out[i].s != d->expect_s) {
-            r->checksum_xor = d->h_out[i].x;
-            r->checksum_sum = d->h_out[i].s;
-            status = CRO_ERR_CHECKSUM;
-            c->set_error("HBM read sweep " + std::to_string(i) + " on " + d->info.gpu_uuid +
-                         " does not reproduce the pattern checksum");
-            break;
-        }
-    }
-    if (verify) {
-        r->copy_checksum_xor = d->h_out[o.read_sweeps].x;
-        r->copy_checksum_sum = d->h_out[o.read_sweeps].s;
-        if (status == CRO_OK && (r->copy_checksum_xor != d->expect_x || r->copy_checksum_sum != d->expect_s)) {
-            status = CRO_ERR_CHECKSUM;
-            c->set_error(std::string("HBM copy destination on ") + d->info.gpu_uuid +
-                         " does not reproduce the pattern checksum");
-        }
-    }
-    // What the memory itself reported: uncorrected volatile ECC errors (nvmlDeviceGetTotalEccErrors).
-    // NVML calls serialise across processes (measured: ~2 ms each with 4 ranks probing, enough to skew the
-    // ranks' all-gather), so the warm probe reuses the count read at init / at the last full-box probe and
-    // only a FAILED probe pays for a fresh read.
-    if (status != CRO_OK) refresh_ecc(c, d);
-    r->ecc_errors = d->ecc_uncorrected;
-    r->status = status;
-    return status;
 }
 
-static int probe_locked(cro_ctx* c, Device* d, cro_probe_result* r) {
-    int rc = probe_enqueue(c, d, r);
-    if (rc) { r->status = rc; return rc; }
-    return probe_finish(c, d, r);
+// Caller holds d->mu.  Waits for the probe enqueued by probe_enqueue and hands out the struct the device wrote.
+static int probe_finish(cro_ctx* c, Device* d, cro_probe_result* r) {
+    CU_TRY(c, cudaSetDevice(d->ordinal));
+    int rc;
+    if ((rc = wait_stream(c, d))) {
+        memset(r, 0, sizeof *r);
+        r->abi_version = CRO_ABI_VERSION;
+        r->status = rc;
+        return rc;
+    }
+    *r = *d->h_result;
+    if (r->status != CRO_OK) {
+        c->set_error(describe_failure(d, *r));
+        // What the memory itself reported: uncorrected volatile ECC errors (nvmlDeviceGetTotalEccErrors).
+        // NVML calls serialise across processes (measured: ~2 ms each with 4 ranks probing, enough to skew the
+        // ranks' all-gather), so the warm probe reuses the count read at init / at the last full-box probe and
+        // only a FAILED probe pays for a fresh read — which then also goes into the device-resident copies.
+        const uint32_t before = d->ecc_uncorrected;
+        refresh_ecc(c, d);
+        if (d->ecc_uncorrected != before) {
+            r->ecc_errors = d->ecc_uncorrected;
+            d->tmpl.ecc_errors = d->ecc_uncorrected;
+            *d->h_result = *r;
+            CU_TRY(c, cudaMemcpyAsync(d->d_result, d->h_result, sizeof *r, cudaMemcpyHostToDevice, d->stream));
+            CU_TRY(c, cudaMemcpyAsync(d->d_tmpl, &d->tmpl, sizeof d->tmpl, cudaMemcpyHostToDevice, d->stream));
+            CU_TRY(c, cudaStreamSynchronize(d->stream));
+        }
+    }
+    return r->status;
 }
 
 // Drains a probe begun with ctx_probe_begin whose result nobody has collected
@@ -679,27 +788,20 @@ static void drain_pending(cro_ctx* c, Device* d) {
     d->have_pending_result = true;
 }
 
-static void drain_pending_fwd(cro_ctx* c, Device* d) { drain_pending(c, d); }
-
-static int publish_result(cro_ctx* c, Device* d, const cro_probe_result* r) {
-    CU_TRY(c, cudaSetDevice(d->ordinal));
-    CU_TRY(c, cudaMemcpyAsync(d->d_result, r, sizeof *r, cudaMemcpyHostToDevice, d->stream));
-    CU_TRY(c, cudaStreamSynchronize(d->stream));
-    return CRO_OK;
-}
-
 int ctx_probe_device(cro_ctx* c, int idx, cro_probe_result* out) {
     Device* d = dev_at(c, idx);
     if (!d || !out) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
     drain_pending(c, d);
     d->have_pending_result = false;   // a synchronous probe supersedes an uncollected asynchronous one
-    int rc = probe_locked(c, d, out);
-    if (rc == CRO_OK || rc == CRO_ERR_CHECKSUM) {
-        int prc = publish_result(c, d, out);
-        if (prc) return prc;
+    int rc = probe_enqueue(c, d);
+    if (rc) {
+        memset(out, 0, sizeof *out);
+        out->abi_version = CRO_ABI_VERSION;
+        out->status = rc;
+        return rc;
     }
-    return rc;
+    return probe_finish(c, d, out);
 }
 
 // Asynchronous form: begin enqueues the probe and returns; end waits and
@@ -710,7 +812,7 @@ int ctx_probe_begin(cro_ctx* c, int idx) {
     if (!d) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
     if (d->pending || d->have_pending_result) return CRO_OK;   // one in flight (or waiting to be collected)
-    int rc = probe_enqueue(c, d, &d->pending_result);
+    int rc = probe_enqueue(c, d);
     if (rc) return rc;
     d->pending = true;
     d->pending_since = std::chrono::steady_clock::now();
@@ -749,7 +851,7 @@ int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out) {
         std::chrono::steady_clock::now() - d->pending_since > std::chrono::seconds(1))
         d->have_pending_result = false;
     if (!d->pending && !d->have_pending_result) {   // nothing begun: behave like the synchronous call
-        int rc = probe_enqueue(c, d, &d->pending_result);
+        int rc = probe_enqueue(c, d);
         if (rc) return rc;
         d->pending = true;
         d->pending_since = std::chrono::steady_clock::now();
@@ -757,12 +859,33 @@ int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out) {
     drain_pending(c, d);
     d->have_pending_result = false;
     *out = d->pending_result;
-    int rc = d->pending_rc;
-    if (rc == CRO_OK || rc == CRO_ERR_CHECKSUM) {
-        int prc = publish_result(c, d, out);
-        if (prc) return prc;
+    return d->pending_rc;
+}
+
+// CUDA-event and %globaltimer times of the sweeps of the device's last finished probe.
+int ctx_sweep_times(cro_ctx* c, int idx, cro_sweep_time* out, int cap, int* n_out) {
+    Device* d = dev_at(c, idx);
+    if (!d || !n_out) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(d->mu);
+    drain_pending(c, d);
+    const int n = d->last_timed ? (int)(1 + d->last_copies + d->last_reads) : 0;
+    *n_out = n;
+    if (n == 0) return CRO_OK;
+    if (!out || cap < n) return CRO_ERR_BUFFER_SMALL;
+    CU_TRY(c, cudaSetDevice(d->ordinal));
+    for (int i = 0; i < n; ++i) {
+        float ms = 0;
+        CU_TRY(c, cudaEventElapsedTime(&ms, d->evpool[(size_t)i], d->evpool[(size_t)i + 1]));
+        cro_sweep_time& t = out[i];
+        memset(&t, 0, sizeof t);
+        const SweepOut& s = d->h_out[i == 0 ? kSlotFill : kSlotSweep0 + i - 1];
+        t.kind = i == 0 ? 0u : (i <= (int)d->last_copies ? 1u : 2u);
+        t.index = i == 0 ? 0u : (t.kind == 1 ? (uint32_t)(i - 1) : (uint32_t)(i - 1 - (int)d->last_copies));
+        t.bytes = t.kind == 1 ? 2 * d->sweep_bytes : d->sweep_bytes;
+        t.event_ns = ms_to_ns(ms);
+        t.timer_ns = s.t1 - s.t0;
     }
-    return rc;
+    return CRO_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -805,38 +928,53 @@ int enable_peers(cro_ctx* c) {
         }
     }
     c->peers_enabled = true;
-    return CRO_OK;
-}
-
-// Sattolo cycle over kChaseSlots slots, mt19937_64 seeded from the owner's
-// minor; slot i lives at next[i*16] (one per 128-byte line).
-int ensure_chase(cro_ctx* c, Device* d) {
-    if (d->d_chase_next) return CRO_OK;
-    std::vector<unsigned long long> perm(kChaseSlots);
-    for (uint32_t i = 0; i < kChaseSlots; ++i) perm[i] = i;
-    std::mt19937_64 rng(0x5A77011000000000ull + (uint64_t)(d->info.device_minor >= 0 ? d->info.device_minor : d->ordinal));
-    for (uint32_t i = kChaseSlots - 1; i > 0; --i) {
-        const uint32_t j = (uint32_t)(rng() % i);
-        std::swap(perm[i], perm[j]);
+    for (int a = 0; a < n; ++a) {     // p2p_access goes into every device's identity template
+        CU_TRY(c, cudaSetDevice(c->devs[a]->ordinal));
+        int rc = stage_template(c, c->devs[(size_t)a].get());
+        if (rc) return rc;
     }
-    std::vector<unsigned long long> lines((size_t)kChaseSlots * 16, 0);
-    for (uint32_t i = 0; i < kChaseSlots; ++i) lines[(size_t)i * 16] = perm[i];
-    CU_TRY(c, cudaSetDevice(d->ordinal));
-    CU_TRY(c, cudaMalloc(&d->d_chase_next, lines.size() * sizeof(unsigned long long)));
-    CU_TRY(c, cudaMemcpy(d->d_chase_next, lines.data(), lines.size() * sizeof(unsigned long long),
-                         cudaMemcpyHostToDevice));
     return CRO_OK;
 }
 
-struct Nccl {
-    int (*CommInitAll)(void**, int, const int*) = nullptr;
-    int (*GroupStart)() = nullptr;
-    int (*GroupEnd)() = nullptr;
-    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
-    const char* (*GetErrorString)(int) = nullptr;
-};
+// Latency permutations: device b holds, for every other device a, the Sattolo cycle a will chase through b's
+// memory (slot i lives at table[i*16], one per 128-byte line), and a remembers where `hops` steps must end.
+int ensure_chase(cro_ctx* c, uint32_t hops) {
+    const int n = (int)c->devs.size();
+    bool built = true;
+    for (auto& d : c->devs) built = built && (int)d->d_chase_tables.size() == n && d->chase_hops_built == hops;
+    if (built) return CRO_OK;
+    Range nv(c, "cro.chase.build");
+    std::vector<uint32_t> perm;
+    std::vector<unsigned long long> wide(kChaseSlots);
+    for (int b = 0; b < n; ++b) {
+        Device* owner = c->devs[(size_t)b].get();
+        CU_TRY(c, cudaSetDevice(owner->ordinal));
+        if ((int)owner->d_chase_tables.size() != n) owner->d_chase_tables.assign((size_t)n, nullptr);
+        for (int a = 0; a < n; ++a) {
+            if (a == b) continue;
+            Device* chaser = c->devs[(size_t)a].get();
+            const int ma = chaser->info.device_minor >= 0 ? chaser->info.device_minor : chaser->ordinal;
+            const int mb = owner->info.device_minor >= 0 ? owner->info.device_minor : owner->ordinal;
+            chase_permutation(ma, mb, &perm);
+            if (!owner->d_chase_tables[(size_t)a]) {
+                CU_TRY(c, cudaMalloc(&owner->d_chase_tables[(size_t)a], (size_t)kChaseSlots * 128));
+                CU_TRY(c, cudaMemset(owner->d_chase_tables[(size_t)a], 0, (size_t)kChaseSlots * 128));
+                for (uint32_t i = 0; i < kChaseSlots; ++i) wide[i] = perm[i];
+                // scatter: 8 bytes into the head of every 128-byte line
+                CU_TRY(c, cudaMemcpy2D(owner->d_chase_tables[(size_t)a], 128, wide.data(), 8, 8, kChaseSlots, cudaMemcpyHostToDevice));
+            }
+            if ((int)chaser->chase_expect.size() != n) chaser->chase_expect.assign((size_t)n, 0u);
+            uint32_t at = 0;
+            for (uint32_t h = 0; h < hops; ++h) at = perm[at];
+            chaser->chase_expect[(size_t)b] = at;
+        }
+    }
+    for (auto& d : c->devs) d->chase_hops_built = hops;
+    return CRO_OK;
+}
 
-int load_nccl(cro_ctx* c, Nccl* n) {
+int load_nccl(cro_ctx* c) {
+    if (c->ncclAllGather) return CRO_OK;
     if (!c->nccl_lib) {
         c->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!c->nccl_lib) c->nccl_lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
@@ -850,20 +988,24 @@ int load_nccl(cro_ctx* c, Nccl* n) {
             return CRO_ERR_NCCL;
         }
     }
-    n->CommInitAll = (int (*)(void**, int, const int*))dlsym(c->nccl_lib, "ncclCommInitAll");
-    n->GroupStart = (int (*)())dlsym(c->nccl_lib, "ncclGroupStart");
-    n->GroupEnd = (int (*)())dlsym(c->nccl_lib, "ncclGroupEnd");
-    n->AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(c->nccl_lib, "ncclAllGather");
-    n->GetErrorString = (const char* (*)(int))dlsym(c->nccl_lib, "ncclGetErrorString");
-    if (!n->CommInitAll || !n->GroupStart || !n->GroupEnd || !n->AllGather) {
+    c->ncclCommInitAll = (int (*)(void**, int, const int*))dlsym(c->nccl_lib, "ncclCommInitAll");
+    c->ncclGroupStart = (int (*)())dlsym(c->nccl_lib, "ncclGroupStart");
+    c->ncclGroupEnd = (int (*)())dlsym(c->nccl_lib, "ncclGroupEnd");
+    c->ncclGetErrorString = (const char* (*)(int))dlsym(c->nccl_lib, "ncclGetErrorString");
+    auto ag = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(c->nccl_lib, "ncclAllGather");
+    if (!c->ncclCommInitAll || !c->ncclGroupStart || !c->ncclGroupEnd || !ag) {
         c->set_error("libnccl lacks a required symbol");
         return CRO_ERR_NCCL;
     }
+    c->ncclAllGather = ag;
     return CRO_OK;
 }
 
 }  // namespace
 
+// One call = the full-box probe (BASELINE config 3).  Everything is ENQUEUED first — per-device probe graphs,
+// the NVLink rounds chained across devices by events, the device-side verdicts, the all-gather, the copy-back —
+// and only then does the host wait, once per device.
 int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
     if (!c || !out || !n_out) return CRO_ERR_INVALID_ARG;
     const int n = (int)c->devs.size();
@@ -872,237 +1014,298 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
     if (n == 0) return CRO_OK;
     std::lock_guard<std::mutex> all(c->all_mu);
     const cro_opts& o = c->opts;
+    Range nv_all(c, "cro.probe_all");
+    const uint64_t t_call = now_ns();
+    c->fullbox = FullBoxTimes{};
+    uint32_t host_syncs = 0;
 
-    // phase 1: every device probes concurrently, one host thread + stream each
-    std::vector<cro_probe_result> res((size_t)n);
-    std::vector<int> rcs((size_t)n, CRO_OK);
-    {
-        std::vector<std::thread> th;
-        for (int i = 0; i < n; ++i)
-            th.emplace_back([&, i] {
-                try {
-                    Device* d = c->devs[(size_t)i].get();
-                    std::lock_guard<std::mutex> g(d->mu);
-                    drain_pending(c, d);
-                    d->have_pending_result = false;
-                    rcs[(size_t)i] = probe_locked(c, d, &res[(size_t)i]);
-                } catch (...) {                   // an exception leaving a thread would terminate the host process
-                    rcs[(size_t)i] = CRO_ERR_INTERNAL;
-                }
-            });
-        for (auto& t : th) t.join();
-    }
-    int worst = CRO_OK;
-    for (int i = 0; i < n; ++i)
-        if (rcs[(size_t)i] != CRO_OK && rcs[(size_t)i] != CRO_ERR_CHECKSUM) return rcs[(size_t)i];
-        else if (rcs[(size_t)i] != CRO_OK) worst = rcs[(size_t)i];
-
-    // phase 2: NVLink P2P, 1-factorised so each GPU is in exactly one pair per round
-    if (n > 1 && !(o.flags & CRO_F_SKIP_P2P)) {
-        int rc = enable_peers(c);
-        if (rc) return rc;
-        std::vector<std::unique_lock<std::mutex>> locks;
-        for (int i = 0; i < n; ++i) locks.emplace_back(c->devs[(size_t)i]->mu);
-        // expected checksum of each owner's first p2p_bytes
-        std::vector<SweepOut> prefix((size_t)n);
-        for (int i = 0; i < n; ++i) {
-            Device* d = c->devs[(size_t)i].get();
-            CU_TRY(c, cudaSetDevice(d->ordinal));
-            if ((rc = ensure_chase(c, d))) return rc;
-            CU_TRY(c, launch_expected(d->plan, std::min<uint64_t>(o.p2p_bytes, d->sweep_bytes), d->seed, d->scratch, &d->d_out[kMaxSweeps - 2], d->stream));
-            c->launches++;
-            CU_TRY(c, cudaMemcpyAsync(&d->h_out[kMaxSweeps - 2], &d->d_out[kMaxSweeps - 2], sizeof(SweepOut),
-                                      cudaMemcpyDeviceToHost, d->stream));
-            CU_TRY(c, cudaStreamSynchronize(d->stream));
-            prefix[(size_t)i] = d->h_out[kMaxSweeps - 2];
-        }
-        for (int a = 0; a < n; ++a)
-            for (int b = 0; b < n; ++b) {
-                if (a == b || b >= 8 || a >= 8) continue;
-                int can = 0;
-                CU_TRY(c, cudaDeviceCanAccessPeer(&can, c->devs[(size_t)a]->ordinal, c->devs[(size_t)b]->ordinal));
-                res[(size_t)a].p2p_access[b] = (uint8_t)can;
-            }
-        for (const auto& round : one_factorisation(n)) {
-            // bandwidth: both directions of every pair in flight at once
-            std::vector<std::pair<int, int>> directed;
-            for (const auto& p : round) {
-                directed.push_back({p.first, p.second});
-                // CRO_P2P_UNIDIR=1 (measurement only, tools/p2p_variants.py): one direction per pair, to see what the
-                // link gives when its other half is idle; the reverse direction's result slots stay zero
-                if (!env_u32("CRO_P2P_UNIDIR", 0)) directed.push_back({p.second, p.first});
-            }
-            for (int rep = 0; rep < 2; ++rep) {   // rep 0 warms the mappings, rep 1 is timed
-                for (const auto& pr : directed) {
-                    Device* a = c->devs[(size_t)pr.first].get();
-                    Device* b = c->devs[(size_t)pr.second].get();
-                    if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
-                    CU_TRY(c, cudaSetDevice(a->ordinal));
-                    CU_TRY(c, cudaEventRecord(a->ev0, a->stream));
-                    // TMA bulk copies straight out of the peer's HBM (cp.async.bulk on the peer-mapped
-                    // address) into this GPU's shared memory, checksummed as they land: 669 GB/s per
-                    // direction with all pairs running both ways, vs 632 GB/s for LDG.128/256
-                    CU_TRY(c, launch_read(a->plan, (unsigned)env_u32("CRO_P2P_READ_VARIANT", READ_TMA), b->region,
-                                          std::min<uint64_t>(o.p2p_bytes, b->sweep_bytes), a->scratch, &a->d_out[0], a->stream));
-                    CU_TRY(c, cudaEventRecord(a->ev1, a->stream));
-                    c->launches++;
-                    CU_TRY(c, cudaMemcpyAsync(&a->h_out[0], &a->d_out[0], sizeof(SweepOut), cudaMemcpyDeviceToHost, a->stream));
-                }
-                for (const auto& pr : directed) {
-                    Device* a = c->devs[(size_t)pr.first].get();
-                    if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
-                    CU_TRY(c, cudaSetDevice(a->ordinal));
-                    CU_TRY(c, cudaStreamSynchronize(a->stream));
-                    if (rep == 0) continue;
-                    float ms = 0;
-                    CU_TRY(c, cudaEventElapsedTime(&ms, a->ev0, a->ev1));
-                    res[(size_t)pr.first].p2p_read_ns[pr.second] = ms_to_ns(ms);
-                    res[(size_t)pr.first].p2p_checksum_xor[pr.second] = a->h_out[0].x;
-                    if (a->h_out[0].x != prefix[(size_t)pr.second].x || a->h_out[0].s != prefix[(size_t)pr.second].s) {
-                        res[(size_t)pr.first].status = CRO_ERR_CHECKSUM;
-                        worst = CRO_ERR_CHECKSUM;
-                        c->set_error(std::string("NVLink read of ") + c->devs[(size_t)pr.second]->info.gpu_uuid +
-                                     " from " + a->info.gpu_uuid + " does not reproduce the pattern checksum");
-                    }
-                }
-            }
-            // push leg: posted NVLink writes.  a streams its own pattern prefix through shared memory
-            // (TMA bulk load from local HBM, TMA bulk store to the peer-mapped address) into the
-            // SCRATCH half of b's region; b then re-reads that half locally and must find a's checksum.
-            // The scratch half is rewritten by every probe's copy sweeps, so nothing needs restoring.
-            if (!(o.flags & CRO_F_SKIP_P2P_WRITE)) {
-                auto push_bytes = [&](const Device* a, const Device* b) {
-                    return std::min<uint64_t>(std::min<uint64_t>(o.p2p_bytes, a->sweep_bytes), b->sweep_bytes);
-                };
-                for (int rep = 0; rep < 2; ++rep) {   // rep 0 maps the peer pages (1/16 of the bytes), rep 1 is timed
-                    for (const auto& pr : directed) {
-                        Device* a = c->devs[(size_t)pr.first].get();
-                        Device* b = c->devs[(size_t)pr.second].get();
-                        if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
-                        uint64_t nb = push_bytes(a, b);
-                        if (rep == 0) nb = std::max<uint64_t>(nb / 16, std::min<uint64_t>(nb, 1u << 20)) & ~uint64_t(15);
-                        CU_TRY(c, cudaSetDevice(a->ordinal));
-                        CU_TRY(c, cudaEventRecord(a->ev0, a->stream));
-                        CU_TRY(c, launch_copy(a->plan, (unsigned)env_u32("CRO_P2P_WRITE_VARIANT", COPY_TMA),
-                                              b->region + b->sweep_bytes, a->region, nb, a->scratch, a->stream));
-                        CU_TRY(c, cudaEventRecord(a->ev1, a->stream));
-                        c->launches++;
-                    }
-                    for (const auto& pr : directed) {
-                        Device* a = c->devs[(size_t)pr.first].get();
-                        if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
-                        CU_TRY(c, cudaSetDevice(a->ordinal));
-                        CU_TRY(c, cudaStreamSynchronize(a->stream));
-                        if (rep == 0) continue;
-                        float ms = 0;
-                        CU_TRY(c, cudaEventElapsedTime(&ms, a->ev0, a->ev1));
-                        res[(size_t)pr.first].p2p_write_ns[pr.second] = ms_to_ns(ms);
-                    }
-                }
-                // every pusher has drained (stream syncs above): the receivers check what landed
-                for (const auto& pr : directed) {
-                    Device* a = c->devs[(size_t)pr.first].get();
-                    Device* b = c->devs[(size_t)pr.second].get();
-                    if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
-                    CU_TRY(c, cudaSetDevice(b->ordinal));
-                    CU_TRY(c, launch_read(b->plan, resolve_read_variant(CRO_READ_AUTO, push_bytes(a, b)), b->region + b->sweep_bytes,
-                                          push_bytes(a, b), b->scratch, &b->d_out[1], b->stream));
-                    c->launches++;
-                    CU_TRY(c, cudaMemcpyAsync(&b->h_out[1], &b->d_out[1], sizeof(SweepOut), cudaMemcpyDeviceToHost, b->stream));
-                }
-                for (const auto& pr : directed) {
-                    Device* a = c->devs[(size_t)pr.first].get();
-                    Device* b = c->devs[(size_t)pr.second].get();
-                    if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
-                    CU_TRY(c, cudaSetDevice(b->ordinal));
-                    CU_TRY(c, cudaStreamSynchronize(b->stream));
-                    // prefix[] holds the checksum of min(p2p_bytes, owner's S) words; a smaller receiver
-                    // region changes the byte count, in which case only the timing is reported
-                    if (push_bytes(a, b) != std::min<uint64_t>(o.p2p_bytes, a->sweep_bytes)) continue;
-                    if (b->h_out[1].x != prefix[(size_t)pr.first].x || b->h_out[1].s != prefix[(size_t)pr.first].s) {
-                        res[(size_t)pr.first].status = CRO_ERR_CHECKSUM;
-                        worst = CRO_ERR_CHECKSUM;
-                        c->set_error(std::string("NVLink push from ") + a->info.gpu_uuid + " into " + b->info.gpu_uuid +
-                                     " did not land the pattern checksum");
-                    }
-                }
-            }
-            // latency: dependent loads into the peer's permutation
-            for (const auto& pr : directed) {
-                Device* a = c->devs[(size_t)pr.first].get();
-                Device* b = c->devs[(size_t)pr.second].get();
-                if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
-                CU_TRY(c, cudaSetDevice(a->ordinal));
-                CU_TRY(c, launch_chase(b->d_chase_next, 0, o.latency_hops, a->d_chase_out, a->stream));
-                c->launches++;
-            }
-            for (const auto& pr : directed) {
-                Device* a = c->devs[(size_t)pr.first].get();
-                if (pr.first >= 8 || pr.second >= 8 || !res[(size_t)pr.first].p2p_access[pr.second]) continue;
-                CU_TRY(c, cudaSetDevice(a->ordinal));
-                unsigned long long h[2] = {0, 0};
-                CU_TRY(c, cudaMemcpyAsync(h, a->d_chase_out, sizeof h, cudaMemcpyDeviceToHost, a->stream));
-                CU_TRY(c, cudaStreamSynchronize(a->stream));
-                res[(size_t)pr.first].p2p_latency_ns_x16[pr.second] =
-                    (uint32_t)std::min<unsigned long long>(0xFFFFFFFFull, h[1] * 16ull / std::max(1u, o.latency_hops));
-            }
-        }
-    }
-
-    // phase 3: ONE all-gather of the 512-byte structs over NVLink
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int i = 0; i < n; ++i) locks.emplace_back(c->devs[(size_t)i]->mu);
     for (int i = 0; i < n; ++i) {
         Device* d = c->devs[(size_t)i].get();
-        std::lock_guard<std::mutex> g(d->mu);
-        refresh_ecc(c, d);                        // the full-box probe is rare enough to afford a fresh read
-        res[(size_t)i].ecc_errors = d->ecc_uncorrected;
-        int rc = publish_result(c, d, &res[(size_t)i]);
-        if (rc) return rc;
+        drain_pending(c, d);
+        d->have_pending_result = false;
     }
+    const bool p2p = n > 1 && !(o.flags & CRO_F_SKIP_P2P);
+    const bool push = p2p && !(o.flags & CRO_F_SKIP_P2P_WRITE);
     const bool use_nccl = n > 1 && !(o.flags & CRO_F_SKIP_NCCL);
+    int rc;
+    // one-time setup (peer mappings, latency tables, communicators) happens BEFORE anything is enqueued
+    if (p2p) {
+        if ((rc = enable_peers(c))) return rc;
+        if ((rc = ensure_chase(c, o.latency_hops))) return rc;
+    }
     if (use_nccl) {
-        Nccl nc;
-        int rc = load_nccl(c, &nc);
-        if (rc) return rc;
+        if ((rc = load_nccl(c))) return rc;
         if (!c->nccl_ready) {
+            Range nv(c, "cro.nccl.init");
             std::vector<int> ords;
             for (auto& d : c->devs) ords.push_back(d->ordinal);
             c->nccl_comms.assign((size_t)n, nullptr);
-            int r = nc.CommInitAll(c->nccl_comms.data(), n, ords.data());
+            int r = c->ncclCommInitAll(c->nccl_comms.data(), n, ords.data());
             if (r != 0) {
-                c->set_error(std::string("ncclCommInitAll: ") + (nc.GetErrorString ? nc.GetErrorString(r) : "error"));
+                c->set_error(std::string("ncclCommInitAll: ") + (c->ncclGetErrorString ? c->ncclGetErrorString(r) : "error"));
                 return CRO_ERR_NCCL;
             }
             c->nccl_ready = true;
         }
-        int r = nc.GroupStart();
-        for (int i = 0; r == 0 && i < n; ++i) {
+    }
+    const auto rounds = p2p ? one_factorisation(n) : std::vector<std::vector<std::pair<int, int>>>();
+    for (int i = 0; i < n && p2p; ++i) {
+        Device* d = c->devs[(size_t)i].get();
+        CU_TRY(c, cudaSetDevice(d->ordinal));
+        while (d->ev_push_done.size() < rounds.size()) {
+            cudaEvent_t e1, e2;
+            CU_TRY(c, cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CU_TRY(c, cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            d->ev_push_done.push_back(e1);
+            d->ev_reread_done.push_back(e2);
+        }
+        refresh_ecc(c, d);                        // the full-box probe is rare enough to afford a fresh read
+        if (d->tmpl.ecc_errors != d->ecc_uncorrected && (rc = stage_template(c, d))) return rc;
+    }
+
+    // ---- phase 1: every device's HBM probe, one graph launch each ---------------------------------------
+    {
+        Range nv(c, "cro.probe_all.hbm");
+        for (int i = 0; i < n; ++i) {
             Device* d = c->devs[(size_t)i].get();
-            r = nc.AllGather(d->d_result, d->d_gather, sizeof(cro_probe_result), /*ncclUint8*/ 1,
-                             c->nccl_comms[(size_t)i], d->stream);
+            if ((rc = probe_enqueue(c, d))) return rc;
+            if (p2p) {
+                // what this device's first p2p_bytes must fold to, for the peers that will read them
+                CU_TRY(c, launch_expected(d->plan, std::min<uint64_t>(o.p2p_bytes, d->sweep_bytes), imm_params(d), d->scratch_pfx,
+                                          &d->d_out[kSlotPrefix], d->aux));
+                c->launches++;
+                CU_TRY(c, cudaEventRecord(d->ev_aux_done, d->aux));
+                CU_TRY(c, cudaStreamWaitEvent(d->stream, d->ev_aux_done, 0));
+                CU_TRY(c, cudaEventRecord(d->ev_hbm_done, d->stream));
+            }
         }
-        int r2 = nc.GroupEnd();
-        if (r != 0 || r2 != 0) {
-            c->set_error(std::string("ncclAllGather: ") + (nc.GetErrorString ? nc.GetErrorString(r ? r : r2) : "error"));
-            return CRO_ERR_NCCL;
+    }
+
+    // ---- phase 2: NVLink rounds, 1-factorised so each GPU is in exactly one pair per round ----------------
+    // Per round and device (partner p):  [wait p's HBM phase, p's previous re-read]  READ p's half A over the
+    // link -> PUSH my prefix into p's half B -> [wait p's push]  RE-READ my own half B locally.  Both directions
+    // of a pair run at once; nothing waits on the host.
+    const bool unidir = env::get("CRO_P2P_UNIDIR") != 0;
+    const unsigned rvp = env::get("CRO_P2P_READ_VARIANT"), wvp = env::get("CRO_P2P_WRITE_VARIANT");
+    auto pair_ok = [&](int a, int b) { return a < 8 && b < 8 && c->devs[(size_t)a]->tmpl.p2p_access[b]; };
+    auto push_bytes = [&](const Device* a, const Device* b) {
+        return std::min<uint64_t>(std::min<uint64_t>(o.p2p_bytes, a->sweep_bytes), b->sweep_bytes);
+    };
+    if (p2p) {
+        Range nv(c, "cro.probe_all.nvlink");
+        for (size_t r = 0; r < rounds.size(); ++r) {
+            std::vector<std::pair<int, int>> directed;
+            for (const auto& p : rounds[r]) {
+                directed.push_back({p.first, p.second});
+                // CRO_P2P_UNIDIR=1 (measurement only, tools/p2p_variants.py): one direction per pair, to see what the
+                // link gives when its other half is idle; the reverse direction's result slots stay zero
+                if (!unidir) directed.push_back({p.second, p.first});
+            }
+            for (const auto& pr : directed) {                       // stage A: read + push
+                Device* a = c->devs[(size_t)pr.first].get();
+                Device* b = c->devs[(size_t)pr.second].get();
+                if (!pair_ok(pr.first, pr.second)) continue;
+                CU_TRY(c, cudaSetDevice(a->ordinal));
+                CU_TRY(c, cudaStreamWaitEvent(a->stream, b->ev_hbm_done, 0));
+                if (r > 0) CU_TRY(c, cudaStreamWaitEvent(a->stream, b->ev_reread_done[r - 1], 0));
+                // TMA bulk copies straight out of the peer's HBM (cp.async.bulk on the peer-mapped address) into
+                // this GPU's shared memory, checksummed as they land
+                CU_TRY(c, launch_read(a->plan, rvp, b->region, std::min<uint64_t>(o.p2p_bytes, b->sweep_bytes), imm_params(a),
+                                      a->scratch, &a->d_out[kSlotP2P0 + 3 * pr.second], a->stream));
+                c->launches++;
+                if (push) {
+                    // posted NVLink writes: a streams its own prefix through shared memory (bulk load from local
+                    // HBM, bulk store to the peer-mapped address, folded on the way) into half B of b's region
+                    CU_TRY(c, launch_copy(a->plan, wvp, b->region + b->sweep_bytes, a->region, push_bytes(a, b), imm_params(a),
+                                          a->scratch, &a->d_out[kSlotP2P0 + 3 * pr.second + 1], a->stream));
+                    c->launches++;
+                }
+                CU_TRY(c, cudaEventRecord(a->ev_push_done[r], a->stream));
+            }
+            for (const auto& pr : directed) {                       // stage B: the receiver checks what landed
+                Device* a = c->devs[(size_t)pr.first].get();          // pusher
+                Device* b = c->devs[(size_t)pr.second].get();         // receiver
+                if (!pair_ok(pr.first, pr.second)) continue;
+                CU_TRY(c, cudaSetDevice(b->ordinal));
+                if (push) {
+                    CU_TRY(c, cudaStreamWaitEvent(b->stream, a->ev_push_done[r], 0));
+                    CU_TRY(c, launch_read(b->plan, resolve_read_variant(CRO_READ_AUTO, push_bytes(a, b)), b->region + b->sweep_bytes,
+                                          push_bytes(a, b), imm_params(b), b->scratch, &b->d_out[kSlotP2P0 + 3 * pr.first + 2], b->stream));
+                    c->launches++;
+                }
+                CU_TRY(c, cudaEventRecord(b->ev_reread_done[r], b->stream));
+            }
+            if (unidir)   // the idle direction's devices still have to publish their round events
+                for (const auto& p : rounds[r]) {
+                    Device* b = c->devs[(size_t)p.second].get();
+                    CU_TRY(c, cudaSetDevice(b->ordinal));
+                    CU_TRY(c, cudaEventRecord(b->ev_push_done[r], b->stream));
+                    Device* a = c->devs[(size_t)p.first].get();
+                    CU_TRY(c, cudaSetDevice(a->ordinal));
+                    CU_TRY(c, cudaEventRecord(a->ev_reread_done[r], a->stream));
+                }
         }
-        std::vector<cro_probe_result> got((size_t)n), ref((size_t)n);
+        // latency: every device chases all its peers at once (one warp per peer, one load in flight each),
+        // after EVERY device has finished its bandwidth legs so the links are quiet
         for (int i = 0; i < n; ++i) {
             Device* d = c->devs[(size_t)i].get();
             CU_TRY(c, cudaSetDevice(d->ordinal));
-            CU_TRY(c, cudaMemcpyAsync(got.data(), d->d_gather, sizeof(cro_probe_result) * (size_t)n,
-                                      cudaMemcpyDeviceToHost, d->stream));
-            CU_TRY(c, cudaStreamSynchronize(d->stream));
-            if (i == 0) ref = got;
-            else if (memcmp(ref.data(), got.data(), sizeof(cro_probe_result) * (size_t)n) != 0) {
+            CU_TRY(c, cudaEventRecord(d->ev_chase_ready, d->stream));
+        }
+        for (int i = 0; i < n; ++i) {
+            Device* d = c->devs[(size_t)i].get();
+            CU_TRY(c, cudaSetDevice(d->ordinal));
+            ChaseArgs ca{};
+            ca.n = (unsigned)n;
+            ca.hops = o.latency_hops;
+            for (int j = 0; j < n; ++j) {
+                if (j == i || !pair_ok(i, j)) continue;
+                CU_TRY(c, cudaStreamWaitEvent(d->stream, c->devs[(size_t)j]->ev_chase_ready, 0));
+                ca.table[j] = c->devs[(size_t)j]->d_chase_tables[(size_t)i];
+            }
+            CU_TRY(c, cudaMemsetAsync(d->d_chase_out, 0, 2 * CRO_MAX_DEVICES * sizeof(unsigned long long), d->stream));
+            CU_TRY(c, launch_chase(ca, d->d_chase_out, d->stream));
+            c->launches++;
+            P2PFinalizeArgs pa{};
+            pa.out = d->d_result;
+            pa.slots = d->d_out;
+            pa.chase_out = d->d_chase_out;
+            pa.n = (unsigned)n;
+            pa.self = (unsigned)i;
+            pa.hops = o.latency_hops;
+            pa.have_push = (push && !unidir) ? 1u : 0u;
+            pa.p2p_bytes = o.p2p_bytes;
+            pa.stamp = d->nonce_cur;
+            for (int j = 0; j < n; ++j) {
+                if (j == i || !pair_ok(i, j)) continue;
+                pa.peer_slots[j] = c->devs[(size_t)j]->d_out;
+                pa.peer_stamp[j] = c->devs[(size_t)j]->nonce_cur;
+                pa.chase_expect[j] = d->chase_expect[(size_t)j];
+            }
+            if (unidir)     // measurement mode: only the pairs' first devices read; check nothing that did not run
+                for (const auto& rd : rounds)
+                    for (const auto& p : rd)
+                        if (p.second == i) pa.peer_slots[p.first] = nullptr;
+            CU_TRY(c, launch_p2p_finalize(pa, d->stream));
+            c->launches++;
+            CU_TRY(c, cudaMemcpyAsync(d->h_chase_out, d->d_chase_out, 2 * CRO_MAX_DEVICES * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream));
+            CU_TRY(c, cudaMemcpyAsync(d->h_out, d->d_out, sizeof(SweepOut) * kSlotCount, cudaMemcpyDeviceToHost, d->stream));
+        }
+    }
+
+    // ---- phase 3: ONE all-gather of the 512-byte structs, enqueued behind the verdict kernels ---------------
+    if (use_nccl) {
+        Range nv(c, "cro.probe_all.allgather");
+        CU_TRY(c, cudaSetDevice(c->devs[0]->ordinal));
+        CU_TRY(c, cudaEventRecord(c->devs[0]->ev0, c->devs[0]->stream));
+        int r = c->ncclGroupStart();
+        for (int i = 0; r == 0 && i < n; ++i) {
+            Device* d = c->devs[(size_t)i].get();
+            r = c->ncclAllGather(d->d_result, d->d_gather, sizeof(cro_probe_result), /*ncclUint8*/ 1,
+                                 c->nccl_comms[(size_t)i], d->stream);
+        }
+        int r2 = c->ncclGroupEnd();
+        if (r != 0 || r2 != 0) {
+            c->set_error(std::string("ncclAllGather: ") + (c->ncclGetErrorString ? c->ncclGetErrorString(r ? r : r2) : "error"));
+            return CRO_ERR_NCCL;
+        }
+        CU_TRY(c, cudaSetDevice(c->devs[0]->ordinal));
+        CU_TRY(c, cudaEventRecord(c->devs[0]->ev1, c->devs[0]->stream));
+        for (int i = 0; i < n; ++i) {
+            Device* d = c->devs[(size_t)i].get();
+            CU_TRY(c, cudaSetDevice(d->ordinal));
+            CU_TRY(c, cudaMemcpyAsync(d->h_gather, d->d_gather, sizeof(cro_probe_result) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+        }
+    } else {
+        for (int i = 0; i < n; ++i) {
+            Device* d = c->devs[(size_t)i].get();
+            CU_TRY(c, cudaSetDevice(d->ordinal));
+            CU_TRY(c, cudaMemcpyAsync(d->h_result, d->d_result, sizeof(cro_probe_result), cudaMemcpyDeviceToHost, d->stream));
+        }
+    }
+    c->fullbox.enqueue_ns = now_ns() - t_call;
+
+    // ---- the only host waits: one per device ------------------------------------------------------------------
+    {
+        Range nv(c, "cro.probe_all.wait");
+        for (int i = 0; i < n; ++i) {
+            Device* d = c->devs[(size_t)i].get();
+            CU_TRY(c, cudaSetDevice(d->ordinal));
+            if ((rc = wait_stream(c, d))) return rc;
+            ++host_syncs;
+        }
+    }
+    int worst = CRO_OK;
+    if (use_nccl) {
+        for (int i = 1; i < n; ++i)
+            if (memcmp(c->devs[0]->h_gather, c->devs[(size_t)i]->h_gather, sizeof(cro_probe_result) * (size_t)n) != 0) {
                 c->set_error("all-gather result differs between rank 0 and rank " + std::to_string(i));
                 return CRO_ERR_NCCL;
             }
-        }
-        memcpy(out, ref.data(), sizeof(cro_probe_result) * (size_t)n);
+        memcpy(out, c->devs[0]->h_gather, sizeof(cro_probe_result) * (size_t)n);
+        float ms = 0;
+        CU_TRY(c, cudaSetDevice(c->devs[0]->ordinal));
+        if (cudaEventElapsedTime(&ms, c->devs[0]->ev0, c->devs[0]->ev1) == cudaSuccess) c->fullbox.gather_ns = ms_to_ns(ms);
     } else {
-        memcpy(out, res.data(), sizeof(cro_probe_result) * (size_t)n);
+        for (int i = 0; i < n; ++i) out[i] = *c->devs[(size_t)i]->h_result;
     }
+    for (int i = 0; i < n; ++i) {
+        Device* d = c->devs[(size_t)i].get();
+        *d->h_result = out[i];
+        if (out[i].status != CRO_OK) {
+            worst = out[i].status;
+            c->set_error(describe_failure(d, out[i]));
+        }
+        c->fullbox.hbm_ns = std::max<uint64_t>(c->fullbox.hbm_ns, out[i].total_ns);
+        if (p2p) {
+            unsigned long long lo = ~0ull, hi = 0;
+            for (int j = 0; j < n; ++j) {
+                if (j == i) continue;
+                for (int k = 0; k < 3; ++k) {
+                    const SweepOut& s = d->h_out[kSlotP2P0 + 3 * j + k];
+                    if (s.stamp != d->nonce_cur) continue;
+                    lo = std::min(lo, s.t0);
+                    hi = std::max(hi, s.t1);
+                }
+                c->fullbox.chase_ns = std::max<uint64_t>(c->fullbox.chase_ns, d->h_chase_out[2 * j + 1]);
+            }
+            if (hi > lo) c->fullbox.p2p_ns = std::max<uint64_t>(c->fullbox.p2p_ns, hi - lo);
+        }
+    }
+    c->fullbox.rounds = (uint32_t)rounds.size();
+    c->fullbox.host_syncs = host_syncs;
+    c->fullbox.wall_ns = now_ns() - t_call;
     return worst;
+}
+
+int ctx_p2p_detail(cro_ctx* c, int idx, int peer, cro_p2p_detail* out) {
+    Device* d = dev_at(c, idx);
+    Device* p = dev_at(c, peer);
+    if (!d || !p || !out || idx == peer) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> all(c->all_mu);
+    memset(out, 0, sizeof *out);
+    const SweepOut& rd = d->h_out[kSlotP2P0 + 3 * peer];
+    const SweepOut& ps = d->h_out[kSlotP2P0 + 3 * peer + 1];
+    const SweepOut& landed = p->h_out[kSlotP2P0 + 3 * idx + 2];   // the peer's re-read of what this device pushed
+    const SweepOut& want = p->h_out[kSlotPrefix];
+    if (rd.stamp == d->nonce_cur) {
+        out->read_ns = rd.t1 - rd.t0;
+        out->read_xor = rd.x; out->read_sum = rd.s; out->read_wsum = rd.w;
+    }
+    if (ps.stamp == d->nonce_cur) out->push_ns = ps.t1 - ps.t0;
+    if (landed.stamp == p->nonce_cur) {
+        out->reread_ns = landed.t1 - landed.t0;
+        out->landed_xor = landed.x; out->landed_sum = landed.s; out->landed_wsum = landed.w;
+    }
+    if (want.stamp == p->nonce_cur) { out->expect_xor = want.x; out->expect_sum = want.s; out->expect_wsum = want.w; }
+    out->chase_end = (uint32_t)d->h_chase_out[2 * peer];
+    out->chase_ns = d->h_chase_out[2 * peer + 1];
+    out->chase_expect = (size_t)peer < d->chase_expect.size() ? d->chase_expect[(size_t)peer] : 0;
+    out->hops = c->opts.latency_hops;
+    out->access = idx < 8 && peer < 8 ? d->tmpl.p2p_access[peer] : 0;
+    return CRO_OK;
 }
 
 }  // namespace cro

@@ -3,8 +3,9 @@
 // Takes the slot of utils.RunNvidiaSmi + utils.CheckGPUVisible in
 // handleAttachingState (internal/controller/composableresource_controller.go:259,275;
 // internal/utils/gpus.go:666-689, 54-86).  One Device per managed GPU holds the
-// resident sweep buffers (2*S bytes: pattern region + copy destination), a
-// stream, events and the reduction scratch, so a warm probe is pure kernel time.
+// resident sweep buffers (2*S bytes: halves A and B), two streams, the timing
+// events, the reduction scratch and the device-written result struct, so a warm
+// probe is one cudaGraphLaunch and one 512-byte copy-back.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -25,25 +26,43 @@ struct Device {
     int index = -1;                // rank: position in the minor-sorted list
     cro_dev_info info{};
     std::mutex mu;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<cudaEvent_t> evpool;   // per-sweep timing events of the full probe
-    unsigned char* region = nullptr;   // [0,S) pattern, [S,2S) copy destination
+    cudaStream_t stream = nullptr; // every sweep
+    cudaStream_t aux = nullptr;    // the closed-form generator (ALU only) runs beside the copy sweeps
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    std::vector<cudaEvent_t> evpool;   // per-sweep timing events of the full probe (bench / tests read them)
+    unsigned char* region = nullptr;   // [0,S) half A, [S,2S) half B
     uint64_t sweep_bytes = 0;
-    uint64_t seed = 0;
+    uint64_t seed_dev = 0;             // seed_base | minor
+    uint64_t seed_cur = 0;             // seed of the pattern half A holds (or will hold after the next fill)
+    uint64_t nonce_cur = 0;            // ... and its nonce
+    uint64_t nonce_next = 0;           // nonce the next probe takes
     bool filled = false;
     KernelPlan plan{};
-    SweepScratch scratch{};
-    SweepOut* d_out = nullptr;         // device sweep-result slots
+    SweepScratch scratch{}, scratch_aux{}, scratch_pfx{};   // main stream / closed form / p2p prefix closed form
+    SweepOut* d_out = nullptr;         // kSlotCount device sweep-result slots
     SweepOut* h_out = nullptr;         // pinned host mirror
-    cro_probe_result* d_result = nullptr;  // all-gather send buffer
+    ProbeParams* d_params = nullptr;   // what the graph's kernels read
+    ProbeParams* h_params = nullptr;   // pinned; refreshed by the host before each launch
+    cro_probe_result* d_tmpl = nullptr;    // identity + options, staged by the host
+    cro_probe_result* d_result = nullptr;  // written by the finalize kernels; the all-gather send buffer
     cro_probe_result* d_gather = nullptr;  // all-gather receive buffer (world entries)
-    unsigned long long* d_chase_next = nullptr;  // latency permutation (peers read it)
+    cro_probe_result* h_result = nullptr;  // pinned copy-back target
+    cro_probe_result* h_gather = nullptr;  // pinned, CRO_MAX_DEVICES entries
+    cro_probe_result tmpl{};               // host copy of d_tmpl
+    // NVLink latency: tables[j] is the permutation device j chases THROUGH this device's memory
+    std::vector<unsigned long long*> d_chase_tables;
+    std::vector<unsigned> chase_expect;    // where this device's chase into peer j must end (hops of the last build)
+    unsigned chase_hops_built = 0;
     unsigned long long* d_chase_out = nullptr;
+    unsigned long long* h_chase_out = nullptr;   // pinned, 2 * CRO_MAX_DEVICES
+    std::vector<cudaEvent_t> ev_push_done, ev_reread_done;   // one per NVLink round
+    cudaEvent_t ev_hbm_done = nullptr, ev_aux_done = nullptr, ev_chase_ready = nullptr;
     // asynchronous probe (ctx_probe_begin / ctx_probe_end)
     bool pending = false, have_pending_result = false;
     int pending_rc = 0;
-    size_t pending_events = 0;
+    size_t pending_events = 0;         // timing events the pending / last probe recorded
+    uint32_t last_reads = 0, last_copies = 0;
+    bool last_timed = false;           // the events of the last probe are valid
     std::chrono::steady_clock::time_point pending_since{};
     cro_probe_result pending_result{};
     // the whole probe captured as one CUDA graph (timing events are external event-record nodes)
@@ -51,8 +70,6 @@ struct Device {
     uint64_t graph_key = 0;
     size_t graph_events = 0;
     bool graph_failed = false;
-    bool have_expected = false;
-    uint64_t expect_x = 0, expect_s = 0;
     unsigned sm_clock_mhz = 0, mem_clock_mhz = 0;
     uint32_t ecc_uncorrected = 0;      // NVML count cached at init / full-box probe / failed probe
 
@@ -62,6 +79,18 @@ struct Device {
     // Releases every CUDA object this device owns (probe.cu).  Runs for half-built devices too,
     // so a cro_probe_init that fails midway (OOM on the sweep region) leaks nothing.
     ~Device();
+};
+
+// Phases of the most recent cro_probe_all, host wall clock + device windows (bench "fullbox").
+struct FullBoxTimes {
+    uint64_t enqueue_ns = 0;       // host time to enqueue everything
+    uint64_t wall_ns = 0;          // host wall clock of the whole call
+    uint64_t hbm_ns = 0;           // max over devices of the HBM probe (device timers)
+    uint64_t p2p_ns = 0;           // first NVLink kernel start .. last NVLink kernel end (device timers, max over devices)
+    uint64_t chase_ns = 0;         // max chase duration
+    uint64_t gather_ns = 0;        // all-gather, CUDA events on rank 0's stream
+    uint32_t rounds = 0;
+    uint32_t host_syncs = 0;       // stream synchronisations the call performed
 };
 
 }  // namespace cro
@@ -77,6 +106,15 @@ struct cro_ctx {
     std::vector<void*> nccl_comms;     // ncclComm_t per device
     bool nccl_ready = false;
     bool peers_enabled = false;
+    bool nvtx = true;
+    std::string proc_root = "/proc";   // where the node's /proc is mounted (tests point it at a fake tree)
+    cro::FullBoxTimes fullbox{};
+    // NCCL entry points, resolved once
+    int (*ncclCommInitAll)(void**, int, const int*) = nullptr;
+    int (*ncclGroupStart)() = nullptr;
+    int (*ncclGroupEnd)() = nullptr;
+    int (*ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*ncclGetErrorString)(int) = nullptr;
 
     void set_error(const std::string& m) {
         std::lock_guard<std::mutex> g(err_mu);
@@ -99,6 +137,8 @@ int ctx_probe_begin(cro_ctx* c, int idx);
 int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out);
 int ctx_probe_poll(cro_ctx* c, int idx);
 int ctx_probe_wait(cro_ctx* c, int idx);
+int ctx_sweep_times(cro_ctx* c, int idx, cro_sweep_time* out, int cap, int* n);
+int ctx_p2p_detail(cro_ctx* c, int idx, int peer, cro_p2p_detail* out);
 
 // single sweeps (each takes the device mutex)
 int ctx_fill(cro_ctx* c, int idx, uint32_t iters, cro_sweep_result* out);
@@ -110,5 +150,10 @@ int ctx_read_words(cro_ctx* c, int idx, uint64_t first, uint64_t n, uint64_t* ou
 
 uint32_t resolve_read_variant(uint32_t v, uint64_t bytes);
 uint32_t resolve_copy_variant(uint32_t v);
+
+// Host restatement of the latency permutation of one directed pair (Sattolo cycle over kChaseSlots slots,
+// mt19937_64 seeded with minor_src * 8 + minor_dst): perm[i] = successor of slot i.
+constexpr uint32_t kChaseSlots = 65536;
+void chase_permutation(int minor_src, int minor_dst, std::vector<uint32_t>* perm);
 
 }  // namespace cro

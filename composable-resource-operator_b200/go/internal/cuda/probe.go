@@ -35,6 +35,12 @@ type ProbeResult struct {
 	SweepBytes   uint64
 	ChecksumXor  uint64
 	ChecksumSum  uint64
+	ChecksumWsum uint64 // position-weighted sum: every word's place matters
+	Nonce        uint32 // probe number on this device; every probe writes a fresh pattern
+	CopyVerified uint8  // copy sweeps whose destination was re-read and matched the closed form
+	FailCode     uint8  // CRO_FAIL_*: which device-side check failed first
+	FailIndex    uint8
+	P2POk        uint8 // bit j: NVLink read / push / chase through peer j verified
 	FillNs       uint64
 	ReadBestNs   uint64
 	CopyBestNs   uint64
@@ -130,6 +136,8 @@ func convert(r *C.cro_probe_result) ProbeResult {
 		Status: int32(r.status), CudaOrdinal: int32(r.cuda_ordinal), DeviceMinor: int32(r.device_minor),
 		GPUUUID: C.GoString(&r.gpu_uuid[0]), PCIBusID: C.GoString(&r.pci_bus_id[0]),
 		SweepBytes: uint64(r.sweep_bytes), ChecksumXor: uint64(r.checksum_xor), ChecksumSum: uint64(r.checksum_sum),
+		ChecksumWsum: uint64(r.checksum_wsum), Nonce: uint32(r.nonce), CopyVerified: uint8(r.copy_verified),
+		FailCode: uint8(r.fail_code), FailIndex: uint8(r.fail_index), P2POk: uint8(r.p2p_ok),
 		FillNs: uint64(r.fill_ns), ReadBestNs: uint64(r.read_best_ns), CopyBestNs: uint64(r.copy_best_ns),
 		EccErrors: uint32(r.ecc_errors),
 	}

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CRO_ABI_VERSION 1u
+#define CRO_ABI_VERSION 2u
 
 /* ---- return codes (0 ok, <0 error; text via cro_strerror) ---------------- */
 #define CRO_OK                  0
@@ -64,6 +64,9 @@ extern "C" {
 #define CRO_COPY_AUTO   0u
 #define CRO_COPY_LDG    1u
 #define CRO_COPY_TMA    2u   /* bulk load -> smem -> bulk store, no register pass   */
+#define CRO_COPY_TMA_FUSED 3u /* the same, and consumer warps fold every tile out of shared memory: the sweep
+                                yields the checksum of its source as read (the probe's default)          */
+#define CRO_READ_LDG256 3u   /* 256-bit LDG flavour                                  */
 
 #define CRO_MAX_DEVICES 16
 
@@ -78,7 +81,7 @@ typedef struct cro_opts {
     uint64_t seed_base;            /* default 0x00C0FFEE00000000; seed = base | minor       */
     uint32_t read_sweeps;          /* default 5                                             */
     uint32_t copy_sweeps;          /* default 5                                             */
-    uint32_t latency_hops;         /* pointer-chase hops; default 4096                      */
+    uint32_t latency_hops;         /* pointer-chase hops per directed pair; default 16384   */
     uint32_t read_variant;         /* CRO_READ_*                                            */
     uint32_t copy_variant;         /* CRO_COPY_*                                            */
     int32_t  deadline_ms;          /* per-call deadline, 0 = none (Go ctx cannot cross cgo) */
@@ -110,6 +113,16 @@ typedef struct cro_dev_info {
 /*
  * Fixed-size, pointer-free, integer-only per-device result: the payload of the
  * single NCCL all-gather.  512 bytes, little-endian.
+ * Offsets 0..351 are Appendix C's; its reserved tail holds the rest.
+ *
+ * The struct is WRITTEN ON THE DEVICE (ABI 2): a one-CTA finalize kernel at the
+ * end of the probe's CUDA graph compares every sweep with the closed form,
+ * takes the sweep times from %globaltimer and fills the all-gather send buffer;
+ * the host only copies it back.  Identity fields are staged once at init.
+ *
+ * Checksum of a sweep over 64-bit words w[0..n): xor = XOR of all words,
+ * sum = wrapping sum, wsum = wrapping sum of w[i] * (2i + 1) — the last one
+ * makes every word's POSITION matter.
  */
 typedef struct cro_probe_result {
     uint32_t abi_version;          /*   0 */
@@ -120,10 +133,11 @@ typedef struct cro_probe_result {
     char     pci_bus_id[24];       /*  64 */
     uint64_t hbm_bytes_total;      /*  88 */
     uint64_t sweep_bytes;          /*  96 */
-    uint64_t seed;                 /* 104 */
-    uint64_t checksum_xor;         /* 112  XOR of all 64-bit pattern words read back */
-    uint64_t checksum_sum;         /* 120  wrapping sum of the same words            */
-    uint64_t fill_ns;              /* 128 */
+    uint64_t seed;                 /* 104  effective pattern seed of THIS probe:
+                                           (seed_base | minor) + nonce * 0xD1B54A32D192ED03 */
+    uint64_t checksum_xor;         /* 112  of the first read sweep (or of the sweep that failed) */
+    uint64_t checksum_sum;         /* 120 */
+    uint64_t fill_ns;              /* 128  sweep times: %globaltimer, first CTA start .. last CTA end */
     uint64_t read_best_ns;         /* 136 */
     uint64_t read_median_ns;       /* 144 */
     uint64_t copy_best_ns;         /* 152 */
@@ -133,7 +147,7 @@ typedef struct cro_probe_result {
     uint32_t mem_clock_mhz;        /* 176 */
     uint32_t ecc_errors;           /* 180  uncorrected volatile ECC errors (NVML), read at init, at
                                            cro_probe_all and after any failed probe */
-    uint64_t p2p_read_ns[8];       /* 184  best time to read p2p_bytes from peer j   */
+    uint64_t p2p_read_ns[8];       /* 184  time to read p2p_bytes out of peer j's HBM over NVLink */
     uint64_t p2p_checksum_xor[8];  /* 248 */
     uint32_t p2p_latency_ns_x16[8];/* 312  mean hop latency x16 (fixed point)        */
     uint8_t  p2p_access[8];        /* 344  cudaDeviceCanAccessPeer                   */
@@ -141,21 +155,58 @@ typedef struct cro_probe_result {
     uint64_t expect_xor;           /* 360  closed-form checksum computed on the device
                                            by an independent generator kernel        */
     uint64_t expect_sum;           /* 368 */
-    uint32_t read_variant;         /* 376  CRO_READ_* actually used                  */
-    uint32_t copy_variant;         /* 380 */
-    uint32_t read_sweeps;          /* 384 */
-    uint32_t copy_sweeps;          /* 388 */
-    uint64_t copy_checksum_xor;    /* 392  checksum of the copy destination (if verified) */
+    uint64_t expect_wsum;          /* 376 */
+    uint64_t checksum_wsum;        /* 384 */
+    uint64_t copy_checksum_xor;    /* 392  checksum of the LAST copy's destination (read back by the first read sweep) */
     uint64_t copy_checksum_sum;    /* 400 */
-    uint32_t rank;                 /* 408  index in the minor-sorted device list      */
-    uint32_t world;                /* 412 */
-    uint64_t total_ns;             /* 416  CUDA-event time of the whole probe (fill..last copy) */
-    uint64_t read_total_ns;        /* 424  sum over the read sweeps  */
-    uint64_t copy_total_ns;        /* 432  sum over the copy sweeps  */
-    uint64_t p2p_write_ns[8];      /* 440  best time to PUSH p2p_bytes into peer j's scratch half
+    uint64_t copy_checksum_wsum;   /* 408 */
+    uint64_t total_ns;             /* 416  first CTA of the fill .. last CTA of the last sweep */
+    uint64_t p2p_write_ns[8];      /* 424  time to PUSH p2p_bytes into peer j's scratch half
                                            (posted NVLink writes; the peer re-reads and checks them) */
-    uint8_t  reserved[8];          /* 504..511 */
+    uint32_t nonce;                /* 488  probe number on this device (0 = first probe of the context) */
+    uint8_t  rank;                 /* 492  index in the minor-sorted device list      */
+    uint8_t  world;                /* 493 */
+    uint8_t  read_variant;         /* 494  CRO_READ_* actually used                  */
+    uint8_t  copy_variant;         /* 495 */
+    uint8_t  read_sweeps;          /* 496 */
+    uint8_t  copy_sweeps;          /* 497 */
+    uint8_t  copy_verified;        /* 498  copy sweeps whose destination was re-read and matched the closed form
+                                           (sweep k+1 folds what sweep k wrote; the first read sweep folds the last) */
+    uint8_t  fail_code;            /* 499  CRO_FAIL_*: which check failed first (0 = none) */
+    uint8_t  fail_index;           /* 500  sweep number / peer index of that check */
+    uint8_t  p2p_ok;               /* 501  bit j: NVLink read of, push into and chase through peer j all verified */
+    uint8_t  reserved8[2];         /* 502 */
+    uint64_t t_start_ns;           /* 504  %globaltimer when the probe's first CTA started */
 } cro_probe_result;
+
+#define CRO_FAIL_NONE        0
+#define CRO_FAIL_EXPECT      1   /* the closed-form slot is stale or short: the generator kernel did not run */
+#define CRO_FAIL_COPY_SRC    2   /* copy sweep fail_index read something else than the pattern */
+#define CRO_FAIL_READ        3   /* read sweep fail_index */
+#define CRO_FAIL_P2P_READ    4   /* NVLink read of peer fail_index */
+#define CRO_FAIL_P2P_PUSH    5   /* what peer fail_index pushed did not land here intact */
+#define CRO_FAIL_P2P_CHASE   6   /* pointer chase through peer fail_index ended on the wrong slot */
+#define CRO_FAIL_STALE       7   /* a sweep slot carries another probe's nonce: that kernel did not run */
+
+/* CUDA-event times of the sweeps of the device's most recent probe, in launch order
+ * (fill, copy sweeps, read sweeps).  kind: 0 fill, 1 copy, 2 read. */
+typedef struct cro_sweep_time {
+    uint32_t kind;
+    uint32_t index;
+    uint64_t bytes;                /* algorithmic bytes of the sweep (S, or 2S for a copy) */
+    uint64_t event_ns;             /* CUDA events on the launching stream                 */
+    uint64_t timer_ns;             /* %globaltimer window the kernel itself recorded      */
+} cro_sweep_time;
+
+/* One directed NVLink pair of the most recent cro_probe_all, in full (the 512-byte struct keeps a digest). */
+typedef struct cro_p2p_detail {
+    uint64_t read_ns, push_ns, reread_ns;
+    uint64_t read_xor, read_sum, read_wsum;        /* what this device folded out of the peer's HBM   */
+    uint64_t landed_xor, landed_sum, landed_wsum;  /* what the PEER found in its scratch half after this device's push */
+    uint64_t expect_xor, expect_sum, expect_wsum;  /* closed form of the peer's first p2p_bytes       */
+    uint64_t chase_ns;
+    uint32_t chase_end, chase_expect, hops, access;
+} cro_p2p_detail;
 
 /* Result of one timed sweep (bench / parity entry points). */
 typedef struct cro_sweep_result {
@@ -165,6 +216,8 @@ typedef struct cro_sweep_result {
     uint64_t checksum_sum;
     uint32_t variant;
     uint32_t launches;             /* kernels launched by this call                      */
+    uint64_t checksum_wsum;        /* position-weighted sum: wrapping sum of w[i] * (2i + 1) */
+    uint64_t timer_ns;             /* %globaltimer window the (last) kernel recorded itself */
 } cro_sweep_result;
 
 /* ---- lifecycle ----------------------------------------------------------- */
@@ -265,8 +318,35 @@ int  cro_read_words(cro_ctx *ctx, int dev_index, uint64_t word_first, uint64_t n
 int  cro_hbm_read_loop(cro_ctx *ctx, int dev_index, uint32_t variant, uint32_t iters, cro_sweep_result *out);
 int  cro_hbm_copy_loop(cro_ctx *ctx, int dev_index, uint32_t variant, uint32_t iters, cro_sweep_result *out);
 int  cro_hbm_fill_loop(cro_ctx *ctx, int dev_index, uint32_t iters, cro_sweep_result *out);
-/* Seed used for a device (seed_base | minor). */
+/* Seed of the pattern the device's region holds now: (seed_base | minor) + nonce * 0xD1B54A32D192ED03, where
+ * nonce counts the probes this context has run on the device (every probe writes a fresh pattern, so a fill or
+ * copy that silently did nothing cannot pass on the previous probe's bytes). */
 int  cro_device_seed(cro_ctx *ctx, int dev_index, uint64_t *seed);
+/* CUDA-event and %globaltimer times of every sweep of the device's most recent probe, in launch order. */
+int  cro_probe_sweep_times(cro_ctx *ctx, int dev_index, cro_sweep_time *out, int cap, int *n);
+/* One directed NVLink pair (dev_index -> peer_index) of the most recent cro_probe_all. */
+int  cro_p2p_detail_get(cro_ctx *ctx, int dev_index, int peer_index, cro_p2p_detail *out);
+/* Phases of the most recent cro_probe_all. */
+typedef struct cro_fullbox_time {
+    uint64_t enqueue_ns;           /* host time spent enqueueing (no waits inside)                      */
+    uint64_t wall_ns;              /* host wall clock of the call                                       */
+    uint64_t hbm_ns;               /* slowest device's HBM probe (%globaltimer)                         */
+    uint64_t p2p_ns;               /* slowest device's NVLink bandwidth rounds, first kernel .. last    */
+    uint64_t chase_ns;             /* slowest pointer chase                                             */
+    uint64_t gather_ns;            /* the all-gather, CUDA events on rank 0's stream                    */
+    uint32_t rounds;               /* NVLink rounds (n-1 for even n)                                    */
+    uint32_t host_syncs;           /* stream synchronisations the call made (one per device)            */
+} cro_fullbox_time;
+int  cro_fullbox_times(cro_ctx *ctx, cro_fullbox_time *out);
+/* Where `hops` steps from slot 0 of the latency permutation of the directed pair (minor_src chases through
+ * minor_dst's memory) end: Sattolo cycle over 65536 slots, mt19937_64 seeded with minor_src * 8 + minor_dst
+ * (SURVEY.md §8d config 3).  Host arithmetic only. */
+int  cro_chase_end(int minor_src, int minor_dst, uint32_t hops, uint32_t *end);
+/* The CRO_* environment knobs are validated like the reference validates its own
+ * (internal/controller/composableresource_adapter.go:42-45): an illegal value fails cro_probe_init with
+ * "the env variable <NAME> has an invalid value: '<v>'".  This checks one (name, value) pair — or, with
+ * name == NULL, the process environment as cro_probe_init would — without needing a GPU. */
+int  cro_validate_env(const char *name, const char *value, char *err_buf, size_t err_cap);
 /* Kernel launches issued by this context so far (bench "gpu_launches"). */
 uint64_t cro_launch_count(cro_ctx *ctx);
 

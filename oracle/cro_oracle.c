@@ -47,39 +47,53 @@ void oracle_fill(uint64_t *buf, uint64_t seed, uint64_t first, uint64_t n_words)
     for (uint64_t i = 0; i < n_words; ++i) buf[i] = oracle_pattern_word(seed, first + i);
 }
 
-/* (XOR-fold, wrapping sum) of words [first, first+n_words) */
-void oracle_checksum(uint64_t seed, uint64_t first, uint64_t n_words, uint64_t *x_out, uint64_t *s_out) {
-    uint64_t x = 0, s = 0;
+/* Checksum of a sweep: (XOR, wrapping sum, position-weighted wrapping sum) of the pattern words
+ * [first, first+n_words), word first+i sitting at position pos0+i of the swept range:
+ *   x = XOR w,  s = sum w,  w = sum w * (2*pos + 1)   (all mod 2^64)
+ * The third component makes every word's position matter (SURVEY.md §8d defines the first two; the probe adds the
+ * third so that swapped or misplaced tiles cannot pass). */
+void oracle_checksum3(uint64_t seed, uint64_t first, uint64_t n_words, uint64_t pos0, uint64_t *x_out, uint64_t *s_out,
+                      uint64_t *w_out) {
+    uint64_t x = 0, s = 0, ws = 0;
     for (uint64_t i = 0; i < n_words; ++i) {
         const uint64_t w = oracle_pattern_word(seed, first + i);
         x ^= w;
         s += w;
+        ws += w * (2 * (pos0 + i) + 1);
     }
     *x_out = x;
     *s_out = s;
+    *w_out = ws;
+}
+/* the two-component form SURVEY.md §8d states */
+void oracle_checksum(uint64_t seed, uint64_t first, uint64_t n_words, uint64_t *x_out, uint64_t *s_out) {
+    uint64_t w;
+    oracle_checksum3(seed, first, n_words, first, x_out, s_out, &w);
 }
 
 /* checksum of a buffer that is already in memory (what a CPU "read sweep" does) */
-void oracle_checksum_buffer(const uint64_t *buf, uint64_t n_words, uint64_t *x_out, uint64_t *s_out) {
-    uint64_t x = 0, s = 0;
+void oracle_checksum_buffer(const uint64_t *buf, uint64_t n_words, uint64_t *x_out, uint64_t *s_out, uint64_t *w_out) {
+    uint64_t x = 0, s = 0, ws = 0;
     for (uint64_t i = 0; i < n_words; ++i) {
         x ^= buf[i];
         s += buf[i];
+        ws += buf[i] * (2 * i + 1);
     }
     *x_out = x;
     *s_out = s;
+    *w_out = ws;
 }
 
 typedef struct {
-    uint64_t seed, first, n, x, s;
+    uint64_t seed, first, n, x, s, w;
 } ck_job;
 static void *ck_worker(void *p) {
     ck_job *j = (ck_job *)p;
-    oracle_checksum(j->seed, j->first, j->n, &j->x, &j->s);
+    oracle_checksum3(j->seed, j->first, j->n, j->first, &j->x, &j->s, &j->w);
     return NULL;
 }
-/* same result with `threads` host threads (XOR / wrapping add are associative) */
-void oracle_checksum_mt(uint64_t seed, uint64_t n_words, int threads, uint64_t *x_out, uint64_t *s_out) {
+/* same result with `threads` host threads (all three components are associative and commutative over words) */
+void oracle_checksum_mt(uint64_t seed, uint64_t n_words, int threads, uint64_t *x_out, uint64_t *s_out, uint64_t *w_out) {
     if (threads < 1) threads = 1;
     if (threads > 256) threads = 256;
     pthread_t th[256];
@@ -91,14 +105,22 @@ void oracle_checksum_mt(uint64_t seed, uint64_t n_words, int threads, uint64_t *
         jobs[t].n = (t == threads - 1) ? n_words - per * (uint64_t)t : per;
         pthread_create(&th[t], NULL, ck_worker, &jobs[t]);
     }
-    uint64_t x = 0, s = 0;
+    uint64_t x = 0, s = 0, w = 0;
     for (int t = 0; t < threads; ++t) {
         pthread_join(th[t], NULL);
         x ^= jobs[t].x;
         s += jobs[t].s;
+        w += jobs[t].w;
     }
     *x_out = x;
     *s_out = s;
+    *w_out = w;
+}
+
+/* seed of probe number `nonce` on a device: the first probe of a context uses SURVEY.md §8d's seed
+ * (seed_base | minor) unchanged, every later one moves on by an odd stride so no two probes share a pattern */
+uint64_t oracle_probe_seed(uint64_t seed_base, int minor, uint64_t nonce) {
+    return (seed_base | (uint64_t)minor) + nonce * 0xD1B54A32D192ED03ull;
 }
 
 /* mt19937_64 (Matsumoto & Nishimura 2004), the generator std::mt19937_64 names */
@@ -126,13 +148,14 @@ static uint64_t mt64_next(mt64 *m) {
     y ^= y >> 43;
     return y;
 }
-/* index reached after `hops` steps from slot 0 of the latency permutation the
- * probe places on device `minor` (Sattolo cycle, 16384 slots) */
-uint32_t oracle_chase_end(int minor, uint32_t hops) {
-    enum { N = 16384 };
+/* Index reached after `hops` steps from slot 0 of the latency permutation of the directed pair
+ * (minor_src chases through minor_dst's memory): Sattolo cycle over 65536 slots driven by
+ * mt19937_64(seed = minor_src * 8 + minor_dst) — SURVEY.md §8d config 3.  perm[i] is the successor of slot i. */
+uint32_t oracle_chase_end(int minor_src, int minor_dst, uint32_t hops) {
+    enum { N = 65536 };
     static uint32_t perm[N];
     mt64 m;
-    mt64_seed(&m, 0x5A77011000000000ull + (uint64_t)minor);
+    mt64_seed(&m, (uint64_t)((long long)minor_src * 8 + (long long)minor_dst));
     for (uint32_t i = 0; i < N; ++i) perm[i] = i;
     for (uint32_t i = N - 1; i > 0; --i) {
         const uint32_t j = (uint32_t)(mt64_next(&m) % i);

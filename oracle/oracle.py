@@ -56,17 +56,30 @@ def pattern_words_np(seed: int, first: int, n_words: int) -> np.ndarray:
         return z ^ (z >> np.uint64(31))
 
 
-def checksum_np(seed: int, first: int, n_words: int, chunk: int = 1 << 22) -> Tuple[int, int]:
-    x, s = 0, 0
+def checksum_np(seed: int, first: int, n_words: int, chunk: int = 1 << 22, pos0: Optional[int] = None) -> Tuple[int, int, int]:
+    """(XOR, wrapping sum, position-weighted sum: sum of w * (2*pos + 1)) of pattern words [first, first+n_words),
+    word first+i at position pos0+i (default: pos0 = first)."""
+    x, s, ws = 0, 0, 0
     done = 0
+    pos0 = first if pos0 is None else pos0
     while done < n_words:
         n = min(chunk, n_words - done)
         w = pattern_words_np(seed, first + done, n)
         x ^= int(np.bitwise_xor.reduce(w))
         with np.errstate(over="ignore"):
             s = (s + int(np.add.reduce(w, dtype=np.uint64))) & MASK
+            pos = np.arange(n, dtype=np.uint64) + np.uint64((pos0 + done) & MASK)
+            ws = (ws + int(np.add.reduce(w * (np.uint64(2) * pos + np.uint64(1)), dtype=np.uint64))) & MASK
         done += n
-    return x, s
+    return x, s, ws
+
+
+NONCE_STRIDE = 0xD1B54A32D192ED03
+
+
+def probe_seed(seed_base: int, minor: int, nonce: int) -> int:
+    """Seed of probe number `nonce` on a device (nonce 0 = SURVEY.md §8d's seed_base | minor)."""
+    return ((seed_base | minor) + nonce * NONCE_STRIDE) & MASK
 
 
 # --------------------------------------------------------------------------
@@ -661,11 +674,14 @@ class COracle:
         L.oracle_pattern_word.restype = u64
         L.oracle_pattern_word.argtypes = [u64, u64]
         L.oracle_checksum.argtypes = [u64, u64, u64, p64, p64]
-        L.oracle_checksum_mt.argtypes = [u64, u64, ctypes.c_int, p64, p64]
+        L.oracle_checksum3.argtypes = [u64, u64, u64, u64, p64, p64, p64]
+        L.oracle_checksum_mt.argtypes = [u64, u64, ctypes.c_int, p64, p64, p64]
         L.oracle_fill.argtypes = [ctypes.c_void_p, u64, u64, u64]
-        L.oracle_checksum_buffer.argtypes = [ctypes.c_void_p, u64, p64, p64]
+        L.oracle_checksum_buffer.argtypes = [ctypes.c_void_p, u64, p64, p64, p64]
+        L.oracle_probe_seed.restype = u64
+        L.oracle_probe_seed.argtypes = [u64, ctypes.c_int, u64]
         L.oracle_chase_end.restype = ctypes.c_uint32
-        L.oracle_chase_end.argtypes = [ctypes.c_int, ctypes.c_uint32]
+        L.oracle_chase_end.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint32]
         for name in ("oracle_parse_gpu_csv", "oracle_parse_proc_csv"):
             getattr(L, name).argtypes = [ctypes.c_char_p] * 4 + [ctypes.c_char_p, ctypes.c_size_t]
         L.oracle_proc_information_to_line.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
@@ -690,16 +706,21 @@ class COracle:
     def pattern_word(self, seed: int, i: int) -> int:
         return int(self.lib.oracle_pattern_word(seed & MASK, i & MASK))
 
-    def checksum(self, seed: int, first: int, n_words: int, threads: int = 1) -> Tuple[int, int]:
-        x, s = ctypes.c_uint64(), ctypes.c_uint64()
-        if threads > 1 and first == 0:
-            self.lib.oracle_checksum_mt(seed & MASK, n_words, threads, ctypes.byref(x), ctypes.byref(s))
+    def checksum(self, seed: int, first: int, n_words: int, threads: int = 1, pos0: Optional[int] = None) -> Tuple[int, int, int]:
+        """(xor, sum, position-weighted sum) of pattern words [first, first+n_words)."""
+        x, s, w = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        if threads > 1 and first == 0 and pos0 in (None, 0):
+            self.lib.oracle_checksum_mt(seed & MASK, n_words, threads, ctypes.byref(x), ctypes.byref(s), ctypes.byref(w))
         else:
-            self.lib.oracle_checksum(seed & MASK, first, n_words, ctypes.byref(x), ctypes.byref(s))
-        return x.value, s.value
+            self.lib.oracle_checksum3(seed & MASK, first, n_words, first if pos0 is None else pos0, ctypes.byref(x),
+                                      ctypes.byref(s), ctypes.byref(w))
+        return x.value, s.value, w.value
 
-    def chase_end(self, minor: int, hops: int) -> int:
-        return int(self.lib.oracle_chase_end(minor, hops))
+    def probe_seed(self, seed_base: int, minor: int, nonce: int) -> int:
+        return int(self.lib.oracle_probe_seed(seed_base & MASK, minor, nonce))
+
+    def chase_end(self, minor_src: int, minor_dst: int, hops: int) -> int:
+        return int(self.lib.oracle_chase_end(minor_src, minor_dst, hops))
 
     # text -----------------------------------------------------------------
     def _text(self, fn, *args, cap: int = 1 << 16) -> Tuple[int, str]:

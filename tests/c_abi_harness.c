@@ -77,7 +77,8 @@ int main(int argc, char **argv) {
         CHECK(cro_enumerate(ctx, devs, CRO_MAX_DEVICES, &n) == CRO_OK && n == 1);
         cro_probe_result r;
         CHECK(cro_probe_device(ctx, 0, &r) == CRO_OK);
-        CHECK(r.status == CRO_OK && r.checksum_xor == r.expect_xor && r.checksum_sum == r.expect_sum);
+        CHECK(r.status == CRO_OK && r.checksum_xor == r.expect_xor && r.checksum_sum == r.expect_sum && r.checksum_wsum == r.expect_wsum);
+        CHECK(r.abi_version == CRO_ABI_VERSION && r.fail_code == CRO_FAIL_NONE && r.copy_verified == r.copy_sweeps);
         CHECK(strcmp(r.gpu_uuid, devs[0].gpu_uuid) == 0);
         CHECK(cro_emit_csv(devs, n, "gpu_uuid", buf, sizeof buf, &len) == CRO_OK);
         int visible = 0;

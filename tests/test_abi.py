@@ -29,7 +29,11 @@ def test_result_struct_layout(cro):
     assert ctypes.sizeof(R) == 512
     offs = {"gpu_uuid": 16, "pci_bus_id": 64, "hbm_bytes_total": 88, "checksum_xor": 112, "fill_ns": 128,
             "sm_count": 168, "p2p_read_ns": 184, "p2p_checksum_xor": 248, "p2p_latency_ns_x16": 312,
-            "p2p_access": 344, "p2p_bytes": 352, "rank": 408, "p2p_write_ns": 440}
+            "p2p_access": 344, "p2p_bytes": 352, "expect_wsum": 376, "checksum_wsum": 384, "copy_checksum_wsum": 408,
+            "total_ns": 416, "p2p_write_ns": 424, "nonce": 488, "rank": 492, "copy_verified": 498, "fail_code": 499,
+            "p2p_ok": 501, "t_start_ns": 504}
+    assert ctypes.sizeof(cro.SweepResult) == 56 and ctypes.sizeof(cro.SweepTime) == 32 and ctypes.sizeof(cro.P2PDetail) == 120
+    assert ctypes.sizeof(cro.FullBoxTime) == 56
     for k, v in offs.items():
         assert getattr(R, k).offset == v, k
 

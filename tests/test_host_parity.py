@@ -180,9 +180,11 @@ def test_probe_annotations_are_additive(cro):
     r = cro.ProbeResult()
     r.status, r.sweep_bytes, r.read_best_ns, r.fill_ns = 0, 4 << 30, 600000, 700000
     r.gpu_uuid = b"GPU-x"
-    r.checksum_xor, r.checksum_sum = 0x1234, 0xabcd
+    r.checksum_xor, r.checksum_sum, r.checksum_wsum = 0x1234, 0xabcd, 0x77
+    r.nonce, r.copy_sweeps, r.copy_verified = 3, 5, 5
     js = json.loads(cro.emit_probe_annotations_json(r))
     assert all(k.startswith("cohdi.io/probe-") for k in js)
     assert js["cohdi.io/probe-hbm-read-gbs"] == "7158.2"          # 4 GiB / 600 us, integer arithmetic
-    assert js["cohdi.io/probe-checksum"] == "0000000000001234:000000000000abcd"
+    assert js["cohdi.io/probe-checksum"] == "0000000000001234:000000000000abcd:0000000000000077"
+    assert js["cohdi.io/probe-nonce"] == "3" and js["cohdi.io/probe-copies-verified"] == "5/5"
     assert list(js) == sorted(js)                                  # Go marshals map keys sorted

@@ -25,7 +25,7 @@ def _worker(rank, world, port, q):
     multirank = importlib.import_module("composable-resource-operator_b200.multirank")
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     r = cro.ProbeResult()
-    r.abi_version, r.status, r.rank, r.world = 1, 0, rank, world
+    r.abi_version, r.status, r.rank, r.world = 2, 0, rank, world
     r.gpu_uuid = ("GPU-%08x-aaaa-bbbb-cccc-dddddddddddd" % rank).encode()
     r.pci_bus_id = ("00000000:%02X:00.0" % (0x1B + rank)).encode()
     r.device_minor = rank

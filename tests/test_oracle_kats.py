@@ -102,9 +102,19 @@ def test_pattern_kats(oracle, coracle):
         assert oracle.pattern_word(seed, i) == word == coracle.pattern_word(seed, i)
     for c in g["checksums"]:
         seed = int(c["seed"], 16)
-        want = (int(c["xor"], 16), int(c["sum"], 16))
+        want = (int(c["xor"], 16), int(c["sum"], 16), int(c["wsum"], 16))
         assert coracle.checksum(seed, c["first"], c["n_words"]) == want
         assert oracle.checksum_np(seed, c["first"], c["n_words"]) == want
+    for p in g["probe_seeds"]:
+        want = int(p["seed"], 16)
+        assert oracle.probe_seed(int(p["seed_base"], 16), p["minor"], p["nonce"]) == want
+        assert coracle.probe_seed(int(p["seed_base"], 16), p["minor"], p["nonce"]) == want
+    # std::mt19937_64's check value from the C++ standard ([rand.predef]): the generator restated in the KAT script is right
+    assert g["mt19937_64_10000th_of_default_seed"] == "9981545732273789042"
+    for c in g["chase_ends"]:
+        assert coracle.chase_end(c["minor_src"], c["minor_dst"], c["hops"]) == c["end"]
+        if c["hops"] == 65536:
+            assert c["end"] == 0          # a Sattolo permutation is ONE cycle through all 65536 slots
 
 
 def test_checksum_properties(coracle):
@@ -113,11 +123,25 @@ def test_checksum_properties(coracle):
     whole = coracle.checksum(seed, 0, n)
     # additivity over a split (XOR / wrapping add are associative)
     a, b = coracle.checksum(seed, 0, 12345), coracle.checksum(seed, 12345, n - 12345)
-    assert (a[0] ^ b[0], (a[1] + b[1]) & ((1 << 64) - 1)) == whole
+    M = (1 << 64) - 1
+    assert (a[0] ^ b[0], (a[1] + b[1]) & M, (a[2] + b[2]) & M) == whole
     # threads do not change the result
     assert coracle.checksum(seed, 0, n, threads=7) == whole
     # empty range
-    assert coracle.checksum(seed, 0, 0) == (0, 0)
+    assert coracle.checksum(seed, 0, 0) == (0, 0, 0)
+    # the position-weighted component sees what XOR and sum cannot: two words swapping places
+    import ctypes
+    buf = (ctypes.c_uint64 * 1024)()
+    coracle.lib.oracle_fill(buf, seed, 0, 1024)
+    def fold(b):
+        x, s, w = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        coracle.lib.oracle_checksum_buffer(b, 1024, ctypes.byref(x), ctypes.byref(s), ctypes.byref(w))
+        return x.value, s.value, w.value
+    clean = fold(buf)
+    assert clean == coracle.checksum(seed, 0, 1024)
+    buf[17], buf[900] = buf[900], buf[17]
+    swapped = fold(buf)
+    assert swapped[:2] == clean[:2] and swapped[2] != clean[2]
 
 
 def test_c_vs_python_parse_fuzz(oracle, coracle):

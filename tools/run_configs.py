@@ -50,7 +50,7 @@ def config3(ctx):
     n = len(res)
     import oracle
     co = oracle.COracle()
-    parity = all((r.checksum_xor, r.checksum_sum) == co.checksum(r.seed, 0, S // 8, threads=os.cpu_count() or 1) for r in res[:2])
+    parity = all(r.checksum == co.checksum(r.seed, 0, S // 8, threads=os.cpu_count() or 1) for r in res[:2])
     return {
         "config": 3, "n_gpus": n, "sweep_bytes": S, "p2p_bytes": int(res[0].p2p_bytes), "cold_s": round(cold, 3),
         "warm_s_median": round(sorted(times)[len(times) // 2], 4), "probes_per_s": round(n / sorted(times)[len(times) // 2], 1),
