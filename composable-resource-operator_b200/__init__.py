@@ -41,6 +41,7 @@ ERR_PARSE, ERR_EXEC, ERR_P2P, ERR_INTERNAL = -11, -12, -13, -14
 F_SKIP_COPY, F_SKIP_P2P, F_SKIP_NCCL, F_NO_NVML, F_VERIFY_COPY, F_LAZY_ALLOC, F_DEGRADE_ON_OOM, F_SKIP_P2P_WRITE = 1, 2, 4, 8, 16, 32, 64, 128
 READ_AUTO, READ_LDG, READ_TMA, READ_LDG256 = 0, 1, 2, 3
 COPY_AUTO, COPY_LDG, COPY_TMA, COPY_TMA_FUSED = 0, 1, 2, 3
+DEV_IN_PROCESS, DEV_NEEDS_HELPER = 1, 2
 FAIL_NONE, FAIL_EXPECT, FAIL_COPY_SRC, FAIL_READ, FAIL_P2P_READ, FAIL_P2P_PUSH, FAIL_P2P_CHASE, FAIL_STALE = range(8)
 
 
@@ -67,7 +68,7 @@ class DevInfo(ctypes.Structure):
         ("gpu_uuid", ctypes.c_char * 48), ("pci_bus_id", ctypes.c_char * 24), ("name", ctypes.c_char * 64),
         ("hbm_bytes_total", ctypes.c_uint64), ("sm_count", ctypes.c_uint32),
         ("cc_major", ctypes.c_uint32), ("cc_minor", ctypes.c_uint32), ("identity_source", ctypes.c_uint32),
-        ("reserved", ctypes.c_uint32 * 4),
+        ("flags", ctypes.c_uint32), ("dev_index", ctypes.c_int32), ("reserved", ctypes.c_uint32 * 2),
     ]
 
 
@@ -159,7 +160,7 @@ EXPORTS = [
     "cro_fabric_check_resource", "cro_fabric_get_resources", "cro_fabric_list_devices",
     "cro_local_node_op", "cro_scan_cmdline_for", "cro_token_from_reply",
     "cro_selftest_exception_barrier", "cro_probe_sweep_times", "cro_p2p_detail_get", "cro_fullbox_times",
-    "cro_chase_end", "cro_validate_env",
+    "cro_chase_end", "cro_validate_env", "cro_node_inventory", "cro_probe_uuid", "cro_set_latency_hops",
 ]
 
 
@@ -204,7 +205,10 @@ def _load() -> ctypes.CDLL:
         "cro_p2p_detail_get": (i32, [vp, i32, i32, ctypes.POINTER(P2PDetail)]),
         "cro_fullbox_times": (i32, [vp, ctypes.POINTER(FullBoxTime)]),
         "cro_chase_end": (i32, [i32, i32, u32, ctypes.POINTER(u32)]),
+        "cro_set_latency_hops": (i32, [vp, u32]),
         "cro_validate_env": (i32, [c, c, c, sz]),
+        "cro_node_inventory": (i32, [c, ctypes.POINTER(DevInfo), i32, ctypes.POINTER(DevInfo), i32, ctypes.POINTER(i32)]),
+        "cro_probe_uuid": (i32, [vp, c, ctypes.POINTER(ProbeResult)]),
         "cro_launch_count": (u64, [vp]),
         "cro_emit_status_json": (i32, [c, c, c, c] + out),
         "cro_emit_scalar_status_json": (i32, [c, c, c, c, c] + out),
@@ -454,6 +458,11 @@ class ProbeContext:
         self._check(lib.cro_enumerate(self.handle, arr, MAX_DEVICES, ctypes.byref(n)))
         return [arr[i] for i in range(n.value)]
 
+    def own_devices(self) -> List[DevInfo]:
+        """The devices this context probes in process, by dev_index (enumerate() lists the whole NODE, fresh)."""
+        mine = [d for d in self.enumerate() if d.flags & DEV_IN_PROCESS]
+        return sorted(mine, key=lambda d: d.dev_index)
+
     def seed(self, dev: int = 0) -> int:
         s = ctypes.c_uint64()
         self._check(lib.cro_device_seed(self.handle, dev, ctypes.byref(s)))
@@ -526,10 +535,36 @@ class ProbeContext:
         self._check(lib.cro_p2p_detail_get(self.handle, dev, peer, ctypes.byref(d)))
         return d
 
+    def set_latency_hops(self, hops: int) -> None:
+        self._check(lib.cro_set_latency_hops(self.handle, hops))
+
     def fullbox_times(self) -> FullBoxTime:
         t = FullBoxTime()
         self._check(lib.cro_fullbox_times(self.handle, ctypes.byref(t)))
         return t
+
+
+def node_inventory(proc_root: Optional[str], in_process: List[DevInfo]) -> List[DevInfo]:
+    """What cro_enumerate answers for a context managing `in_process` on a node whose /proc is at proc_root:
+    the driver's registry is re-read, devices attached later are flagged DEV_NEEDS_HELPER, removed ones are dropped."""
+    arr = (DevInfo * max(1, len(in_process)))(*in_process)
+    out = (DevInfo * 64)()
+    n = ctypes.c_int()
+    rc = lib.cro_node_inventory(_b(proc_root), arr, len(in_process), out, 64, ctypes.byref(n))
+    if rc != OK:
+        raise ProbeError(rc, "cro_node_inventory")
+    return [out[i] for i in range(n.value)]
+
+
+def probe_uuid(ctx: Optional["ProbeContext"], uuid: str) -> ProbeResult:
+    """cro_probe_uuid: in-process probe, or the helper process for a GPU attached after init (ctx may be None)."""
+    r = ProbeResult()
+    rc = lib.cro_probe_uuid(ctx.handle if ctx is not None else None, _b(uuid), ctypes.byref(r))
+    if rc not in (OK, ERR_CHECKSUM):
+        buf = ctypes.create_string_buffer(1024)
+        lib.cro_last_error(ctx.handle if ctx is not None else None, buf, 1024)
+        raise ProbeError(rc, buf.value.decode("utf-8", "replace"))
+    return r
 
 
 def chase_end(minor_src: int, minor_dst: int, hops: int) -> int:

@@ -18,6 +18,7 @@
 #include "nodes.hpp"
 #include "gpus.hpp"
 #include "env.hpp"
+#include "inventory.hpp"
 #include <memory>
 #include <new>
 #include <stdexcept>
@@ -107,11 +108,32 @@ int cro_device_count(cro_ctx* ctx, int* n) try {
 
 int cro_enumerate(cro_ctx* ctx, cro_dev_info* out, int cap, int* n) try {
     if (!ctx || !n) return CRO_ERR_INVALID_ARG;
-    *n = (int)ctx->devs.size();
+    std::vector<cro_dev_info> inv;
+    int rc = ctx_inventory(ctx, &inv);      // fresh every call: the reference re-execs nvidia-smi per reconcile
+    if (rc) return rc;
+    *n = (int)inv.size();
     if (*n == 0) return CRO_OK;
     if (!out || cap < *n) return CRO_ERR_BUFFER_SMALL;
-    for (int i = 0; i < *n; ++i) out[i] = ctx->devs[(size_t)i]->info;
+    for (int i = 0; i < *n; ++i) out[i] = inv[(size_t)i];
     return CRO_OK;
+} CRO_API_CATCH
+
+int cro_node_inventory(const char* proc_root, const cro_dev_info* in_process, int n_in, cro_dev_info* out, int cap, int* n) try {
+    if (!n || n_in < 0 || (n_in > 0 && !in_process)) return CRO_ERR_INVALID_ARG;
+    const std::string root = proc_root && *proc_root ? proc_root : "/proc";
+    std::vector<cro_dev_info> mine(in_process, in_process + n_in);
+    const bool have = inventory::ProcRegistryExists(root);
+    const std::vector<cro_dev_info> inv =
+        inventory::Merge(mine, have, have ? inventory::FromProc(identity::ScanProc(root)) : std::vector<inventory::Seen>());
+    *n = (int)inv.size();
+    if (*n == 0) return CRO_OK;
+    if (!out || cap < *n) return CRO_ERR_BUFFER_SMALL;
+    for (int i = 0; i < *n; ++i) out[i] = inv[(size_t)i];
+    return CRO_OK;
+} CRO_API_CATCH
+
+int cro_probe_uuid(cro_ctx* ctx, const char* gpu_uuid, cro_probe_result* out) try {
+    return ctx_probe_uuid(ctx, gpu_uuid, out);
 } CRO_API_CATCH
 
 int cro_emit_csv(const cro_dev_info* devs, int n, const char* query, char* buf, size_t cap, size_t* len) try {
@@ -241,6 +263,13 @@ int cro_fullbox_times(cro_ctx* ctx, cro_fullbox_time* out) try {
     out->gather_ns = f.gather_ns;
     out->rounds = f.rounds;
     out->host_syncs = f.host_syncs;
+    return CRO_OK;
+} CRO_API_CATCH
+
+int cro_set_latency_hops(cro_ctx* ctx, uint32_t hops) try {
+    if (!ctx || hops == 0 || hops > (1u << 24)) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(ctx->all_mu);
+    ctx->opts.latency_hops = hops;      // the next cro_probe_all recomputes where each chase must end
     return CRO_OK;
 } CRO_API_CATCH
 

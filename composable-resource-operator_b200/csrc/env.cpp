@@ -37,7 +37,7 @@ const Knob kKnobs[] = {
     {"CRO_COPY_VARIANT", 0, 3, 0, 0, "CRO_COPY_* forced (0 = checksumming TMA copy)"},
     {"CRO_USE_GRAPH", 0, 1, 1, 0, "replay the probe as one CUDA graph"},
     {"CRO_EXPECT_OVERLAP", 0, 1, 1, 0, "closed-form generator on a side stream under the copy sweeps"},
-    {"CRO_EXPECT_CTAS", 1, 8, 2, 0, "CTAs per SM of the closed-form generator (it must leave room for the copy's CTA)"},
+    {"CRO_EXPECT_CTAS", 1, 8, 1, 0, "CTAs per SM of the closed-form generator (it must leave room for the copy's CTA)"},
     {"CRO_P2P_UNIDIR", 0, 1, 0, 0, "measurement only: one direction per NVLink pair"},
     {"CRO_P2P_READ_VARIANT", 1, 3, 2, 0, "kernel of the NVLink read leg"},
     {"CRO_P2P_WRITE_VARIANT", 1, 3, 3, 0, "kernel of the NVLink push leg"},

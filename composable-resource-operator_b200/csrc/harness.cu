@@ -467,6 +467,7 @@ public:
                                       bool* visible) override {
         *visible = false;
         bool listed = false;
+        wanted_ = r.Status.DeviceID;
         // while detaching, the cluster is looked at AFTER the fabric removed the device
         const bool after = r.Status.State == "Detaching";
         const gojson::Value* slices = in_->get(after && in_->get("resource_slices_after_remove") ? "resource_slices_after_remove" : "resource_slices");
@@ -490,11 +491,10 @@ public:
         if (!listed) return controller::Error::Nil();
         if (in_->get_bool("probe") && ctx_ && !after) {
             // the strong check: the device must also deliver its HBM pattern
-            int idx = -1;
-            for (size_t i = 0; i < ctx_->devs.size(); ++i)
-                if (fixed_str(ctx_->devs[i]->info.gpu_uuid, 48) == r.Status.DeviceID) idx = (int)i;
-            if (idx < 0) return controller::Error::Nil();
-            int rc = ctx_probe_device(ctx_, idx, &probe_result);
+            // by UUID: a device this context holds is probed in process, one that reached the node after
+            // cro_probe_init through the helper process; CRO_ERR_NO_DEVICE = not on the node (any more)
+            int rc = ctx_probe_uuid(ctx_, r.Status.DeviceID.c_str(), &probe_result);
+            if (rc == CRO_ERR_NO_DEVICE) return controller::Error::Nil();
             probed = true;
             if (rc != CRO_OK) {
                 char msg[512] = {0};
@@ -522,8 +522,11 @@ private:
             const gojson::Value* ee = en->get("exec_err");
             if (ee && ee->kind == gojson::Value::String) { exec_err_s = ee->str; exec_err = exec_err_s.c_str(); }
         } else if (ctx_) {
+            // a FRESH look at the node on every reconcile, like the reference's exec of nvidia-smi (gpus.go:886)
             std::vector<cro_dev_info> infos;
-            for (auto& d : ctx_->devs) infos.push_back(d->info);
+            ctx_inventory(ctx_, &infos);
+            if (!wanted_.empty() && !identity::CheckGPUVisible(infos.data(), (int)infos.size(), wanted_))
+                ctx_inventory(ctx_, &infos, true);      // the fabric named a device the quick look does not show: look properly
             identity::EmitCsv(infos.data(), (int)infos.size(), "gpu_uuid", &out, nullptr);
         } else {
             return controller::Error::New("no probe context and no enumeration text");
@@ -538,6 +541,7 @@ private:
     }
     cro_ctx* ctx_;
     const gojson::Value* in_;
+    std::string wanted_;      // Status.DeviceID of the resource being reconciled, once known
 };
 
 }  // namespace
@@ -754,8 +758,7 @@ int cro_local_node_op(cro_ctx* ctx, const char* request_json, char* buf, size_t 
         return CRO_ERR_PARSE;
     }
     std::vector<cro_dev_info> devs;
-    if (ctx)
-        for (auto& d : ctx->devs) devs.push_back(d->info);
+    if (ctx) ctx_inventory(ctx, &devs);      // never the init-time snapshot: a drained GPU must stop being listed
     gpus::LocalExec::Options o;
     o.proc_root = in->get_string("proc_root");
     o.allow_mutation = in->get_bool("allow_mutation");

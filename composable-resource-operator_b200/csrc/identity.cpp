@@ -341,6 +341,22 @@ struct NvmlPciInfo {  // nvmlPciInfo_t (v3 layout)
 using nvmlDevice_t = void*;
 }  // namespace
 
+std::string ProcRegistryListing(const std::string& proc_root) {
+    const std::string base = (proc_root.empty() ? std::string("/proc") : proc_root) + "/driver/nvidia/gpus";
+    DIR* d = opendir(base.c_str());
+    if (!d) return std::string();
+    std::vector<std::string> names;
+    while (dirent* e = readdir(d)) {
+        if (e->d_name[0] == '.') continue;
+        names.push_back(std::string(e->d_name) + ":" + std::to_string((unsigned long long)e->d_ino));
+    }
+    closedir(d);
+    std::sort(names.begin(), names.end());
+    std::string out = "P";
+    for (const std::string& n : names) out += "|" + n;
+    return out;
+}
+
 bool ScanNvml(std::vector<NvmlGpu>* out, std::string* err) {
     void* h = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
     if (!h) {

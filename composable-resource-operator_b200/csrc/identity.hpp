@@ -67,6 +67,11 @@ struct ProcGpu {
 };
 // Scans <root>/driver/nvidia/gpus/*/information (root defaults to /proc).
 std::vector<ProcGpu> ScanProc(const std::string& proc_root);
+// The registry's directory listing alone — "<name>:<inode>" per GPU, sorted, joined by '|' — without opening any
+// `information` file: reading those goes through the driver (and its locks: ~14 ms per read while nvidia-smi polls),
+// listing the directory does not.  A GPU that leaves or joins the bus changes the listing; a re-created entry gets a
+// new inode.  Empty string: the registry directory does not exist.
+std::string ProcRegistryListing(const std::string& proc_root);
 
 struct NvmlGpu {
     std::string uuid;      // "GPU-..."

@@ -971,12 +971,22 @@ cudaError_t plan_kernels(int device, KernelPlan* plan) {
             return e;
         plan->copy_fused = {sms * (occ > 0 ? occ : 1), (int)plan->fused_threads, smem};
     }
+    // An SM changes its L1 / shared-memory split only when it is empty, so a kernel that asks for the default split
+    // keeps the copy's CTA (128 KiB of shared memory) off every SM it occupies — measured: the first copy sweep waited
+    // for the whole generator.  Every kernel of the probe therefore asks for the SAME split, the largest shared memory.
+    for (const void* fn : {(const void*)hbm_expected_kernel, (const void*)hbm_fill_kernel<kFillThreads, kFillUnroll>,
+                           (const void*)hbm_read_ldg_kernel<kReadThreads, false>, (const void*)hbm_read_ldg_kernel<kReadThreads, true>,
+                           (const void*)hbm_read_tma_kernel, (const void*)hbm_copy_fused_kernel, (const void*)hbm_copy_tma_kernel,
+                           (const void*)probe_finalize_kernel})
+        if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+            return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hbm_expected_kernel, 256, 0)) !=
         cudaSuccess)
         return e;
     // The generator runs BESIDE the copy sweeps: it may not fill the SM, or the copy's CTA (160 threads, 128 KiB of
-    // shared memory) would have to wait for it to drain.  2 CTAs of 256 threads per SM keep the ALUs ~busy and leave
-    // the copy's consumer warps their issue slots.
+    // shared memory) would have to wait for it to drain; and the fewer of its warps compete with the copy's consumer
+    // warps for issue slots the better.  Measured per probe (S = 4 GiB): 9.69 ms with 1 CTA of 256 threads per SM,
+    // 10.13 with 2, 10.32 with 4, 10.57 with the generator in line (profiles/r02_expect_overlap.md).
     plan->expect = {sms * std::min<int>(occ > 0 ? occ : 1, (int)env::get("CRO_EXPECT_CTAS")), 256, 0};
     return cudaSuccess;
 }

@@ -22,6 +22,7 @@
 
 #include "env.hpp"
 #include "identity.hpp"
+#include "inventory.hpp"
 
 namespace cro {
 
@@ -862,6 +863,110 @@ int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out) {
     return d->pending_rc;
 }
 
+// ---------------------------------------------------------------------------
+// the node's inventory, fresh on every query (inventory.hpp)
+// ---------------------------------------------------------------------------
+int ctx_inventory(cro_ctx* c, std::vector<cro_dev_info>* out, bool force) {
+    if (!c || !out) return CRO_ERR_INVALID_ARG;
+    std::vector<cro_dev_info> mine;
+    for (auto& d : c->devs) mine.push_back(d->info);
+    std::lock_guard<std::mutex> g(c->inv_mu);
+    const bool nvml_ok = !(c->opts.flags & CRO_F_NO_NVML);
+    // Every call looks at the node: the registry's directory listing (a readdir, ~10 us, no driver lock).  The
+    // `information` files are read again when that listing differs from the last one, when the last full read is
+    // older than a second (a different GPU in the same slot may reuse name AND inode), or when the caller insists.
+    std::string key = identity::ProcRegistryListing(c->proc_root);
+    const bool have_proc = !key.empty();
+    if (!have_proc) key = "-";
+    const auto now = std::chrono::steady_clock::now();
+    const bool nvml_due = !have_proc && nvml_ok && now - c->inv_nvml_at > std::chrono::seconds(1);
+    const bool stale = now - c->inv_full_at > std::chrono::seconds(1);
+    if (c->inv_valid && key == c->inv_key && !nvml_due && !force && !(have_proc && stale)) {
+        *out = c->inv;
+        return CRO_OK;
+    }
+    c->inv_rescans++;
+    c->inv_full_at = now;
+    std::vector<identity::ProcGpu> proc;
+    if (have_proc) proc = identity::ScanProc(c->proc_root);
+    std::vector<inventory::Seen> seen;
+    bool have_scan = have_proc;
+    if (have_proc) {
+        seen = inventory::FromProc(proc);
+        // the common case — the node holds exactly the devices this context manages — needs nothing more
+        bool same = seen.size() == mine.size();
+        for (const auto& s : seen) {
+            bool found = false;
+            for (const auto& m : mine) found = found || s.uuid == std::string(m.gpu_uuid, strnlen(m.gpu_uuid, sizeof m.gpu_uuid));
+            same = same && found;
+        }
+        if (same) have_scan = false;          // Merge then keeps the context's own (nvidia-smi) order
+    }
+    if (have_scan || !have_proc) {
+        std::vector<identity::NvmlGpu> nv;
+        if (nvml_ok && identity::ScanNvml(&nv, nullptr)) {   // init + shutdown: NVML sees hot-plugged devices only after a re-init
+            c->inv_nvml_at = now;
+            std::vector<inventory::Seen> ordered;
+            for (const auto& g2 : nv) {                        // nvidia-smi lists in NVML index order
+                bool on_node = !have_proc;
+                for (const auto& s : seen) on_node = on_node || s.uuid == g2.uuid;
+                if (!on_node) continue;
+                inventory::Seen s;
+                s.uuid = g2.uuid; s.bus_id = g2.bus_id; s.minor = g2.minor; s.source = 1;
+                ordered.push_back(s);
+            }
+            for (const auto& s : seen) {                       // on the bus but not (yet) known to NVML: keep, at the end
+                bool in = false;
+                for (const auto& o2 : ordered) in = in || o2.uuid == s.uuid;
+                if (!in) ordered.push_back(s);
+            }
+            seen = ordered;
+            have_scan = true;
+        }
+    }
+    c->inv = inventory::Merge(mine, have_scan, seen);
+    c->inv_key = key;
+    c->inv_valid = true;
+    *out = c->inv;
+    return CRO_OK;
+}
+
+int ctx_probe_uuid(cro_ctx* c, const char* uuid, cro_probe_result* out) {
+    if (!uuid || !out) return CRO_ERR_INVALID_ARG;
+    const std::string want = uuid;
+    uint64_t sweep = 1ull << 30;              // helper default: 1 GiB already sweeps at ~7 TB/s and starts ~4x sooner
+    if (!c) env::reload(nullptr);            // no context ever validated the environment for this caller
+    int deadline = (int)env::get("CRO_HELPER_TIMEOUT_MS");
+    if (c) {
+        std::vector<cro_dev_info> inv;
+        int rc = ctx_inventory(c, &inv);
+        if (rc) return rc;
+        const cro_dev_info* hit = nullptr;
+        for (int attempt = 0; attempt < 2 && !hit; ++attempt) {
+            // told about a UUID the cached list lacks: look again, properly, before saying "not on this node"
+            if (attempt == 1 && (rc = ctx_inventory(c, &inv, true))) return rc;
+            for (const auto& d : inv)
+                if (want == std::string(d.gpu_uuid, strnlen(d.gpu_uuid, sizeof d.gpu_uuid))) hit = &d;
+        }
+        if (!hit) {
+            c->set_error("device '" + want + "' is not on this node");
+            return CRO_ERR_NO_DEVICE;
+        }
+        if (hit->flags & CRO_DEV_IN_PROCESS) return ctx_probe_device(c, hit->dev_index, out);
+        sweep = std::min<uint64_t>(c->opts.sweep_bytes, sweep);
+        if (c->opts.deadline_ms > 0) deadline = c->opts.deadline_ms;
+    }
+    std::string err;
+    if (c && c->nvtx) nvtxRangePushA("cro.probe.helper");
+    const int rc = inventory::RunHelper("", want, sweep, deadline, out, &err);
+    if (c && c->nvtx) nvtxRangePop();
+    if (rc != CRO_OK && !err.empty()) {
+        if (c) c->set_error(err);
+        else set_thread_error(err);
+    }
+    return rc;
+}
+
 // CUDA-event and %globaltimer times of the sweeps of the device's last finished probe.
 int ctx_sweep_times(cro_ctx* c, int idx, cro_sweep_time* out, int cap, int* n_out) {
     Device* d = dev_at(c, idx);
@@ -976,13 +1081,16 @@ int ensure_chase(cro_ctx* c, uint32_t hops) {
 int load_nccl(cro_ctx* c) {
     if (c->ncclAllGather) return CRO_OK;
     if (!c->nccl_lib) {
-        c->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!c->nccl_lib) c->nccl_lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        // 1. whatever NCCL the host process already carries (a torch host brings its own, newer than the system's:
+        //    loading the system copy first would make the host's later import fail on a missing symbol)
+        c->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL);
+        // 2. an explicit path, 3. the system library — never RTLD_GLOBAL: our copy must not answer anyone else's symbols
         if (!c->nccl_lib) {
-            // torch wheels carry their own copy
             const char* extra = getenv("CRO_NCCL_PATH");
-            if (extra) c->nccl_lib = dlopen(extra, RTLD_NOW | RTLD_GLOBAL);
+            if (extra && *extra) c->nccl_lib = dlopen(extra, RTLD_NOW | RTLD_LOCAL);
         }
+        if (!c->nccl_lib) c->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!c->nccl_lib) c->nccl_lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
         if (!c->nccl_lib) {
             c->set_error("libnccl.so.2 not found (set CRO_NCCL_PATH)");
             return CRO_ERR_NCCL;

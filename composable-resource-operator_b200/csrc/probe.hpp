@@ -108,6 +108,14 @@ struct cro_ctx {
     bool peers_enabled = false;
     bool nvtx = true;
     std::string proc_root = "/proc";   // where the node's /proc is mounted (tests point it at a fake tree)
+    // the node's inventory as of the last enumeration (inventory.hpp)
+    std::mutex inv_mu;
+    std::string inv_key;               // uuid/minor set the cached list was built from
+    std::vector<cro_dev_info> inv;
+    bool inv_valid = false;
+    std::chrono::steady_clock::time_point inv_full_at{};   // last time the `information` files were read
+    std::chrono::steady_clock::time_point inv_nvml_at{};   // last NVML re-initialisation (rate limit when /proc is absent)
+    std::atomic<uint64_t> inv_rescans{0};                  // times the inventory had to be rebuilt
     cro::FullBoxTimes fullbox{};
     // NCCL entry points, resolved once
     int (*ncclCommInitAll)(void**, int, const int*) = nullptr;
@@ -138,6 +146,12 @@ int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out);
 int ctx_probe_poll(cro_ctx* c, int idx);
 int ctx_probe_wait(cro_ctx* c, int idx);
 int ctx_sweep_times(cro_ctx* c, int idx, cro_sweep_time* out, int cap, int* n);
+// Fresh inventory of the node merged with the context's own devices (inventory.hpp).
+// force: re-read every `information` file even if the registry's listing looks unchanged (done by itself once a
+// second, and by the callers whenever a UUID they were told about is NOT in the list they got).
+int ctx_inventory(cro_ctx* c, std::vector<cro_dev_info>* out, bool force = false);
+// Probe by UUID: in-process device, helper process for one attached after init, CRO_ERR_NO_DEVICE when not on the node.
+int ctx_probe_uuid(cro_ctx* c, const char* uuid, cro_probe_result* out);
 int ctx_p2p_detail(cro_ctx* c, int idx, int peer, cro_p2p_detail* out);
 
 // single sweeps (each takes the device mutex)

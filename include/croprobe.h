@@ -107,8 +107,17 @@ typedef struct cro_dev_info {
     uint32_t sm_count;
     uint32_t cc_major, cc_minor;
     uint32_t identity_source;      /* 1 NVML, 2 /proc, 3 CUDA runtime only                  */
-    uint32_t reserved[4];
+    uint32_t flags;                /* CRO_DEV_*                                             */
+    int32_t  dev_index;            /* index for cro_probe_device / cro_hbm_*; -1: not in this process */
+    uint32_t reserved[2];
 } cro_dev_info;
+
+/* The node's inventory is re-read on EVERY cro_enumerate (the reference execs a fresh nvidia-smi on every
+ * reconcile, internal/utils/gpus.go:666-689); the devices a context can probe itself are fixed at cro_probe_init
+ * because CUDA's device list is fixed at cuInit. */
+#define CRO_DEV_IN_PROCESS    0x1u  /* managed by this context: probe it with cro_probe_device(dev_index)       */
+#define CRO_DEV_NEEDS_HELPER  0x2u  /* on the node but attached after cro_probe_init: cro_probe_uuid probes it
+                                       through a one-shot helper process (croprobe-cli) with its own cuInit     */
 
 /*
  * Fixed-size, pointer-free, integer-only per-device result: the payload of the
@@ -237,8 +246,22 @@ int  cro_device_count(cro_ctx *ctx, int *n);
 
 /* Replaces getGPUInfoFromNvidiaPod / getGPUInfoFromCroNodeAgentPod /
  * getGPUInfoFromProcInCroNodeAgentPod (internal/utils/gpus.go:878-919,
- * 921-962, 1014-1089).  Rows are sorted by device_minor (nvidia-smi order). */
+ * 921-962, 1014-1089).  Rows are in nvidia-smi order.  The answer is FRESH on every call: the driver's
+ * registry under /proc/driver/nvidia/gpus is re-read (and NVML re-initialised when that shows a change), so a GPU
+ * composed after cro_probe_init is listed (CRO_DEV_NEEDS_HELPER) and a GPU drained off the bus is not. */
 int  cro_enumerate(cro_ctx *ctx, cro_dev_info *out, int cap, int *n);
+
+/* The same merge without a context (ctx-free, no CUDA call): what cro_enumerate answers for a context managing
+ * `in_process` on a node whose /proc is mounted at proc_root (NULL = "/proc").  Only /proc is consulted. */
+int  cro_node_inventory(const char *proc_root, const cro_dev_info *in_process, int n_in_process,
+                        cro_dev_info *out, int cap, int *n);
+
+/* Probe by UUID — the form the reconcile step uses (Status.DeviceID is a UUID,
+ * internal/controller/composableresource_controller.go:231-233).  In-process devices: cro_probe_device.  Devices
+ * that reached the node after cro_probe_init: a helper process (`croprobe-cli probe-raw`, CUDA_VISIBLE_DEVICES=<uuid>,
+ * deadline CRO_HELPER_TIMEOUT_MS).  A UUID the node does not list: CRO_ERR_NO_DEVICE — the reference's
+ * "found = false", not an error of the probe.  ctx may be NULL (every device then goes through the helper). */
+int  cro_probe_uuid(cro_ctx *ctx, const char *gpu_uuid, cro_probe_result *out);
 
 /* Text that `nvidia-smi --query-gpu=<query> --format=csv,noheader,nounits`
  * would print for these devices, so the unchanged Go parser at
@@ -338,6 +361,8 @@ typedef struct cro_fullbox_time {
     uint32_t host_syncs;           /* stream synchronisations the call made (one per device)            */
 } cro_fullbox_time;
 int  cro_fullbox_times(cro_ctx *ctx, cro_fullbox_time *out);
+/* Pointer-chase length of the following cro_probe_all calls (1 .. 16777216 hops per directed pair). */
+int  cro_set_latency_hops(cro_ctx *ctx, uint32_t hops);
 /* Where `hops` steps from slot 0 of the latency permutation of the directed pair (minor_src chases through
  * minor_dst's memory) end: Sattolo cycle over 65536 slots, mt19937_64 seeded with minor_src * 8 + minor_dst
  * (SURVEY.md §8d config 3).  Host arithmetic only. */

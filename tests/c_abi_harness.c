@@ -74,12 +74,20 @@ int main(int argc, char **argv) {
         CHECK(rc == CRO_OK && ctx != NULL);
         cro_dev_info devs[CRO_MAX_DEVICES];
         int n = 0;
-        CHECK(cro_enumerate(ctx, devs, CRO_MAX_DEVICES, &n) == CRO_OK && n == 1);
+        CHECK(cro_enumerate(ctx, devs, CRO_MAX_DEVICES, &n) == CRO_OK && n >= 1);   /* the whole NODE, fresh */
+        int mine = -1;
+        for (int i = 0; i < n; ++i)
+            if (devs[i].flags & CRO_DEV_IN_PROCESS) { CHECK(mine < 0 && devs[i].dev_index == 0); mine = i; }
+        CHECK(mine >= 0);
+        devs[0] = devs[mine];
         cro_probe_result r;
         CHECK(cro_probe_device(ctx, 0, &r) == CRO_OK);
         CHECK(r.status == CRO_OK && r.checksum_xor == r.expect_xor && r.checksum_sum == r.expect_sum && r.checksum_wsum == r.expect_wsum);
         CHECK(r.abi_version == CRO_ABI_VERSION && r.fail_code == CRO_FAIL_NONE && r.copy_verified == r.copy_sweeps);
         CHECK(strcmp(r.gpu_uuid, devs[0].gpu_uuid) == 0);
+        cro_probe_result r2;
+        CHECK(cro_probe_uuid(ctx, devs[0].gpu_uuid, &r2) == CRO_OK && r2.nonce == r.nonce + 1);
+        CHECK(cro_probe_uuid(ctx, "GPU-00000000-dead-beef-0000-000000000000", &r2) == CRO_ERR_NO_DEVICE);
         CHECK(cro_emit_csv(devs, n, "gpu_uuid", buf, sizeof buf, &len) == CRO_OK);
         int visible = 0;
         CHECK(cro_check_gpu_visible(devs, n, devs[0].gpu_uuid, &visible) == CRO_OK && visible == 1);

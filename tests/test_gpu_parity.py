@@ -120,7 +120,7 @@ def test_fault_is_detected_and_located(cro, coracle, ctx_small):
 def test_every_probe_writes_a_fresh_pattern(cro, coracle, ctx_small):
     """A fill or copy that silently did nothing must not pass on the previous probe's bytes: each probe takes the next
     nonce, so its pattern (and closed form) differs from whatever is still in HBM."""
-    d = ctx_small.enumerate()[0]
+    d = ctx_small.own_devices()[0]
     r1 = ctx_small.probe_device(0)
     r2 = ctx_small.probe_device(0)
     assert r2.nonce == r1.nonce + 1 and r1.seed != r2.seed and r1.checksum != r2.checksum
@@ -155,7 +155,7 @@ def test_probe_catches_corruption_in_either_half(cro, coracle):
 
 def test_probe_result_fields(cro, coracle, ctx_small):
     r = ctx_small.probe_device(0)
-    d = ctx_small.enumerate()[0]
+    d = ctx_small.own_devices()[0]
     assert r.abi_version == 2 and r.status == 0 and r.world == 1 and r.rank == 0
     assert r.gpu_uuid == d.gpu_uuid and r.pci_bus_id == d.pci_bus_id and r.device_minor == d.device_minor
     assert r.sweep_bytes == 64 << 20 and r.read_sweeps == 3 and r.copy_sweeps == 2
@@ -170,7 +170,7 @@ def test_device_written_struct_equals_host_assembly(cro, coracle, ctx_small):
     identity from the enumeration, checksums from the oracle, times from the per-sweep %globaltimer windows — and
     compare field by field; the CUDA-event times of the same sweeps must agree with the device's own timers."""
     r = ctx_small.probe_device(0)
-    d = ctx_small.enumerate()[0]
+    d = ctx_small.own_devices()[0]
     times = ctx_small.sweep_times(0)
     assert [t.kind for t in times] == [0] + [1] * r.copy_sweeps + [2] * r.read_sweeps
     want = coracle.checksum(r.seed, 0, r.sweep_bytes // 8)
@@ -265,7 +265,7 @@ def test_identity_strings_match_nvidia_smi(cro):
 def test_reconcile_attach_live(cro, oracle):
     import __graft_entry__ as g
     with cro.ProbeContext(sweep_bytes=32 << 20, devices=[0], read_sweeps=1, copy_sweeps=1) as c:
-        uuid = c.enumerate()[0].gpu_uuid.decode()
+        uuid = c.own_devices()[0].gpu_uuid.decode()
         base = {"name": "cr-0", "spec": {"type": "gpu", "model": "NVIDIA-B200", "target_node": "worker-0"},
                 "status": {"state": "Attaching"}, "device_resource_type": "DEVICE_PLUGIN", "probe": True}
         out = cro.reconcile_attach(c, dict(base, provider={"device_id": uuid, "cdi_device_id": "res-0-0"}))
@@ -359,15 +359,22 @@ def test_oom_fails_loudly_or_degrades(cro, coracle):
     """A sweep region that does not fit (2*S = 192 GiB > 180 GB): CRO_ERR_OOM by default; with
     CRO_F_DEGRADE_ON_OOM the probe halves S until it fits and says so in the result."""
     S = 96 << 30
-    import torch
-    torch.cuda.init()
-    free_before = torch.cuda.mem_get_info(0)[0]
+    import pynvml                                      # not torch: a host that loads torch AFTER libcroprobe has loaded the
+    pynvml.nvmlInit()                                  # system NCCL would trip over the older libnccl.so.2 (see load_nccl)
+    uuid0 = None
+    with cro.ProbeContext(sweep_bytes=1 << 20, devices=[0], flags=cro.F_LAZY_ALLOC) as c0:
+        uuid0 = c0.own_devices()[0].gpu_uuid.decode()
+    try:
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid0)
+    except TypeError:
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid0.encode())
+    used_before = pynvml.nvmlDeviceGetMemoryInfo(h).used
     for _ in range(3):                                   # a failed init must release what it had already built
         with pytest.raises(cro.ProbeError) as e:
             cro.ProbeContext(sweep_bytes=S, devices=[0])
         assert e.value.code == cro.ERR_OOM
         assert "cudaMalloc" in str(e.value) and "asked for" in str(e.value)      # cro_last_error(NULL) carries the reason
-    assert free_before - torch.cuda.mem_get_info(0)[0] < (64 << 20)
+    assert pynvml.nvmlDeviceGetMemoryInfo(h).used - used_before < (768 << 20)   # the CUDA context itself stays; no region leaked
     with cro.ProbeContext(sweep_bytes=S, devices=[0], flags=cro.F_DEGRADE_ON_OOM, read_sweeps=1, copy_sweeps=1) as c:
         r = c.probe_device(0)
         assert r.status == 0 and r.sweep_bytes == 48 << 30
@@ -397,7 +404,7 @@ def test_concurrent_callers_are_serialised_per_device(cro, coracle):
                         results.append(("probe", r.seed, r.checksum))
                     else:
                         out = cro.reconcile_attach(c, {"status": {"state": "Attaching"}, "probe": True, "spec": {"type": "gpu", "model": "m", "target_node": "n"},
-                                                       "provider": {"device_id": c.enumerate()[0].gpu_uuid.decode(), "cdi_device_id": "r"}})
+                                                       "provider": {"device_id": c.own_devices()[0].gpu_uuid.decode(), "cdi_device_id": "r"}})
                         assert out["status"]["state"] == "Online"
             except Exception as e:   # noqa: BLE001
                 errors.append(repr(e))
@@ -412,7 +419,7 @@ def test_concurrent_callers_are_serialised_per_device(cro, coracle):
             if r[0] == "probe":
                 seeds[r[1]] = r[2]
                 assert r[2] == coracle.checksum(r[1], 0, n_words)
-        d = c.enumerate()[0]
+        d = c.own_devices()[0]
         legal = {coracle.checksum(coracle.probe_seed(0x00C0FFEE00000000, max(d.device_minor, 0), k), 0, n_words) for k in range(64)}
         assert all(r[1] in legal for r in results if r[0] == "read")
         assert len(seeds) == sum(1 for r in results if r[0] == "probe")      # no two probes shared a nonce
@@ -490,3 +497,91 @@ def test_storm_and_churn_with_live_probe(cro):
             c.run()
             d = c.dump()
             assert d["requests"] == {} and d["resources"] == {}
+
+
+def test_probe_by_uuid_in_process_and_through_the_helper(cro, coracle):
+    """cro_probe_uuid: a device the context holds is probed in process; a device it does NOT hold — the position a GPU
+    composed after cuInit is in — is probed by the helper process (fresh cuInit, CUDA_VISIBLE_DEVICES=<uuid>), and its
+    512-byte verdict comes back over a pipe.  With no context at all every device goes through the helper."""
+    with cro.ProbeContext(sweep_bytes=64 << 20, devices=[0], read_sweeps=2, copy_sweeps=1) as c:
+        mine = c.own_devices()[0]
+        node = c.enumerate()                          # the whole node, fresh
+        assert any(d.gpu_uuid == mine.gpu_uuid and d.flags & cro.DEV_IN_PROCESS for d in node)
+        r = cro.probe_uuid(c, mine.gpu_uuid.decode())
+        assert r.status == 0 and r.gpu_uuid == mine.gpu_uuid and r.sweep_bytes == 64 << 20
+        assert r.checksum == coracle.checksum(r.seed, 0, r.sweep_bytes // 8)
+        others = [d for d in node if d.flags & cro.DEV_NEEDS_HELPER]
+        if others:                                    # multi-GPU box: a GPU this context cannot touch
+            o = others[0]
+            assert o.dev_index == -1 and o.cuda_ordinal == -1
+            rh = cro.probe_uuid(c, o.gpu_uuid.decode())
+            assert rh.status == 0 and rh.gpu_uuid == o.gpu_uuid and rh.nonce == 0 and rh.copy_verified == rh.copy_sweeps
+            assert rh.checksum == rh.expect == coracle.checksum(rh.seed, 0, rh.sweep_bytes // 8, threads=os.cpu_count() or 1)
+            out = cro.reconcile_attach(c, {"status": {"state": "Attaching"}, "probe": True, "spec": {"type": "gpu", "model": "m", "target_node": "n"},
+                                           "provider": {"device_id": o.gpu_uuid.decode(), "cdi_device_id": "r"}})
+            assert out["status"]["state"] == "Online" and out["probe"]["cohdi.io/probe-device-id"] == o.gpu_uuid.decode()
+        with pytest.raises(cro.ProbeError) as e:
+            cro.probe_uuid(c, "GPU-00000000-dead-beef-0000-000000000000")
+        assert e.value.code == cro.ERR_NO_DEVICE
+    # no context: the helper does everything (1 GiB first sweep)
+    rh = cro.probe_uuid(None, mine.gpu_uuid.decode())
+    assert rh.status == 0 and rh.gpu_uuid == mine.gpu_uuid and rh.sweep_bytes == 1 << 30
+    assert rh.checksum == coracle.checksum(rh.seed, 0, rh.sweep_bytes // 8, threads=os.cpu_count() or 1)
+
+
+def test_illegal_knob_fails_the_init_with_the_references_wording(cro, monkeypatch):
+    """composableresource_adapter.go:44: "the env variable X has an invalid value: 'v'" — same sentence, same refusal."""
+    monkeypatch.setenv("CRO_TMA_READ_TILE", "12345")          # not a multiple of 16
+    with pytest.raises(cro.ProbeError) as e:
+        cro.ProbeContext(sweep_bytes=1 << 20, devices=[0])
+    assert e.value.code == cro.ERR_INVALID_ARG and "the env variable CRO_TMA_READ_TILE has an invalid value: '12345'" in str(e.value)
+    monkeypatch.setenv("CRO_TMA_READ_TILE", "16384")
+    monkeypatch.setenv("CRO_TMA_READ_STAGES", "8")
+    with cro.ProbeContext(sweep_bytes=256 << 20, devices=[0], read_sweeps=1, copy_sweeps=1, read_variant=cro.READ_TMA) as c:
+        assert c.probe_device(0).status == 0
+
+
+def test_fill_that_did_not_happen_is_caught(cro, coracle):
+    """with a constant seed a fill that silently does nothing passes on the previous probe's bytes.  Here the
+    region is left holding probe k's pattern and is then read against probe k+1's closed form: every component differs."""
+    S = 32 << 20
+    with cro.ProbeContext(sweep_bytes=S, devices=[0], read_sweeps=1, copy_sweeps=1) as c:
+        r1 = c.probe_device(0)
+        stale = c.hbm_read_checksum(0, 1).checksum            # what is in HBM now: probe 1's pattern
+        assert stale == r1.checksum
+        r2 = c.probe_device(0)
+        assert r2.expect != stale and all(a != b for a, b in zip(r2.expect, stale))
+        assert r2.status == 0 and r2.checksum == r2.expect
+
+
+def test_live_context_follows_a_changing_node(cro, tmp_path, monkeypatch):
+    """the device list must not be the init-time snapshot.  A real context (device 0) is pointed at a
+    fake driver registry (CRO_PROC_ROOT) holding its own GPU; GPUs are then added to and removed from that registry
+    between calls and cro_enumerate / the attach reconcile must follow at once."""
+    from test_inventory import put, drop, U, BUS, INFO
+    with cro.ProbeContext(sweep_bytes=1 << 20, devices=[0], flags=cro.F_LAZY_ALLOC) as c0:
+        me = c0.own_devices()[0]
+    root = str(tmp_path)
+    d = os.path.join(root, "driver", "nvidia", "gpus", "0000:1b:00.0")
+    os.makedirs(d)
+    with open(os.path.join(d, "information"), "w") as f:
+        f.write(INFO % (7, me.gpu_uuid.decode(), "0000:1b:00.0", max(me.device_minor, 0)))
+    monkeypatch.setenv("CRO_PROC_ROOT", root)
+    with cro.ProbeContext(sweep_bytes=16 << 20, devices=[0], flags=cro.F_NO_NVML, read_sweeps=1, copy_sweeps=1) as c:
+        assert [(x.gpu_uuid, x.flags) for x in c.enumerate()] == [(me.gpu_uuid, cro.DEV_IN_PROCESS)]
+        put(root, 2)                                               # hot-plug: a GPU the CUDA context has never seen
+        got = {x.gpu_uuid.decode(): x for x in c.enumerate()}
+        assert set(got) == {me.gpu_uuid.decode(), U[2]} and got[U[2]].flags == cro.DEV_NEEDS_HELPER and got[U[2]].dev_index == -1
+        base = {"status": {"state": "Attaching"}, "probe": False, "spec": {"type": "gpu", "model": "m", "target_node": "n"},
+                "device_resource_type": "DEVICE_PLUGIN"}
+        out = cro.reconcile_attach(c, dict(base, provider={"device_id": U[2], "cdi_device_id": "r"}))
+        assert out["status"]["state"] == "Online"                  # the reference's membership rule sees the new GPU
+        drop(root, 2)                                              # ... and it is drained off the bus again
+        assert [x.gpu_uuid for x in c.enumerate()] == [me.gpu_uuid]
+        out = cro.reconcile_attach(c, dict(base, provider={"device_id": U[2], "cdi_device_id": "r"}))
+        assert out["status"]["state"] == "Attaching" and out["requeue_after_s"] == 30
+        # the context's OWN device leaves the bus: it stops being listed (Detaching then sees visible=false)
+        os.remove(os.path.join(d, "information")); os.rmdir(d)
+        assert c.enumerate() == []
+        out = cro.reconcile_attach(c, dict(base, provider={"device_id": me.gpu_uuid.decode(), "cdi_device_id": "r"}))
+        assert out["status"]["state"] == "Attaching"

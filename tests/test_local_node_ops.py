@@ -56,7 +56,7 @@ def test_local_checks_on_the_box(cro):
     """Real read-only checks: this very process holds a CUDA context on GPU 0, so the load check finds a compute app
     and the open-file scan finds a holder of /dev/nvidia<minor> — both are the reference's refusals, spelled its way."""
     with cro.ProbeContext(sweep_bytes=64 << 20, devices=[0], read_sweeps=1, copy_sweeps=1) as ctx:
-        info = ctx.enumerate()[0]
+        info = ctx.own_devices()[0]
         uuid = info.gpu_uuid.decode()
         ctx.probe_device(0)
         base = {"node": "worker-0", "device_id": uuid, "driver_container": True}
