@@ -809,16 +809,23 @@ public:
             // Non-blocking reconcile: the first pass begins the probe on the device's stream and
             // asks for a requeue; a later pass collects it.  One reconcile worker therefore keeps
             // every GPU of the box busy (a device serves one attach at a time, in arrival order).
-            auto owner = c_->probe_owner_.find(idx);
-            if (owner == c_->probe_owner_.end()) {
-                if (ctx_probe_begin(c_->ctx_, idx) != CRO_OK)
-                    return Error::New("cuda probe failed: could not start the probe");
-                c_->probe_owner_[idx] = r.Name;
+            std::deque<std::string>& owners = c_->probe_owner_[idx];
+            size_t pos = 0;
+            while (pos < owners.size() && owners[pos] != r.Name) ++pos;
+            if (pos == owners.size()) {       // not probing yet
+                if (owners.size() < 2) {      // a free lane: enqueue behind whatever is running on the device
+                    if (ctx_probe_begin(c_->ctx_, idx) != CRO_OK) {
+                        if (owners.empty()) c_->probe_owner_.erase(idx);
+                        return Error::New("cuda probe failed: could not start the probe");
+                    }
+                    owners.push_back(r.Name);
+                } else if (c_->probe_waiting_.insert(r.Name).second) {
+                    c_->dev_waiters_[idx].push_back(r.Name);   // both lanes taken: queue behind them
+                }
                 probePending = true;
                 return Error::Nil();
             }
-            if (owner->second != r.Name) {   // the device is serving another attach: queue behind it
-                if (c_->probe_waiting_.insert(r.Name).second) c_->dev_waiters_[idx].push_back(r.Name);
+            if (pos > 0) {                    // ours is the second in line: results come out oldest first
                 probePending = true;
                 return Error::Nil();
             }
@@ -947,12 +954,13 @@ void Cluster::pollProbes(bool block) {
     std::vector<int> orphaned;
     bool woke = false;
     for (const auto& kv : probe_owner_) {
-        auto it = resources_.find(kv.second);
+        if (kv.second.empty()) continue;
+        auto it = resources_.find(kv.second.front());
         if (it == resources_.end() || it->second.obj.Status.State != "Attaching") {
             orphaned.push_back(kv.first);
         } else if (!probe_notified_.count(kv.first) && ctx_probe_poll(ctx_, kv.first)) {
             probe_notified_.insert(kv.first);
-            enqueueResourceFront(kv.second);   // its owner can collect now
+            enqueueResourceFront(kv.second.front());   // its owner can collect now
             woke = true;
         }
     }
@@ -966,12 +974,12 @@ void Cluster::pollProbes(bool block) {
         // nothing else to reconcile: wait for WHICHEVER device finishes first (blocking on one
         // particular stream would leave the others idle once they drift apart)
         bool any_unnotified = false;
-        for (const auto& kv : probe_owner_) any_unnotified |= !probe_notified_.count(kv.first);
+        for (const auto& kv : probe_owner_) any_unnotified |= !kv.second.empty() && !probe_notified_.count(kv.first);
         while (any_unnotified && !woke) {
             for (const auto& kv : probe_owner_) {
-                if (probe_notified_.count(kv.first) || !ctx_probe_poll(ctx_, kv.first)) continue;
+                if (kv.second.empty() || probe_notified_.count(kv.first) || !ctx_probe_poll(ctx_, kv.first)) continue;
                 probe_notified_.insert(kv.first);
-                enqueueResourceFront(kv.second);
+                enqueueResourceFront(kv.second.front());
                 woke = true;
             }
             if (!woke) usleep(20);
@@ -981,7 +989,11 @@ void Cluster::pollProbes(bool block) {
 
 // The attach that owned `dev` is done with it: the next one queued behind it gets a turn.
 void Cluster::releaseDevice(int dev) {
-    probe_owner_.erase(dev);
+    auto own = probe_owner_.find(dev);
+    if (own != probe_owner_.end()) {
+        if (!own->second.empty()) own->second.pop_front();       // the oldest probe has been collected
+        if (own->second.empty()) probe_owner_.erase(own);
+    }
     probe_notified_.erase(dev);
     auto q = dev_waiters_.find(dev);
     if (q == dev_waiters_.end()) return;

@@ -171,7 +171,9 @@ private:
     std::deque<std::string> req_queue_, res_queue_;
     std::set<std::string> req_queued_, res_queued_;
     std::set<std::string> req_timers_, res_timers_;
-    std::map<int, std::string> probe_owner_;                    // device -> the attach whose probe is in flight on it
+    std::map<int, std::deque<std::string>> probe_owner_;        // device -> the attaches whose probes are in flight on it, oldest
+                                                                // first (up to two: the second one's kernels are queued behind
+                                                                // the first's, so the GPU never waits for the host)
     std::set<int> probe_notified_;                              // devices whose owner has been told "done"
     std::map<int, std::deque<std::string>> dev_waiters_;        // attaches queued behind a device's owner
     std::set<std::string> probe_waiting_;                       // names present in some dev_waiters_ queue

@@ -31,7 +31,10 @@ namespace {
 constexpr uint64_t kDefaultSweep = 4ull << 30;
 constexpr uint64_t kDefaultP2P = 1ull << 30;
 constexpr uint64_t kDefaultSeedBase = 0x00C0FFEE00000000ull;
-constexpr uint32_t kDefaultHops = 16384;
+// 4096 hops: the mean hop latency is the same to 0.1 % at 1 Ki, 4 Ki, 16 Ki and 64 Ki hops (1860.4 / 1862.7 / 1861.7 /
+// 1861.6 ns on a 2-GPU box, profiles/r02_latency_vs_hops.md), and 64 Ki hops of ~1.7 us would be 3x the rest of the
+// full-box probe.  SURVEY.md §8d's 64 Ki is one cro_set_latency_hops / latency_hops away; bench.py runs it every time.
+constexpr uint32_t kDefaultHops = 4096;
 
 #define CU_TRY(ctx, expr)                                                              \
     do {                                                                               \
@@ -55,7 +58,7 @@ struct Range {
 };
 
 Params imm_params(const Device* d) { return Params{ProbeParams{d->seed_cur, d->nonce_cur}, nullptr}; }
-Params graph_params(const Device* d) { return Params{ProbeParams{0, 0}, d->d_params}; }
+Params graph_params(const Lane& L) { return Params{ProbeParams{0, 0}, L.d_params}; }
 uint64_t seed_of(const Device* d, uint64_t nonce) { return d->seed_dev + nonce * kNonceStride; }
 
 int ensure_region(cro_ctx* c, Device* d) {
@@ -71,7 +74,8 @@ int ensure_region(cro_ctx* c, Device* d) {
         if (e == cudaSuccess) {
             if (s != d->sweep_bytes) {
                 d->sweep_bytes = s;
-                if (d->graph_exec) { cudaGraphExecDestroy(d->graph_exec); d->graph_exec = nullptr; }
+                for (Lane& L : d->lanes)
+                    if (L.graph_exec) { cudaGraphExecDestroy(L.graph_exec); L.graph_exec = nullptr; }
             }
             break;
         }
@@ -350,17 +354,22 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
         if (rc) return rc;
         if ((rc = alloc_scratch(c.get(), &d->scratch_aux, max_grid))) return rc;
         if ((rc = alloc_scratch(c.get(), &d->scratch_pfx, max_grid))) return rc;
-        CU_TRY(c.get(), cudaMalloc(&d->d_out, sizeof(SweepOut) * kSlotCount));
-        CU_TRY(c.get(), cudaMemset(d->d_out, 0xFF, sizeof(SweepOut) * kSlotCount));   // no slot starts with a plausible stamp
-        CU_TRY(c.get(), cudaMallocHost(&d->h_out, sizeof(SweepOut) * kSlotCount));
-        CU_TRY(c.get(), cudaMalloc(&d->d_params, sizeof(ProbeParams)));
-        CU_TRY(c.get(), cudaMallocHost(&d->h_params, sizeof(ProbeParams)));
+        for (int k = 0; k < 2; ++k) {
+            Lane& L = d->lanes[k];
+            const size_t slots = k == 0 ? (size_t)kSlotCount : 64;
+            CU_TRY(c.get(), cudaMalloc(&L.d_out, sizeof(SweepOut) * slots));
+            CU_TRY(c.get(), cudaMemset(L.d_out, 0xFF, sizeof(SweepOut) * slots));   // no slot starts with a plausible stamp
+            CU_TRY(c.get(), cudaMallocHost(&L.h_out, sizeof(SweepOut) * slots));
+            CU_TRY(c.get(), cudaMalloc(&L.d_params, sizeof(ProbeParams)));
+            CU_TRY(c.get(), cudaMallocHost(&L.h_params, sizeof(ProbeParams)));
+            CU_TRY(c.get(), cudaMalloc(&L.d_result, sizeof(cro_probe_result)));
+            CU_TRY(c.get(), cudaMallocHost(&L.h_result, sizeof(cro_probe_result)));
+            CU_TRY(c.get(), cudaMemset(L.d_result, 0, sizeof(cro_probe_result)));
+            CU_TRY(c.get(), cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+        }
         CU_TRY(c.get(), cudaMalloc(&d->d_tmpl, sizeof(cro_probe_result)));
-        CU_TRY(c.get(), cudaMalloc(&d->d_result, sizeof(cro_probe_result)));
         CU_TRY(c.get(), cudaMalloc(&d->d_gather, sizeof(cro_probe_result) * CRO_MAX_DEVICES));
-        CU_TRY(c.get(), cudaMallocHost(&d->h_result, sizeof(cro_probe_result)));
         CU_TRY(c.get(), cudaMallocHost(&d->h_gather, sizeof(cro_probe_result) * CRO_MAX_DEVICES));
-        CU_TRY(c.get(), cudaMemset(d->d_result, 0, sizeof(cro_probe_result)));
         CU_TRY(c.get(), cudaMalloc(&d->d_chase_out, 2 * CRO_MAX_DEVICES * sizeof(unsigned long long)));
         CU_TRY(c.get(), cudaMallocHost(&d->h_chase_out, 2 * CRO_MAX_DEVICES * sizeof(unsigned long long)));
         if (!(opts.flags & CRO_F_LAZY_ALLOC)) {
@@ -399,20 +408,23 @@ Device::~Device() {
     free_scratch(&scratch);
     free_scratch(&scratch_aux);
     free_scratch(&scratch_pfx);
-    cudaFree(d_out);
-    if (h_out) cudaFreeHost(h_out);
-    cudaFree(d_params);
-    if (h_params) cudaFreeHost(h_params);
+    for (Lane& L : lanes) {
+        cudaFree(L.d_out);
+        if (L.h_out) cudaFreeHost(L.h_out);
+        cudaFree(L.d_params);
+        if (L.h_params) cudaFreeHost(L.h_params);
+        cudaFree(L.d_result);
+        if (L.h_result) cudaFreeHost(L.h_result);
+        if (L.graph_exec) cudaGraphExecDestroy(L.graph_exec);
+        for (cudaEvent_t e : L.evpool) cudaEventDestroy(e);
+        if (L.ev_done) cudaEventDestroy(L.ev_done);
+    }
     cudaFree(d_tmpl);
-    cudaFree(d_result);
     cudaFree(d_gather);
-    if (h_result) cudaFreeHost(h_result);
     if (h_gather) cudaFreeHost(h_gather);
     for (unsigned long long* t : d_chase_tables) cudaFree(t);
     cudaFree(d_chase_out);
     if (h_chase_out) cudaFreeHost(h_chase_out);
-    if (graph_exec) cudaGraphExecDestroy(graph_exec);
-    for (cudaEvent_t e : evpool) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_push_done) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_reread_done) cudaEventDestroy(e);
     for (cudaEvent_t e : {ev0, ev1, ev_fork, ev_join, ev_hbm_done, ev_aux_done, ev_chase_ready})
@@ -603,10 +615,10 @@ static int read_half(uint32_t copies, uint32_t k) {
     return (k & 1u) ? 1 - last_dst : last_dst;
 }
 
-// Caller holds d->mu and has the device current.  Enqueues one whole probe on the device's stream and returns
-// without waiting: params refresh, fill, copy sweeps, read sweeps, the closed-form generator on the side
-// stream, the finalize kernel that writes the result struct, and the copy-back of that struct.
-static int probe_enqueue(cro_ctx* c, Device* d) {
+// Caller holds d->mu.  Enqueues one whole probe on the device's stream, using lane L's buffers, and returns without
+// waiting: params refresh, fill, copy sweeps, read sweeps, the closed-form generator on the side stream, the finalize
+// kernel that writes the result struct, and the copy-back of that struct.
+static int probe_enqueue(cro_ctx* c, Device* d, Lane& L) {
     const cro_opts& o = c->opts;
     Range nv(c, "cro.probe.enqueue");
     CU_TRY(c, cudaSetDevice(d->ordinal));
@@ -620,17 +632,17 @@ static int probe_enqueue(cro_ctx* c, Device* d) {
         if ((rc = stage_template(c, d))) return rc;
     }
 
-    // events: one before the fill, one after every sweep (pool lives with the device)
+    // events: one before the fill, one after every sweep (pool lives with the lane)
     const size_t need = 2 + R + C;
-    while (d->evpool.size() < need) {
+    while (L.evpool.size() < need) {
         cudaEvent_t e;
         CU_TRY(c, cudaEventCreate(&e));
-        d->evpool.push_back(e);
+        L.evpool.push_back(e);
     }
-    std::vector<cudaEvent_t>& ev = d->evpool;
+    std::vector<cudaEvent_t>& ev = L.evpool;
     const bool overlap = env::get("CRO_EXPECT_OVERLAP") != 0;
     unsigned char* half[2] = {d->region, d->region + d->sweep_bytes};
-    const Params gp = graph_params(d);
+    const Params gp = graph_params(L);
 
     size_t k = 0;
     // The whole probe as one sequence; `external` records the timing events as external event-record
@@ -638,9 +650,9 @@ static int probe_enqueue(cro_ctx* c, Device* d) {
     auto issue = [&](bool external) -> int {
         const unsigned flag = external ? cudaEventRecordExternal : cudaEventRecordDefault;
         k = 0;
-        CU_TRY(c, cudaMemcpyAsync(d->d_params, d->h_params, sizeof(ProbeParams), cudaMemcpyHostToDevice, d->stream));
+        CU_TRY(c, cudaMemcpyAsync(L.d_params, L.h_params, sizeof(ProbeParams), cudaMemcpyHostToDevice, d->stream));
         CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
-        CU_TRY(c, launch_fill(d->plan, half[0], d->sweep_bytes, gp, d->scratch, &d->d_out[kSlotFill], d->stream));
+        CU_TRY(c, launch_fill(d->plan, half[0], d->sweep_bytes, gp, d->scratch, &L.d_out[kSlotFill], d->stream));
         CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
         // the closed form: ALU only, so it runs beside the copy sweeps (which leave the ALUs idle)
         cudaStream_t es = overlap ? d->aux : d->stream;
@@ -648,25 +660,25 @@ static int probe_enqueue(cro_ctx* c, Device* d) {
             CU_TRY(c, cudaEventRecord(d->ev_fork, d->stream));
             CU_TRY(c, cudaStreamWaitEvent(d->aux, d->ev_fork, 0));
         }
-        CU_TRY(c, launch_expected(d->plan, d->sweep_bytes, gp, d->scratch_aux, &d->d_out[kSlotExpect], es));
+        CU_TRY(c, launch_expected(d->plan, d->sweep_bytes, gp, d->scratch_aux, &L.d_out[kSlotExpect], es));
         if (overlap) CU_TRY(c, cudaEventRecord(d->ev_join, d->aux));
         for (uint32_t i = 0; i < C; ++i) {
             const int s = copy_src_half(i);
             CU_TRY(c, launch_copy(d->plan, cv, half[1 - s], half[s], d->sweep_bytes, gp, d->scratch,
-                                  &d->d_out[kSlotSweep0 + i], d->stream));
+                                  &L.d_out[kSlotSweep0 + i], d->stream));
             CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
         }
         for (uint32_t i = 0; i < R; ++i) {
             CU_TRY(c, launch_read(d->plan, rv, half[read_half(C, i)], d->sweep_bytes, gp, d->scratch,
-                                  &d->d_out[kSlotSweep0 + C + i], d->stream));
+                                  &L.d_out[kSlotSweep0 + C + i], d->stream));
             CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
         }
         if (overlap) CU_TRY(c, cudaStreamWaitEvent(d->stream, d->ev_join, 0));
         FinalizeArgs fa{};
         fa.tmpl = d->d_tmpl;
-        fa.out = d->d_result;
-        fa.slots = d->d_out;
-        fa.pp = d->d_params;
+        fa.out = L.d_result;
+        fa.slots = L.d_out;
+        fa.pp = L.d_params;
         fa.sweep_bytes = d->sweep_bytes;
         fa.read_sweeps = R;
         fa.copy_sweeps = C;
@@ -674,29 +686,34 @@ static int probe_enqueue(cro_ctx* c, Device* d) {
         fa.copy_variant = C ? cv : 0;
         fa.fused = (cv == COPY_TMA_FUSED) ? 1u : 0u;
         CU_TRY(c, launch_finalize(fa, d->stream));
-        CU_TRY(c, cudaMemcpyAsync(d->h_result, d->d_result, sizeof(cro_probe_result), cudaMemcpyDeviceToHost, d->stream));
-        CU_TRY(c, cudaMemcpyAsync(d->h_out, d->d_out, sizeof(SweepOut) * 64, cudaMemcpyDeviceToHost, d->stream));
+        CU_TRY(c, cudaMemcpyAsync(L.h_result, L.d_result, sizeof(cro_probe_result), cudaMemcpyDeviceToHost, d->stream));
+        CU_TRY(c, cudaMemcpyAsync(L.h_out, L.d_out, sizeof(SweepOut) * 64, cudaMemcpyDeviceToHost, d->stream));
         return CRO_OK;
     };
 
     // this probe's seed: the host refreshes the 16 bytes the graph's first node copies to the device
     const uint64_t nonce = d->nonce_next++;
-    d->h_params->seed = seed_of(d, nonce);
-    d->h_params->nonce = nonce;
-    d->seed_cur = d->h_params->seed;
+    L.h_params->seed = seed_of(d, nonce);
+    L.h_params->nonce = nonce;
+    d->seed_cur = L.h_params->seed;
     d->nonce_cur = nonce;
 
     // One graph launch instead of ~40 runtime calls per probe (matters when one host thread feeds 8 GPUs).
     // The graph is tied to the options it was captured with; any capture problem falls back to direct launches.
     const uint64_t graph_key = ((uint64_t)rv << 48) ^ ((uint64_t)cv << 40) ^ ((uint64_t)R << 24) ^ ((uint64_t)C << 8) ^
                                (overlap ? 1u : 0u) ^ (d->sweep_bytes << 1);
-    if (env::get("CRO_USE_GRAPH") && !d->graph_failed) {
-        if (d->graph_exec && d->graph_key != graph_key) {
-            cudaGraphExecDestroy(d->graph_exec);
-            d->graph_exec = nullptr;
+    if (env::get("CRO_USE_GRAPH") && !L.graph_failed) {
+        if (L.graph_exec && L.graph_key != graph_key) {
+            cudaGraphExecDestroy(L.graph_exec);
+            L.graph_exec = nullptr;
         }
-        if (!d->graph_exec) {
+        if (!L.graph_exec) {
             Range nvc(c, "cro.probe.capture");
+            // capture needs an idle capture origin: a probe still running on the stream is fine (capture records, it
+            // does not execute), but cudaStreamBeginCapture on a stream with a pending cross-stream join is not —
+            // so the first use of a lane waits for the stream once
+            cudaStreamSynchronize(d->stream);
+            cudaStreamSynchronize(d->aux);
             cudaGraph_t graph = nullptr;
             bool ok = cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             if (ok) {
@@ -704,31 +721,34 @@ static int probe_enqueue(cro_ctx* c, Device* d) {
                 const cudaError_t ec = cudaStreamEndCapture(d->stream, &graph);
                 ok = irc == CRO_OK && ec == cudaSuccess && graph != nullptr;
             }
-            if (ok) ok = cudaGraphInstantiate(&d->graph_exec, graph, 0) == cudaSuccess;
+            if (ok) ok = cudaGraphInstantiate(&L.graph_exec, graph, 0) == cudaSuccess;
             if (graph) cudaGraphDestroy(graph);
             if (!ok) {
                 cudaGetLastError();
-                d->graph_exec = nullptr;
-                d->graph_failed = true;
+                L.graph_exec = nullptr;
+                L.graph_failed = true;
             } else {
-                d->graph_key = graph_key;
-                d->graph_events = k;
+                L.graph_key = graph_key;
+                L.graph_events = k;
             }
         }
     }
-    if (d->graph_exec) {
-        CU_TRY(c, cudaGraphLaunch(d->graph_exec, d->stream));
-        k = d->graph_events;
+    if (L.graph_exec) {
+        CU_TRY(c, cudaGraphLaunch(L.graph_exec, d->stream));
+        k = L.graph_events;
     } else {
         int irc = issue(false);
         if (irc) return irc;
     }
+    CU_TRY(c, cudaEventRecord(L.ev_done, d->stream));
     d->filled = true;
     c->launches += 3 + R + C;       // fill + closed form + sweeps + finalize
-    d->pending_events = k;
-    d->last_reads = R;
-    d->last_copies = C;
-    d->last_timed = true;
+    L.events = k;
+    L.reads = R;
+    L.copies = C;
+    L.timed = true;
+    L.in_flight = true;
+    L.since = std::chrono::steady_clock::now();
     return CRO_OK;
 }
 
@@ -749,17 +769,41 @@ static std::string describe_failure(const Device* d, const cro_probe_result& r) 
     }
 }
 
-// Caller holds d->mu.  Waits for the probe enqueued by probe_enqueue and hands out the struct the device wrote.
-static int probe_finish(cro_ctx* c, Device* d, cro_probe_result* r) {
+// Waits for a lane's probe, honouring opts.deadline_ms (see wait_stream).
+static int wait_lane(cro_ctx* c, Lane& L) {
+    if (c->opts.deadline_ms <= 0) {
+        CU_TRY(c, cudaEventSynchronize(L.ev_done));
+        return CRO_OK;
+    }
+    const auto until = std::chrono::steady_clock::now() + std::chrono::milliseconds(c->opts.deadline_ms);
+    for (;;) {
+        cudaError_t q = cudaEventQuery(L.ev_done);
+        if (q == cudaSuccess) return CRO_OK;
+        if (q != cudaErrorNotReady) {
+            c->set_error(std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+            return CRO_ERR_CUDA;
+        }
+        if (std::chrono::steady_clock::now() > until) {
+            c->set_error("probe deadline of " + std::to_string(c->opts.deadline_ms) + " ms exceeded");
+            return CRO_ERR_DEADLINE;
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+}
+
+// Caller holds d->mu.  Waits for the probe enqueued on lane L and hands out the struct the device wrote.
+static int probe_finish(cro_ctx* c, Device* d, Lane& L, cro_probe_result* r) {
     CU_TRY(c, cudaSetDevice(d->ordinal));
-    int rc;
-    if ((rc = wait_stream(c, d))) {
+    int rc = wait_lane(c, L);
+    L.in_flight = false;
+    d->last_lane = (int)(&L - d->lanes);
+    if (rc) {
         memset(r, 0, sizeof *r);
         r->abi_version = CRO_ABI_VERSION;
         r->status = rc;
         return rc;
     }
-    *r = *d->h_result;
+    *r = *L.h_result;
     if (r->status != CRO_OK) {
         c->set_error(describe_failure(d, *r));
         // What the memory itself reported: uncorrected volatile ECC errors (nvmlDeviceGetTotalEccErrors).
@@ -771,8 +815,8 @@ static int probe_finish(cro_ctx* c, Device* d, cro_probe_result* r) {
         if (d->ecc_uncorrected != before) {
             r->ecc_errors = d->ecc_uncorrected;
             d->tmpl.ecc_errors = d->ecc_uncorrected;
-            *d->h_result = *r;
-            CU_TRY(c, cudaMemcpyAsync(d->d_result, d->h_result, sizeof *r, cudaMemcpyHostToDevice, d->stream));
+            *L.h_result = *r;
+            CU_TRY(c, cudaMemcpyAsync(L.d_result, L.h_result, sizeof *r, cudaMemcpyHostToDevice, d->stream));
             CU_TRY(c, cudaMemcpyAsync(d->d_tmpl, &d->tmpl, sizeof d->tmpl, cudaMemcpyHostToDevice, d->stream));
             CU_TRY(c, cudaStreamSynchronize(d->stream));
         }
@@ -780,13 +824,18 @@ static int probe_finish(cro_ctx* c, Device* d, cro_probe_result* r) {
     return r->status;
 }
 
-// Drains a probe begun with ctx_probe_begin whose result nobody has collected
-// yet, so another operation may use the stream / result slots.  Caller holds d->mu.
+// Drains every probe still in flight on the device (oldest first) into d->done, so another operation may use the
+// stream / the region.  Caller holds d->mu.
 static void drain_pending(cro_ctx* c, Device* d) {
-    if (!d->pending) return;
-    d->pending_rc = probe_finish(c, d, &d->pending_result);
-    d->pending = false;
-    d->have_pending_result = true;
+    while (d->lane_count > 0) {
+        Lane& L = d->lanes[d->lane_head];
+        Device::Collected col;
+        col.rc = probe_finish(c, d, L, &col.r);
+        col.at = std::chrono::steady_clock::now();
+        d->done.push_back(col);
+        d->lane_head ^= 1;
+        --d->lane_count;
+    }
 }
 
 int ctx_probe_device(cro_ctx* c, int idx, cro_probe_result* out) {
@@ -794,52 +843,64 @@ int ctx_probe_device(cro_ctx* c, int idx, cro_probe_result* out) {
     if (!d || !out) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
     drain_pending(c, d);
-    d->have_pending_result = false;   // a synchronous probe supersedes an uncollected asynchronous one
-    int rc = probe_enqueue(c, d);
+    d->done.clear();                  // a synchronous probe supersedes uncollected asynchronous ones
+    d->lane_head = 0;
+    Lane& L = d->lanes[0];            // always lane 0: its result buffer is the all-gather send buffer
+    int rc = probe_enqueue(c, d, L);
     if (rc) {
         memset(out, 0, sizeof *out);
         out->abi_version = CRO_ABI_VERSION;
         out->status = rc;
         return rc;
     }
-    return probe_finish(c, d, out);
+    return probe_finish(c, d, L, out);
 }
 
-// Asynchronous form: begin enqueues the probe and returns; end waits and
-// evaluates.  Lets ONE host thread (the reference's single reconcile worker)
-// keep every attached GPU busy: probes of different devices overlap.
+// Asynchronous form: begin enqueues a probe and returns; end waits for the OLDEST one and evaluates it.  Up to two
+// probes per device may be in flight — the second one's kernels are already queued behind the first's, so the GPU
+// does not idle while the host collects one result and starts the next.  Lets ONE host thread (the reference's single
+// reconcile worker) keep every attached GPU busy.
 int ctx_probe_begin(cro_ctx* c, int idx) {
     Device* d = dev_at(c, idx);
     if (!d) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
-    if (d->pending || d->have_pending_result) return CRO_OK;   // one in flight (or waiting to be collected)
-    int rc = probe_enqueue(c, d);
+    if (d->lane_count + (int)d->done.size() >= 2) return CRO_OK;   // two in flight (or waiting to be collected): no-op
+    Lane& L = d->lanes[(d->lane_head + d->lane_count) & 1];
+    if (L.in_flight) return CRO_OK;
+    int rc = probe_enqueue(c, d, L);
     if (rc) return rc;
-    d->pending = true;
-    d->pending_since = std::chrono::steady_clock::now();
+    ++d->lane_count;
     return CRO_OK;
 }
 
-// 1 when a probe begun on this device has finished (or none is in flight), 0 while it runs.
+// 1 when the oldest probe begun on this device has finished (or none is in flight), 0 while it runs.
 int ctx_probe_poll(cro_ctx* c, int idx) {
     Device* d = dev_at(c, idx);
     if (!d) return 1;
     std::lock_guard<std::mutex> g(d->mu);
-    if (!d->pending) return 1;
+    if (!d->done.empty() || d->lane_count == 0) return 1;
     cudaSetDevice(d->ordinal);
     // anything but "still running" counts as finished: a failed stream must not keep a poller spinning —
     // cro_probe_end then reports the CUDA error
-    return cudaStreamQuery(d->stream) == cudaErrorNotReady ? 0 : 1;
+    return cudaEventQuery(d->lanes[d->lane_head].ev_done) == cudaErrorNotReady ? 0 : 1;
 }
 
-// Blocks until the probe in flight on this device (if any) has finished; does not collect it.
+// Probes in flight or finished-but-uncollected on this device (0..2).
+int ctx_probe_depth(cro_ctx* c, int idx) {
+    Device* d = dev_at(c, idx);
+    if (!d) return 0;
+    std::lock_guard<std::mutex> g(d->mu);
+    return d->lane_count + (int)d->done.size();
+}
+
+// Blocks until the oldest probe in flight on this device (if any) has finished; does not collect it.
 int ctx_probe_wait(cro_ctx* c, int idx) {
     Device* d = dev_at(c, idx);
     if (!d) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
-    if (!d->pending) return CRO_OK;
+    if (!d->done.empty() || d->lane_count == 0) return CRO_OK;
     CU_TRY(c, cudaSetDevice(d->ordinal));
-    CU_TRY(c, cudaStreamSynchronize(d->stream));
+    CU_TRY(c, cudaEventSynchronize(d->lanes[d->lane_head].ev_done));
     return CRO_OK;
 }
 
@@ -847,20 +908,52 @@ int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out) {
     Device* d = dev_at(c, idx);
     if (!d || !out) return CRO_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
-    // a prefetched result nobody collected for more than a second says nothing about the device NOW
-    if (d->have_pending_result && !d->pending &&
-        std::chrono::steady_clock::now() - d->pending_since > std::chrono::seconds(1))
-        d->have_pending_result = false;
-    if (!d->pending && !d->have_pending_result) {   // nothing begun: behave like the synchronous call
-        int rc = probe_enqueue(c, d);
-        if (rc) return rc;
-        d->pending = true;
-        d->pending_since = std::chrono::steady_clock::now();
+    // a drained result nobody collected for more than a second says nothing about the device NOW
+    while (!d->done.empty() && std::chrono::steady_clock::now() - d->done.front().at > std::chrono::seconds(1)) d->done.pop_front();
+    if (d->done.empty()) {
+        if (d->lane_count == 0) {      // nothing begun: behave like the synchronous call
+            Lane& L0 = d->lanes[d->lane_head];
+            int rc = probe_enqueue(c, d, L0);
+            if (rc) return rc;
+            ++d->lane_count;
+        }
+        Lane& L = d->lanes[d->lane_head];
+        const int rc = probe_finish(c, d, L, out);
+        d->lane_head ^= 1;
+        --d->lane_count;
+        return rc;
     }
+    *out = d->done.front().r;
+    const int rc = d->done.front().rc;
+    d->done.pop_front();
+    return rc;
+}
+
+// CUDA-event and %globaltimer times of the sweeps of the device's last collected probe.
+int ctx_sweep_times(cro_ctx* c, int idx, cro_sweep_time* out, int cap, int* n_out) {
+    Device* d = dev_at(c, idx);
+    if (!d || !n_out) return CRO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(d->mu);
     drain_pending(c, d);
-    d->have_pending_result = false;
-    *out = d->pending_result;
-    return d->pending_rc;
+    Lane& L = d->lanes[d->last_lane];
+    const int n = L.timed ? (int)(1 + L.copies + L.reads) : 0;
+    *n_out = n;
+    if (n == 0) return CRO_OK;
+    if (!out || cap < n) return CRO_ERR_BUFFER_SMALL;
+    CU_TRY(c, cudaSetDevice(d->ordinal));
+    for (int i = 0; i < n; ++i) {
+        float ms = 0;
+        CU_TRY(c, cudaEventElapsedTime(&ms, L.evpool[(size_t)i], L.evpool[(size_t)i + 1]));
+        cro_sweep_time& t = out[i];
+        memset(&t, 0, sizeof t);
+        const SweepOut& s = L.h_out[i == 0 ? kSlotFill : kSlotSweep0 + i - 1];
+        t.kind = i == 0 ? 0u : (i <= (int)L.copies ? 1u : 2u);
+        t.index = i == 0 ? 0u : (t.kind == 1 ? (uint32_t)(i - 1) : (uint32_t)(i - 1 - (int)L.copies));
+        t.bytes = t.kind == 1 ? 2 * d->sweep_bytes : d->sweep_bytes;
+        t.event_ns = ms_to_ns(ms);
+        t.timer_ns = s.t1 - s.t0;
+    }
+    return CRO_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -965,32 +1058,6 @@ int ctx_probe_uuid(cro_ctx* c, const char* uuid, cro_probe_result* out) {
         else set_thread_error(err);
     }
     return rc;
-}
-
-// CUDA-event and %globaltimer times of the sweeps of the device's last finished probe.
-int ctx_sweep_times(cro_ctx* c, int idx, cro_sweep_time* out, int cap, int* n_out) {
-    Device* d = dev_at(c, idx);
-    if (!d || !n_out) return CRO_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> g(d->mu);
-    drain_pending(c, d);
-    const int n = d->last_timed ? (int)(1 + d->last_copies + d->last_reads) : 0;
-    *n_out = n;
-    if (n == 0) return CRO_OK;
-    if (!out || cap < n) return CRO_ERR_BUFFER_SMALL;
-    CU_TRY(c, cudaSetDevice(d->ordinal));
-    for (int i = 0; i < n; ++i) {
-        float ms = 0;
-        CU_TRY(c, cudaEventElapsedTime(&ms, d->evpool[(size_t)i], d->evpool[(size_t)i + 1]));
-        cro_sweep_time& t = out[i];
-        memset(&t, 0, sizeof t);
-        const SweepOut& s = d->h_out[i == 0 ? kSlotFill : kSlotSweep0 + i - 1];
-        t.kind = i == 0 ? 0u : (i <= (int)d->last_copies ? 1u : 2u);
-        t.index = i == 0 ? 0u : (t.kind == 1 ? (uint32_t)(i - 1) : (uint32_t)(i - 1 - (int)d->last_copies));
-        t.bytes = t.kind == 1 ? 2 * d->sweep_bytes : d->sweep_bytes;
-        t.event_ns = ms_to_ns(ms);
-        t.timer_ns = s.t1 - s.t0;
-    }
-    return CRO_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -1132,7 +1199,8 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
     for (int i = 0; i < n; ++i) {
         Device* d = c->devs[(size_t)i].get();
         drain_pending(c, d);
-        d->have_pending_result = false;
+        d->done.clear();
+        d->lane_head = 0;
     }
     const bool p2p = n > 1 && !(o.flags & CRO_F_SKIP_P2P);
     const bool push = p2p && !(o.flags & CRO_F_SKIP_P2P_WRITE);
@@ -1169,8 +1237,6 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
             d->ev_push_done.push_back(e1);
             d->ev_reread_done.push_back(e2);
         }
-        refresh_ecc(c, d);                        // the full-box probe is rare enough to afford a fresh read
-        if (d->tmpl.ecc_errors != d->ecc_uncorrected && (rc = stage_template(c, d))) return rc;
     }
 
     // ---- phase 1: every device's HBM probe, one graph launch each ---------------------------------------
@@ -1178,7 +1244,7 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
         Range nv(c, "cro.probe_all.hbm");
         for (int i = 0; i < n; ++i) {
             Device* d = c->devs[(size_t)i].get();
-            if ((rc = probe_enqueue(c, d))) return rc;
+            if ((rc = probe_enqueue(c, d, d->lanes[0]))) return rc;
             if (p2p) {
                 // what this device's first p2p_bytes must fold to, for the peers that will read them
                 CU_TRY(c, launch_expected(d->plan, std::min<uint64_t>(o.p2p_bytes, d->sweep_bytes), imm_params(d), d->scratch_pfx,
@@ -1335,6 +1401,17 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
     }
     c->fullbox.enqueue_ns = now_ns() - t_call;
 
+    // While the GPUs work: a fresh ECC read per device (NVML, ~3 ms each — on the critical path it would cost the box
+    // more than the NVLink rounds of one pair).  The structs being gathered right now carry the count staged before
+    // this call; a count that moved is staged for the next probe, and a FAILING probe re-reads it at once anyway.
+    std::vector<int> restage;
+    if (n > 1)
+        for (int i = 0; i < n; ++i) {
+            Device* d = c->devs[(size_t)i].get();
+            refresh_ecc(c, d);
+            if (d->tmpl.ecc_errors != d->ecc_uncorrected) restage.push_back(i);
+        }
+
     // ---- the only host waits: one per device ------------------------------------------------------------------
     {
         Range nv(c, "cro.probe_all.wait");
@@ -1344,6 +1421,10 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
             if ((rc = wait_stream(c, d))) return rc;
             ++host_syncs;
         }
+    }
+    for (int i = 0; i < n; ++i) {
+        c->devs[(size_t)i]->lanes[0].in_flight = false;
+        c->devs[(size_t)i]->last_lane = 0;
     }
     int worst = CRO_OK;
     if (use_nccl) {
@@ -1381,6 +1462,11 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
             }
             if (hi > lo) c->fullbox.p2p_ns = std::max<uint64_t>(c->fullbox.p2p_ns, hi - lo);
         }
+    }
+    for (int i : restage) {
+        Device* d = c->devs[(size_t)i].get();
+        CU_TRY(c, cudaSetDevice(d->ordinal));
+        if ((rc = stage_template(c, d))) return rc;
     }
     c->fullbox.rounds = (uint32_t)rounds.size();
     c->fullbox.host_syncs = host_syncs;

@@ -11,6 +11,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -21,6 +22,30 @@
 
 namespace cro {
 
+// Everything ONE probe in flight owns.  A device has two lanes, so a second probe can be enqueued behind a running
+// one (cro_probe_begin twice): its kernels start the moment the first probe's finalize kernel retires, with no host
+// round trip in between — what keeps a GPU busy when one reconcile worker feeds eight of them.
+struct Lane {
+    ProbeParams* d_params = nullptr;   // what the graph's kernels read
+    ProbeParams* h_params = nullptr;   // pinned; refreshed by the host before each launch
+    SweepOut* d_out = nullptr;         // device sweep-result slots (lane 0: kSlotCount, lane 1: the first 64)
+    SweepOut* h_out = nullptr;         // pinned host mirror
+    cro_probe_result* d_result = nullptr;  // written by the finalize kernels; lane 0's is the all-gather send buffer
+    cro_probe_result* h_result = nullptr;  // pinned copy-back target
+    std::vector<cudaEvent_t> evpool;   // per-sweep timing events of the full probe (bench / tests read them)
+    cudaEvent_t ev_done = nullptr;     // recorded behind the probe's last copy-back
+    // the whole probe captured as one CUDA graph (timing events are external event-record nodes)
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_key = 0;
+    size_t graph_events = 0;
+    bool graph_failed = false;
+    size_t events = 0;                 // timing events the in-flight / last probe recorded
+    uint32_t reads = 0, copies = 0;
+    bool timed = false;                // the events of the last probe on this lane are valid
+    bool in_flight = false;
+    std::chrono::steady_clock::time_point since{};
+};
+
 struct Device {
     int ordinal = -1;              // CUDA ordinal
     int index = -1;                // rank: position in the minor-sorted list
@@ -29,7 +54,10 @@ struct Device {
     cudaStream_t stream = nullptr; // every sweep
     cudaStream_t aux = nullptr;    // the closed-form generator (ALU only) runs beside the copy sweeps
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
-    std::vector<cudaEvent_t> evpool;   // per-sweep timing events of the full probe (bench / tests read them)
+    Lane lanes[2];
+    int lane_head = 0;                 // oldest probe in flight
+    int lane_count = 0;                // probes in flight (0..2)
+    int last_lane = 0;                 // lane of the most recently COLLECTED probe (cro_probe_sweep_times)
     unsigned char* region = nullptr;   // [0,S) half A, [S,2S) half B
     uint64_t sweep_bytes = 0;
     uint64_t seed_dev = 0;             // seed_base | minor
@@ -39,14 +67,13 @@ struct Device {
     bool filled = false;
     KernelPlan plan{};
     SweepScratch scratch{}, scratch_aux{}, scratch_pfx{};   // main stream / closed form / p2p prefix closed form
-    SweepOut* d_out = nullptr;         // kSlotCount device sweep-result slots
-    SweepOut* h_out = nullptr;         // pinned host mirror
-    ProbeParams* d_params = nullptr;   // what the graph's kernels read
-    ProbeParams* h_params = nullptr;   // pinned; refreshed by the host before each launch
+    // lane 0's buffers under their old names: the synchronous probe, the single sweeps and cro_probe_all use lane 0
+    SweepOut*& d_out = lanes[0].d_out;
+    SweepOut*& h_out = lanes[0].h_out;
+    cro_probe_result*& d_result = lanes[0].d_result;
+    cro_probe_result*& h_result = lanes[0].h_result;
     cro_probe_result* d_tmpl = nullptr;    // identity + options, staged by the host
-    cro_probe_result* d_result = nullptr;  // written by the finalize kernels; the all-gather send buffer
     cro_probe_result* d_gather = nullptr;  // all-gather receive buffer (world entries)
-    cro_probe_result* h_result = nullptr;  // pinned copy-back target
     cro_probe_result* h_gather = nullptr;  // pinned, CRO_MAX_DEVICES entries
     cro_probe_result tmpl{};               // host copy of d_tmpl
     // NVLink latency: tables[j] is the permutation device j chases THROUGH this device's memory
@@ -57,19 +84,9 @@ struct Device {
     unsigned long long* h_chase_out = nullptr;   // pinned, 2 * CRO_MAX_DEVICES
     std::vector<cudaEvent_t> ev_push_done, ev_reread_done;   // one per NVLink round
     cudaEvent_t ev_hbm_done = nullptr, ev_aux_done = nullptr, ev_chase_ready = nullptr;
-    // asynchronous probe (ctx_probe_begin / ctx_probe_end)
-    bool pending = false, have_pending_result = false;
-    int pending_rc = 0;
-    size_t pending_events = 0;         // timing events the pending / last probe recorded
-    uint32_t last_reads = 0, last_copies = 0;
-    bool last_timed = false;           // the events of the last probe are valid
-    std::chrono::steady_clock::time_point pending_since{};
-    cro_probe_result pending_result{};
-    // the whole probe captured as one CUDA graph (timing events are external event-record nodes)
-    cudaGraphExec_t graph_exec = nullptr;
-    uint64_t graph_key = 0;
-    size_t graph_events = 0;
-    bool graph_failed = false;
+    // asynchronous probes (ctx_probe_begin / ctx_probe_end): results drained off the stream but not yet collected
+    struct Collected { cro_probe_result r; int rc; std::chrono::steady_clock::time_point at; };
+    std::deque<Collected> done;
     unsigned sm_clock_mhz = 0, mem_clock_mhz = 0;
     uint32_t ecc_uncorrected = 0;      // NVML count cached at init / full-box probe / failed probe
 
@@ -145,6 +162,7 @@ int ctx_probe_begin(cro_ctx* c, int idx);
 int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out);
 int ctx_probe_poll(cro_ctx* c, int idx);
 int ctx_probe_wait(cro_ctx* c, int idx);
+int ctx_probe_depth(cro_ctx* c, int idx);
 int ctx_sweep_times(cro_ctx* c, int idx, cro_sweep_time* out, int cap, int* n);
 // Fresh inventory of the node merged with the context's own devices (inventory.hpp).
 // force: re-read every `information` file even if the registry's listing looks unchanged (done by itself once a

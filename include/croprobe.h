@@ -81,7 +81,7 @@ typedef struct cro_opts {
     uint64_t seed_base;            /* default 0x00C0FFEE00000000; seed = base | minor       */
     uint32_t read_sweeps;          /* default 5                                             */
     uint32_t copy_sweeps;          /* default 5                                             */
-    uint32_t latency_hops;         /* pointer-chase hops per directed pair; default 16384   */
+    uint32_t latency_hops;         /* pointer-chase hops per directed pair; default 4096    */
     uint32_t read_variant;         /* CRO_READ_*                                            */
     uint32_t copy_variant;         /* CRO_COPY_*                                            */
     int32_t  deadline_ms;          /* per-call deadline, 0 = none (Go ctx cannot cross cgo) */
@@ -309,10 +309,13 @@ int  cro_normalize(int kind, const char *in, char *buf, size_t cap, size_t *len)
 int  cro_probe_device(cro_ctx *ctx, int dev_index, cro_probe_result *out);
 
 /* Asynchronous form of cro_probe_device: begin enqueues the whole probe on the
- * device's stream and returns at once; end waits and evaluates.  One host
- * thread (the reference's single reconcile worker, MaxConcurrentReconciles=1)
- * can keep every attached GPU busy this way.  At most one probe per device is
- * in flight; a second begin is a no-op; end without begin probes synchronously. */
+ * device's stream and returns at once; end waits for the OLDEST probe begun on
+ * the device and hands out its result.  One host thread (the reference's single
+ * reconcile worker, MaxConcurrentReconciles=1) can keep every attached GPU busy
+ * this way.  Up to TWO probes per device may be in flight: the second one's
+ * kernels are queued behind the first's on the device, so the GPU does not idle
+ * while the host collects a result and starts the next attach's probe.  A third
+ * begin is a no-op; end without begin probes synchronously. */
 int  cro_probe_begin(cro_ctx *ctx, int dev_index);
 int  cro_probe_end(cro_ctx *ctx, int dev_index, cro_probe_result *out);
 

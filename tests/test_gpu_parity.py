@@ -460,16 +460,21 @@ def test_async_probe_begin_end(cro, coracle):
     with cro.ProbeContext(sweep_bytes=32 << 20, devices=[0], read_sweeps=2, copy_sweeps=1) as c:
         n_words = (32 << 20) // 8
         c.probe_begin(0)
-        c.probe_begin(0)                       # second begin is a no-op
-        r = c.probe_end(0)
+        c.probe_begin(0)                       # second begin: a second probe, queued on the device behind the first
+        c.probe_begin(0)                       # third begin is a no-op (two lanes)
+        r = c.probe_end(0)                     # results come out oldest first
         assert r.status == 0 and r.nonce == 0 and r.checksum == coracle.checksum(r.seed, 0, n_words)
-        r2 = c.probe_end(0)                    # end without begin probes synchronously
+        r2 = c.probe_end(0)
         assert r2.status == 0 and r2.nonce == 1 and r2.checksum == coracle.checksum(r2.seed, 0, n_words)
+        assert r2.t_start_ns >= r.t_start_ns + r.total_ns          # back to back on the device, never interleaved
+        assert c.launch_count() == 2 * (3 + 2 + 1)                 # exactly two probes ran
+        rs = c.probe_end(0)                    # end without begin probes synchronously
+        assert rs.status == 0 and rs.nonce == 2
         c.probe_begin(0)
         s = c.hbm_read_checksum(0, 1)          # another op first drains the in-flight probe
         assert s.checksum == coracle.checksum(c.seed(0), 0, n_words)
         r3 = c.probe_end(0)
-        assert r3.status == 0 and r3.read_best_ns > 0 and r3.nonce == 2 and r3.seed == c.seed(0)
+        assert r3.status == 0 and r3.read_best_ns > 0 and r3.nonce == 3 and r3.seed == c.seed(0)
 
 
 def test_storm_and_churn_with_live_probe(cro):
