@@ -456,6 +456,9 @@ def storm_leg(cro, ctx, n_req, probe=True):
                 "reconciles": st["request_reconciles"] + st["resource_reconciles"], "reconcile_p50_us": st["reconcile_p50_ns"] / 1e3,
                 "reconcile_p99_us": st["reconcile_p99_ns"] / 1e3, "errors": st["reconcile_errors"], "probe_failures": st["probe_failures"],
                 "busiest_gpu_children": max(per_node),
+                # per GPU: probes, device time busy (its own %globaltimer), first probe start .. last probe end
+                "gpus": st.get("gpus"), "gpu_busy_frac_of_span": [round(g["busy_us"] / max(1, g["span_us"]), 4) for g in st.get("gpus", [])],
+                "bound_s_busiest_gpu": round(max((g["busy_us"] for g in st.get("gpus", [])), default=0) / 1e6, 3),
                 "note": "single reconcile worker per controller (reference default), physical GPUs multiplexed across CRs, timers immediate"}
 
 
@@ -474,8 +477,7 @@ def churn_leg(cro, ctx, cycles, probe=True):
                 names.append(name)
                 assert c.apply(name, {"type": "gpu", "model": "NVIDIA-B200", "size": 1, "target_node": "worker-%d" % ((width * cyc + j) % n)}) == ""
             st = c.run()
-            d = c.dump()
-            assert all(d["requests"][x]["status"]["state"] == "Running" for x in names), d["requests"]
+            assert st["requests_running"] == width, st
             for x in names:
                 c.delete(x)
             st = c.run()

@@ -837,6 +837,12 @@ public:
             cro_probe_result pr;
             ++c_->stats.probes;
             int rc = ctx_probe_end(c_->ctx_, idx, &pr);
+            if (rc == CRO_OK && idx < 16) {   // how busy the reconcile worker kept this GPU (the device's own %globaltimer)
+                Stats::Gpu& g = c_->stats.gpu[idx];
+                if (g.probes++ == 0) g.first_start_ns = pr.t_start_ns;
+                g.busy_ns += pr.total_ns;
+                g.last_end_ns = pr.t_start_ns + pr.total_ns;
+            }
             c_->releaseDevice(idx);
             if (rc != CRO_OK) {
                 ++c_->stats.probe_failures;
@@ -1169,6 +1175,15 @@ std::string Cluster::StatsJSON() const {
     w.field("reconcile_errors", stats.reconcile_errors).field("timer_rounds", stats.timer_rounds);
     w.field("reconcile_p50_ns", pct(0.50)).field("reconcile_p99_ns", pct(0.99));
     w.field("wall_us", (long long)(stats.wall_s * 1e6));
+    w.key("gpus").begin_array();
+    for (const Stats::Gpu& g : stats.gpu) {
+        if (!g.probes) continue;
+        w.begin_object();
+        w.field("probes", g.probes).field("busy_us", (long long)(g.busy_ns / 1000));
+        w.field("span_us", (long long)((g.last_end_ns - g.first_start_ns) / 1000));
+        w.end_object();
+    }
+    w.end_array();
     w.field("timers", std::string("RequeueAfter fires when the queue drains; stops when a round changes nothing"));
     w.end_object();
     return w.take();

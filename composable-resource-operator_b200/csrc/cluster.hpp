@@ -105,6 +105,8 @@ struct Stats {
     long long probes = 0, probe_failures = 0, timer_rounds = 0, reconcile_errors = 0;
     std::vector<long long> reconcile_ns;   // one entry per Reconcile call
     double wall_s = 0;
+    struct Gpu { long long probes = 0; unsigned long long busy_ns = 0, first_start_ns = 0, last_end_ns = 0; };
+    Gpu gpu[16];                           // per probe-context device: how busy the worker kept it (device timers)
 };
 
 class Cluster {

@@ -4,6 +4,7 @@
 #include <mutex>
 
 #include <dirent.h>
+#include <fcntl.h>
 #include <dlfcn.h>
 #include <sys/stat.h>
 
@@ -348,7 +349,13 @@ std::string ProcRegistryListing(const std::string& proc_root) {
     std::vector<std::string> names;
     while (dirent* e = readdir(d)) {
         if (e->d_name[0] == '.') continue;
-        names.push_back(std::string(e->d_name) + ":" + std::to_string((unsigned long long)e->d_ino));
+        // name : inode : change time.  procfs hands a re-created entry the lowest free inode NUMBER — usually the one
+        // it had — but a new inode object, whose times are the moment it was made.
+        struct stat st;
+        std::string tag = std::string(e->d_name) + ":" + std::to_string((unsigned long long)e->d_ino);
+        if (fstatat(dirfd(d), e->d_name, &st, AT_SYMLINK_NOFOLLOW) == 0)
+            tag += ":" + std::to_string((long long)st.st_ctim.tv_sec) + "." + std::to_string((long)st.st_ctim.tv_nsec);
+        names.push_back(tag);
     }
     closedir(d);
     std::sort(names.begin(), names.end());

@@ -67,10 +67,11 @@ struct ProcGpu {
 };
 // Scans <root>/driver/nvidia/gpus/*/information (root defaults to /proc).
 std::vector<ProcGpu> ScanProc(const std::string& proc_root);
-// The registry's directory listing alone — "<name>:<inode>" per GPU, sorted, joined by '|' — without opening any
-// `information` file: reading those goes through the driver (and its locks: ~14 ms per read while nvidia-smi polls),
-// listing the directory does not.  A GPU that leaves or joins the bus changes the listing; a re-created entry gets a
-// new inode.  Empty string: the registry directory does not exist.
+// The registry's directory listing alone — "<name>:<inode>:<ctime>" per GPU, sorted, joined by '|' — without opening
+// any `information` file: reading those goes through the driver and its locks (measured ~14 ms per read while
+// nvidia-smi polls, 100+ ms for a whole 8-GPU box), listing and stat-ing the directory does not.  A GPU that leaves or
+// joins the bus changes the listing; a re-created entry is a new inode object with new times even when procfs hands it
+// its old inode number.  Empty string: the registry directory does not exist.
 std::string ProcRegistryListing(const std::string& proc_root);
 
 struct NvmlGpu {

@@ -966,14 +966,15 @@ int ctx_inventory(cro_ctx* c, std::vector<cro_dev_info>* out, bool force) {
     std::lock_guard<std::mutex> g(c->inv_mu);
     const bool nvml_ok = !(c->opts.flags & CRO_F_NO_NVML);
     // Every call looks at the node: the registry's directory listing (a readdir, ~10 us, no driver lock).  The
-    // `information` files are read again when that listing differs from the last one, when the last full read is
-    // older than a second (a different GPU in the same slot may reuse name AND inode), or when the caller insists.
+    // `information` files are read again when that listing differs from the last one, when the caller insists (it was
+    // told about a UUID the list lacks), and otherwise every 30 s — the reference's own requeue period
+    // (composableresource_controller.go:223,285) — because each such read goes through the driver's locks.
     std::string key = identity::ProcRegistryListing(c->proc_root);
     const bool have_proc = !key.empty();
     if (!have_proc) key = "-";
     const auto now = std::chrono::steady_clock::now();
     const bool nvml_due = !have_proc && nvml_ok && now - c->inv_nvml_at > std::chrono::seconds(1);
-    const bool stale = now - c->inv_full_at > std::chrono::seconds(1);
+    const bool stale = now - c->inv_full_at > std::chrono::seconds(30);
     if (c->inv_valid && key == c->inv_key && !nvml_due && !force && !(have_proc && stale)) {
         *out = c->inv;
         return CRO_OK;

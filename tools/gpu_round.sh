@@ -13,13 +13,13 @@ TAG=${1:-rXX}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 export PYTHONUNBUFFERED=1
-timeout 120 python -m pytest tests -m gpu -x -q > "$OUT/gpu_tests.log" 2>&1; echo "gpu tests rc=$?" | tee -a "$OUT/gpu_tests.log"
+timeout 300 python -m pytest tests -m gpu -x -q > "$OUT/gpu_tests.log" 2>&1; echo "gpu tests rc=$?" | tee -a "$OUT/gpu_tests.log"
 timeout 60 python -c 'import __graft_entry__ as g; g.smoke()' > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/smoke.log"
-timeout 150 python bench.py 2> "$OUT/bench.err" | tail -1 > "$OUT/bench.json"; echo "bench rc=$?"
+timeout 240 python bench.py 2> "$OUT/bench.err" | tail -1 > "$OUT/bench.json"; echo "bench rc=$?"
 timeout 150 python bench.py --impl reference 2> "$OUT/bench_reference.err" | tail -1 > "$OUT/bench_reference.json"; echo "reference arm rc=$?"
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
-    python bench.py --steps 2 --warmup 1 > "$OUT/bench_under_ncu.log" 2>&1; echo "launch list rc=$?"
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:hbm_ -f -o "$OUT/full" \
+    python bench.py --steps 2 --warmup 1 --no-cold --no-cpu-baseline > "$OUT/bench_under_ncu.log" 2>&1; echo "launch list rc=$?"
+timeout 200 ncu --set full --clock-control none --import-source on -k "regex:hbm_|finalize" -f -o "$OUT/full" \
     python tools/ncu_capture_target.py 1 > "$OUT/ncu_full.log" 2>&1; echo "full capture rc=$?"
 tail -3 "$OUT/gpu_tests.log"; tail -1 "$OUT/smoke.log"
 python - "$OUT" <<'PY'
