@@ -12,9 +12,16 @@ namespace cro {
 namespace capi {
 
 
+// Copies a text out through a caller-allocated buffer.  *len always receives the FULL length; when the buffer is too
+// small the caller still gets a NUL-terminated prefix (never stale bytes from an earlier call) and CRO_ERR_BUFFER_SMALL.
 inline int copy_out(const std::string& s, char* buf, size_t cap, size_t* len) {
     if (len) *len = s.size();
-    if (!buf || cap < s.size() + 1) return CRO_ERR_BUFFER_SMALL;
+    if (!buf || cap == 0) return CRO_ERR_BUFFER_SMALL;
+    if (cap < s.size() + 1) {
+        memcpy(buf, s.data(), cap - 1);
+        buf[cap - 1] = '\0';
+        return CRO_ERR_BUFFER_SMALL;
+    }
     memcpy(buf, s.data(), s.size());
     buf[s.size()] = '\0';
     return CRO_OK;

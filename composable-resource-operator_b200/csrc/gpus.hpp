@@ -124,6 +124,7 @@ public:
     struct Options {
         std::string proc_root;                 // "" = /proc
         bool allow_mutation = false;
+        int exec_deadline_ms = 60000;          // per spawned command; expiry = SIGKILL + "context deadline exceeded"
         const cro_dev_info* devs = nullptr;    // devices a probe context enumerated (optional)
         int n_devs = -1;
     };

@@ -1,10 +1,14 @@
 // gpus_local.cpp — the Kube / Exec seams of gpus.hpp answered ON the node: what a node agent that links
 // libcroprobe does instead of the operator's SPDY execs into other pods (internal/utils/gpus.go:788-815).
 #include <poll.h>
+#include <signal.h>
+#include <time.h>
+#include <errno.h>
 #include <spawn.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "detach.hpp"
@@ -18,18 +22,38 @@ namespace gpus {
 
 namespace {
 
-bool mutating(const std::vector<std::string>& argv) {
-    for (size_t i = 0; i < argv.size(); ++i) {
-        const std::string& a = argv[i];
-        if (a == "-pm" || a == "-r" || a == "-m") return true;                       // persistence mode, drain -m / -r
-        if (a.size() >= 3 && a.compare(a.size() - 3, 3, "/rm") == 0) return true;
-        if (a.find("modprobe") != std::string::npos || a.find("/tee ") != std::string::npos) return true;
+// The dry-run gate is an ALLOW-list: only the argv shapes known to read (the queries and status commands of
+// internal/utils/gpus.go: --query-gpu :886, --query-compute-apps :131, `drain -p <bus> -q` :968, lsmod :1105) are
+// executed while allow_mutation is false; anything else — including a command added later that nobody classified —
+// is logged as skipped.
+bool read_only(const std::vector<std::string>& argv) {
+    if (argv.empty()) return false;
+    const std::string& exe = argv[0];
+    auto base_is = [&](const char* name) {
+        const size_t slash = exe.rfind('/');
+        return (slash == std::string::npos ? exe : exe.substr(slash + 1)) == name;
+    };
+    if (base_is("lsmod")) return argv.size() == 1;
+    if (base_is("nvidia-smi")) {
+        if (argv.size() == 3 && argv[2] == "--format=csv,noheader,nounits" &&
+            (argv[1].compare(0, 12, "--query-gpu=") == 0 || argv[1].compare(0, 21, "--query-compute-apps=") == 0))
+            return true;
+        if (argv.size() == 5 && argv[1] == "drain" && argv[2] == "-p" && argv[4] == "-q") return true;
     }
     return false;
 }
 
-// posix_spawn + pipes; the error text is kubectl-exec's ("command terminated with exit code N").
-ExecResult spawn(const std::vector<std::string>& argv) {
+long long now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (long long)ts.tv_sec * 1000 + ts.tv_nsec / 1000000;
+}
+
+// posix_spawn + pipes; the error text is kubectl-exec's ("command terminated with exit code N").  The child has
+// `deadline_ms` to finish (the reference's exec is bound to the reconcile's context; a wedged nvidia-smi on a GPU that
+// is mid-drain must not hang the agent thread): on expiry it is killed, reaped, and the call fails like a cancelled
+// context does ("context deadline exceeded").
+ExecResult spawn(const std::vector<std::string>& argv, int deadline_ms) {
     ExecResult r;
     if (argv.empty()) { r.failed = true; r.exec_err = "empty command"; return r; }
     int out[2], err[2];
@@ -59,8 +83,15 @@ ExecResult spawn(const std::vector<std::string>& argv) {
     pollfd fds[2] = {{out[0], POLLIN, 0}, {err[0], POLLIN, 0}};
     int open_fds = 2;
     char buf[4096];
+    const long long until = now_ms() + (deadline_ms > 0 ? deadline_ms : 60000);
+    bool timed_out = false;
     while (open_fds > 0) {
-        if (poll(fds, 2, -1) < 0) break;
+        const long long left = until - now_ms();
+        if (left <= 0) { timed_out = true; break; }
+        const int pr = poll(fds, 2, (int)std::min<long long>(left, 1000));
+        if (pr < 0 && errno == EINTR) continue;
+        if (pr < 0) break;
+        if (pr == 0) continue;
         for (int i = 0; i < 2; ++i) {
             if (fds[i].fd < 0 || !(fds[i].revents & (POLLIN | POLLHUP | POLLERR))) continue;
             const ssize_t n = read(fds[i].fd, buf, sizeof buf);
@@ -71,7 +102,22 @@ ExecResult spawn(const std::vector<std::string>& argv) {
     for (pollfd& f : fds)
         if (f.fd >= 0) close(f.fd);               // poll() failed mid-way: do not leak the read ends
     int status = 0;
-    waitpid(pid, &status, 0);
+    if (!timed_out) {
+        // the pipes are closed; the process itself gets the rest of the deadline to exit
+        for (;;) {
+            const pid_t w = waitpid(pid, &status, WNOHANG);
+            if (w == pid || (w < 0 && errno != EINTR)) break;
+            if (now_ms() > until) { timed_out = true; break; }
+            usleep(500);
+        }
+    }
+    if (timed_out) {
+        kill(pid, SIGKILL);
+        waitpid(pid, &status, 0);
+        r.failed = true;
+        r.exec_err = "context deadline exceeded";
+        return r;
+    }
     if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) {
         r.failed = true;
         r.exec_err = "command terminated with exit code " + std::to_string(WIFEXITED(status) ? WEXITSTATUS(status) : 128 + WTERMSIG(status));
@@ -121,12 +167,12 @@ ExecResult LocalExec::Run(const Pod&, const std::string&, const ExecRequest& req
                     break;
                 }
             }
-            if (mutating(argv) && !o_.allow_mutation) {
+            if (!read_only(argv) && !o_.allow_mutation) {
                 le.how = "skipped (dry run)";
                 break;
             }
             le.how = "spawned";
-            r = spawn(argv);
+            r = spawn(argv, o_.exec_deadline_ms);
             break;
         }
     }

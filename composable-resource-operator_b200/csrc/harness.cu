@@ -612,6 +612,18 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
     controller::NodeOps* node_ops = scripted ? static_cast<controller::NodeOps*>(&cluster_ops) : &node;
     controller::ComposableResourceReconciler rec(provider, node_ops);
     store.updates = &rec.statusUpdates;
+    // "status_update_failures": {"after": N, "error": "..."} — Status().Update succeeds N times, then answers the error
+    // (the API server refusing a write: conflict, webhook, etcd); the handler stops where the reference stops
+    long long writes_ok = -1, writes_seen = 0;
+    std::string write_error;
+    if (const gojson::Value* wf = in->get("status_update_failures")) {
+        writes_ok = wf->get_int("after");
+        write_error = wf->get_string("error", "Operation cannot be fulfilled");
+    }
+    rec.writer = [&](const controller::ComposableResource&) {
+        ++writes_seen;
+        return (writes_ok >= 0 && writes_seen > writes_ok) ? controller::Error::New(write_error) : controller::Error::Nil();
+    };
     controller::Result result;
     controller::Error err;
     if (!adapterErr.ok()) {
@@ -639,6 +651,7 @@ int cro_reconcile_attach(cro_ctx* ctx, const char* in_json, char* buf, size_t ca
     w.key("status_updates").begin_array();
     for (const auto& s : rec.statusUpdates) w.raw(s.MarshalJSON());
     w.end_array();
+    w.field("failed_status_updates", (long long)rec.failedUpdates);
     if (node.probed) w.key("probe").string_map(probe_annotations(node.probe_result));
     if (scripted) {     // every pod-exec the step issued, in order: pod, container, the URL query the mocks match on, argv
         w.key("exec_log").begin_array();
@@ -749,6 +762,33 @@ int cro_scan_cmdline_for(const char* proc_root, const char* needle, int* found) 
     return CRO_OK;
 } CRO_API_CATCH
 
+int cro_local_exec(const char* request_json, char* buf, size_t cap, size_t* len) try {
+    if (!request_json) return CRO_ERR_INVALID_ARG;
+    std::string perr;
+    gojson::ValuePtr in = gojson::parse(request_json, &perr);
+    if (!in || in->kind != gojson::Value::Object) {
+        copy_out("bad request: " + perr, buf, cap, len);
+        return CRO_ERR_PARSE;
+    }
+    gpus::LocalExec::Options o;
+    o.allow_mutation = in->get_bool("allow_mutation");
+    if (in->get("exec_deadline_ms")) o.exec_deadline_ms = (int)in->get_int("exec_deadline_ms");
+    gpus::LocalExec exec(o);
+    gpus::ExecRequest req;
+    req.kind = gpus::ExecRequest::Command;
+    if (const gojson::Value* av = in->get("argv"))
+        for (const auto& a : av->arr)
+            if (a->kind == gojson::Value::String) req.argv.push_back(a->str);
+    gpus::Pod pod;
+    const gpus::ExecResult r = exec.Run(pod, "", req);
+    gojson::Writer w;
+    w.begin_object();
+    w.field("how", exec.log.empty() ? std::string() : exec.log.back().how);
+    w.field("failed", r.failed).field("exec_err", r.exec_err).field("stdout", r.std_out).field("stderr", r.std_err);
+    w.end_object();
+    return copy_out(w.take(), buf, cap, len);
+} CRO_API_CATCH
+
 int cro_local_node_op(cro_ctx* ctx, const char* request_json, char* buf, size_t cap, size_t* len) try {
     if (!request_json) return CRO_ERR_INVALID_ARG;
     std::string perr;
@@ -762,6 +802,7 @@ int cro_local_node_op(cro_ctx* ctx, const char* request_json, char* buf, size_t 
     gpus::LocalExec::Options o;
     o.proc_root = in->get_string("proc_root");
     o.allow_mutation = in->get_bool("allow_mutation");
+    if (in->get("exec_deadline_ms")) o.exec_deadline_ms = (int)in->get_int("exec_deadline_ms");
     if (ctx) { o.devs = devs.data(); o.n_devs = (int)devs.size(); }
     gpus::LocalExec exec(o);
     const std::string node = in->get_string("node", "local");

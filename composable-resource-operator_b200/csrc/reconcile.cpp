@@ -130,10 +130,16 @@ CMAddingResult CMCheckAddingResources(const std::string& machineBody,
     return out;
 }
 
+// A callee panicked: unwind at once, no status write on the way (see Error::panicked).
+#define CRO_UNWIND(e) do { if ((e).panicked() || (e).recovered()) return Error::Recovered(e); } while (0)
+// `if err := r.Status().Update(ctx, resource); err != nil { return r.requeueOnErr(resource, err, ...) }`
+#define CRO_UPDATE_OR_REQUEUE(resource) do { Error ue__ = statusUpdate(*(resource)); if (!ue__.ok()) return requeueOnErr((resource), ue__); } while (0)
+
 Error ComposableResourceReconciler::requeueOnErr(ComposableResource* resource, const Error& err) {
+    CRO_UNWIND(err);                       // a panic never reaches requeueOnErr in the reference
     if (resource) {
         resource->Status.Error = err.msg;
-        statusUpdate(*resource);
+        (void)statusUpdate(*resource);     // :428-430: a failure of THIS write is only logged
     }
     return err;
 }
@@ -148,8 +154,7 @@ Error ComposableResourceReconciler::handleNoneState(ComposableResource* resource
     }
     resource->Status.State = "Attaching";
     resource->Status.Error = "";
-    statusUpdate(*resource);
-    return Error::Nil();
+    return statusUpdate(*resource);        // :197 `return ctrl.Result{}, r.Status().Update(ctx, resource)`
 }
 
 Error ComposableResourceReconciler::handleAttachingState(ComposableResource* resource,
@@ -159,13 +164,11 @@ Error ComposableResourceReconciler::handleAttachingState(ComposableResource* res
     if (resource->DeletionTimestampSet) {
         if (resource->Status.DeviceID.empty()) {
             resource->Status.State = "Deleting";
-            statusUpdate(*resource);
-            return Error::Nil();
+            return statusUpdate(*resource);            // :206
         }
         if (!resource->Status.Error.empty()) {
             resource->Status.State = "Detaching";
-            statusUpdate(*resource);
-            return Error::Nil();
+            return statusUpdate(*resource);            // :210
         }
         // DeviceID set, no error: keeps attaching
     }
@@ -173,6 +176,7 @@ Error ComposableResourceReconciler::handleAttachingState(ComposableResource* res
     if (resource->Status.DeviceID.empty()) {
         std::string deviceID, cdiDeviceID;
         Error err = provider_->AddResource(*resource, &deviceID, &cdiDeviceID);
+        CRO_UNWIND(err);                               // e.g. res_op_status[:1] on "" (fti/fm/client.go:195)
         if (!err.ok()) {
             if (err.msg == ErrWaitingDeviceAttaching) {  // errors.Is on the sentinel
                 result->RequeueAfterSeconds = 30;
@@ -183,39 +187,43 @@ Error ComposableResourceReconciler::handleAttachingState(ComposableResource* res
         resource->Status.Error = "";
         resource->Status.DeviceID = deviceID;
         resource->Status.CDIDeviceID = cdiDeviceID;
-        statusUpdate(*resource);
+        CRO_UPDATE_OR_REQUEUE(resource);               // :233-235: nothing below runs when the IDs could not be stored
     }
 
     if (deviceResourceType == "DEVICE_PLUGIN") {
-        (void)node_->CheckNoGPULoads(resource->Spec.TargetNode);  // logged only
+        Error le = node_->CheckNoGPULoads(resource->Spec.TargetNode);  // an error is logged only; a panic is not an error
+        CRO_UNWIND(le);
         for (const char* ds : {"nvidia-device-plugin-daemonset", "nvidia-dcgm"}) {
             Error err = node_->RestartDaemonset("nvidia-gpu-operator", ds);
+            CRO_UNWIND(err);
             if (!err.ok()) {
                 resource->Status.Error = err.msg;
-                statusUpdate(*resource);
+                CRO_UPDATE_OR_REQUEUE(resource);       // :247-250, :255-258
             }
         }
     } else if (deviceResourceType == "DRA") {
         Error err = node_->RunNvidiaSmi(resource->Spec.TargetNode);
+        CRO_UNWIND(err);                               // e.g. parts[i] on a short CSV row (gpus.go:912-914)
         if (!err.ok()) {
             resource->Status.Error = err.msg;
-            statusUpdate(*resource);
+            CRO_UPDATE_OR_REQUEUE(resource);           // :262-265
         }
         err = node_->RestartDaemonset("nvidia-dra-driver-gpu", "nvidia-dra-driver-gpu-kubelet-plugin");
+        CRO_UNWIND(err);
         if (!err.ok()) {
             resource->Status.Error = err.msg;
-            statusUpdate(*resource);
+            CRO_UPDATE_OR_REQUEUE(resource);           // :269-272
         }
     }
 
     bool visible = false;
     Error err = node_->CheckGPUVisible(deviceResourceType, *resource, &visible);
+    CRO_UNWIND(err);
     if (!err.ok()) return requeueOnErr(resource, err);
     if (visible) {
         resource->Status.State = "Online";
         resource->Status.Error = "";
-        statusUpdate(*resource);
-        return Error::Nil();
+        return statusUpdate(*resource);                // :282
     }
     result->RequeueAfterSeconds = 30;
     return Error::Nil();
@@ -225,8 +233,7 @@ Error ComposableResourceReconciler::handleOnlineState(ComposableResource* resour
     *result = Result();
     if (resource->DeletionTimestampSet) {   // :292-295
         resource->Status.State = "Detaching";
-        statusUpdate(*resource);
-        return Error::Nil();
+        return statusUpdate(*resource);
     }
     auto lb = resource->Labels.find("cohdi.io/ready-to-detach-device-id");
     if (lb != resource->Labels.end() && !lb->second.empty()) {   // :297-302
@@ -234,8 +241,9 @@ Error ComposableResourceReconciler::handleOnlineState(ComposableResource* resour
         return Error::Nil();
     }
     Error err = provider_->CheckResource(*resource);   // :305-315: recorded, never returned
+    CRO_UNWIND(err);                                    // ... unless it panicked (fti/fm/client.go:346, cm/client.go:291)
     resource->Status.Error = err.ok() ? std::string() : err.msg;
-    statusUpdate(*resource);
+    CRO_UPDATE_OR_REQUEUE(resource);
     result->RequeueAfterSeconds = 30;
     return Error::Nil();
 }
@@ -249,6 +257,7 @@ Error ComposableResourceReconciler::handleDetachingState(ComposableResource* res
             Error err = deviceResourceType == "DEVICE_PLUGIN"
                             ? node_->CheckNoGPULoadsFor(resource->Spec.TargetNode, nullptr)
                             : node_->CheckNoGPULoadsFor(resource->Spec.TargetNode, &resource->Status.DeviceID);
+            CRO_UNWIND(err);
             if (!err.ok()) return requeueOnErr(resource, err);
         }
         if (deviceResourceType == "DRA") {   // :344-348
@@ -288,11 +297,10 @@ Error ComposableResourceReconciler::handleDetachingState(ComposableResource* res
         resource->Status.Error = "";
         resource->Status.DeviceID = "";
         resource->Status.CDIDeviceID = "";
-        statusUpdate(*resource);
+        CRO_UPDATE_OR_REQUEUE(resource);   // :401-403
     }
     resource->Status.State = "Deleting";   // :405-406
-    statusUpdate(*resource);
-    return Error::Nil();
+    return statusUpdate(*resource);
 }
 
 }  // namespace controller

@@ -8,6 +8,7 @@
 // toolchain is absent in the build image, hence C++ above the C ABI.)
 #pragma once
 #include <functional>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -24,6 +25,15 @@ struct Error {
     static Error Nil() { return Error(); }
     static Error New(const std::string& m) { Error e; e.set = true; e.msg = m; return e; }
     bool ok() const { return !set; }
+    // A Go run-time panic, restated as the text the runtime would print ("runtime error: index out of range [1] with
+    // length 1", ...).  It is NOT an ordinary error: in the reference it unwinds through the handler and through
+    // requeueOnErr — no Status().Update is issued on the way — until controller-runtime's Reconcile wrapper recovers it
+    // (sigs.k8s.io/controller-runtime v0.21.0 pkg/internal/controller/controller.go: `err = fmt.Errorf("panic: %v
+    // [recovered]", r)`; RecoverPanic defaults to true).  Callers test panicked() after every call that may produce one
+    // and return Recovered() at once.
+    bool panicked() const { return set && msg.compare(0, 15, "runtime error: ") == 0; }
+    bool recovered() const { return set && msg.compare(0, 7, "panic: ") == 0; }
+    static Error Recovered(const Error& e) { return e.recovered() ? e : New("panic: " + e.msg + " [recovered]"); }
 };
 
 extern const std::string ErrWaitingDeviceAttaching;  // "device is attaching to the cluster"
@@ -111,13 +121,23 @@ public:
     // composableresource_controller.go:320-407
     Error handleDetachingState(ComposableResource* resource, const std::string& deviceResourceType,
                                Result* result);
-    // Every Status().Update the reference would issue, in order.
+    // Every Status().Update the reference would issue, in order (attempts: a failing one is listed too).
     std::vector<ComposableResourceStatus> statusUpdates;
+    int failedUpdates = 0;
+    // The API server's answer to Status().Update; unset = every write succeeds.  The handlers stop where the
+    // reference stops when a write fails (`if err := r.Status().Update(...); err != nil { return r.requeueOnErr(...) }`,
+    // composableresource_controller.go:233-235, :248-250, ...).
+    std::function<Error(const ComposableResource&)> writer;
     // composableresource_controller.go:423-433
     Error requeueOnErr(ComposableResource* resource, const Error& err);
 
 private:
-    void statusUpdate(const ComposableResource& r) { statusUpdates.push_back(r.Status); }
+    Error statusUpdate(const ComposableResource& r) {
+        statusUpdates.push_back(r.Status);
+        Error e = writer ? writer(r) : Error::Nil();
+        if (!e.ok()) ++failedUpdates;
+        return e;
+    }
     CdiProvider* provider_;
     NodeOps* node_;
 };

@@ -458,6 +458,10 @@ int  cro_cm_check_adding_resources(const char *machine_body, const char *existin
  *            "load_check":{"stdout","stderr","exec_err","pod_name","driver_enabled"},
  *            "drain":{"error" | "fd_scan":{"stdout","stderr","exec_err"},"rke2":bool},
  *            "create_taint_error","delete_taint_error",
+ *            "status_update_failures":{"after":N,"error":".."}   (the API server refuses Status().Update from attempt
+ *                   N+1 on: the handler stops where the reference stops; out_json then carries "failed_status_updates"),
+ *            an error text that starts "runtime error: " is a Go panic: no status write, reconcile error
+ *            "panic: <text> [recovered]" (what controller-runtime's Reconcile wrapper makes of it),
  *            the DaemonSet restart rule (internal/utils/nodes.go:35-76) instead of canned errors:
  *            "daemonsets":{"ns/name":{"desired","ready","current","unavailable","misscheduled",
  *                                     "restarted_at":"<RFC3339>"}}, "now":"<RFC3339>",
@@ -579,6 +583,13 @@ int  cro_sim_dump(cro_sim *sim, char *buf, size_t cap, size_t *len);
  *         "exec_log": [{"kind","argv","how": "native"|"spawned"|"skipped (dry run)","failed"}..]}
  */
 int  cro_local_node_op(cro_ctx *ctx, const char *request_json, char *buf, size_t cap, size_t *len);
+/* One command through the same local executor cro_local_node_op uses, for hosts that drive the flows themselves:
+ * request_json = {"argv": [...], "allow_mutation": bool, "exec_deadline_ms": N}.  While allow_mutation is false only
+ * the argv shapes known to READ are executed (nvidia-smi --query-gpu / --query-compute-apps, `nvidia-smi drain -p <bus>
+ * -q`, lsmod, each optionally behind `/bin/chroot /host-root`); everything else is reported "skipped (dry run)".  A
+ * child that outlives exec_deadline_ms (default 60 s) is killed and reaped: "context deadline exceeded".
+ * Reply: {"how": "spawned"|"skipped (dry run)"|"native", "failed": bool, "exec_err", "stdout", "stderr"}. */
+int  cro_local_exec(const char *request_json, char *buf, size_t cap, size_t *len);
 /* The cmdline scan of checkResetGPUCommandStillRunning (gpus.go:1182-1226), natively:
  * *found = 1 if another process's command line mentions `needle`. */
 int  cro_scan_cmdline_for(const char *proc_root, const char *needle, int *found);

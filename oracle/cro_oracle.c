@@ -692,6 +692,8 @@ typedef struct {
     int driver_pod_missing;                /* gpus.go:835 */
     const char *ds_err[3];                 /* restart errors: device-plugin, dcgm, dra-kubelet-plugin */
     const char *slice_uuids;               /* DRA: '\n'-joined ResourceSlice uuid attributes, or NULL */
+    int update_fail_after;                 /* Status().Update succeeds this many times, then fails (-1: never fails) */
+    const char *update_fail_error;         /* ... with this text */
 } oracle_attach_in;
 
 static void set_str(char *dst, size_t cap, const char *s) {
@@ -699,27 +701,54 @@ static void set_str(char *dst, size_t cap, const char *s) {
 }
 
 /* returns 0 (nil error) or 1 (error text in err); *n_updates counts Status().Update calls */
+/* A Go run-time panic restated as its text: it unwinds through the handler and through requeueOnErr without any
+ * Status().Update, and controller-runtime v0.21.0's Reconcile wrapper turns it into "panic: <text> [recovered]". */
+static int is_go_panic(const char *e) { return e && strncmp(e, "runtime error: ", 15) == 0; }
+static void recovered(char *err, size_t err_cap, const char *text) {
+    char tmp[1100];
+    snprintf(tmp, sizeof tmp, "panic: %s [recovered]", text);
+    set_str(err, err_cap, tmp);
+}
+typedef struct { const oracle_attach_in *in; int *n; } attach_writer;
+/* one Status().Update: 0 = stored, 1 = the API server refused (text in w->in->update_fail_error) */
+static int attach_write(attach_writer *w) {
+    ++*w->n;
+    return w->in->update_fail_after >= 0 && *w->n > w->in->update_fail_after;
+}
+/* requeueOnErr :423-433 — a panic never gets here; a failure of its own write is only logged */
+static int attach_requeue_on_err(attach_writer *w, oracle_status *st, char *err, size_t err_cap, const char *text) {
+    char copy[1100];
+    snprintf(copy, sizeof copy, "%s", text ? text : "");
+    if (is_go_panic(copy)) { recovered(err, err_cap, copy); return 1; }
+    set_str(err, err_cap, copy);
+    set_str(st->error, sizeof st->error, copy);
+    (void)attach_write(w);
+    return 1;
+}
+/* `if err := r.Status().Update(...); err != nil { return r.requeueOnErr(resource, err, ...) }` */
+#define ATTACH_WRITE_OR_REQUEUE() \
+    do { if (attach_write(&w)) return attach_requeue_on_err(&w, st, err, err_cap, in->update_fail_error); } while (0)
+/* `return ctrl.Result{}, r.Status().Update(ctx, resource)` */
+#define ATTACH_RETURN_WRITE() \
+    do { if (attach_write(&w)) { set_str(err, err_cap, in->update_fail_error); return 1; } return 0; } while (0)
+
 int oracle_attach_step(const oracle_attach_in *in, oracle_status *st, int *requeue_after_s, char *err, size_t err_cap,
                        int *n_updates) {
     *requeue_after_s = 0;
     *n_updates = 0;
     err[0] = 0;
+    attach_writer w = {in, n_updates};
     if (in->deleting) { /* :203-213 */
-        if (st->device_id[0] == 0) { set_str(st->state, sizeof st->state, "Deleting"); ++*n_updates; return 0; }
-        if (st->error[0] != 0) { set_str(st->state, sizeof st->state, "Detaching"); ++*n_updates; return 0; }
+        if (st->device_id[0] == 0) { set_str(st->state, sizeof st->state, "Deleting"); ATTACH_RETURN_WRITE(); }
+        if (st->error[0] != 0) { set_str(st->state, sizeof st->state, "Detaching"); ATTACH_RETURN_WRITE(); }
     }
     if (st->device_id[0] == 0) { /* :217-237 */
         if (in->provider_waiting) { *requeue_after_s = 30; return 0; }
-        if (in->provider_error && in->provider_error[0]) {
-            set_str(err, err_cap, in->provider_error);
-            set_str(st->error, sizeof st->error, err); /* requeueOnErr :423-433 */
-            ++*n_updates;
-            return 1;
-        }
+        if (in->provider_error && in->provider_error[0]) return attach_requeue_on_err(&w, st, err, err_cap, in->provider_error);
         st->error[0] = 0;
         set_str(st->device_id, sizeof st->device_id, in->provider_device_id);
         set_str(st->cdi_device_id, sizeof st->cdi_device_id, in->provider_cdi_device_id);
-        ++*n_updates;
+        ATTACH_WRITE_OR_REQUEUE();
     }
     const int dra = strcmp(in->device_resource_type, "DRA") == 0;
     const int dp = strcmp(in->device_resource_type, "DEVICE_PLUGIN") == 0;
@@ -728,7 +757,11 @@ int oracle_attach_step(const oracle_attach_in *in, oracle_status *st, int *reque
              in->target_node ? in->target_node : "");
     if (dp) { /* :239-257 */
         for (int k = 0; k < 2; ++k)
-            if (in->ds_err[k] && in->ds_err[k][0]) { set_str(st->error, sizeof st->error, in->ds_err[k]); ++*n_updates; }
+            if (in->ds_err[k] && in->ds_err[k][0]) {
+                if (is_go_panic(in->ds_err[k])) { recovered(err, err_cap, in->ds_err[k]); return 1; }
+                set_str(st->error, sizeof st->error, in->ds_err[k]);
+                ATTACH_WRITE_OR_REQUEUE();
+            }
     } else if (dra) { /* :258-273 */
         char e2[1024];
         int failed = 0;
@@ -738,8 +771,16 @@ int oracle_attach_step(const oracle_attach_in *in, oracle_status *st, int *reque
             int rc = oracle_parse_gpu_csv(in->std_out, in->std_err, in->exec_err, "gpu_uuid", js, sizeof js);
             if (rc == ORACLE_ERR_EXEC || rc == ORACLE_ERR_PARSE) { set_str(e2, sizeof e2, js); failed = 1; }
         }
-        if (failed) { set_str(st->error, sizeof st->error, e2); ++*n_updates; }
-        if (in->ds_err[2] && in->ds_err[2][0]) { set_str(st->error, sizeof st->error, in->ds_err[2]); ++*n_updates; }
+        if (failed) {
+            if (is_go_panic(e2)) { recovered(err, err_cap, e2); return 1; }   /* parts[i] on a short row, gpus.go:912-914 */
+            set_str(st->error, sizeof st->error, e2);
+            ATTACH_WRITE_OR_REQUEUE();
+        }
+        if (in->ds_err[2] && in->ds_err[2][0]) {
+            if (is_go_panic(in->ds_err[2])) { recovered(err, err_cap, in->ds_err[2]); return 1; }
+            set_str(st->error, sizeof st->error, in->ds_err[2]);
+            ATTACH_WRITE_OR_REQUEUE();
+        }
     }
     /* :275-286 CheckGPUVisible */
     int visible = 0;
@@ -754,21 +795,16 @@ int oracle_attach_step(const oracle_attach_in *in, oracle_status *st, int *reque
             p = e + 1;
         }
     } else {
-        if (in->driver_pod_missing) {
-            set_str(err, err_cap, pod_err);
-            set_str(st->error, sizeof st->error, err);
-            ++*n_updates;
-            return 1;
-        }
-        int v = oracle_check_gpu_visible(in->std_out, in->std_err, in->exec_err, st->device_id, err, err_cap);
-        if (v < 0) { set_str(st->error, sizeof st->error, err); ++*n_updates; return 1; }
+        if (in->driver_pod_missing) return attach_requeue_on_err(&w, st, err, err_cap, pod_err);
+        char verr[1100];
+        int v = oracle_check_gpu_visible(in->std_out, in->std_err, in->exec_err, st->device_id, verr, sizeof verr);
+        if (v < 0) return attach_requeue_on_err(&w, st, err, err_cap, verr);
         visible = v;
     }
     if (visible) {
         set_str(st->state, sizeof st->state, "Online");
         st->error[0] = 0;
-        ++*n_updates;
-        return 0;
+        ATTACH_RETURN_WRITE();
     }
     *requeue_after_s = 30;
     return 0;

@@ -577,35 +577,70 @@ class AttachInput:
     driver_pod_missing: bool = False
     ds_err: Dict[str, str] = field(default_factory=dict)  # "ns/name" -> error
     slice_uuids: Optional[List[str]] = None
+    update_fail_after: Optional[int] = None    # Status().Update succeeds this many times, then fails ...
+    update_fail_error: str = ""                # ... with this text
+
+
+def is_go_panic(err: str) -> bool:
+    """A Go run-time panic restated as its text.  It unwinds through the handler AND through requeueOnErr — no
+    Status().Update on the way — until controller-runtime's Reconcile wrapper recovers it (controller-runtime v0.21.0
+    pkg/internal/controller/controller.go: fmt.Errorf("panic: %v [recovered]", r); RecoverPanic defaults to true)."""
+    return err.startswith("runtime error: ")
+
+
+def recovered(err: str) -> str:
+    return err if err.startswith("panic: ") else "panic: %s [recovered]" % err
 
 
 def attach_step(inp: AttachInput, st: Status) -> Tuple[Status, int, str, int]:
     """internal/controller/composableresource_controller.go:200-287 (+ requeueOnErr :423-433).
 
-    Returns (status, requeue_after_s, reconcile_error, n_status_updates)."""
+    Returns (status, requeue_after_s, reconcile_error, n_status_updates) — updates ATTEMPTED; from attempt number
+    inp.update_fail_after + 1 on, Status().Update answers inp.update_fail_error and the handler stops where the
+    reference stops (`if err := r.Status().Update(...); err != nil { return r.requeueOnErr(...) }`)."""
     st = Status(st.state, st.error, st.device_id, st.cdi_device_id)
     updates = 0
     pod_err = "no Pod with label 'app.kubernetes.io/component=nvidia-driver' found on node %s" % inp.target_node
+
+    def write() -> str:
+        nonlocal updates
+        updates += 1
+        if inp.update_fail_after is not None and updates > inp.update_fail_after:
+            return inp.update_fail_error
+        return ""
+
+    def requeue_on_err(err: str):
+        if is_go_panic(err):                      # never reaches requeueOnErr: no write
+            return st, 0, recovered(err), updates
+        st.error = err
+        write()                                   # :428-430: a failure of this write is only logged
+        return st, 0, err, updates
+
     if inp.deleting:
         if st.device_id == "":
             st.state = "Deleting"
-            return st, 0, "", 1
+            return st, 0, write(), updates        # :206 `return ctrl.Result{}, r.Status().Update(ctx, resource)`
         if st.error != "":
             st.state = "Detaching"
-            return st, 0, "", 1
+            return st, 0, write(), updates
     if st.device_id == "":
         if inp.provider_waiting:
             return st, 30, "", updates
         if inp.provider_error:
-            st.error = inp.provider_error
-            return st, 0, inp.provider_error, updates + 1
+            return requeue_on_err(inp.provider_error)
         st.error, st.device_id, st.cdi_device_id = "", inp.provider_device_id, inp.provider_cdi_device_id
-        updates += 1
+        e = write()
+        if e:
+            return requeue_on_err(e)              # :233-235
     if inp.device_resource_type == "DEVICE_PLUGIN":
         for ds in ("nvidia-gpu-operator/nvidia-device-plugin-daemonset", "nvidia-gpu-operator/nvidia-dcgm"):
             if inp.ds_err.get(ds):
+                if is_go_panic(inp.ds_err[ds]):
+                    return st, 0, recovered(inp.ds_err[ds]), updates
                 st.error = inp.ds_err[ds]
-                updates += 1
+                e = write()
+                if e:
+                    return requeue_on_err(e)
     elif inp.device_resource_type == "DRA":
         e = ""
         if inp.driver_pod_missing:
@@ -615,12 +650,20 @@ def attach_step(inp: AttachInput, st: Status) -> Tuple[Status, int, str, int]:
             if r.code != OK:
                 e = r.error
         if e:
+            if is_go_panic(e):                    # parts[i] on a short CSV row (gpus.go:912-914): RunNvidiaSmi panics
+                return st, 0, recovered(e), updates
             st.error = e
-            updates += 1
+            w = write()
+            if w:
+                return requeue_on_err(w)
         ds = "nvidia-dra-driver-gpu/nvidia-dra-driver-gpu-kubelet-plugin"
         if inp.ds_err.get(ds):
+            if is_go_panic(inp.ds_err[ds]):
+                return st, 0, recovered(inp.ds_err[ds]), updates
             st.error = inp.ds_err[ds]
-            updates += 1
+            w = write()
+            if w:
+                return requeue_on_err(w)
     if inp.device_resource_type == "DRA" and inp.slice_uuids is not None:
         visible, err = (st.device_id in inp.slice_uuids), ""
     elif inp.driver_pod_missing:
@@ -628,11 +671,10 @@ def attach_step(inp: AttachInput, st: Status) -> Tuple[Status, int, str, int]:
     else:
         visible, err = check_gpu_visible(inp.std_out, inp.std_err, inp.exec_err, st.device_id)
     if err:
-        st.error = err
-        return st, 0, err, updates + 1
+        return requeue_on_err(err)
     if visible:
         st.state, st.error = "Online", ""
-        return st, 0, "", updates + 1
+        return st, 0, write(), updates            # :282
     return st, 30, "", updates
 
 
@@ -650,7 +692,8 @@ class _CAttachIn(ctypes.Structure):
                 ("provider_error", ctypes.c_char_p), ("provider_device_id", ctypes.c_char_p),
                 ("provider_cdi_device_id", ctypes.c_char_p), ("std_out", ctypes.c_char_p),
                 ("std_err", ctypes.c_char_p), ("exec_err", ctypes.c_char_p), ("driver_pod_missing", ctypes.c_int),
-                ("ds_err", ctypes.c_char_p * 3), ("slice_uuids", ctypes.c_char_p)]
+                ("ds_err", ctypes.c_char_p * 3), ("slice_uuids", ctypes.c_char_p),
+                ("update_fail_after", ctypes.c_int), ("update_fail_error", ctypes.c_char_p)]
 
 
 def build_c_oracle() -> str:
@@ -787,6 +830,8 @@ class COracle:
         for k, n in enumerate(names):
             cin.ds_err[k] = _b(inp.ds_err[n]) if inp.ds_err.get(n) else None
         cin.slice_uuids = _b("\n".join(inp.slice_uuids)) if inp.slice_uuids is not None else None
+        cin.update_fail_after = -1 if inp.update_fail_after is None else inp.update_fail_after
+        cin.update_fail_error = _b(inp.update_fail_error)
         cst = _CStatus(_b(st.state), _b(st.error), _b(st.device_id), _b(st.cdi_device_id))
         rq, nu = ctypes.c_int(), ctypes.c_int()
         err = ctypes.create_string_buffer(1024)

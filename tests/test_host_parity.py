@@ -138,13 +138,16 @@ def test_attach_fuzz_vs_oracle(cro, oracle):
     for _ in range(1500):
         inp = oracle.AttachInput(
             deleting=rng.random() < 0.2, device_resource_type=rng.choice(["DEVICE_PLUGIN", "DRA"]),
-            provider_waiting=rng.random() < 0.1, provider_error=rng.choice(["", "", "", "boom <x> & \"y\""]),
+            provider_waiting=rng.random() < 0.1,
+            provider_error=rng.choice(["", "", "", "boom <x> & \"y\"", "runtime error: slice bounds out of range [:1] with length 0"]),
             provider_device_id=rng.choice(["GPU-aaaa", "GPU-bbbb"]), provider_cdi_device_id="res-1",
             std_out=rng.choice(["", "GPU-aaaa\nGPU-bbbb\n", " GPU-cccc ", "No devices were found\n", "GPU-aaaa\n\nGPU-cccc"]),
             std_err=rng.choice(["", "", "", "oops"]), exec_err=rng.choice([None, None, None, "exit status 1"]),
             driver_pod_missing=rng.random() < 0.1,
-            ds_err=rng.choice([{}, {}, {ds[1]: "daemonsets.apps \"nvidia-dcgm\" not found"}, {ds[2]: "x"}, {ds[0]: "y", ds[1]: "z"}]),
-            slice_uuids=rng.choice([None, None, [], ["GPU-aaaa"], ["GPU-bbbb", "GPU-cccc"]]))
+            ds_err=rng.choice([{}, {}, {ds[1]: "daemonsets.apps \"nvidia-dcgm\" not found"}, {ds[2]: "x"}, {ds[0]: "y", ds[1]: "z"},
+                               {ds[1]: "runtime error: invalid memory address or nil pointer dereference"}]),
+            slice_uuids=rng.choice([None, None, [], ["GPU-aaaa"], ["GPU-bbbb", "GPU-cccc"]]),
+            update_fail_after=rng.choice([None, None, None, 0, 1, 2]), update_fail_error="Operation cannot be fulfilled on composableresources")
         st = oracle.Status("Attaching", rng.choice(["", "old error"]), rng.choice(["", "GPU-aaaa", "GPU-zzzz"]), rng.choice(["", "res-0"]))
         want_st, want_rq, want_err, want_n = oracle.attach_step(inp, st)
         req = {"name": inp.name, "spec": {"type": "gpu", "model": "m", "target_node": inp.target_node},
@@ -156,6 +159,8 @@ def test_attach_fuzz_vs_oracle(cro, oracle):
                "driver_pod_missing": inp.driver_pod_missing, "daemonset_errors": inp.ds_err}
         if inp.slice_uuids is not None:
             req["resource_slices"] = [{"devices": [{"attributes": {"uuid": u}} for u in inp.slice_uuids]}]
+        if inp.update_fail_after is not None:
+            req["status_update_failures"] = {"after": inp.update_fail_after, "error": inp.update_fail_error}
         out = cro.reconcile_attach(None, req)
         assert g.json_status(out) == want_st.to_json(), (inp, st, out["_raw"])
         assert out["requeue_after_s"] == want_rq and out["error"] == want_err, (inp, st, out["_raw"])
@@ -188,3 +193,46 @@ def test_probe_annotations_are_additive(cro):
     assert js["cohdi.io/probe-checksum"] == "0000000000001234:000000000000abcd:0000000000000077"
     assert js["cohdi.io/probe-nonce"] == "3" and js["cohdi.io/probe-copies-verified"] == "5/5"
     assert list(js) == sorted(js)                                  # Go marshals map keys sorted
+
+
+def test_go_panics_unwind_without_a_status_write(cro, oracle):
+    """a Go panic is not an error.  parts[i] on a short CSV row (gpus.go:912-914) panics inside
+    CheckGPUVisible: the reference unwinds past requeueOnErr (no Status().Update) and controller-runtime reports
+    "panic: ... [recovered]" — so Status.Error must stay what it was."""
+    base = {"name": "cr", "spec": {"type": "gpu", "model": "m", "target_node": "worker-0"}, "probe": False,
+            "status": {"state": "Attaching", "error": "older", "device_id": "GPU-aaaa", "cdi_device_id": "res-0"},
+            "device_resource_type": "DEVICE_PLUGIN"}
+    # the FM reply's res_op_status is "": OptionStatus[:1] panics inside AddResource (fti/fm/client.go:195)
+    out = cro.reconcile_attach(None, dict(base, status={"state": "Attaching"},
+                                          provider={"error": "runtime error: slice bounds out of range [:1] with length 0"}))
+    assert out["error"] == "panic: runtime error: slice bounds out of range [:1] with length 0 [recovered]"
+    assert out["status_updates"] == [] and out["status"] == {"state": "Attaching"}
+    # an ORDINARY provider error is written into Status.Error by requeueOnErr (:423-433)
+    out = cro.reconcile_attach(None, dict(base, status={"state": "Attaching"}, provider={"error": "fabric said no"}))
+    assert out["error"] == "fabric said no" and out["status"]["error"] == "fabric said no" and len(out["status_updates"]) == 1
+    # Online: CheckResource's error is recorded, never returned — but a panic inside it is not an error
+    on = dict(base, status={"state": "Online", "device_id": "GPU-aaaa", "cdi_device_id": "res-0"})
+    out = cro.reconcile_attach(None, dict(on, provider={"check_resource_error": "runtime error: index out of range [0] with length 0"}))
+    assert out["error"] == "panic: runtime error: index out of range [0] with length 0 [recovered]" and out["status_updates"] == []
+    out = cro.reconcile_attach(None, dict(on, provider={"check_resource_error": "device is in Critical state"}))
+    assert out["error"] == "" and out["status"]["error"] == "device is in Critical state" and out["requeue_after_s"] == 30
+
+
+def test_a_refused_status_write_stops_the_handler_where_the_reference_stops(cro, oracle):
+    """composableresource_controller.go:233-235: if the IDs cannot be stored, nothing after it runs — no daemonset
+    restart, no visibility check — and requeueOnErr's own write of the error may fail too (only logged)."""
+    req = {"name": "cr", "spec": {"type": "gpu", "model": "m", "target_node": "worker-0"}, "probe": False,
+           "status": {"state": "Attaching"}, "device_resource_type": "DEVICE_PLUGIN",
+           "provider": {"device_id": "GPU-aaaa", "cdi_device_id": "res-0"},
+           "enumeration": {"stdout": "GPU-aaaa\n", "stderr": "", "exec_err": None},
+           "daemonset_errors": {"nvidia-gpu-operator/nvidia-dcgm": "daemonsets.apps \"nvidia-dcgm\" not found"}}
+    ok = cro.reconcile_attach(None, req)
+    assert ok["status"]["state"] == "Online" and len(ok["status_updates"]) == 3 and ok["failed_status_updates"] == 0
+    conflict = "Operation cannot be fulfilled on composableresources.cro.hpsys.ibm.ie.com \"cr\": the object has been modified"
+    out = cro.reconcile_attach(None, dict(req, status_update_failures={"after": 0, "error": conflict}))
+    assert out["error"] == conflict and out["status"]["state"] == "Attaching"
+    assert len(out["status_updates"]) == 2 and out["failed_status_updates"] == 2       # the IDs, then requeueOnErr's own attempt
+    assert "daemonset_restarts" not in out or out["daemonset_restarts"] == []           # never got there
+    out = cro.reconcile_attach(None, dict(req, status_update_failures={"after": 2, "error": conflict}))
+    assert out["error"] == conflict and out["status"]["state"] == "Online"              # in memory; the write of "Online" was refused
+    assert len(out["status_updates"]) == 3 and out["failed_status_updates"] == 1

@@ -77,3 +77,48 @@ def test_local_checks_on_the_box(cro):
         assert out["exec_log"][2]["argv"][2].startswith('TARGET_FILE="/dev/nvidia%d"' % info.device_minor)
         assert out["error"].startswith("check /dev/nvidiaX command failed: there is a process ") and "occupied the nvidiaX file" in out["error"]
         print("local drain dry run:", out["error"].strip(), hows)
+
+
+def test_dry_run_gate_is_an_allow_list(cro):
+    """a deny-list lets any command nobody classified run for real.  Only known READ shapes are executed."""
+    skipped = [["/usr/bin/nvidia-smi", "-i", DEV, "-pm", "0"], ["/usr/bin/nvidia-smi", "drain", "-p", "0000:1F:00.0", "-m", "1"],
+               ["/usr/bin/nvidia-smi", "drain", "-p", "0000:1F:00.0", "-r"], ["/usr/bin/rm", "-f", "/dev/nvidia0"],
+               ["/usr/sbin/modprobe", "-r", "nvidia_uvm"], ["/bin/sh", "-c", "echo 1 > /sys/bus/pci/devices/0000:1f:00.0/remove"],
+               ["/usr/bin/nvidia-smi", "--gpu-reset"],                       # never classified by anyone: must NOT run
+               ["/usr/bin/touch", "/tmp/cro-should-not-exist"], ["/usr/sbin/lsmod", "--extra"],
+               ["/bin/chroot", "/host-root", "/usr/bin/rm", "-f", "/dev/nvidia0"]]
+    for argv in skipped:
+        out = cro.local_exec(argv)
+        assert out["how"] == "skipped (dry run)" and not out["failed"], (argv, out)
+    assert not os.path.exists("/tmp/cro-should-not-exist")
+    for argv in (["/usr/bin/nvidia-smi", "--query-gpu=gpu_uuid", "--format=csv,noheader,nounits"],
+                 ["/bin/chroot", "/host-root", "/usr/bin/nvidia-smi", "--query-compute-apps=gpu_uuid,process_name", "--format=csv,noheader,nounits"],
+                 ["/bin/chroot", "/host-root", "/usr/bin/nvidia-smi", "drain", "-p", "0000:1F:00.0", "-q"], ["/usr/sbin/lsmod"]):
+        out = cro.local_exec(argv)
+        assert out["how"] == "spawned", (argv, out)      # (fails to exec here: no such binary — but it WAS attempted)
+    # with mutation allowed the same unknown command is executed
+    out = cro.local_exec(["/bin/sh", "-c", "echo hello; echo oops >&2; exit 3"], allow_mutation=True)
+    assert out["how"] == "spawned" and out["failed"] and out["exec_err"] == "command terminated with exit code 3"
+    assert out["stdout"] == "hello\n" and out["stderr"] == "oops\n"
+
+
+def test_wedged_command_is_killed_at_the_deadline(cro):
+    """A nvidia-smi stuck on a GPU that is mid-drain must not hang the agent: deadline, SIGKILL, reap."""
+    import time
+    t0 = time.monotonic()
+    out = cro.local_exec(["/bin/sh", "-c", "echo started; sleep 30"], allow_mutation=True, exec_deadline_ms=300)
+    assert time.monotonic() - t0 < 5
+    assert out["failed"] and out["exec_err"] == "context deadline exceeded" and out["stdout"] == "started\n"
+    # a child that closes its pipes and lingers is reaped by the same deadline
+    t0 = time.monotonic()
+    out = cro.local_exec(["/bin/sh", "-c", "exec >/dev/null 2>&1; sleep 30"], allow_mutation=True, exec_deadline_ms=300)
+    assert time.monotonic() - t0 < 5 and out["exec_err"] == "context deadline exceeded"
+
+
+def test_small_error_buffer_gets_a_truncated_message_not_stale_bytes(cro):
+    import ctypes
+    err = ctypes.create_string_buffer(b"STALE-STALE-STALE-STALE", 24)
+    rc = cro.lib.cro_fm_parse_scale_up_response(b'{"data":{"machines":[]}}', b"cr", b"gpu", b"m", ctypes.create_string_buffer(64), 64,
+                                                ctypes.create_string_buffer(64), 64, err, 24)
+    assert rc == cro.ERR_PARSE
+    assert err.value == b"can not find the added "           # 23 bytes of the reference's sentence + NUL

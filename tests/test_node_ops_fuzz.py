@@ -50,25 +50,38 @@ def test_gpus_cpp_vs_python_restatement(cro):
 
         c = no.Cluster(cluster, slices)
         status_error = ""
+
+        def is_panic(e):                 # a Go run-time panic: unwinds at once, no status write, "panic: ... [recovered]"
+            return e.startswith("runtime error: ")
+
+        def rec(e):
+            return "panic: %s [recovered]" % e if is_panic(e) else e
+        want_err = ""
         if state == "Attaching":         # composableresource_controller.go:239-286 with the ids already present
+            stop = False
             if dtype == "DEVICE_PLUGIN":
-                no.check_no_gpu_loads(c, "worker-0", None)                          # result only logged
+                e = no.check_no_gpu_loads(c, "worker-0", None)                      # an ERROR is only logged ...
+                if is_panic(e):                                                     # ... a panic is not an error
+                    want_err, stop = rec(e), True
             else:
                 err = no.run_nvidia_smi(c, "worker-0")
-                if err:
+                if is_panic(err):
+                    want_err, stop = rec(err), True
+                elif err:
                     status_error = err                                              # recorded, flow continues
-            vis, err = no.check_gpu_visible(c, dtype, "worker-0", DEV)
-            want_err = err
-            if not err and vis:
-                status_error = ""
+            if not stop:
+                vis, err = no.check_gpu_visible(c, dtype, "worker-0", DEV)
+                want_err = rec(err)
+                if not err and vis:
+                    status_error = ""
         else:                            # :320-407 up to the point where the canned provider says "removed"
-            want_err = ""
             if not req["spec"]["force_detach"]:
-                want_err = no.check_no_gpu_loads(c, "worker-0", None if dtype == "DEVICE_PLUGIN" else DEV)
+                want_err = rec(no.check_no_gpu_loads(c, "worker-0", None if dtype == "DEVICE_PLUGIN" else DEV))
             if not want_err:
-                want_err = no.drain_gpu(c, "worker-0", DEV, dtype)
+                want_err = rec(no.drain_gpu(c, "worker-0", DEV, dtype))
             if not want_err:
-                vis, want_err = no.check_gpu_visible(c, dtype, "worker-0", DEV)
+                vis, e = no.check_gpu_visible(c, dtype, "worker-0", DEV)
+                want_err = rec(e)
         assert out["error"] == want_err, (it, req, out["error"], want_err)
         got = [(x["pod"], x["container"], x["query"], x["kind"], x["detached"]) for x in out["exec_log"]]
         want = [(x["pod"], x["container"], x["query"], x["kind"], x["detached"]) for x in c.log]

@@ -180,15 +180,17 @@ def test_c_vs_python_attach_fuzz(oracle, coracle):
             deleting=rng.random() < 0.2,
             device_resource_type=rng.choice(["DEVICE_PLUGIN", "DRA"]),
             provider_waiting=rng.random() < 0.1,
-            provider_error=rng.choice(["", "", "", "boom <x>"]),
+            provider_error=rng.choice(["", "", "", "boom <x>", "runtime error: slice bounds out of range [:1] with length 0"]),
             provider_device_id=rng.choice(uuids), provider_cdi_device_id="res-1",
             std_out=rng.choice(["", "GPU-aaaa\nGPU-bbbb\n", " GPU-cccc ", "No devices were found\n", "GPU-aaaa\n\nGPU-cccc"]),
             std_err=rng.choice(["", "", "", "oops"]),
             exec_err=rng.choice([None, None, None, "exit status 1"]),
             driver_pod_missing=rng.random() < 0.1,
             ds_err=rng.choice([{}, {}, {"nvidia-gpu-operator/nvidia-dcgm": "daemonsets.apps \"nvidia-dcgm\" not found"},
-                               {"nvidia-dra-driver-gpu/nvidia-dra-driver-gpu-kubelet-plugin": "x"}]),
-            slice_uuids=rng.choice([None, None, [], ["GPU-aaaa"], ["GPU-bbbb", "GPU-cccc"]]))
+                               {"nvidia-dra-driver-gpu/nvidia-dra-driver-gpu-kubelet-plugin": "x"},
+                               {"nvidia-gpu-operator/nvidia-dcgm": "runtime error: invalid memory address or nil pointer dereference"}]),
+            slice_uuids=rng.choice([None, None, [], ["GPU-aaaa"], ["GPU-bbbb", "GPU-cccc"]]),
+            update_fail_after=rng.choice([None, None, None, 0, 1, 2]), update_fail_error="Operation cannot be fulfilled")
         st = oracle.Status("Attaching", rng.choice(["", "old error"]), rng.choice(["", "GPU-aaaa", "GPU-zzzz"]), rng.choice(["", "res-0"]))
         assert oracle.attach_step(inp, st) == coracle.attach_step(inp, st), (inp, st)
 

@@ -43,10 +43,17 @@ def run(cro, kind, state, body):
         "env": {"DEVICE_RESOURCE_TYPE": "DRA", "CDI_PROVIDER_TYPE": "FTI_CDI", "FTI_CDI_API_TYPE": kind, "FTI_CDI_TENANT_ID": "t", "FTI_CDI_CLUSTER_ID": "c"},
         "fabric": fabric, "enumeration": {"stdout": "", "stderr": ""}, "resource_slices": []})
     client = (fc.CMClient if kind == "CM" else fc.FMClient)(fc.Fabric(fabric), "t", "c")
+
+    def unwrap(e):       # a Go panic in the client surfaces as controller-runtime's "panic: <text> [recovered]", with no status write
+        if e.startswith("panic: ") and e.endswith(" [recovered]"):
+            assert out["status_updates"] == [], out
+            return e[len("panic: "):-len(" [recovered]")]
+        return e
     if online:
-        return out["status"].get("error", ""), client.check("gpu", MODEL, "worker-0", DEV)
+        got = unwrap(out["error"]) if out["error"] else out["status"].get("error", "")
+        return got, client.check("gpu", MODEL, "worker-0", DEV)
     d, c, err = client.add("cr", "gpu", MODEL, "worker-0")
-    return out["error"], ("" if err == fc.ERR_ATTACHING else err)
+    return unwrap(out["error"]), ("" if err == fc.ERR_ATTACHING else err)
 
 
 def paths(v, at=()):
