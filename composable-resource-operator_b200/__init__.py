@@ -160,7 +160,7 @@ EXPORTS = [
     "cro_fabric_check_resource", "cro_fabric_get_resources", "cro_fabric_list_devices",
     "cro_local_node_op", "cro_scan_cmdline_for", "cro_token_from_reply",
     "cro_selftest_exception_barrier", "cro_probe_sweep_times", "cro_p2p_detail_get", "cro_fullbox_times",
-    "cro_chase_end", "cro_validate_env", "cro_node_inventory", "cro_probe_uuid", "cro_set_latency_hops", "cro_local_exec",
+    "cro_chase_end", "cro_validate_env", "cro_node_inventory", "cro_probe_uuid", "cro_set_latency_hops", "cro_local_exec", "cro_metrics_text",
 ]
 
 
@@ -206,6 +206,7 @@ def _load() -> ctypes.CDLL:
         "cro_fullbox_times": (i32, [vp, ctypes.POINTER(FullBoxTime)]),
         "cro_chase_end": (i32, [i32, i32, u32, ctypes.POINTER(u32)]),
         "cro_set_latency_hops": (i32, [vp, u32]),
+        "cro_metrics_text": (i32, [vp] + out),
         "cro_validate_env": (i32, [c, c, c, sz]),
         "cro_node_inventory": (i32, [c, ctypes.POINTER(DevInfo), i32, ctypes.POINTER(DevInfo), i32, ctypes.POINTER(i32)]),
         "cro_probe_uuid": (i32, [vp, c, ctypes.POINTER(ProbeResult)]),
@@ -535,6 +536,12 @@ class ProbeContext:
         d = P2PDetail()
         self._check(lib.cro_p2p_detail_get(self.handle, dev, peer, ctypes.byref(d)))
         return d
+
+    def metrics_text(self) -> str:
+        """Prometheus text exposition of the context's counters and per-GPU gauges."""
+        rc, raw = _text_call(lib.cro_metrics_text, self.handle)
+        self._check(rc)
+        return raw.decode()
 
     def set_latency_hops(self, hops: int) -> None:
         self._check(lib.cro_set_latency_hops(self.handle, hops))

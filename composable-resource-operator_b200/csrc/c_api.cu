@@ -273,6 +273,11 @@ int cro_set_latency_hops(cro_ctx* ctx, uint32_t hops) try {
     return CRO_OK;
 } CRO_API_CATCH
 
+int cro_metrics_text(cro_ctx* ctx, char* buf, size_t cap, size_t* len) try {
+    if (!ctx) return CRO_ERR_INVALID_ARG;
+    return copy_out(ctx_metrics_text(ctx), buf, cap, len);
+} CRO_API_CATCH
+
 int cro_chase_end(int minor_src, int minor_dst, uint32_t hops, uint32_t* end) try {
     if (!end) return CRO_ERR_INVALID_ARG;
     std::vector<uint32_t> perm;

@@ -146,6 +146,16 @@ Cluster::Cluster(cro_ctx* ctx, const gojson::Value& cfg) : ctx_(ctx), rng_(20260
             if (u->kind == gojson::Value::String) uuids_.push_back(u->str);
     if (uuids_.empty() && ctx)
         for (auto& d : ctx->devs) uuids_.push_back(std::string(d->info.gpu_uuid, strnlen(d->info.gpu_uuid, 48)));
+    if (probe_ && ctx) {
+        // "warm probe contexts" (SURVEY.md §8d config 4): both lanes of every device run once before the clock starts, so
+        // no graph capture / instantiation (milliseconds of host time each) falls into the reconcile loop
+        for (size_t i = 0; i < ctx->devs.size(); ++i) { ctx_probe_begin(ctx, (int)i); ctx_probe_begin(ctx, (int)i); }
+        for (size_t i = 0; i < ctx->devs.size(); ++i) {
+            cro_probe_result warm;
+            ctx_probe_end(ctx, (int)i, &warm);
+            ctx_probe_end(ctx, (int)i, &warm);
+        }
+    }
     if (uuids_.empty()) uuids_.push_back("GPU-00000000-0000-0000-0000-000000000000");
 }
 
@@ -437,6 +447,8 @@ public:
     explicit RequestReconciler(Cluster* c) : c_(c) {}
 
     Error requeueOnErr(ComposabilityRequest* r, const Error& err) {   // :627-637
+        // a Go panic never reaches requeueOnErr: it unwinds to controller-runtime's wrapper, no status write on the way
+        if (err.panicked() || err.recovered()) return Error::Recovered(err);
         if (r) {
             r->Status.Error = err.msg;
             try { c_->updateRequest(*r); } catch (const ApiFault&) {}   // best effort (:631-634): the original error wins
@@ -818,6 +830,7 @@ public:
                         if (owners.empty()) c_->probe_owner_.erase(idx);
                         return Error::New("cuda probe failed: could not start the probe");
                     }
+                    if (!owners.empty() && idx < 16) ++c_->stats.gpu[idx].begins_behind_running;
                     owners.push_back(r.Name);
                 } else if (c_->probe_waiting_.insert(r.Name).second) {
                     c_->dev_waiters_[idx].push_back(r.Name);   // both lanes taken: queue behind them
@@ -840,6 +853,12 @@ public:
             if (rc == CRO_OK && idx < 16) {   // how busy the reconcile worker kept this GPU (the device's own %globaltimer)
                 Stats::Gpu& g = c_->stats.gpu[idx];
                 if (g.probes++ == 0) g.first_start_ns = pr.t_start_ns;
+                else if (pr.t_start_ns > g.last_end_ns) {          // the device sat idle between two probes for this long
+                    const unsigned long long gap = pr.t_start_ns - g.last_end_ns;
+                    g.gap_ns += gap;
+                    g.max_gap_ns = std::max(g.max_gap_ns, gap);
+                    if (gap > 100000) ++g.gaps_over_100us;
+                }
                 g.busy_ns += pr.total_ns;
                 g.last_end_ns = pr.t_start_ns + pr.total_ns;
             }
@@ -1181,6 +1200,8 @@ std::string Cluster::StatsJSON() const {
         w.begin_object();
         w.field("probes", g.probes).field("busy_us", (long long)(g.busy_ns / 1000));
         w.field("span_us", (long long)((g.last_end_ns - g.first_start_ns) / 1000));
+        w.field("idle_between_probes_us", (long long)(g.gap_ns / 1000)).field("max_gap_us", (long long)(g.max_gap_ns / 1000));
+        w.field("gaps_over_100us", g.gaps_over_100us).field("begins_behind_running", g.begins_behind_running);
         w.end_object();
     }
     w.end_array();

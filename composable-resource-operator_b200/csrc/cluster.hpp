@@ -105,7 +105,10 @@ struct Stats {
     long long probes = 0, probe_failures = 0, timer_rounds = 0, reconcile_errors = 0;
     std::vector<long long> reconcile_ns;   // one entry per Reconcile call
     double wall_s = 0;
-    struct Gpu { long long probes = 0; unsigned long long busy_ns = 0, first_start_ns = 0, last_end_ns = 0; };
+    struct Gpu {
+        long long probes = 0, begins_behind_running = 0, gaps_over_100us = 0;
+        unsigned long long busy_ns = 0, first_start_ns = 0, last_end_ns = 0, gap_ns = 0, max_gap_ns = 0;
+    };
     Gpu gpu[16];                           // per probe-context device: how busy the worker kept it (device timers)
 };
 

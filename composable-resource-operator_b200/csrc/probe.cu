@@ -709,11 +709,8 @@ static int probe_enqueue(cro_ctx* c, Device* d, Lane& L) {
         }
         if (!L.graph_exec) {
             Range nvc(c, "cro.probe.capture");
-            // capture needs an idle capture origin: a probe still running on the stream is fine (capture records, it
-            // does not execute), but cudaStreamBeginCapture on a stream with a pending cross-stream join is not —
-            // so the first use of a lane waits for the stream once
-            cudaStreamSynchronize(d->stream);
-            cudaStreamSynchronize(d->aux);
+            // a probe still running on the stream does not matter: capture records, it does not execute — and it must
+            // not wait either (one host thread feeds eight GPUs: a 10 ms wait here starves the other seven)
             cudaGraph_t graph = nullptr;
             bool ok = cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             if (ok) {
@@ -804,7 +801,11 @@ static int probe_finish(cro_ctx* c, Device* d, Lane& L, cro_probe_result* r) {
         return rc;
     }
     *r = *L.h_result;
+    d->last = *r;
+    d->have_last = true;
+    c->m_probes++;
     if (r->status != CRO_OK) {
+        c->m_probe_failures++;
         c->set_error(describe_failure(d, *r));
         // What the memory itself reported: uncorrected volatile ECC errors (nvmlDeviceGetTotalEccErrors).
         // NVML calls serialise across processes (measured: ~2 ms each with 4 ranks probing, enough to skew the
@@ -927,6 +928,52 @@ int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out) {
     const int rc = d->done.front().rc;
     d->done.pop_front();
     return rc;
+}
+
+// Prometheus text exposition of what the context has seen (the operator registers collectors with the
+// controller-runtime metrics registry, cmd/main.go:66,119-125; a Go collector forwards these lines).
+std::string ctx_metrics_text(cro_ctx* c) {
+    std::string o;
+    auto counter = [&](const char* name, const char* help, uint64_t v) {
+        o += std::string("# HELP ") + name + " " + help + "\n# TYPE " + name + " counter\n" + name + " " + std::to_string(v) + "\n";
+    };
+    counter("cro_probe_total", "HBM probes collected by this context.", c->m_probes.load());
+    counter("cro_probe_failures_total", "Probes whose device-side verdict was not ok.", c->m_probe_failures.load());
+    counter("cro_fullbox_probe_total", "cro_probe_all calls (concurrent probes + NVLink rounds + all-gather).", c->m_fullbox.load());
+    counter("cro_helper_probe_total", "Probes of devices attached after cuInit, run through the helper process.", c->m_helper_probes.load());
+    counter("cro_helper_probe_failures_total", "Helper-process probes that failed or timed out.", c->m_helper_failures.load());
+    counter("cro_inventory_rescans_total", "Times the node inventory was rebuilt from the driver registry.", c->inv_rescans.load());
+    counter("cro_kernel_launches_total", "CUDA kernels launched by this context.", c->launches.load());
+    struct G { const char* name; const char* help; };
+    const G gauges[] = {{"cro_probe_status", "Status of the device's last probe (0 ok, <0 a CRO_ERR_* code)."},
+                        {"cro_probe_hbm_read_bytes_per_second", "Best read sweep of the last probe."},
+                        {"cro_probe_hbm_copy_bytes_per_second", "Best copy sweep of the last probe (read + written bytes)."},
+                        {"cro_probe_hbm_fill_bytes_per_second", "Fill sweep of the last probe."},
+                        {"cro_probe_copies_verified", "Copy sweeps of the last probe whose destination was re-read and matched."},
+                        {"cro_probe_ecc_uncorrected", "Uncorrected volatile ECC errors as last read from NVML."},
+                        {"cro_probe_nonce", "Probes run on the device by this context."}};
+    for (const G& g : gauges) {
+        o += std::string("# HELP ") + g.name + " " + g.help + "\n# TYPE " + g.name + " gauge\n";
+        for (auto& dp : c->devs) {
+            Device* d = dp.get();
+            std::lock_guard<std::mutex> lk(d->mu);
+            if (!d->have_last) continue;
+            const cro_probe_result& r = d->last;
+            const std::string uuid(r.gpu_uuid, strnlen(r.gpu_uuid, sizeof r.gpu_uuid));
+            auto rate = [](uint64_t bytes, uint64_t ns) -> long long { return ns ? (long long)((unsigned __int128)bytes * 1000000000ull / ns) : 0; };
+            long long v = 0;
+            const std::string n = g.name;
+            if (n == "cro_probe_status") v = r.status;
+            else if (n == "cro_probe_hbm_read_bytes_per_second") v = rate(r.sweep_bytes, r.read_best_ns);
+            else if (n == "cro_probe_hbm_copy_bytes_per_second") v = rate(2 * r.sweep_bytes, r.copy_best_ns);
+            else if (n == "cro_probe_hbm_fill_bytes_per_second") v = rate(r.sweep_bytes, r.fill_ns);
+            else if (n == "cro_probe_copies_verified") v = r.copy_verified;
+            else if (n == "cro_probe_ecc_uncorrected") v = r.ecc_errors;
+            else v = r.nonce;
+            o += n + "{gpu_uuid=\"" + uuid + "\",minor=\"" + std::to_string(r.device_minor) + "\"} " + std::to_string(v) + "\n";
+        }
+    }
+    return o;
 }
 
 // CUDA-event and %globaltimer times of the sweeps of the device's last collected probe.
@@ -1054,6 +1101,10 @@ int ctx_probe_uuid(cro_ctx* c, const char* uuid, cro_probe_result* out) {
     if (c && c->nvtx) nvtxRangePushA("cro.probe.helper");
     const int rc = inventory::RunHelper("", want, sweep, deadline, out, &err);
     if (c && c->nvtx) nvtxRangePop();
+    if (c) {
+        c->m_helper_probes++;
+        if (rc != CRO_OK) c->m_helper_failures++;
+    }
     if (rc != CRO_OK && !err.empty()) {
         if (c) c->set_error(err);
         else set_thread_error(err);
@@ -1441,9 +1492,14 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
     } else {
         for (int i = 0; i < n; ++i) out[i] = *c->devs[(size_t)i]->h_result;
     }
+    c->m_fullbox++;
     for (int i = 0; i < n; ++i) {
         Device* d = c->devs[(size_t)i].get();
         *d->h_result = out[i];
+        d->last = out[i];
+        d->have_last = true;
+        c->m_probes++;
+        if (out[i].status != CRO_OK) c->m_probe_failures++;
         if (out[i].status != CRO_OK) {
             worst = out[i].status;
             c->set_error(describe_failure(d, out[i]));

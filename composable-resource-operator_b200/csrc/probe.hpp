@@ -89,6 +89,8 @@ struct Device {
     std::deque<Collected> done;
     unsigned sm_clock_mhz = 0, mem_clock_mhz = 0;
     uint32_t ecc_uncorrected = 0;      // NVML count cached at init / full-box probe / failed probe
+    cro_probe_result last{};           // the most recent collected result (cro_metrics_text)
+    bool have_last = false;
 
     Device() = default;
     Device(const Device&) = delete;
@@ -116,6 +118,8 @@ struct cro_ctx {
     cro_opts opts{};
     std::vector<std::unique_ptr<cro::Device>> devs;   // minor-sorted
     std::atomic<uint64_t> launches{0};
+    // gauges / counters behind cro_metrics_text (the operator's Prometheus registry, cmd/main.go:66,119-125)
+    std::atomic<uint64_t> m_probes{0}, m_probe_failures{0}, m_fullbox{0}, m_helper_probes{0}, m_helper_failures{0};
     std::mutex err_mu;
     std::string last_error;
     std::mutex all_mu;                 // serialises cro_probe_all
@@ -163,6 +167,7 @@ int ctx_probe_end(cro_ctx* c, int idx, cro_probe_result* out);
 int ctx_probe_poll(cro_ctx* c, int idx);
 int ctx_probe_wait(cro_ctx* c, int idx);
 int ctx_probe_depth(cro_ctx* c, int idx);
+std::string ctx_metrics_text(cro_ctx* c);
 int ctx_sweep_times(cro_ctx* c, int idx, cro_sweep_time* out, int cap, int* n);
 // Fresh inventory of the node merged with the context's own devices (inventory.hpp).
 // force: re-read every `information` file even if the registry's listing looks unchanged (done by itself once a

@@ -171,25 +171,40 @@ func (c *Context) ProbeAll() ([]ProbeResult, error) {
 	return out, nil
 }
 
-// ProbeUUID probes the one device whose UUID is deviceID.  found=false mirrors
-// the reference's "not yet visible" (false, nil) + RequeueAfter 30 s.
+// ProbeUUID probes the one device whose UUID is deviceID (Status.DeviceID,
+// internal/controller/composableresource_controller.go:231-233).  The library
+// re-reads the node's inventory on every call (the reference execs a fresh
+// nvidia-smi per reconcile, internal/utils/gpus.go:666-689): a device this
+// context holds is probed in process, a device that reached the node AFTER
+// cro_probe_init — which no running CUDA process can see — is probed by a
+// one-shot helper process with its own cuInit.  found=false (CRO_ERR_NO_DEVICE)
+// mirrors the reference's "not yet visible" (false, nil) + RequeueAfter 30 s.
 func (c *Context) ProbeUUID(deviceID string) (r ProbeResult, found bool, err error) {
-	var devs [C.CRO_MAX_DEVICES]C.cro_dev_info
-	var n C.int
-	if rc := C.cro_enumerate(c.h, &devs[0], C.CRO_MAX_DEVICES, &n); rc != C.CRO_OK {
-		return r, false, errorOf(c.h, rc)
+	id := C.CString(deviceID)
+	defer C.free(unsafe.Pointer(id))
+	var res C.cro_probe_result
+	rc := C.cro_probe_uuid(c.h, id, &res)
+	if rc == C.CRO_ERR_NO_DEVICE {
+		return r, false, nil
 	}
-	for i := 0; i < int(n); i++ {
-		if C.GoString(&devs[i].gpu_uuid[0]) != deviceID {
-			continue
-		}
-		var res C.cro_probe_result
-		if rc := C.cro_probe_device(c.h, C.int(i), &res); rc != C.CRO_OK {
-			return convert(&res), true, errorOf(c.h, rc)
-		}
-		return convert(&res), true, nil
+	if rc != C.CRO_OK {
+		return convert(&res), true, errorOf(c.h, rc)
 	}
-	return r, false, nil
+	return convert(&res), true, nil
+}
+
+// MetricsText is the Prometheus text exposition of the context's counters and
+// per-GPU gauges; a prometheus.Collector registered with
+// sigs.k8s.io/controller-runtime/pkg/metrics.Registry (cmd/main.go:66,119-125
+// wires that registry) forwards it.
+func (c *Context) MetricsText() (string, error) {
+	buf := (*C.char)(C.malloc(16384))
+	defer C.free(unsafe.Pointer(buf))
+	var ln C.size_t
+	if rc := C.cro_metrics_text(c.h, buf, 16384, &ln); rc != C.CRO_OK {
+		return "", errorOf(c.h, rc)
+	}
+	return C.GoStringN(buf, C.int(ln)), nil
 }
 
 // Visible is the decision of utils.CheckGPUVisible (internal/utils/gpus.go:73-84)

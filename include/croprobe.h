@@ -364,6 +364,12 @@ typedef struct cro_fullbox_time {
     uint32_t host_syncs;           /* stream synchronisations the call made (one per device)            */
 } cro_fullbox_time;
 int  cro_fullbox_times(cro_ctx *ctx, cro_fullbox_time *out);
+/* Prometheus text exposition (counters and per-GPU gauges of the last probe) for the operator's metrics registry
+ * (cmd/main.go:66,119-125 wires controller-runtime's registry; a Go collector forwards these lines):
+ * cro_probe_total, cro_probe_failures_total, cro_fullbox_probe_total, cro_helper_probe_total,
+ * cro_inventory_rescans_total, cro_kernel_launches_total, cro_probe_status{gpu_uuid,minor},
+ * cro_probe_hbm_{read,copy,fill}_bytes_per_second{..}, cro_probe_copies_verified{..}, cro_probe_ecc_uncorrected{..}. */
+int  cro_metrics_text(cro_ctx *ctx, char *buf, size_t cap, size_t *len);
 /* Pointer-chase length of the following cro_probe_all calls (1 .. 16777216 hops per directed pair). */
 int  cro_set_latency_hops(cro_ctx *ctx, uint32_t hops);
 /* Where `hops` steps from slot 0 of the latency permutation of the directed pair (minor_src chases through

@@ -590,3 +590,21 @@ def test_live_context_follows_a_changing_node(cro, tmp_path, monkeypatch):
         assert c.enumerate() == []
         out = cro.reconcile_attach(c, dict(base, provider={"device_id": me.gpu_uuid.decode(), "cdi_device_id": "r"}))
         assert out["status"]["state"] == "Attaching"
+
+
+def test_metrics_text_is_prometheus_exposition(cro):
+    with cro.ProbeContext(sweep_bytes=64 << 20, devices=[0], read_sweeps=1, copy_sweeps=1) as c:
+        c.probe_device(0)
+        c.probe_device(0)
+        c.enumerate()
+        text = c.metrics_text()
+        uuid = c.own_devices()[0].gpu_uuid.decode()
+        lines = [ln for ln in text.splitlines() if ln and not ln.startswith("#")]
+        vals = {ln.rsplit(" ", 1)[0]: int(ln.rsplit(" ", 1)[1]) for ln in lines}
+        assert vals["cro_probe_total"] == 2 and vals["cro_probe_failures_total"] == 0 and vals["cro_kernel_launches_total"] == 10
+        key = 'cro_probe_status{gpu_uuid="%s",minor="%d"}' % (uuid, c.own_devices()[0].device_minor)
+        assert vals[key] == 0 and vals[key.replace("cro_probe_status", "cro_probe_nonce")] == 1
+        assert vals[key.replace("cro_probe_status", "cro_probe_copies_verified")] == 1
+        assert vals[key.replace("cro_probe_status", "cro_probe_hbm_read_bytes_per_second")] > 10**11
+        families = {ln.split(" ")[2] for ln in text.splitlines() if ln.startswith("# TYPE ")}
+        assert all(k.split("{")[0] in families for k in vals)      # every sample belongs to a declared family
