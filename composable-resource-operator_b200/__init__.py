@@ -39,6 +39,7 @@ ERR_CHECKSUM, ERR_BUFFER_SMALL, ERR_NCCL, ERR_DEADLINE, ERR_UNSUPPORTED = -6, -7
 ERR_PARSE, ERR_EXEC, ERR_P2P, ERR_INTERNAL = -11, -12, -13, -14
 
 F_SKIP_COPY, F_SKIP_P2P, F_SKIP_NCCL, F_NO_NVML, F_VERIFY_COPY, F_LAZY_ALLOC, F_DEGRADE_ON_OOM, F_SKIP_P2P_WRITE = 1, 2, 4, 8, 16, 32, 64, 128
+F_TEST_INJECT = 256
 READ_AUTO, READ_LDG, READ_TMA, READ_LDG256 = 0, 1, 2, 3
 COPY_AUTO, COPY_LDG, COPY_TMA, COPY_TMA_FUSED = 0, 1, 2, 3
 DEV_IN_PROCESS, DEV_NEEDS_HELPER = 1, 2
@@ -58,7 +59,9 @@ class Opts(ctypes.Structure):
         ("read_sweeps", ctypes.c_uint32), ("copy_sweeps", ctypes.c_uint32), ("latency_hops", ctypes.c_uint32),
         ("read_variant", ctypes.c_uint32), ("copy_variant", ctypes.c_uint32), ("deadline_ms", ctypes.c_int32),
         ("n_devices", ctypes.c_int32), ("devices", ctypes.c_int32 * MAX_DEVICES),
-        ("rank_base", ctypes.c_uint32), ("world_override", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 6),
+        ("rank_base", ctypes.c_uint32), ("world_override", ctypes.c_uint32),
+        ("test_inject_after", ctypes.c_uint32), ("reserved0", ctypes.c_uint32),
+        ("test_inject_word", ctypes.c_uint64), ("test_inject_mask", ctypes.c_uint64),
     ]
 
 
@@ -400,7 +403,8 @@ class ProbeContext:
     def __init__(self, sweep_bytes: int = 0, devices: Optional[List[int]] = None, flags: int = 0,
                  read_sweeps: int = 0, copy_sweeps: int = 0, read_variant: int = READ_AUTO,
                  copy_variant: int = COPY_AUTO, p2p_bytes: int = 0, latency_hops: int = 0,
-                 deadline_ms: int = 0, seed_base: int = 0, rank_base: int = 0, world: int = 0) -> None:
+                 deadline_ms: int = 0, seed_base: int = 0, rank_base: int = 0, world: int = 0,
+                 inject: Optional[Tuple[int, int, int]] = None) -> None:
         o = Opts()
         o.abi_version = ABI_VERSION
         o.flags = flags
@@ -412,6 +416,9 @@ class ProbeContext:
         o.read_variant, o.copy_variant = read_variant, copy_variant
         o.deadline_ms = deadline_ms
         o.rank_base, o.world_override = rank_base, world
+        if inject is not None:            # (after sweep number, word index, xor mask): fault injection inside the probe
+            o.flags |= F_TEST_INJECT
+            o.test_inject_after, o.test_inject_word, o.test_inject_mask = inject
         if devices:
             o.n_devices = len(devices)
             for i, d in enumerate(devices):

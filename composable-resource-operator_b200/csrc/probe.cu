@@ -652,8 +652,16 @@ static int probe_enqueue(cro_ctx* c, Device* d, Lane& L) {
         k = 0;
         CU_TRY(c, cudaMemcpyAsync(L.d_params, L.h_params, sizeof(ProbeParams), cudaMemcpyHostToDevice, d->stream));
         CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
+        uint32_t sweep_no = 0;
+        auto maybe_inject = [&]() -> int {      // CRO_F_TEST_INJECT: corrupt one word behind a chosen sweep
+            if ((o.flags & CRO_F_TEST_INJECT) && o.test_inject_after == sweep_no && o.test_inject_word < 2 * (d->sweep_bytes / 8))
+                CU_TRY(c, launch_xor_word(d->region, o.test_inject_word, o.test_inject_mask, d->stream));
+            ++sweep_no;
+            return CRO_OK;
+        };
         CU_TRY(c, launch_fill(d->plan, half[0], d->sweep_bytes, gp, d->scratch, &L.d_out[kSlotFill], d->stream));
         CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
+        if (maybe_inject()) return CRO_ERR_CUDA;
         // the closed form: ALU only, so it runs beside the copy sweeps (which leave the ALUs idle)
         cudaStream_t es = overlap ? d->aux : d->stream;
         if (overlap) {
@@ -667,11 +675,13 @@ static int probe_enqueue(cro_ctx* c, Device* d, Lane& L) {
             CU_TRY(c, launch_copy(d->plan, cv, half[1 - s], half[s], d->sweep_bytes, gp, d->scratch,
                                   &L.d_out[kSlotSweep0 + i], d->stream));
             CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
+            if (maybe_inject()) return CRO_ERR_CUDA;
         }
         for (uint32_t i = 0; i < R; ++i) {
             CU_TRY(c, launch_read(d->plan, rv, half[read_half(C, i)], d->sweep_bytes, gp, d->scratch,
                                   &L.d_out[kSlotSweep0 + C + i], d->stream));
             CU_TRY(c, cudaEventRecordWithFlags(ev[k++], d->stream, flag));
+            if (maybe_inject()) return CRO_ERR_CUDA;
         }
         if (overlap) CU_TRY(c, cudaStreamWaitEvent(d->stream, d->ev_join, 0));
         FinalizeArgs fa{};
@@ -701,7 +711,8 @@ static int probe_enqueue(cro_ctx* c, Device* d, Lane& L) {
     // One graph launch instead of ~40 runtime calls per probe (matters when one host thread feeds 8 GPUs).
     // The graph is tied to the options it was captured with; any capture problem falls back to direct launches.
     const uint64_t graph_key = ((uint64_t)rv << 48) ^ ((uint64_t)cv << 40) ^ ((uint64_t)R << 24) ^ ((uint64_t)C << 8) ^
-                               (overlap ? 1u : 0u) ^ (d->sweep_bytes << 1);
+                               (overlap ? 1u : 0u) ^ (d->sweep_bytes << 1) ^
+                               ((o.flags & CRO_F_TEST_INJECT) ? ((uint64_t)o.test_inject_after << 56) ^ (o.test_inject_word * 0x9E3779B97F4A7C15ull) ^ o.test_inject_mask : 0);
     if (env::get("CRO_USE_GRAPH") && !L.graph_failed) {
         if (L.graph_exec && L.graph_key != graph_key) {
             cudaGraphExecDestroy(L.graph_exec);

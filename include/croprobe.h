@@ -56,6 +56,10 @@ extern "C" {
 #define CRO_F_DEGRADE_ON_OOM  0x0040u  /* busy device: halve S (>= 64 MiB) instead of failing;
                                           the result's sweep_bytes says what was swept  */
 #define CRO_F_SKIP_P2P_WRITE  0x0080u  /* cro_probe_all: peer reads only, no push leg */
+#define CRO_F_TEST_INJECT     0x0100u  /* fault injection INSIDE the probe (tests of the device-side verdict): after sweep
+                                          number test_inject_after (launch order: 0 = the fill, 1.. = copies, then reads)
+                                          XOR test_inject_mask into 64-bit word test_inject_word of the region (half A is
+                                          words [0, S/8), half B [S/8, 2S/8)) */
 
 /* read-sweep kernel variants */
 #define CRO_READ_AUTO   0u
@@ -89,7 +93,10 @@ typedef struct cro_opts {
     int32_t  devices[CRO_MAX_DEVICES]; /* CUDA ordinals to manage                           */
     uint32_t rank_base;            /* one-process-per-GPU hosts: this process's first rank  */
     uint32_t world_override;       /* ... and the job's world size (0 = devices managed)    */
-    uint32_t reserved[6];
+    uint32_t test_inject_after;    /* CRO_F_TEST_INJECT: see above                          */
+    uint32_t reserved0;
+    uint64_t test_inject_word;
+    uint64_t test_inject_mask;
 } cro_opts;
 
 /*

@@ -608,3 +608,41 @@ def test_metrics_text_is_prometheus_exposition(cro):
         assert vals[key.replace("cro_probe_status", "cro_probe_hbm_read_bytes_per_second")] > 10**11
         families = {ln.split(" ")[2] for ln in text.splitlines() if ln.startswith("# TYPE ")}
         assert all(k.split("{")[0] in families for k in vals)      # every sample belongs to a declared family
+
+
+@pytest.mark.parametrize("after,half,code,index,verified", [
+    (0, 0, "FAIL_COPY_SRC", 0, 0),     # the fill is corrupted: copy 0 reads something else than the pattern
+    (1, 1, "FAIL_COPY_SRC", 1, 0),     # copy 0's destination (B) is corrupted: copy 1, which reads it, says so
+    (2, 0, "FAIL_COPY_SRC", 2, 1),     # copy 1's destination (A): copy 0's was fine (1 verified), copy 2 trips
+    (3, 1, "FAIL_READ", 0, 2),         # the last copy's destination (B): read sweep 0 re-reads it
+    (4, 0, "FAIL_READ", 1, 3),         # after read 0: half A, read by read sweep 1
+    (5, 0, "FAIL_NONE", 0, 3),         # after the last sweep that reads half A: nobody looks again — and nothing was written
+])
+def test_device_side_verdict_names_the_sweep_that_caught_it(cro, coracle, after, half, code, index, verified):
+    """Fault injection INSIDE the probe (a one-word XOR kernel behind a chosen sweep of the captured graph): the finalize
+    kernel's verdict must name the first sweep that read the corrupted half, and count the copies verified before it.
+    Probe shape: fill, 3 copies (A->B, B->A, A->B), 2 reads (B, A)."""
+    S = 32 << 20
+    n = S // 8
+    word = half * n + 123457
+    with cro.ProbeContext(sweep_bytes=S, devices=[0], read_sweeps=2, copy_sweeps=3, inject=(after, word, 1 << 33)) as c:
+        r = c.probe_device(0, allow_checksum_error=True)
+        want = coracle.checksum(r.seed, 0, n)
+        assert r.expect == want
+        assert r.fail_code == getattr(cro, code) and (r.fail_code == 0 or r.fail_index == index), (r.fail_code, r.fail_index)
+        assert r.status == (0 if code == "FAIL_NONE" else cro.ERR_CHECKSUM)
+        assert r.copy_verified == verified
+        if code == "FAIL_READ":
+            # the struct shows the checksum of the sweep that failed: exactly one bit off in xor, the weighted sum moved by that word's weight
+            w = coracle.pattern_word(r.seed, 123457)
+            assert r.checksum_xor == want[0] ^ (1 << 33)
+            assert r.checksum_wsum == (want[2] + ((w ^ (1 << 33)) - w) * (2 * 123457 + 1)) & MASK
+        if code != "FAIL_NONE":
+            assert "sweep" in cro_last_error(cro, c)
+
+
+def cro_last_error(cro, c):
+    import ctypes
+    buf = ctypes.create_string_buffer(1024)
+    cro.lib.cro_last_error(c.handle, buf, 1024)
+    return buf.value.decode()
