@@ -126,6 +126,7 @@ std::string ComposabilityRequestStatus::MarshalJSON() const {
 Cluster::Cluster(cro_ctx* ctx, const gojson::Value& cfg) : ctx_(ctx), rng_(20260921) {
     deviceResourceType_ = cfg.get_string("device_resource_type", "DEVICE_PLUGIN");
     probe_ = cfg.get_bool("probe") && ctx != nullptr;
+    stats.tracing = cfg.get_bool("trace");
     if (cfg.get("seed")) rng_.seed((unsigned long long)cfg.get_int("seed"));
     if (const gojson::Value* ns = cfg.get("nodes"))
         for (const auto& n : ns->arr) {
@@ -832,8 +833,10 @@ public:
                     }
                     if (!owners.empty() && idx < 16) ++c_->stats.gpu[idx].begins_behind_running;
                     owners.push_back(r.Name);
+                    c_->traceEvent('b', idx);
                 } else if (c_->probe_waiting_.insert(r.Name).second) {
                     c_->dev_waiters_[idx].push_back(r.Name);   // both lanes taken: queue behind them
+                    c_->traceEvent('w', idx);
                 }
                 probePending = true;
                 return Error::Nil();
@@ -850,6 +853,7 @@ public:
             cro_probe_result pr;
             ++c_->stats.probes;
             int rc = ctx_probe_end(c_->ctx_, idx, &pr);
+            c_->traceEvent('c', idx);
             if (rc == CRO_OK && idx < 16) {   // how busy the reconcile worker kept this GPU (the device's own %globaltimer)
                 Stats::Gpu& g = c_->stats.gpu[idx];
                 if (g.probes++ == 0) g.first_start_ns = pr.t_start_ns;
@@ -1093,7 +1097,14 @@ void Cluster::Run(long long max_reconciles) {
     long long changes_at_flush = -1;
     for (;;) {
         while ((!req_queue_.empty() || !res_queue_.empty()) && n < max_reconciles) {
-            if ((n & 3) == 0) pollProbes(false);
+            // Look for finished probes every 100 us of reconciling.  (Round 1 polled when n % 4 == 0 — but n advances
+            // by two per turn while both queues hold work, so an odd n never hit a multiple of four again and finished
+            // probes sat uncollected until a queue drained: one ~200 ms hole per GPU at the start of a storm.)
+            const auto now_poll = clk::now();
+            if (now_poll - last_poll_ >= std::chrono::microseconds(100)) {
+                last_poll_ = now_poll;
+                pollProbes(false);
+            }
             // one worker per controller (MaxConcurrentReconciles default 1), interleaved
             if (!res_queue_.empty()) {
                 const std::string key = res_queue_.front();
@@ -1125,7 +1136,9 @@ void Cluster::Run(long long max_reconciles) {
         }
         if (n >= max_reconciles) break;
         if (!probe_owner_.empty()) {   // nothing else to do: wait for the next probe to finish
+            const auto b0 = clk::now();
             pollProbes(true);
+            stats.blocked_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(clk::now() - b0).count();
             continue;
         }
         // queue drained: fire the RequeueAfter timers, unless the last round changed nothing
@@ -1194,6 +1207,18 @@ std::string Cluster::StatsJSON() const {
     w.field("reconcile_errors", stats.reconcile_errors).field("timer_rounds", stats.timer_rounds);
     w.field("reconcile_p50_ns", pct(0.50)).field("reconcile_p99_ns", pct(0.99));
     w.field("wall_us", (long long)(stats.wall_s * 1e6));
+    long long total_ns = 0, max_ns = 0;
+    for (long long x : stats.reconcile_ns) { total_ns += x; max_ns = std::max(max_ns, x); }
+    w.field("reconcile_total_us", total_ns / 1000).field("reconcile_max_us", max_ns / 1000).field("worker_blocked_us", stats.blocked_ns / 1000);
+    if (stats.tracing) {
+        w.key("trace").begin_array();
+        for (const Stats::Ev& e : stats.trace) {
+            w.begin_array();
+            w.value((long long)e.t_us).value(std::string(1, e.what)).value((long long)e.dev);
+            w.end_array();
+        }
+        w.end_array();
+    }
     w.key("gpus").begin_array();
     for (const Stats::Gpu& g : stats.gpu) {
         if (!g.probes) continue;

@@ -16,6 +16,7 @@
 //     the fake fabric hands out the UUID of the physical GPU mapped to the node;
 //   * map iteration that Go leaves unordered is done in key order.
 #pragma once
+#include <chrono>
 #include <deque>
 #include <map>
 #include <random>
@@ -110,6 +111,10 @@ struct Stats {
         unsigned long long busy_ns = 0, first_start_ns = 0, last_end_ns = 0, gap_ns = 0, max_gap_ns = 0;
     };
     Gpu gpu[16];                           // per probe-context device: how busy the worker kept it (device timers)
+    long long blocked_ns = 0;              // worker time spent waiting for a probe with nothing else to reconcile
+    struct Ev { long long t_us; char what; int dev; };
+    std::vector<Ev> trace;                 // first events of the probe slot: b(egin) c(ollect) w(ait queued) r(elease wakes)
+    bool tracing = false;
 };
 
 class Cluster {
@@ -126,6 +131,14 @@ public:
     Error Plant(const gojson::Value& object);
     // runs both controllers until the cluster is quiescent (or max_reconciles)
     void Run(long long max_reconciles);
+    void traceEvent(char what, int dev) {
+        if (!stats.tracing || stats.trace.size() >= 4000) return;
+        const long long t = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        if (stats.trace.empty()) trace_t0_ = t;
+        stats.trace.push_back({t - trace_t0_, what, dev});
+    }
+    long long trace_t0_ = 0;
+    std::chrono::steady_clock::time_point last_poll_{};
     // exactly one Reconcile of the request controller on `name` (the reference's tests drive it this way)
     Error ReconcileRequestOnce(const std::string& name);
     Error ReconcileResourceOnce(const std::string& name);

@@ -1,5 +1,5 @@
 set -u
-OUT=gpurun_out/r02i
+OUT=gpurun_out/r02j
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
 nvidia-smi -L | wc -l
@@ -10,7 +10,7 @@ python - <<'PY'
 import json
 for n in (8, 4):
     try:
-        d = json.loads(open("gpurun_out/r02i/bench_n%d.json" % n).read())
+        d = json.loads(open("gpurun_out/r02j/bench_n%d.json" % n).read())
     except Exception as e:
         print(n, "no line", e); continue
     print("N=%d value %.1f e2e %.1f parity %s" % (n, d["value"], d["e2e"]["value"], d["parity_ok"]))
