@@ -242,6 +242,15 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
 
     std::unique_ptr<cro_ctx> c(new cro_ctx);
     c->opts = opts;
+    // CRO_TRACE_INIT=1: where the cold start goes, phase by phase, on stderr (the hot-plug helper pays all of it)
+    const bool trace_init = getenv("CRO_TRACE_INIT") && getenv("CRO_TRACE_INIT")[0] == '1';
+    uint64_t t_phase = now_ns();
+    auto phase = [&](const char* name) {
+        if (!trace_init) return;
+        const uint64_t t = now_ns();
+        fprintf(stderr, "cro_probe_init: %-28s %8.3f ms\n", name, (double)(t - t_phase) / 1e6);
+        t_phase = t;
+    };
     {
         // the CRO_* knobs, validated the way the reference validates its own environment
         // (internal/controller/composableresource_adapter.go:42-45)
@@ -255,8 +264,10 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
             if (*pr) c->proc_root = pr;
     }
 
+    phase("options + environment");
     int n_cuda = 0;
     cudaError_t e = cudaGetDeviceCount(&n_cuda);
+    phase("cuInit (cudaGetDeviceCount)");
     if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) {
         // No usable GPU.  A probe library without a GPU must say so loudly:
         // there is no CPU fallback on this path.
@@ -284,6 +295,7 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
     bool have_nvml = false;
     if (!(opts.flags & CRO_F_NO_NVML)) have_nvml = identity::ScanNvml(&nvml, nullptr);
 
+    phase("identity scan (/proc, NVML)");
     struct Keyed { std::unique_ptr<Device> d; long long key; };
     std::vector<Keyed> keyed;
     for (int ord : ordinals) {
@@ -340,14 +352,17 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
         d->sweep_bytes = opts.sweep_bytes;
         d->seed_dev = opts.seed_base | (uint64_t)(d->info.device_minor >= 0 ? d->info.device_minor : d->ordinal);
         d->seed_cur = d->seed_dev;
+        phase("device properties");
         CU_TRY(c.get(), cudaSetDevice(d->ordinal));
         CU_TRY(c.get(), cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        phase("primary context + stream");
         CU_TRY(c.get(), cudaStreamCreateWithFlags(&d->aux, cudaStreamNonBlocking));
         CU_TRY(c.get(), cudaEventCreate(&d->ev0));
         CU_TRY(c.get(), cudaEventCreate(&d->ev1));
         for (cudaEvent_t* ev : {&d->ev_fork, &d->ev_join, &d->ev_hbm_done, &d->ev_aux_done, &d->ev_chase_ready})
             CU_TRY(c.get(), cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         CU_TRY(c.get(), plan_kernels(d->ordinal, &d->plan));
+        phase("kernel plan (module load)");
         const int max_grid = std::max({d->plan.fill.grid, d->plan.read_ldg.grid, d->plan.read_ldg256.grid,
                                        d->plan.read_tma.grid, d->plan.copy_fused.grid, d->plan.expect.grid, 1});
         int rc = alloc_scratch(c.get(), &d->scratch, max_grid);
@@ -372,8 +387,10 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
         CU_TRY(c.get(), cudaMallocHost(&d->h_gather, sizeof(cro_probe_result) * CRO_MAX_DEVICES));
         CU_TRY(c.get(), cudaMalloc(&d->d_chase_out, 2 * CRO_MAX_DEVICES * sizeof(unsigned long long)));
         CU_TRY(c.get(), cudaMallocHost(&d->h_chase_out, 2 * CRO_MAX_DEVICES * sizeof(unsigned long long)));
+        phase("buffers (device + pinned)");
         if (!(opts.flags & CRO_F_LAZY_ALLOC)) {
             if ((rc = ensure_region(c.get(), d))) return rc;
+            phase("sweep region");
         }
         refresh_ecc(c.get(), d);
         c->devs.push_back(std::move(keyed[i].d));
@@ -383,6 +400,7 @@ int ctx_create(const cro_opts* o, cro_ctx** out) {
         int rc = stage_template(c.get(), d.get());
         if (rc) return rc;
     }
+    phase("identity template");
     *out = c.release();
     return CRO_OK;
 }
@@ -395,6 +413,7 @@ void set_thread_error(const std::string& m) noexcept {
 
 }  // namespace cro
 cro_ctx::~cro_ctx() {
+    if (inv_thread.joinable()) inv_thread.join();     // a background inventory refresh still reads this context
     if (!last_error.empty()) cro::g_init_error = last_error;
 }
 namespace cro {
@@ -1017,28 +1036,12 @@ int ctx_sweep_times(cro_ctx* c, int idx, cro_sweep_time* out, int cap, int* n_ou
 // ---------------------------------------------------------------------------
 // the node's inventory, fresh on every query (inventory.hpp)
 // ---------------------------------------------------------------------------
-int ctx_inventory(cro_ctx* c, std::vector<cro_dev_info>* out, bool force) {
-    if (!c || !out) return CRO_ERR_INVALID_ARG;
-    std::vector<cro_dev_info> mine;
-    for (auto& d : c->devs) mine.push_back(d->info);
-    std::lock_guard<std::mutex> g(c->inv_mu);
+// The slow part of an inventory refresh: reads the registry's `information` files (each read goes through the
+// driver) and, when the node holds other devices than this context, re-initialises NVML for nvidia-smi's ordering.
+// Touches nothing of the context but its options, so it can run on a side thread.
+static std::vector<cro_dev_info> build_inventory(const cro_ctx* c, const std::vector<cro_dev_info>& mine, bool have_proc,
+                                                 bool* scanned_nvml) {
     const bool nvml_ok = !(c->opts.flags & CRO_F_NO_NVML);
-    // Every call looks at the node: the registry's directory listing (a readdir, ~10 us, no driver lock).  The
-    // `information` files are read again when that listing differs from the last one, when the caller insists (it was
-    // told about a UUID the list lacks), and otherwise every 30 s — the reference's own requeue period
-    // (composableresource_controller.go:223,285) — because each such read goes through the driver's locks.
-    std::string key = identity::ProcRegistryListing(c->proc_root);
-    const bool have_proc = !key.empty();
-    if (!have_proc) key = "-";
-    const auto now = std::chrono::steady_clock::now();
-    const bool nvml_due = !have_proc && nvml_ok && now - c->inv_nvml_at > std::chrono::seconds(1);
-    const bool stale = now - c->inv_full_at > std::chrono::seconds(30);
-    if (c->inv_valid && key == c->inv_key && !nvml_due && !force && !(have_proc && stale)) {
-        *out = c->inv;
-        return CRO_OK;
-    }
-    c->inv_rescans++;
-    c->inv_full_at = now;
     std::vector<identity::ProcGpu> proc;
     if (have_proc) proc = identity::ScanProc(c->proc_root);
     std::vector<inventory::Seen> seen;
@@ -1057,7 +1060,7 @@ int ctx_inventory(cro_ctx* c, std::vector<cro_dev_info>* out, bool force) {
     if (have_scan || !have_proc) {
         std::vector<identity::NvmlGpu> nv;
         if (nvml_ok && identity::ScanNvml(&nv, nullptr)) {   // init + shutdown: NVML sees hot-plugged devices only after a re-init
-            c->inv_nvml_at = now;
+            *scanned_nvml = true;
             std::vector<inventory::Seen> ordered;
             for (const auto& g2 : nv) {                        // nvidia-smi lists in NVML index order
                 bool on_node = !have_proc;
@@ -1076,7 +1079,51 @@ int ctx_inventory(cro_ctx* c, std::vector<cro_dev_info>* out, bool force) {
             have_scan = true;
         }
     }
-    c->inv = inventory::Merge(mine, have_scan, seen);
+    return inventory::Merge(mine, have_scan, seen);
+}
+
+int ctx_inventory(cro_ctx* c, std::vector<cro_dev_info>* out, bool force) {
+    if (!c || !out) return CRO_ERR_INVALID_ARG;
+    std::vector<cro_dev_info> mine;
+    for (auto& d : c->devs) mine.push_back(d->info);
+    std::unique_lock<std::mutex> g(c->inv_mu);
+    const bool nvml_ok = !(c->opts.flags & CRO_F_NO_NVML);
+    // Every call looks at the node: the registry's directory listing (readdir + stat, ~10 us, no driver lock).  The
+    // `information` files are read again
+    //   * at once, when that listing differs from the last one or the caller insists (it was told about a UUID the
+    //     list lacks);
+    //   * in the BACKGROUND every 30 s — the reference's own requeue period (composableresource_controller.go:223,285)
+    //     — because each such read goes through the driver's locks (100+ ms for a full box while nvidia-smi polls) and
+    //     a reconcile must not pay for a refresh that will almost always confirm what is known.
+    std::string key = identity::ProcRegistryListing(c->proc_root);
+    const bool have_proc = !key.empty();
+    if (!have_proc) key = "-";
+    const auto now = std::chrono::steady_clock::now();
+    const bool nvml_due = !have_proc && nvml_ok && now - c->inv_nvml_at > std::chrono::seconds(1);
+    if (c->inv_valid && key == c->inv_key && !nvml_due && !force) {
+        if (have_proc && now - c->inv_full_at > std::chrono::seconds(30) && !c->inv_refreshing) {
+            c->inv_refreshing = true;
+            c->inv_full_at = now;
+            c->inv_rescans++;
+            if (c->inv_thread.joinable()) c->inv_thread.join();     // the previous refresh ended long ago
+            c->inv_thread = std::thread([c, mine, key]() {
+                bool nv = false;
+                std::vector<cro_dev_info> fresh;
+                try { fresh = build_inventory(c, mine, true, &nv); } catch (...) { fresh.clear(); nv = false; }
+                std::lock_guard<std::mutex> lk(c->inv_mu);
+                if (c->inv_key == key && (!fresh.empty() || c->inv.empty())) c->inv = fresh;   // a newer listing wins
+                if (nv) c->inv_nvml_at = std::chrono::steady_clock::now();
+                c->inv_refreshing = false;
+            });
+        }
+        *out = c->inv;
+        return CRO_OK;
+    }
+    c->inv_rescans++;
+    c->inv_full_at = now;
+    bool nv = false;
+    c->inv = build_inventory(c, mine, have_proc, &nv);
+    if (nv) c->inv_nvml_at = now;
     c->inv_key = key;
     c->inv_valid = true;
     *out = c->inv;

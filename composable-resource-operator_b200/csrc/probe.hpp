@@ -15,6 +15,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/croprobe.h"
@@ -134,6 +135,8 @@ struct cro_ctx {
     std::string inv_key;               // uuid/minor set the cached list was built from
     std::vector<cro_dev_info> inv;
     bool inv_valid = false;
+    bool inv_refreshing = false;       // a background full re-read is under way
+    std::thread inv_thread;
     std::chrono::steady_clock::time_point inv_full_at{};   // last time the `information` files were read
     std::chrono::steady_clock::time_point inv_nvml_at{};   // last NVML re-initialisation (rate limit when /proc is absent)
     std::atomic<uint64_t> inv_rescans{0};                  // times the inventory had to be rebuilt
