@@ -973,11 +973,11 @@ cudaError_t plan_kernels(int device, KernelPlan* plan) {
     }
     // An SM changes its L1 / shared-memory split only when it is empty, so a kernel that asks for the default split
     // keeps the copy's CTA (128 KiB of shared memory) off every SM it occupies — measured: the first copy sweep waited
-    // for the whole generator.  Every kernel of the probe therefore asks for the SAME split, the largest shared memory.
-    for (const void* fn : {(const void*)hbm_expected_kernel, (const void*)hbm_fill_kernel<kFillThreads, kFillUnroll>,
-                           (const void*)hbm_read_ldg_kernel<kReadThreads, false>, (const void*)hbm_read_ldg_kernel<kReadThreads, true>,
-                           (const void*)hbm_read_tma_kernel, (const void*)hbm_copy_fused_kernel, (const void*)hbm_copy_tma_kernel,
-                           (const void*)probe_finalize_kernel})
+    // for the whole generator.  The generator and the kernels it may run beside therefore ask for the SAME split, the
+    // largest shared memory.  (Not the LDG kernels and the fill: they never run beside the generator, and the smallest L1
+    // costs the LDG sweeps 12 % — 7.30 -> 6.42 TB/s, profiles/r02_size_sweep.jsonl vs r02_fused_copy_first_look.jsonl.)
+    for (const void* fn : {(const void*)hbm_expected_kernel, (const void*)hbm_read_tma_kernel, (const void*)hbm_copy_fused_kernel,
+                           (const void*)hbm_copy_tma_kernel, (const void*)probe_finalize_kernel})
         if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
             return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hbm_expected_kernel, 256, 0)) !=
@@ -999,7 +999,12 @@ static int clamp_grid(int planned, uint64_t bytes, uint64_t tile_bytes) {
 
 cudaError_t launch_fill(const KernelPlan& p, void* base, uint64_t bytes, const Params& pr,
                         const SweepScratch& sc, SweepOut* out, cudaStream_t st) {
-    hbm_fill_kernel<kFillThreads, kFillUnroll><<<clamp_grid(p.fill.grid, bytes, kFillThreads * kFillUnroll * 16), p.fill.block, 0, st>>>(
+    // Few tiles per CTA: with a fixed grid a 16 GiB fill strides 14 tiles per CTA, the SMs drift apart and the DRAM
+    // window spreads (7.50 TB/s at 4 GiB but 7.16 at 16 GiB and 6.76 at 32 GiB); the grid therefore grows with the sweep.
+    constexpr uint64_t kTile = (uint64_t)kFillThreads * kFillUnroll * 16;
+    const uint64_t tiles = (bytes + kTile - 1) / kTile;
+    const int planned = (int)std::min<uint64_t>(std::max<uint64_t>((uint64_t)p.fill.grid, tiles / 4), 0x7FFFFFFFull);
+    hbm_fill_kernel<kFillThreads, kFillUnroll><<<clamp_grid(planned, bytes, kTile), p.fill.block, 0, st>>>(
         static_cast<uint4*>(base), bytes >> 4, pr.imm, pr.pp, sc, out);
     return cudaGetLastError();
 }

@@ -153,11 +153,12 @@ void free_scratch(SweepScratch* sc) {
 }  // namespace
 
 uint32_t resolve_read_variant(uint32_t v, uint64_t bytes) {
-    // AUTO: the TMA ring wins from ~1 GiB up (7.46 vs 7.31 TB/s at 4 GiB); for small sweeps its fixed
-    // cost (one CTA per SM, atomic tile claims) loses to plain LDG (profiles/r01_size_sweep.jsonl).
+    // AUTO: the TMA ring wins from 256 MiB up (5.69 vs 5.57 TB/s there, 7.40 vs 6.42 at 4 GiB); for small sweeps its
+    // fixed cost (one CTA per SM, atomic tile claims) loses to plain 256-bit LDG (1.21 vs 2.03 TB/s at 16 MiB,
+    // profiles/r02_size_sweep.jsonl).
     if (v == CRO_READ_AUTO) {
         v = env::get("CRO_READ_VARIANT");
-        if (v == CRO_READ_AUTO) v = bytes <= (128ull << 20) ? CRO_READ_LDG : CRO_READ_TMA;
+        if (v == CRO_READ_AUTO) v = bytes <= (128ull << 20) ? CRO_READ_LDG256 : CRO_READ_TMA;
     }
     return (v == READ_LDG || v == READ_TMA || v == READ_LDG256) ? v : (uint32_t)READ_TMA;
 }

@@ -185,7 +185,7 @@ def test_device_written_struct_equals_host_assembly(cro, coracle, ctx_small):
         "fill_ns": times[0].timer_ns, "read_best_ns": reads[0], "read_median_ns": reads[len(reads) // 2],
         "copy_best_ns": copies[0], "copy_median_ns": copies[len(copies) // 2],
         "sm_count": d.sm_count, "read_sweeps": 3, "copy_sweeps": 2, "copy_verified": 2, "fail_code": 0, "fail_index": 0,
-        "rank": 0, "world": 1, "read_variant": cro.READ_LDG, "copy_variant": cro.COPY_TMA_FUSED, "p2p_ok": 0,
+        "rank": 0, "world": 1, "read_variant": cro.READ_LDG256, "copy_variant": cro.COPY_TMA_FUSED, "p2p_ok": 0,
     }
     for k, v in host.items():
         assert getattr(r, k) == v, (k, getattr(r, k), v)
