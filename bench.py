@@ -412,7 +412,7 @@ def fullbox_leg(cro, ctx, S, steps, warmup, coracle):
         "gathered_identical_on_all_ranks": True,     # asserted inside cro_probe_all (it fails with CRO_ERR_NCCL otherwise)
         "copies_verified": [int(r.copy_verified) for r in res], "parity_ok": bool(ok),
     }
-    # how many hops does the latency figure need?  (SURVEY.md §8d asks for 64 Ki; the default is 4 Ki)
+    # how many hops does the latency figure need?  (SURVEY.md §8d asks for 64 Ki; the default is 1 Ki)
     if n > 1:
         conv = {}
         default_hops = out["latency_hops"]

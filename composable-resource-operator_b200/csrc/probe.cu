@@ -31,10 +31,11 @@ namespace {
 constexpr uint64_t kDefaultSweep = 4ull << 30;
 constexpr uint64_t kDefaultP2P = 1ull << 30;
 constexpr uint64_t kDefaultSeedBase = 0x00C0FFEE00000000ull;
-// 4096 hops: the mean hop latency is the same to 0.1 % at 1 Ki, 4 Ki, 16 Ki and 64 Ki hops (1860.4 / 1862.7 / 1861.7 /
-// 1861.6 ns on a 2-GPU box, profiles/r02_latency_vs_hops.md), and 64 Ki hops of ~1.7 us would be 3x the rest of the
-// full-box probe.  SURVEY.md §8d's 64 Ki is one cro_set_latency_hops / latency_hops away; bench.py runs it every time.
-constexpr uint32_t kDefaultHops = 4096;
+// 1024 hops: the mean hop latency — and every pair's own value — is the same to 0.1 % at 1 Ki, 4 Ki, 16 Ki and 64 Ki hops
+// (8 GPUs: 1779.4 / 1780.0 / 1780.4 / 1780.6 ns; 2 GPUs: 1860.4 / 1862.7 / 1861.7 / 1861.6; profiles/r02_latency_vs_hops.md),
+// while 64 Ki hops of ~1.8 us would be 122 ms, three times the rest of the full-box probe.  SURVEY.md §8d's 64 Ki is one
+// cro_set_latency_hops / latency_hops away, and bench.py runs all four lengths every time.
+constexpr uint32_t kDefaultHops = 1024;
 
 #define CU_TRY(ctx, expr)                                                              \
     do {                                                                               \

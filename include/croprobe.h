@@ -85,7 +85,7 @@ typedef struct cro_opts {
     uint64_t seed_base;            /* default 0x00C0FFEE00000000; seed = base | minor       */
     uint32_t read_sweeps;          /* default 5                                             */
     uint32_t copy_sweeps;          /* default 5                                             */
-    uint32_t latency_hops;         /* pointer-chase hops per directed pair; default 4096    */
+    uint32_t latency_hops;         /* pointer-chase hops per directed pair; default 1024    */
     uint32_t read_variant;         /* CRO_READ_*                                            */
     uint32_t copy_variant;         /* CRO_COPY_*                                            */
     int32_t  deadline_ms;          /* per-call deadline, 0 = none (Go ctx cannot cross cgo) */
