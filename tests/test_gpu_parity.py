@@ -646,3 +646,27 @@ def cro_last_error(cro, c):
     buf = ctypes.create_string_buffer(1024)
     cro.lib.cro_last_error(c.handle, buf, 1024)
     return buf.value.decode()
+
+
+def test_probe_all_over_an_odd_number_of_devices(cro, coracle):
+    """K_3: the 1-factorisation has a bye in every round (one GPU sits a round out and publishes no round events);
+    every directed pair must still be read, pushed, chased and verified exactly once."""
+    S, P, HOPS = 64 << 20, 16 << 20, 512
+    with cro.ProbeContext(sweep_bytes=1 << 20, flags=cro.F_LAZY_ALLOC) as c0:
+        total = c0.device_count()
+    if total < 3:
+        pytest.skip("needs three GPUs")
+    with cro.ProbeContext(sweep_bytes=S, p2p_bytes=P, devices=[0, 1, 2], read_sweeps=1, copy_sweeps=1, latency_hops=HOPS) as c:
+        devs = c.own_devices()
+        for rep in range(2):
+            res = c.probe_all()
+            assert len(res) == 3 and c.fullbox_times().rounds == 3 and c.fullbox_times().host_syncs == 3
+            for i, r in enumerate(res):
+                assert r.status == 0 and r.world == 3 and r.p2p_ok == (7 & ~(1 << i)), (i, r.status, r.fail_code, r.fail_index, r.p2p_ok)
+                for j in range(3):
+                    if j == i:
+                        continue
+                    d = c.p2p_detail(i, j)
+                    assert (d.read_xor, d.read_sum, d.read_wsum) == coracle.checksum(res[j].seed, 0, P // 8)
+                    assert (d.landed_xor, d.landed_sum, d.landed_wsum) == coracle.checksum(r.seed, 0, P // 8)
+                    assert d.chase_end == coracle.chase_end(max(devs[i].device_minor, 0), max(devs[j].device_minor, 0), HOPS)
