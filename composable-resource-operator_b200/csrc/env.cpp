@@ -38,6 +38,7 @@ const Knob kKnobs[] = {
     {"CRO_USE_GRAPH", 0, 1, 1, 0, "replay the probe as one CUDA graph"},
     {"CRO_EXPECT_OVERLAP", 0, 1, 1, 0, "closed-form generator on a side stream under the copy sweeps"},
     {"CRO_EXPECT_CTAS", 1, 8, 1, 0, "CTAs per SM of the closed-form generator (it must leave room for the copy's CTA)"},
+    {"CRO_CARVEOUT_FILL", 0, 1, 1, 0, "the fill kernel asks for the largest shared memory too (it runs beside a generator in cro_probe_all)"},
     {"CRO_P2P_UNIDIR", 0, 1, 0, 0, "measurement only: one direction per NVLink pair"},
     {"CRO_P2P_READ_VARIANT", 1, 3, 2, 0, "kernel of the NVLink read leg"},
     {"CRO_P2P_WRITE_VARIANT", 1, 3, 3, 0, "kernel of the NVLink push leg"},

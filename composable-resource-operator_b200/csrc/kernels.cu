@@ -974,11 +974,17 @@ cudaError_t plan_kernels(int device, KernelPlan* plan) {
     // An SM changes its L1 / shared-memory split only when it is empty, so a kernel that asks for the default split
     // keeps the copy's CTA (128 KiB of shared memory) off every SM it occupies — measured: the first copy sweep waited
     // for the whole generator.  The generator and the kernels it may run beside therefore ask for the SAME split, the
-    // largest shared memory.  (Not the LDG kernels and the fill: they never run beside the generator, and the smallest L1
-    // costs the LDG sweeps 12 % — 7.30 -> 6.42 TB/s, profiles/r02_size_sweep.jsonl vs r02_fused_copy_first_look.jsonl.)
+    // largest shared memory.  That includes the fill: in cro_probe_all it runs beside the generator of the NVLink prefix
+    // (measured: the full-box HBM phase is 9.96 ms with it, 10.56 ms without, tools/r02_ab.py).  Not the LDG kernels:
+    // they never run beside a generator, and the smallest L1 costs them 12 % (7.30 -> 6.42 TB/s at 4 GiB,
+    // profiles/r02_fused_copy_first_look.jsonl vs r02_size_sweep.jsonl).
     for (const void* fn : {(const void*)hbm_expected_kernel, (const void*)hbm_read_tma_kernel, (const void*)hbm_copy_fused_kernel,
                            (const void*)hbm_copy_tma_kernel, (const void*)probe_finalize_kernel})
         if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+            return e;
+    if (env::get("CRO_CARVEOUT_FILL"))     // the fill: it does run beside a generator in cro_probe_all (the p2p prefix's)
+        if ((e = cudaFuncSetAttribute((const void*)hbm_fill_kernel<kFillThreads, kFillUnroll>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
             return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hbm_expected_kernel, 256, 0)) !=
         cudaSuccess)
