@@ -163,7 +163,7 @@ EXPORTS = [
     "cro_fabric_check_resource", "cro_fabric_get_resources", "cro_fabric_list_devices",
     "cro_local_node_op", "cro_scan_cmdline_for", "cro_token_from_reply",
     "cro_selftest_exception_barrier", "cro_probe_sweep_times", "cro_p2p_detail_get", "cro_fullbox_times",
-    "cro_chase_end", "cro_validate_env", "cro_node_inventory", "cro_probe_uuid", "cro_set_latency_hops", "cro_local_exec", "cro_metrics_text",
+    "cro_chase_end", "cro_validate_env", "cro_node_inventory", "cro_probe_uuid", "cro_set_latency_hops", "cro_local_exec", "cro_metrics_text", "cro_describe_wire_type",
 ]
 
 
@@ -240,6 +240,7 @@ def _load() -> ctypes.CDLL:
         "cro_selftest_exception_barrier": (i32, [i32]),
         "cro_local_node_op": (i32, [vp, c] + out),
         "cro_local_exec": (i32, [c] + out),
+        "cro_describe_wire_type": (i32, [c] + out),
         "cro_scan_cmdline_for": (i32, [c, c, ctypes.POINTER(i32)]),
         "cro_sim_reconcile_resource": (i32, [vp, c, c, sz]),
         "cro_sim_sync_upstream": (i32, [vp, c, ctypes.c_longlong, c, sz]),
@@ -627,6 +628,11 @@ def local_node_op(ctx: Optional["ProbeContext"], request: Dict) -> Dict:
     """One node-side operation of internal/utils/gpus.go run locally (scans native, read-only commands spawned,
     mutating ones only with allow_mutation).  See cro_local_node_op in include/croprobe.h."""
     return json.loads(_text(lib.cro_local_node_op, ctx.handle if ctx is not None else None, _b(json.dumps(request))))
+
+
+def describe_wire_type(name: str) -> Dict:
+    """The reply struct a fabric decoder walks, as the library describes it (declaration order)."""
+    return json.loads(_text(lib.cro_describe_wire_type, _b(name)))
 
 
 def local_exec(argv: List[str], allow_mutation: bool = False, exec_deadline_ms: int = 0) -> Dict:

@@ -19,6 +19,7 @@
 #include "gpus.hpp"
 #include "env.hpp"
 #include "inventory.hpp"
+#include "gotypes.hpp"
 #include <memory>
 #include <new>
 #include <stdexcept>
@@ -276,6 +277,38 @@ int cro_set_latency_hops(cro_ctx* ctx, uint32_t hops) try {
 int cro_metrics_text(cro_ctx* ctx, char* buf, size_t cap, size_t* len) try {
     if (!ctx) return CRO_ERR_INVALID_ARG;
     return copy_out(ctx_metrics_text(ctx), buf, cap, len);
+} CRO_API_CATCH
+
+static void describe_type(const gojson::GoType& t, gojson::Writer* w) {
+    w->begin_object();
+    w->field("type", t.name);
+    if (t.kind == gojson::GoType::Struct) {
+        w->field("struct", t.structName);
+        w->key("fields").begin_array();
+        for (const auto& f : t.fields) {
+            w->begin_object();
+            w->field("json", f.first);
+            w->key("of");
+            describe_type(*f.second, w);
+            w->end_object();
+        }
+        w->end_array();
+    } else if (t.kind == gojson::GoType::Slice && t.elem) {
+        w->key("elem");
+        describe_type(*t.elem, w);
+    }
+    w->end_object();
+}
+
+int cro_describe_wire_type(const char* name, char* buf, size_t cap, size_t* len) try {
+    const std::string n = S(name);
+    const gojson::GoType* t = n == "FMScaleUpResponse" ? &gotypes::FMScaleUpResponse()
+                              : n == "FMGetMachineResponse" ? &gotypes::FMGetMachineResponse()
+                              : n == "CMMachineData" ? &gotypes::CMMachineData() : nullptr;
+    if (!t) return CRO_ERR_INVALID_ARG;
+    gojson::Writer w;
+    describe_type(*t, &w);
+    return copy_out(w.take(), buf, cap, len);
 } CRO_API_CATCH
 
 int cro_chase_end(int minor_src, int minor_dst, uint32_t hops, uint32_t* end) try {

@@ -7,6 +7,7 @@
 #include <fcntl.h>
 #include <poll.h>
 #include <signal.h>
+#include <spawn.h>
 #include <sys/stat.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -15,6 +16,8 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+
+extern char** environ;
 
 namespace cro {
 namespace inventory {
@@ -117,20 +120,29 @@ int RunHelper(const std::string& helper_path, const std::string& uuid, uint64_t 
         return CRO_ERR_EXEC;
     }
     const std::string mib = std::to_string(std::max<uint64_t>(1, sweep_bytes >> 20));
-    const pid_t pid = fork();
-    if (pid < 0) {
+    // posix_spawn, not fork: the host process is multi-threaded (CUDA's own threads at least), and the child's
+    // environment — CUDA_VISIBLE_DEVICES=<uuid>, so that the helper's cuInit sees this one GPU and nothing else — is
+    // built here, before the spawn, instead of with setenv() in a forked child (not async-signal-safe).
+    std::vector<std::string> env_store;
+    for (char** e = environ; e && *e; ++e)
+        if (strncmp(*e, "CUDA_VISIBLE_DEVICES=", 21) != 0) env_store.push_back(*e);
+    env_store.push_back("CUDA_VISIBLE_DEVICES=" + uuid);
+    std::vector<char*> envp;
+    for (std::string& e : env_store) envp.push_back(const_cast<char*>(e.c_str()));
+    envp.push_back(nullptr);
+    const char* argv[] = {helper.c_str(), "probe-raw", uuid.c_str(), mib.c_str(), nullptr};
+    posix_spawn_file_actions_t fa;
+    posix_spawn_file_actions_init(&fa);
+    posix_spawn_file_actions_adddup2(&fa, fds[1], 1);
+    posix_spawn_file_actions_addclose(&fa, fds[0]);
+    posix_spawn_file_actions_addclose(&fa, fds[1]);
+    pid_t pid = 0;
+    const int src = posix_spawn(&pid, helper.c_str(), &fa, nullptr, const_cast<char* const*>(argv), envp.data());
+    posix_spawn_file_actions_destroy(&fa);
+    if (src != 0) {
         close(fds[0]); close(fds[1]);
-        if (err) *err = std::string("fork: ") + strerror(errno);
+        if (err) *err = std::string("posix_spawn of the probe helper: ") + strerror(src);
         return CRO_ERR_EXEC;
-    }
-    if (pid == 0) {
-        // child: only async-signal-safe calls between fork and exec
-        dup2(fds[1], 1);
-        close(fds[0]);
-        close(fds[1]);
-        setenv("CUDA_VISIBLE_DEVICES", uuid.c_str(), 1);     // the helper's cuInit sees this one GPU and nothing else
-        execl(helper.c_str(), helper.c_str(), "probe-raw", uuid.c_str(), mib.c_str(), (char*)nullptr);
-        _exit(127);
     }
     close(fds[1]);
     unsigned char buf[sizeof(cro_probe_result)];

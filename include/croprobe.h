@@ -371,6 +371,10 @@ typedef struct cro_fullbox_time {
     uint32_t host_syncs;           /* stream synchronisations the call made (one per device)            */
 } cro_fullbox_time;
 int  cro_fullbox_times(cro_ctx *ctx, cro_fullbox_time *out);
+/* The reply structs the fabric decoders walk ("FMScaleUpResponse", "FMGetMachineResponse", "CMMachineData"), as
+ * JSON: {"type","struct","fields":[{"json","of":{...}}]} in declaration order — so that a test can hold them against
+ * the declarations in the reference's Go source (the .go files of internal/cdi/fti/fm/api, and internal/cdi/fti/cm/api/machine.go). */
+int  cro_describe_wire_type(const char *name, char *buf, size_t cap, size_t *len);
 /* Prometheus text exposition (counters and per-GPU gauges of the last probe) for the operator's metrics registry
  * (cmd/main.go:66,119-125 wires controller-runtime's registry; a Go collector forwards these lines):
  * cro_probe_total, cro_probe_failures_total, cro_fullbox_probe_total, cro_helper_probe_total,
