@@ -1017,6 +1017,9 @@ cudaError_t launch_fill(const KernelPlan& p, void* base, uint64_t bytes, const P
 
 cudaError_t launch_read(const KernelPlan& p, unsigned variant, const void* base, uint64_t bytes,
                         const Params& pr, const SweepScratch& sc, SweepOut* out, cudaStream_t st) {
+    // 256-bit loads need a 32-byte aligned base; half B of a region whose S is an odd multiple of 16 bytes is only
+    // 16-byte aligned (found by the ragged-size parity tests): such a sweep takes the 128-bit flavour.
+    if (variant == READ_LDG256 && (reinterpret_cast<uintptr_t>(base) & 31u)) variant = READ_LDG;
     if (variant == READ_TMA) {
         hbm_read_tma_kernel<<<clamp_grid(p.read_tma.grid, bytes, p.read_tile), p.read_tma.block, p.read_tma.smem, st>>>(
             static_cast<const unsigned char*>(base), bytes, p.read_tile, p.read_stages, p.read_chunk,
