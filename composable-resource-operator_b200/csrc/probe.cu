@@ -1513,16 +1513,21 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
     }
     c->fullbox.enqueue_ns = now_ns() - t_call;
 
-    // While the GPUs work: a fresh ECC read per device (NVML, ~3 ms each — on the critical path it would cost the box
-    // more than the NVLink rounds of one pair).  The structs being gathered right now carry the count staged before
-    // this call; a count that moved is staged for the next probe, and a FAILING probe re-reads it at once anyway.
+    // While the GPUs work: a fresh ECC read per device (NVML, 3–5 ms each — on the critical path it would cost the box
+    // more than the NVLink rounds of one pair; and eight of them can outlast the 36 ms the GPUs need, so a device is
+    // asked at most once a second).  The structs being gathered right now carry the count staged before this call; a
+    // count that moved is staged for the next probe, and a FAILING probe re-reads it at once anyway.
     std::vector<int> restage;
-    if (n > 1)
+    if (n > 1) {
+        const auto t_now = std::chrono::steady_clock::now();
         for (int i = 0; i < n; ++i) {
             Device* d = c->devs[(size_t)i].get();
+            if (t_now - d->ecc_at < std::chrono::seconds(1)) continue;
+            d->ecc_at = t_now;
             refresh_ecc(c, d);
             if (d->tmpl.ecc_errors != d->ecc_uncorrected) restage.push_back(i);
         }
+    }
 
     // ---- the only host waits: one per device ------------------------------------------------------------------
     {

@@ -90,6 +90,7 @@ struct Device {
     std::deque<Collected> done;
     unsigned sm_clock_mhz = 0, mem_clock_mhz = 0;
     uint32_t ecc_uncorrected = 0;      // NVML count cached at init / full-box probe / failed probe
+    std::chrono::steady_clock::time_point ecc_at{};   // last NVML read by cro_probe_all
     cro_probe_result last{};           // the most recent collected result (cro_metrics_text)
     bool have_last = false;
 
