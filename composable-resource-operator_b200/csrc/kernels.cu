@@ -876,7 +876,7 @@ p2p_finalize_kernel(const P2PFinalizeArgs a) {
         if (a.have_push) {
             const SweepOut& rr = a.slots[kSlotP2P0 + 3 * j + 2];      // my re-read of what j pushed into me
             const SweepOut mine = a.slots[kSlotPrefix];
-            if (ps.stamp != a.stamp || !same_fold(ps, mine)) { fail(CRO_FAIL_P2P_PUSH, j); ok = false; }
+            if (a.push_folded && (ps.stamp != a.stamp || !same_fold(ps, mine))) { fail(CRO_FAIL_P2P_PUSH, j); ok = false; }
             if (rr.stamp != a.stamp || !same_fold(rr, want)) { fail(CRO_FAIL_P2P_PUSH, j); ok = false; }
         }
         if (a.hops) {

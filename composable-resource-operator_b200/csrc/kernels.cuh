@@ -141,6 +141,7 @@ struct P2PFinalizeArgs {
     unsigned self;
     unsigned hops;
     unsigned have_push;
+    unsigned push_folded;                         // the push kernel carries a checksum of its source (COPY_TMA_FUSED)
     unsigned long long p2p_bytes;
     unsigned long long stamp;                     // nonce every p2p slot this device wrote must carry
     unsigned long long peer_stamp[CRO_MAX_DEVICES];   // ... and the nonce of peer j's closed-form slot

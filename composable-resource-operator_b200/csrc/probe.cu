@@ -1462,6 +1462,7 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
             pa.self = (unsigned)i;
             pa.hops = o.latency_hops;
             pa.have_push = (push && !unidir) ? 1u : 0u;
+            pa.push_folded = wvp == COPY_TMA_FUSED ? 1u : 0u;   // the plain copies land bytes but fold nothing: only the receiver checks
             pa.p2p_bytes = o.p2p_bytes;
             pa.stamp = d->nonce_cur;
             for (int j = 0; j < n; ++j) {

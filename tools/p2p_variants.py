@@ -15,8 +15,9 @@ cro = importlib.import_module("composable-resource-operator_b200")
 
 for variant, extra in ((3, {}), (1, {}), (2, {}), (2, {"CRO_TMA_READ_STAGES": 6, "CRO_TMA_READ_TILE": 32768}),
                        (2, {"CRO_TMA_READ_STAGES": 3, "CRO_TMA_READ_TILE": 65536}), (1, {"CRO_READ_WAVES": 2}),
-                       (2, {"CRO_P2P_WRITE_VARIANT": 1}), (2, {"CRO_TMA_COPY_TILE": 65536, "CRO_TMA_COPY_STAGES": 3}),
-                       (2, {"CRO_TMA_COPY_TILE": 16384, "CRO_TMA_COPY_STAGES": 8}),
+                       (2, {"CRO_FUSED_TILE": 65536, "CRO_FUSED_STAGES": 3}), (2, {"CRO_FUSED_TILE": 16384, "CRO_FUSED_STAGES": 8}),
+                       # (the plain push variants — CRO_P2P_WRITE_VARIANT=1/2 — still land and get verified by the receiver, but
+                       #  carry no timing slot of their own since the struct's times come from the kernels' own windows)
                        (2, {"CRO_P2P_UNIDIR": 1}), (1, {"CRO_P2P_UNIDIR": 1})):
     os.environ["CRO_P2P_READ_VARIANT"] = str(variant)
     for k, v in extra.items():
