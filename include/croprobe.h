@@ -51,7 +51,8 @@ extern "C" {
 #define CRO_F_SKIP_P2P        0x0002u  /* cro_probe_all: no NVLink rounds          */
 #define CRO_F_SKIP_NCCL       0x0004u  /* cro_probe_all: host gather, no NCCL      */
 #define CRO_F_NO_NVML         0x0008u  /* identity from /proc + CUDA runtime only  */
-#define CRO_F_VERIFY_COPY     0x0010u  /* re-checksum the copy destination         */
+#define CRO_F_VERIFY_COPY     0x0010u  /* accepted, no effect: since ABI 2 every copy destination is re-read and
+                                          compared inside the probe (copy_verified)                            */
 #define CRO_F_LAZY_ALLOC      0x0020u  /* allocate sweep buffers at first probe    */
 #define CRO_F_DEGRADE_ON_OOM  0x0040u  /* busy device: halve S (>= 64 MiB) instead of failing;
                                           the result's sweep_bytes says what was swept  */
