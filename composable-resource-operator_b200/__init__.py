@@ -635,9 +635,14 @@ def describe_wire_type(name: str) -> Dict:
     return json.loads(_text(lib.cro_describe_wire_type, _b(name)))
 
 
-def local_exec(argv: List[str], allow_mutation: bool = False, exec_deadline_ms: int = 0) -> Dict:
-    """One command through the node-local executor (read-only allow-list while allow_mutation is false; deadline)."""
-    req = {"argv": argv, "allow_mutation": allow_mutation}
+def local_exec(argv: List[str], allow_mutation: bool = False, exec_deadline_ms: int = 0, native_nvml: bool = True,
+               nvml_lib: str = "") -> Dict:
+    """One command through the node-local executor (read-only allow-list while allow_mutation is false; deadline).
+    The detach side's nvidia-smi invocations (compute apps, drain -q/-m/-r, -pm) are answered through NVML in this
+    process when it is there ("how": "native"); nvml_lib names another libnvidia-ml (tests load a stand-in)."""
+    req = {"argv": argv, "allow_mutation": allow_mutation, "native_nvml": native_nvml}
+    if nvml_lib:
+        req["nvml_lib"] = nvml_lib
     if exec_deadline_ms:
         req["exec_deadline_ms"] = exec_deadline_ms
     return json.loads(_text(lib.cro_local_exec, _b(json.dumps(req))))

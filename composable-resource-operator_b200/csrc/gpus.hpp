@@ -115,7 +115,8 @@ protected:
 
 // ---- the seams answered on the node itself (gpus_local.cpp) --------------------------------------------
 // Scans are native /proc walks, `nvidia-smi --query-gpu=...` is answered from already-enumerated devices
-// when they are handed in, other commands are spawned with the chroot prefix dropped.  Commands that change
+// when they are handed in, the compute-apps / drain / persistence-mode invocations go through this process's
+// NVML session (nvml_ops.hpp) when there is one, other commands are spawned with the chroot prefix dropped.  Commands that change
 // the node (persistence mode, drain -m / -r, rm, modprobe, the sysfs remove) are only run with
 // allow_mutation; otherwise they are logged as skipped and succeed, which makes DrainGPU a dry run that
 // still performs every read-only check for real.
@@ -127,6 +128,8 @@ public:
         int exec_deadline_ms = 60000;          // per spawned command; expiry = SIGKILL + "context deadline exceeded"
         const cro_dev_info* devs = nullptr;    // devices a probe context enumerated (optional)
         int n_devs = -1;
+        bool native_nvml = true;               // answer the detach side's nvidia-smi invocations through NVML (nvml_ops.hpp)
+        std::string nvml_lib;                  // "" = libnvidia-ml.so.1
     };
     struct LogEntry { int kind = 0; std::vector<std::string> argv; std::string how; bool failed = false; };
     explicit LocalExec(const Options& o);

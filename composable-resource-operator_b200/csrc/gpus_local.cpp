@@ -14,6 +14,7 @@
 #include "detach.hpp"
 #include "gpus.hpp"
 #include "identity.hpp"
+#include "nvml_ops.hpp"
 
 extern char** environ;
 
@@ -41,6 +42,33 @@ bool read_only(const std::vector<std::string>& argv) {
         if (argv.size() == 5 && argv[1] == "drain" && argv[2] == "-p" && argv[4] == "-q") return true;
     }
     return false;
+}
+
+// nvidia-smi's answer shaped as an exec result: stdout text, and a non-zero exit as kubectl-exec words it.
+bool answer_with_nvml(const std::vector<std::string>& argv, const std::string& lib, ExecResult* r) {
+    if (argv.empty()) return false;
+    const size_t slash = argv[0].rfind('/');
+    if ((slash == std::string::npos ? argv[0] : argv[0].substr(slash + 1)) != "nvidia-smi") return false;
+    nvml::Reply rep;
+    if (argv.size() == 3 && argv[1] == "--query-compute-apps=gpu_uuid,process_name" && argv[2] == "--format=csv,noheader,nounits")
+        rep = nvml::ComputeApps(lib);
+    else if (argv.size() == 5 && argv[1] == "drain" && argv[2] == "-p" && argv[4] == "-q")
+        rep = nvml::DrainQuery(lib, argv[3]);
+    else if (argv.size() == 5 && argv[1] == "drain" && argv[2] == "-p" && argv[4] == "-r")
+        rep = nvml::DrainRemove(lib, argv[3]);
+    else if (argv.size() == 6 && argv[1] == "drain" && argv[2] == "-p" && argv[4] == "-m" && (argv[5] == "0" || argv[5] == "1"))
+        rep = nvml::DrainModify(lib, argv[3], argv[5] == "1");
+    else if (argv.size() == 5 && argv[1] == "-i" && argv[3] == "-pm" && (argv[4] == "0" || argv[4] == "1"))
+        rep = nvml::SetPersistence(lib, argv[2], argv[4] == "1");
+    else
+        return false;
+    if (!rep.available) return false;
+    r->std_out = rep.std_out;
+    if (rep.exit_code != 0) {
+        r->failed = true;
+        r->exec_err = "command terminated with exit code " + std::to_string(rep.exit_code);
+    }
+    return true;
 }
 
 long long now_ms() {
@@ -169,6 +197,12 @@ ExecResult LocalExec::Run(const Pod&, const std::string&, const ExecRequest& req
             }
             if (!read_only(argv) && !o_.allow_mutation) {
                 le.how = "skipped (dry run)";
+                break;
+            }
+            // the detach side's nvidia-smi invocations through this process's NVML session (nvml_ops.hpp); without
+            // NVML here (or with native_nvml off) the command is spawned like any other
+            if (o_.native_nvml && answer_with_nvml(argv, o_.nvml_lib, &r)) {
+                le.how = "native";
                 break;
             }
             le.how = "spawned";

@@ -773,6 +773,8 @@ int cro_local_exec(const char* request_json, char* buf, size_t cap, size_t* len)
     gpus::LocalExec::Options o;
     o.allow_mutation = in->get_bool("allow_mutation");
     if (in->get("exec_deadline_ms")) o.exec_deadline_ms = (int)in->get_int("exec_deadline_ms");
+    if (in->get("native_nvml")) o.native_nvml = in->get_bool("native_nvml");
+    o.nvml_lib = in->get_string("nvml_lib");
     gpus::LocalExec exec(o);
     gpus::ExecRequest req;
     req.kind = gpus::ExecRequest::Command;
@@ -804,6 +806,8 @@ int cro_local_node_op(cro_ctx* ctx, const char* request_json, char* buf, size_t 
     o.allow_mutation = in->get_bool("allow_mutation");
     if (in->get("exec_deadline_ms")) o.exec_deadline_ms = (int)in->get_int("exec_deadline_ms");
     if (ctx) { o.devs = devs.data(); o.n_devs = (int)devs.size(); }
+    if (in->get("native_nvml")) o.native_nvml = in->get_bool("native_nvml");
+    o.nvml_lib = in->get_string("nvml_lib");
     gpus::LocalExec exec(o);
     const std::string node = in->get_string("node", "local");
     gpus::LocalKube kube(node, in->get_bool("driver_container", true));

@@ -606,6 +606,12 @@ int  cro_local_node_op(cro_ctx *ctx, const char *request_json, char *buf, size_t
  * the argv shapes known to READ are executed (nvidia-smi --query-gpu / --query-compute-apps, `nvidia-smi drain -p <bus>
  * -q`, lsmod, each optionally behind `/bin/chroot /host-root`); everything else is reported "skipped (dry run)".  A
  * child that outlives exec_deadline_ms (default 60 s) is killed and reaped: "context deadline exceeded".
+ * The detach side's nvidia-smi invocations — --query-compute-apps=gpu_uuid,process_name (gpus.go:125,134), drain -p <bus>
+ * -q (:970), and with allow_mutation: -i <uuid> -pm 0|1 (:267), drain -p <bus> -m 0|1 (:269), drain -p <bus> -r (:311) —
+ * are answered through NVML inside this process when libnvidia-ml is there ("how": "native": no child process, no
+ * second NVML init), with nvidia-smi's stdout and exit code (the two queries are pinned byte for byte against the real
+ * nvidia-smi on a B200 box; the three mutating texts are not — the reference never parses them).  "native_nvml": false
+ * spawns instead; "nvml_lib": "<path>" names another libnvidia-ml (tests).  Both keys work in cro_local_node_op too.
  * Reply: {"how": "spawned"|"skipped (dry run)"|"native", "failed": bool, "exec_err", "stdout", "stderr"}. */
 int  cro_local_exec(const char *request_json, char *buf, size_t cap, size_t *len);
 /* The cmdline scan of checkResetGPUCommandStillRunning (gpus.go:1182-1226), natively:

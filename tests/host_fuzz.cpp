@@ -16,6 +16,7 @@
 #include "gpus.hpp"
 #include "identity.hpp"
 #include "nodes.hpp"
+#include "nvml_ops.hpp"
 #include "provider.hpp"
 #include "reconcile.hpp"
 
@@ -35,6 +36,7 @@ static const char* kCorpus[] = {
     "No devices were found\n",
     "GPU-1, python3\nGPU-2, pytorch\n",
     "",
+    "0000:1F:00.0", "00000000:40:00.0", "40:00",
     "\n\n , ,\n",
     // awk over /proc/driver/nvidia/gpus/*/information
     "Model: NVIDIA B200\nGPU UUID: GPU-7cc45b7b\nDevice Minor: 3\nBus Location: 0000:1f:00.0\n",
@@ -128,6 +130,8 @@ static void one(const std::string& in, const std::string& err_text) {
         std::string out;
         for (int kind = 0; kind < 6; ++kind) sink += (size_t)identity::Normalize(kind, in, &out) + out.size();
         sink += identity::TrimSpace(in).size() + identity::Split(in, q.empty() ? "," : ", ").size();
+        unsigned domain = 0, bus = 0, device = 0;          // the `-p <bus>` argument of the drain commands
+        if (nvml::ParseBusId(in, &domain, &bus, &device)) sink += domain + bus + device;
     }
     {
         const std::string target = "GPU-1";

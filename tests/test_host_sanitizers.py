@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "composable-resource-operator_b200", "csrc")
-HOST_SOURCES = ["gojson.cpp", "identity.cpp", "reconcile.cpp", "detach.cpp", "fabric.cpp", "provider.cpp", "nodes.cpp", "gpus.cpp", "gpus_local.cpp", "gotypes.cpp"]
+HOST_SOURCES = ["gojson.cpp", "identity.cpp", "reconcile.cpp", "detach.cpp", "fabric.cpp", "provider.cpp", "nodes.cpp", "gpus.cpp", "gpus_local.cpp", "gotypes.cpp", "nvml_ops.cpp"]
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="g++ unavailable")

@@ -67,7 +67,8 @@ def test_local_checks_on_the_box(cro):
         out = cro.local_node_op(ctx, dict(base, op="check_gpu_visible", device_resource_type="DEVICE_PLUGIN", device_id="GPU-nope"))
         assert out["visible"] is False
         out = cro.local_node_op(ctx, dict(base, op="check_no_gpu_loads", device_resource_type="DEVICE_PLUGIN"))
-        assert out["exec_log"][0]["how"] == "spawned" and out["exec_log"][0]["argv"][1] == "--query-compute-apps=gpu_uuid,process_name"
+        # the compute-apps query goes through this process's NVML session, no child process (csrc/nvml_ops.cpp)
+        assert out["exec_log"][0]["how"] == "native" and out["exec_log"][0]["argv"][1] == "--query-compute-apps=gpu_uuid,process_name"
         assert out["error"] == "" or out["error"].startswith("found gpu loads on node 'worker-0': '[GPUUUID: '")
         # dry run of the drain: enumeration (with device_minor, which driver 580's nvidia-smi refuses to print) is native,
         # persistence mode is skipped, and the open-file scan stops the drain because WE hold the device node
@@ -94,7 +95,7 @@ def test_dry_run_gate_is_an_allow_list(cro):
     for argv in (["/usr/bin/nvidia-smi", "--query-gpu=gpu_uuid", "--format=csv,noheader,nounits"],
                  ["/bin/chroot", "/host-root", "/usr/bin/nvidia-smi", "--query-compute-apps=gpu_uuid,process_name", "--format=csv,noheader,nounits"],
                  ["/bin/chroot", "/host-root", "/usr/bin/nvidia-smi", "drain", "-p", "0000:1F:00.0", "-q"], ["/usr/sbin/lsmod"]):
-        out = cro.local_exec(argv)
+        out = cro.local_exec(argv, native_nvml=False)
         assert out["how"] == "spawned", (argv, out)      # (fails to exec here: no such binary — but it WAS attempted)
     # with mutation allowed the same unknown command is executed
     out = cro.local_exec(["/bin/sh", "-c", "echo hello; echo oops >&2; exit 3"], allow_mutation=True)
