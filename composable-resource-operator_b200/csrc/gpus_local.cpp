@@ -52,6 +52,8 @@ bool answer_with_nvml(const std::vector<std::string>& argv, const std::string& l
     nvml::Reply rep;
     if (argv.size() == 3 && argv[1] == "--query-compute-apps=gpu_uuid,process_name" && argv[2] == "--format=csv,noheader,nounits")
         rep = nvml::ComputeApps(lib);
+    else if (argv.size() == 3 && argv[1].compare(0, 12, "--query-gpu=") == 0 && argv[2] == "--format=csv,noheader,nounits")
+        rep = nvml::QueryGpu(lib, argv[1].substr(12));
     else if (argv.size() == 5 && argv[1] == "drain" && argv[2] == "-p" && argv[4] == "-q")
         rep = nvml::DrainQuery(lib, argv[3]);
     else if (argv.size() == 5 && argv[1] == "drain" && argv[2] == "-p" && argv[4] == "-r")

@@ -1,6 +1,8 @@
 // nvml_ops.cpp — see nvml_ops.hpp.
 #include "nvml_ops.hpp"
 
+#include "identity.hpp"
+
 #include <dlfcn.h>
 
 #include <cstdio>
@@ -44,6 +46,8 @@ struct Session {
     int (*modifyDrain)(PciInfo*, int) = nullptr;
     int (*removeGpu)(PciInfo*, int, int) = nullptr;
     int (*setPersistence)(nvmlDevice_t, int) = nullptr;
+    int (*minor)(nvmlDevice_t, unsigned*) = nullptr;          // optional
+    int (*name)(nvmlDevice_t, char*, unsigned) = nullptr;     // optional
     const char* (*errorString)(int) = nullptr;
 };
 
@@ -70,6 +74,8 @@ Session* session(const std::string& lib) {
         s->modifyDrain = (int (*)(PciInfo*, int))sym("nvmlDeviceModifyDrainState");
         s->removeGpu = (int (*)(PciInfo*, int, int))sym("nvmlDeviceRemoveGpu_v2");
         s->setPersistence = (int (*)(nvmlDevice_t, int))sym("nvmlDeviceSetPersistenceMode");
+        s->minor = (int (*)(nvmlDevice_t, unsigned*))sym("nvmlDeviceGetMinorNumber");
+        s->name = (int (*)(nvmlDevice_t, char*, unsigned))sym("nvmlDeviceGetName");
         s->errorString = (const char* (*)(int))sym("nvmlErrorString");
         s->ok = init && s->count && s->byIndex && s->byUuid && s->uuid && s->pci && s->procs && s->procName && s->queryDrain &&
                 s->modifyDrain && s->removeGpu && s->setPersistence && init() == kSuccess;
@@ -156,6 +162,40 @@ bool ParseBusId(const std::string& text, unsigned* domain, unsigned* bus, unsign
     if (!hex_field(parts[parts.size() - 2], bus) || *bus > 0xff) return false;
     if (!hex_field(dev, device) || *device > 0x1f) return false;
     return true;
+}
+
+Reply QueryGpu(const std::string& lib, const std::string& query) {
+    Session* s = session(lib);
+    if (!s->ok) return unavailable();
+    Reply r;
+    unsigned n = 0;
+    if (s->count(&n) != kSuccess) return unavailable();
+    std::vector<cro_dev_info> devs;
+    for (unsigned i = 0; i < n; ++i) {
+        nvmlDevice_t dev = nullptr;
+        if (s->byIndex(i, &dev) != kSuccess) continue;           // e.g. a GPU that fell off the bus
+        cro_dev_info d;
+        memset(&d, 0, sizeof d);
+        d.cuda_ordinal = -1;
+        d.device_minor = -1;
+        d.dev_index = -1;
+        d.identity_source = 1;
+        char uuid[96] = {0};
+        if (s->uuid(dev, uuid, sizeof uuid) != kSuccess) continue;
+        snprintf(d.gpu_uuid, sizeof d.gpu_uuid, "%.47s", uuid);
+        PciInfo p;
+        memset(&p, 0, sizeof p);
+        if (s->pci(dev, &p) == kSuccess) snprintf(d.pci_bus_id, sizeof d.pci_bus_id, "%.23s", p.busId);
+        unsigned minor = 0;
+        if (s->minor && s->minor(dev, &minor) == kSuccess) d.device_minor = (int)minor;
+        char name[96] = {0};
+        if (s->name && s->name(dev, name, sizeof name) == kSuccess) snprintf(d.name, sizeof d.name, "%.63s", name);
+        devs.push_back(d);
+    }
+    std::string err;
+    if (identity::EmitCsv(devs.data(), (int)devs.size(), query, &r.std_out, &err) != CRO_OK) return unavailable();   // a field only nvidia-smi knows
+    r.available = true;
+    return r;
 }
 
 Reply ComputeApps(const std::string& lib) {

@@ -25,6 +25,9 @@ struct Reply {
 };
 
 // `lib` = path of libnvidia-ml ("" = libnvidia-ml.so.1); each distinct path keeps its own session for the process.
+// --query-gpu=<query> --format=csv,noheader,nounits (gpus.go:886,929) for a caller without a probe context; fields:
+// gpu_uuid, device_minor, pci.bus_id, name, index.  Another field: not available (spawn the real nvidia-smi).
+Reply QueryGpu(const std::string& lib, const std::string& query);
 Reply ComputeApps(const std::string& lib);                                         // gpu_uuid, process_name
 Reply DrainQuery(const std::string& lib, const std::string& bus_id);               // drain -p <bus> -q
 Reply DrainModify(const std::string& lib, const std::string& bus_id, bool on);     // drain -p <bus> -m 0|1

@@ -207,6 +207,28 @@ func (c *Context) MetricsText() (string, error) {
 	return C.GoStringN(buf, C.int(ln)), nil
 }
 
+// LocalNodeOp runs one node-side operation of internal/utils/gpus.go on the node
+// itself (a cro-node-agent that links libcroprobe): request is
+// {"op": "check_no_gpu_loads"|"run_nvidia_smi"|"check_gpu_visible"|"drain",
+// "node", "device_id", "device_resource_type", "driver_container",
+// "allow_mutation"}.  The flows, their exec sequence and their error strings are
+// the reference's (CheckNoGPULoads :88-186, DrainGPU :188-664); the /proc scans
+// are native and the nvidia-smi steps (compute apps, drain -q / -m 1 / -r,
+// -pm 0) are NVML calls in this process, so a detach pre-flight is a handful of
+// library calls instead of 3-8 SPDY execs.  The reply's "error" is what the
+// reference would have returned ("" = nil); "exec_log" says how each step ran.
+func (c *Context) LocalNodeOp(requestJSON string) (string, error) {
+	req := C.CString(requestJSON)
+	defer C.free(unsafe.Pointer(req))
+	buf := (*C.char)(C.malloc(65536))
+	defer C.free(unsafe.Pointer(buf))
+	var ln C.size_t
+	if rc := C.cro_local_node_op(c.h, req, buf, 65536, &ln); rc != C.CRO_OK {
+		return "", errorOf(c.h, rc)
+	}
+	return C.GoStringN(buf, C.int(ln)), nil
+}
+
 // Visible is the decision of utils.CheckGPUVisible (internal/utils/gpus.go:73-84)
 // strengthened: listed AND the probe reproduced the HBM pattern.
 func Visible(results []ProbeResult, deviceID string) bool {

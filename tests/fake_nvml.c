@@ -99,6 +99,18 @@ int nvmlDeviceGetUUID(void *dev, char *out, unsigned cap) {
     snprintf(out, cap, "%s", g_gpus[i].uuid);
     return 0;
 }
+int nvmlDeviceGetMinorNumber(void *dev, unsigned *minor) {
+    int i = (int)(size_t)dev - 1;
+    if (i < 0 || i >= g_n) return 2;
+    *minor = (unsigned)i;
+    return 0;
+}
+int nvmlDeviceGetName(void *dev, char *out, unsigned cap) {
+    int i = (int)(size_t)dev - 1;
+    if (i < 0 || i >= g_n) return 2;
+    snprintf(out, cap, "NVIDIA B200");
+    return 0;
+}
 int nvmlDeviceGetPciInfo_v3(void *dev, PciInfo *p) {
     int i = (int)(size_t)dev - 1;
     if (i < 0 || i >= g_n) return 2;

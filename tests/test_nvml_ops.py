@@ -152,3 +152,53 @@ def test_native_answers_equal_the_real_nvidia_smi(cro):
             assert native["how"] == "native" and real["how"] == "spawned"
             assert {k: native[k] for k in ("stdout", "stderr", "failed", "exec_err")} == {k: real[k] for k in ("stdout", "stderr", "failed", "exec_err")}, spelling
         print("native == nvidia-smi:", native["stdout"].strip())
+
+
+def test_query_gpu_without_a_probe_context(cro, fake_lib, node):
+    out = cro.local_exec([SMI, "--query-gpu=device_minor,gpu_uuid,pci.bus_id", FMT], nvml_lib=fake_lib)
+    assert out["how"] == "native" and out["stdout"] == "0, %s, 00000000:40:00.0\n1, %s, 00000000:41:00.0\n" % (A, B)
+    # a field this library does not know is nvidia-smi's to answer
+    out = cro.local_exec([SMI, "--query-gpu=temperature.gpu", FMT], nvml_lib=fake_lib)
+    assert out["how"] == "spawned"
+    (node / "gpus").write_text("")
+    out = cro.local_exec([SMI, "--query-gpu=gpu_uuid", FMT], nvml_lib=fake_lib)
+    assert out["stdout"] == "No devices were found\n"
+
+
+def test_whole_drain_is_library_calls(cro, fake_lib, node, tmp_path):
+    """DrainGPU, OCP + DEVICE_PLUGIN flavour (gpus.go:556-664), on the node with mutation allowed: enumerate, persistence
+    mode off, open-file scan of /dev/nvidia<minor>, maintenance mode, remove — no child process anywhere."""
+    proc = tmp_path / "proc"
+    (proc / "100" / "fd").mkdir(parents=True)
+    (proc / "100" / "cmdline").write_bytes(b"/usr/bin/sleep\09\0")
+    (proc / "100" / "comm").write_text("sleep\n")
+    req = {"op": "drain", "node": "worker-0", "device_id": B, "device_resource_type": "DEVICE_PLUGIN", "driver_container": True,
+           "allow_mutation": True, "nvml_lib": fake_lib, "proc_root": str(proc)}
+    res = cro.local_node_op(None, req)
+    assert res["error"] == "", res
+    assert [(x["kind"], x["how"]) for x in res["exec_log"]] == [("command", "native"), ("command", "native"), ("fd_scan", "native"),
+                                                                ("command", "native"), ("command", "native")]
+    assert [x["argv"][1:] for x in res["exec_log"] if x["kind"] == "command"] == [
+        ["--query-gpu=device_minor,gpu_uuid,pci.bus_id", FMT], ["-i", B, "-pm", "0"],
+        ["drain", "-p", ":41:00.0".join(["0000", ""]), "-m", "1"], ["drain", "-p", "0000:41:00.0", "-r"]]
+    assert calls(node) == ["set_persistence %s 0" % B, "modify_drain 00000000:41:00.0 1 domain=0 bus=41 device=0",
+                           "remove_gpu 00000000:41:00.0 gpu_state=1 link_state=0"]
+    # the same request as a dry run changes nothing
+    (node / "calls").unlink()
+    res = cro.local_node_op(None, dict(req, allow_mutation=False))
+    assert res["error"] == "" and calls(node) == []
+    assert [x["how"] for x in res["exec_log"]] == ["native", "skipped (dry run)", "native", "skipped (dry run)", "skipped (dry run)"]
+    # a GPU that is no longer enumerated was already drained (gpus.go:366)
+    res = cro.local_node_op(None, dict(req, device_id="GPU-gone"))
+    assert res["error"] == "" and len(res["exec_log"]) == 1
+
+
+def test_a_refused_maintenance_mode_stops_the_drain_where_the_reference_stops(cro, fake_lib, node, tmp_path):
+    (node / "fail").write_text("nvmlDeviceModifyDrainState 4\n")
+    proc = tmp_path / "proc"
+    proc.mkdir()
+    res = cro.local_node_op(None, {"op": "drain", "node": "worker-0", "device_id": A, "device_resource_type": "DEVICE_PLUGIN",
+                                   "driver_container": True, "allow_mutation": True, "nvml_lib": fake_lib, "proc_root": str(proc)})
+    assert res["error"] == ("detach command 'set maintenance mode' failed: 'command terminated with exit code 255', stderr: '', "
+                            "stdout: 'Failed to set the GPU drain state: Insufficient Permissions\n'")
+    assert calls(node) == ["set_persistence %s 0" % A]          # no remove after the refusal
