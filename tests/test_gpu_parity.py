@@ -220,6 +220,21 @@ def test_full_size_probe_matches_oracle(cro, coracle):
         assert r2.checksum == r2.expect == coracle.checksum(r2.seed, 0, S // 8, threads=os.cpu_count() or 1)
 
 
+@pytest.mark.parametrize("mib", [256, 1024, 16384])
+def test_the_other_sweep_sizes_of_config_2(cro, coracle, mib):
+    """SURVEY.md §8d config 2 also names S = 256 MiB, 1 GiB and 16 GiB (word indices beyond 2^31 at the last one):
+    whole probe, every sweep and every copy destination, bit-exact against the C oracle's closed form."""
+    S = mib << 20
+    with cro.ProbeContext(sweep_bytes=S, devices=[0]) as c:
+        r = c.probe_device(0)
+        want = coracle.checksum(r.seed, 0, S // 8, threads=os.cpu_count() or 1)
+        assert r.status == 0 and r.sweep_bytes == S and r.copy_verified == 5
+        assert r.checksum == r.copy_checksum == r.expect == want
+        for rv in VARIANTS:
+            assert c.hbm_read_checksum(0, rv).checksum == want
+            assert c.hbm_read_checksum(0, rv, dst=True).checksum == want
+
+
 def test_identity_strings_match_nvidia_smi(cro):
     """cro_emit_csv must print what the reference's exec of nvidia-smi prints (gpus.go:886)."""
     smi = shutil.which("nvidia-smi")
