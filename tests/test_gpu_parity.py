@@ -235,6 +235,29 @@ def test_the_other_sweep_sizes_of_config_2(cro, coracle, mib):
             assert c.hbm_read_checksum(0, rv, dst=True).checksum == want
 
 
+def test_deadline_is_honoured_and_the_context_survives(cro, coracle):
+    """cro_opts.deadline_ms stands in for the Go context that cannot cross cgo (threading): a probe that
+    outlasts it returns CRO_ERR_DEADLINE at once — the kernels cannot be recalled and finish on the device — and the
+    context stays usable: the next sweep queues behind them and finds the pattern the timed-out probe wrote."""
+    import time
+    S = 4 << 30                                   # 9.7 ms of sweeps against a 2 ms deadline
+    with cro.ProbeContext(sweep_bytes=S, devices=[0], deadline_ms=2) as c:
+        c.hbm_fill(0)                             # module load, first launches: not what the deadline is about
+        time.sleep(0.05)
+        t0 = time.monotonic()
+        with pytest.raises(cro.ProbeError) as e:
+            c.probe_device(0)
+        waited = time.monotonic() - t0
+        assert e.value.code == cro.ERR_DEADLINE and "deadline of 2 ms exceeded" in str(e.value)
+        assert waited < 1.0                       # (the first probe also captures its graph)
+        time.sleep(0.1)                           # the device finishes what was enqueued
+        want = coracle.checksum(c.seed(0), 0, S // 8, threads=os.cpu_count() or 1)
+        assert c.hbm_read_checksum(0, cro.READ_TMA).checksum == want
+        assert c.hbm_read_checksum(0, cro.READ_TMA, dst=True).checksum == want
+    with cro.ProbeContext(sweep_bytes=S, devices=[0], deadline_ms=2000) as c:
+        assert c.probe_device(0).status == 0
+
+
 def test_identity_strings_match_nvidia_smi(cro):
     """cro_emit_csv must print what the reference's exec of nvidia-smi prints (gpus.go:886)."""
     smi = shutil.which("nvidia-smi")
