@@ -403,6 +403,7 @@ def fullbox_leg(cro, ctx, S, steps, warmup, coracle):
                       "host_enqueue": round(med([f.enqueue_ns for f in fts]) / 1e6, 3)},
         "allgather_us": round(med([f.gather_ns for f in fts]) / 1e3, 1),
         "host_syncs_per_call": int(fts[-1].host_syncs), "rounds": int(fts[-1].rounds),
+        "gather": {0: "host", 1: "ncclAllGather (in library)", 2: "host (degraded: no usable libnccl — replicas only)"}[int(fts[-1].gather)],
         "hbm_read_gbs": stats([gbs(S, r.read_best_ns) for r in res]), "hbm_copy_gbs": stats([gbs(2 * S, r.copy_best_ns) for r in res]),
         "nvlink_read_gbs": rs, "nvlink_push_gbs": ps, "latency_ns": stats([round(x, 1) for x in lat]),
         "matrix_flat": bool(rs and (rs["max"] - rs["min"]) <= 0.05 * rs["mean"]),

@@ -140,7 +140,11 @@ class P2PDetail(ctypes.Structure):
 class FullBoxTime(ctypes.Structure):
     _fields_ = [("enqueue_ns", ctypes.c_uint64), ("wall_ns", ctypes.c_uint64), ("hbm_ns", ctypes.c_uint64),
                 ("p2p_ns", ctypes.c_uint64), ("chase_ns", ctypes.c_uint64), ("gather_ns", ctypes.c_uint64),
-                ("rounds", ctypes.c_uint32), ("host_syncs", ctypes.c_uint32)]
+                ("rounds", ctypes.c_uint32), ("host_syncs", ctypes.c_uint32), ("gather", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32)]
+
+
+GATHER_HOST, GATHER_NCCL, GATHER_DEGRADED = 0, 1, 2
 
 
 assert ctypes.sizeof(ProbeResult) == 512, ctypes.sizeof(ProbeResult)
@@ -456,6 +460,12 @@ class ProbeContext:
             lib.cro_last_error(self.handle, buf, 1024)
             raise ProbeError(rc, buf.value.decode("utf-8", "replace"))
         return rc
+
+    def last_error(self) -> str:
+        """Text of this thread's most recent failing (or degrading) call on the context."""
+        buf = ctypes.create_string_buffer(1024)
+        lib.cro_last_error(self.handle, buf, 1024)
+        return buf.value.decode("utf-8", "replace")
 
     def device_count(self) -> int:
         n = ctypes.c_int()

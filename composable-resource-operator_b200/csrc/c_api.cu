@@ -264,6 +264,8 @@ int cro_fullbox_times(cro_ctx* ctx, cro_fullbox_time* out) try {
     out->gather_ns = f.gather_ns;
     out->rounds = f.rounds;
     out->host_syncs = f.host_syncs;
+    out->gather = f.gather;
+    out->reserved = 0;
     return CRO_OK;
 } CRO_API_CATCH
 

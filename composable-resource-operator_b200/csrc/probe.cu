@@ -1260,6 +1260,11 @@ int ensure_chase(cro_ctx* c, uint32_t hops) {
 int load_nccl(cro_ctx* c) {
     if (c->ncclAllGather) return CRO_OK;
     if (!c->nccl_lib) {
+        const char* path = getenv("CRO_NCCL_PATH");
+        if (path && strcmp(path, "off") == 0) {          // the host does not want NCCL in its process
+            c->set_error("NCCL switched off (CRO_NCCL_PATH=off): host-side gather");
+            return CRO_ERR_NCCL;
+        }
         // 1. whatever NCCL the host process already carries (a torch host brings its own, newer than the system's:
         //    loading the system copy first would make the host's later import fail on a missing symbol)
         c->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL);
@@ -1316,15 +1321,21 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
     }
     const bool p2p = n > 1 && !(o.flags & CRO_F_SKIP_P2P);
     const bool push = p2p && !(o.flags & CRO_F_SKIP_P2P_WRITE);
-    const bool use_nccl = n > 1 && !(o.flags & CRO_F_SKIP_NCCL);
+    bool use_nccl = n > 1 && !(o.flags & CRO_F_SKIP_NCCL);
+    bool nccl_degraded = false;
     int rc;
     // one-time setup (peer mappings, latency tables, communicators) happens BEFORE anything is enqueued
     if (p2p) {
         if ((rc = enable_peers(c))) return rc;
         if ((rc = ensure_chase(c, o.latency_hops))) return rc;
     }
+    if (use_nccl && load_nccl(c) != CRO_OK) {
+        // no usable libnccl in reach: the structs still come back, per device over pinned memory ("replicas only",
+        // SURVEY.md §8e) — the call says so (cro_fullbox_time.gather, last error) instead of failing the attach
+        use_nccl = false;
+        nccl_degraded = true;
+    }
     if (use_nccl) {
-        if ((rc = load_nccl(c))) return rc;
         if (!c->nccl_ready) {
             Range nv(c, "cro.nccl.init");
             std::vector<int> ords;
@@ -1593,6 +1604,7 @@ int ctx_probe_all(cro_ctx* c, cro_probe_result* out, int cap, int* n_out) {
     }
     c->fullbox.rounds = (uint32_t)rounds.size();
     c->fullbox.host_syncs = host_syncs;
+    c->fullbox.gather = use_nccl ? CRO_GATHER_NCCL : nccl_degraded ? CRO_GATHER_DEGRADED : CRO_GATHER_HOST;
     c->fullbox.wall_ns = now_ns() - t_call;
     return worst;
 }

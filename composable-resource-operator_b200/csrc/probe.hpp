@@ -112,6 +112,7 @@ struct FullBoxTimes {
     uint64_t gather_ns = 0;        // all-gather, CUDA events on rank 0's stream
     uint32_t rounds = 0;
     uint32_t host_syncs = 0;       // stream synchronisations the call performed
+    uint32_t gather = 0;           // CRO_GATHER_*
 };
 
 }  // namespace cro

@@ -370,7 +370,13 @@ typedef struct cro_fullbox_time {
     uint64_t gather_ns;            /* the all-gather, CUDA events on rank 0's stream                    */
     uint32_t rounds;               /* NVLink rounds (n-1 for even n)                                    */
     uint32_t host_syncs;           /* stream synchronisations the call made (one per device)            */
+    uint32_t gather;               /* CRO_GATHER_*: how the result structs were brought together        */
+    uint32_t reserved;
 } cro_fullbox_time;
+#define CRO_GATHER_HOST      0u    /* copied back per device, assembled on the host (one device, or CRO_F_SKIP_NCCL) */
+#define CRO_GATHER_NCCL      1u    /* ncclAllGather on the devices' streams, every rank holds the same array         */
+#define CRO_GATHER_DEGRADED  2u    /* NCCL was asked for but no usable libnccl is in reach: host-side gather over
+                                      pinned memory instead — "replicas only" (SURVEY.md §8e); cro_last_error says why */
 int  cro_fullbox_times(cro_ctx *ctx, cro_fullbox_time *out);
 /* The reply structs the fabric decoders walk ("FMScaleUpResponse", "FMGetMachineResponse", "CMMachineData"), as
  * JSON: {"type","struct","fields":[{"json","of":{...}}]} in declaration order — so that a test can hold them against

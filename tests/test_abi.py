@@ -33,7 +33,7 @@ def test_result_struct_layout(cro):
             "total_ns": 416, "p2p_write_ns": 424, "nonce": 488, "rank": 492, "copy_verified": 498, "fail_code": 499,
             "p2p_ok": 501, "t_start_ns": 504}
     assert ctypes.sizeof(cro.SweepResult) == 56 and ctypes.sizeof(cro.SweepTime) == 32 and ctypes.sizeof(cro.P2PDetail) == 120
-    assert ctypes.sizeof(cro.FullBoxTime) == 56
+    assert ctypes.sizeof(cro.FullBoxTime) == 64
     for k, v in offs.items():
         assert getattr(R, k).offset == v, k
 

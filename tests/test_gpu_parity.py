@@ -370,7 +370,28 @@ def test_multi_device_probe_all(cro, coracle):
                     assert d.read_ns == r.p2p_read_ns[j] and d.push_ns == r.p2p_write_ns[j]
             t = c.fullbox_times()
             assert t.host_syncs == n and t.rounds == (n - 1 if n % 2 == 0 else n) and t.gather_ns > 0
-            assert t.p2p_ns > 0 and t.chase_ns > 0 and t.hbm_ns > 0
+            assert t.p2p_ns > 0 and t.chase_ns > 0 and t.hbm_ns > 0 and t.gather == cro.GATHER_NCCL
+
+
+def test_without_nccl_the_full_box_probe_degrades_to_a_host_gather(cro, coracle, monkeypatch):
+    """SURVEY.md §8e, "If NCCL unavailable": host-side gather over pinned memory, reported as such — not a failed attach."""
+    monkeypatch.setenv("CRO_NCCL_PATH", "off")
+    S, P = 64 << 20, 16 << 20
+    with cro.ProbeContext(sweep_bytes=S, p2p_bytes=P, read_sweeps=1, copy_sweeps=1, latency_hops=256) as c:
+        n = c.device_count()
+        if n < 2:
+            pytest.skip("needs two devices")
+        res = c.probe_all()
+        t = c.fullbox_times()
+        assert t.gather == cro.GATHER_DEGRADED and t.gather_ns == 0 and t.host_syncs == n
+        assert "CRO_NCCL_PATH=off" in c.last_error()
+        for i, r in enumerate(res):
+            assert r.status == 0 and r.rank == i and r.checksum == coracle.checksum(r.seed, 0, S // 8)
+            assert all(r.p2p_ok & (1 << j) for j in range(n) if j != i)
+    monkeypatch.delenv("CRO_NCCL_PATH")
+    with cro.ProbeContext(sweep_bytes=S, p2p_bytes=P, read_sweeps=1, copy_sweeps=1, latency_hops=256, flags=cro.F_SKIP_NCCL) as c:
+        c.probe_all()
+        assert c.fullbox_times().gather == cro.GATHER_HOST
 
 
 def test_peer_push_lands_the_pushers_pattern(cro, coracle):
