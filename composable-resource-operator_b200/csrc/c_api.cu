@@ -36,6 +36,7 @@ static_assert(offsetof(cro_probe_result, p2p_bytes) == 352, "layout");
 static_assert(offsetof(cro_probe_result, p2p_write_ns) == 424, "layout");
 static_assert(offsetof(cro_probe_result, nonce) == 488, "layout");
 static_assert(offsetof(cro_probe_result, t_start_ns) == 504, "layout");
+static_assert(sizeof(cro_fullbox_time) == 64 && offsetof(cro_fullbox_time, gather) == 56, "cro_fullbox_time layout");
 static_assert(sizeof(cro_sweep_result) == 56, "layout");
 
 using namespace cro::capi;
