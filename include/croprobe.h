@@ -329,7 +329,10 @@ int  cro_probe_end(cro_ctx *ctx, int dev_index, cro_probe_result *out);
 
 /* Concurrent probe of every managed device, NVLink P2P rounds, then ONE
  * ncclAllGather of the 512-byte result structs.  out[] receives the gathered
- * array as rank 0 holds it (asserted byte-identical on every rank). */
+ * array as rank 0 holds it (asserted byte-identical on every rank).
+ * NCCL is dlopen'ed at the first call: the copy the host process already carries if there is one, else
+ * $CRO_NCCL_PATH, else libnccl.so.2 — never with RTLD_GLOBAL.  CRO_NCCL_PATH=off, or no usable library: the structs
+ * come back per device over pinned memory instead and cro_fullbox_time.gather reports CRO_GATHER_DEGRADED. */
 int  cro_probe_all(cro_ctx *ctx, cro_probe_result *out, int cap, int *n);
 
 /* Device address of this device's result struct (the all-gather send buffer),
