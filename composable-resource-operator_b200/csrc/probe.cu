@@ -154,12 +154,13 @@ void free_scratch(SweepScratch* sc) {
 }  // namespace
 
 uint32_t resolve_read_variant(uint32_t v, uint64_t bytes) {
-    // AUTO: the TMA ring wins from 256 MiB up (5.69 vs 5.57 TB/s there, 7.40 vs 6.42 at 4 GiB); for small sweeps its
-    // fixed cost (one CTA per SM, atomic tile claims) loses to plain 256-bit LDG (1.21 vs 2.03 TB/s at 16 MiB,
-    // profiles/r02_size_sweep.jsonl).
+    // AUTO: the TMA ring has the higher asymptote (7.47 vs 7.36 TB/s at 4 GiB) but ~5.5 us more constant cost per launch
+    // (ring ramp and drain, profiles/r02_fixed_cost.md), so small sweeps go to plain 256-bit LDG.  Whole probes, median of
+    // 30 (profiles/r02_auto_threshold.jsonl): 256 MiB 732 us with LDG.256 vs 755 with TMA, 512 MiB 1342 vs 1357, 1 GiB
+    // 2594 vs 2551, 2 GiB 5133 vs 5104 — the crossover sits between 512 MiB and 1 GiB.
     if (v == CRO_READ_AUTO) {
         v = env::get("CRO_READ_VARIANT");
-        if (v == CRO_READ_AUTO) v = bytes <= (128ull << 20) ? CRO_READ_LDG256 : CRO_READ_TMA;
+        if (v == CRO_READ_AUTO) v = bytes <= (512ull << 20) ? CRO_READ_LDG256 : CRO_READ_TMA;
     }
     return (v == READ_LDG || v == READ_TMA || v == READ_LDG256) ? v : (uint32_t)READ_TMA;
 }

@@ -63,7 +63,7 @@ extern "C" {
                                           words [0, S/8), half B [S/8, 2S/8)) */
 
 /* read-sweep kernel variants */
-#define CRO_READ_AUTO   0u
+#define CRO_READ_AUTO   0u   /* by sweep size: 256-bit LDG up to 512 MiB, the TMA ring above (measured crossover) */
 #define CRO_READ_LDG    1u   /* ld.global.nc.L1::no_allocate 128-bit, unrolled      */
 #define CRO_READ_TMA    2u   /* cp.async.bulk (1-D TMA) smem ring + LDS.128 reduce  */
 #define CRO_COPY_AUTO   0u
